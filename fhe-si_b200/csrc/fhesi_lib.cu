@@ -1,0 +1,898 @@
+// fhesi_lib.cu -- context set-up and the C ABI of libfhesi_b200.so (include/fhesi.h).
+// Built for sm_100a only; there is no CPU fallback anywhere in this library.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fhesi.h"
+#include "kernels_generic.cuh"
+#include "kernels_fused.cuh"
+
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(FHESI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+#define CKL()                                                                            \
+  do {                                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                 \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(FHESI_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct ProfRec {
+  int id;
+  cudaEvent_t e0, e1;
+};
+struct Arena {
+  void *ptr = nullptr;
+  size_t cap = 0;
+};
+
+struct fhesi_ctx {
+  fhesi_info info{};
+  DevCtx dc{};
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::vector<void *> tables;  // device allocations owned by the context
+  Arena scratch;
+  std::vector<PrimeConst> h_pc;
+  u32 chunk = 128;  // ciphertexts per pass through the scratch arena
+  bool use_fused = true;
+  // launch accounting / per-kernel CUDA-event profiler (bench.py "roofline", "gpu_launches")
+  uint64_t launches = 0;
+  bool prof_on = false;
+  std::vector<std::string> prof_names;
+  std::vector<ProfRec> prof_recs;
+  Arena stage;  // device staging for the *_host entry points
+  Arena work;   // tprod / scaled-down intermediates of the generic mult_relin composition
+};
+static void prof_clear(fhesi_ctx *c);
+static void prof_begin(fhesi_ctx *c, const char *name) {
+  c->launches++;
+  if (!c->prof_on) return;
+  int id = -1;
+  for (size_t i = 0; i < c->prof_names.size(); ++i)
+    if (c->prof_names[i] == name) id = (int)i;
+  if (id < 0) {
+    id = (int)c->prof_names.size();
+    c->prof_names.push_back(name);
+  }
+  ProfRec r{id, nullptr, nullptr};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, c->stream);
+  c->prof_recs.push_back(r);
+}
+static void prof_end(fhesi_ctx *c) {
+  if (c->prof_on) cudaEventRecord(c->prof_recs.back().e1, c->stream);
+}
+#define KL(c, kern, grid, block, smem, ...)                                \
+  do {                                                                     \
+    prof_begin((c), #kern);                                                \
+    FHESI_LAUNCH(kern, grid, block, smem, (c)->stream, __VA_ARGS__);       \
+    prof_end((c));                                                         \
+  } while (0)
+struct fhesi_ksw {
+  fhesi_ctx *ctx;
+  u32 *d_key;  // [Lk][parts*D][2][N] key form
+  u32 parts;
+};
+struct fhesi_key {
+  fhesi_ctx *ctx;
+  u32 *d_key;  // [Le][parts][1][N] key form  (and its transpose view [Le][1][parts][N])
+  u32 parts;
+};
+
+const char *fhesi_last_error(void) { return g_err.c_str(); }
+const char *fhesi_version(void) { return "fhesi_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+static u32 ilog2_ceil(u64 x) {
+  u32 k = 0;
+  while ((1ull << k) < x) ++k;
+  return k;
+}
+template <class T>
+static int upload(fhesi_ctx *c, const std::vector<T> &h, const T **d) {
+  void *p = nullptr;
+  CK(cudaMalloc(&p, h.size() * sizeof(T) + 16));
+  CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  c->tables.push_back(p);
+  *d = (const T *)p;
+  return 0;
+}
+
+int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSize, uint64_t xi,
+                     int device, fhesi_ctx **out) {
+  if (!out) return fail(FHESI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (m < 6 || (m & 1)) return fail(FHESI_ERR_UNSUPPORTED, "m must be 2*p' with p' an odd prime");
+  const u32 h = m / 2;
+  if (!(h & 1) || !h_is_prime(h))
+    return fail(FHESI_ERR_UNSUPPORTED, "m must be 2*p' with p' an odd prime");
+  if (logQ < 8 || logQ > 512) return fail(FHESI_ERR_UNSUPPORTED, "logQ must be in [8, 512]");
+  if (decompSize < 1 || decompSize > 3)
+    return fail(FHESI_ERR_UNSUPPORTED, "decompSize must be 1..3 (digits must stay below 2^29)");
+  if (p_pt < 2 || p_pt >= (1ull << 29)) return fail(FHESI_ERR_UNSUPPORTED, "p must be in [2, 2^29)");
+  if (xi < 1) xi = 1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(FHESI_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(FHESI_ERR_INVALID, "bad device index");
+  CK(cudaSetDevice(device));
+
+  fhesi_ctx *c = new fhesi_ctx();
+  c->device = device;
+  const u32 n = h - 1;
+  u32 N = 2;
+  while (N < 2 * n - 1) N <<= 1;
+  if (N > 2048) {
+    delete c;
+    return fail(FHESI_ERR_UNSUPPORTED, "phi(m) > 1024 not supported");
+  }
+  const u32 W = (logQ + 31) / 32, dbits = 8 * decompSize;
+  const u32 D = (logQ + dbits - 1) / dbits;
+
+  // number of 30-bit primes needed by each stage (DESIGN.md "chain sizing")
+  const double lg2n = std::log2(2.0 * n), lgp = std::log2((double)p_pt);
+  const double need_t = 2.0 * logQ - 2 + lgp + lg2n + std::log2(3.0) + std::log2((double)xi) + 1 + 0.1;
+  const double need_k = dbits + (logQ - 1) + lg2n + std::log2(3.0 * D) + 1 + 0.1;
+  const double need_e = logQ + lg2n + 10 + 1 + 0.1;
+  std::vector<u32> primes;
+  double bits = 0;
+  u32 Lt = 0, Lk = 0, Le = 0;
+  for (u64 q = ((1ull << 30) - 1) / N * N + 1; q > (1ull << 29) && Lt == 0; q -= N) {
+    if (q >= (1ull << 30) || !h_is_prime(q)) continue;
+    primes.push_back((u32)q);
+    bits += std::log2((double)q);
+    if (!Lk && bits >= need_k) Lk = (u32)primes.size();
+    if (!Le && bits >= need_e) Le = (u32)primes.size();
+    if (bits >= need_t) Lt = (u32)primes.size();
+    if (primes.size() >= FHESI_MAX_PRIMES) break;
+  }
+  if (!Lt || !Lk || !Le) {
+    delete c;
+    return fail(FHESI_ERR_UNSUPPORTED, "parameter set needs more than FHESI_MAX_PRIMES primes");
+  }
+  if (Lk > Lt) Lk = Lt;
+  if (Le > Lt) Le = Lt;
+  const u32 L = Lt;
+
+  fhesi_info &I = c->info;
+  I.m = m; I.n = n; I.logQ = logQ; I.W = W; I.decompSize = decompSize; I.D = D; I.N = N;
+  I.Lt = Lt; I.Lk = Lk; I.Le = Le; I.p = p_pt; I.xi = xi; I.device = device;
+  for (u32 i = 0; i < L; ++i) I.primes[i] = primes[i];
+
+  // per-prime constants and tables
+  const u32 CW = W + 2;
+  std::vector<PrimeConst> pc(L);
+  std::vector<u32> twf((size_t)L * N), twi((size_t)L * N), cw((size_t)L * CW), gar((size_t)L * L, 0);
+  // floor(2^logQ / p_pt) mod q needs 2^logQ mod p_pt
+  const u64 rem_q = h_powmod(2, logQ, p_pt);
+  for (u32 l = 0; l < L; ++l) {
+    const u64 q = primes[l];
+    PrimeConst &P = pc[l];
+    memset(&P, 0, sizeof(P));
+    P.p = (u32)q;
+    u32 inv = 1;  // Newton: inv = q^-1 mod 2^32
+    for (int it = 0; it < 5; ++it) inv *= 2 - (u32)q * inv;
+    P.pinv = (u32)(0 - inv);
+    const u64 R = (1ull << 32) % q, R2 = h_mulmod(R, R, q);
+    const u64 ninv = h_invmod(N % q, q);
+    P.r1 = (u32)R; P.r2 = (u32)R2;
+    P.ninv_r = (u32)h_mulmod(ninv, R, q);
+    P.ninv_r2 = (u32)h_mulmod(ninv, R2, q);
+    P.tensor_c = (u32)h_mulmod(h_mulmod(p_pt % q, ninv, q), R2, q);
+    P.ptxt_r = (u32)h_mulmod(p_pt % q, R, q);
+    const u64 two_q = h_powmod(2, logQ, q);
+    const u64 scale = h_mulmod((two_q + q - rem_q % q) % q, h_invmod(p_pt % q, q), q);
+    P.scale_r = (u32)h_mulmod(scale, R, q);
+    // primitive N-th root of unity: z^((q-1)/N) for a quadratic non-residue z
+    u64 z = 2;
+    while (h_powmod(z, (q - 1) / 2, q) != q - 1) ++z;
+    const u64 w = h_powmod(z, (q - 1) / N, q), wi = h_invmod(w, q);
+    for (u32 hh = 1; hh < N; hh <<= 1) {
+      const u64 step = h_powmod(w, N / (2 * hh), q), istep = h_powmod(wi, N / (2 * hh), q);
+      u64 a = R, b = R;  // Montgomery form of 1
+      for (u32 j = 0; j < hh; ++j) {
+        twf[(size_t)l * N + hh + j] = (u32)a;
+        twi[(size_t)l * N + hh + j] = (u32)b;
+        a = h_mulmod(a, step, q);
+        b = h_mulmod(b, istep, q);
+      }
+    }
+    twf[(size_t)l * N] = twi[(size_t)l * N] = (u32)R;
+    u64 t = R;  // 2^(32k) * R
+    for (u32 k = 0; k < CW; ++k) {
+      cw[(size_t)l * CW + k] = (u32)t;
+      t = h_mulmod(t, R, q);
+    }
+    for (u32 i = 0; i < l; ++i)
+      gar[(size_t)l * L + i] = (u32)h_mulmod(h_invmod(primes[i] % q, q), R, q);
+  }
+  // prefix products and their halves, L words each
+  std::vector<u32> Pf((size_t)(L + 1) * L, 0), Ph((size_t)(L + 1) * L, 0);
+  {
+    std::vector<u32> cur(L, 0);
+    cur[0] = 1;
+    for (u32 l = 0; l <= L; ++l) {
+      for (u32 k = 0; k < L; ++k) Pf[(size_t)l * L + k] = cur[k];
+      u32 carry = 0;
+      for (int k = (int)L - 1; k >= 0; --k) {
+        Ph[(size_t)l * L + k] = (cur[k] >> 1) | (carry << 31);
+        carry = cur[k] & 1;
+      }
+      if (l < L) {
+        u64 cy = 0;
+        for (u32 k = 0; k < L; ++k) {
+          u64 t = (u64)cur[k] * primes[l] + cy;
+          cur[k] = (u32)t;
+          cy = t >> 32;
+        }
+      }
+    }
+  }
+  DevCtx &dc = c->dc;
+  dc.n = n; dc.N = N; dc.logN = ilog2_ceil(N); dc.W = W; dc.logQ = logQ; dc.D = D; dc.dbits = dbits;
+  dc.h = h; dc.Lmax = L; dc.CW = CW; dc.ptxt = (u32)p_pt;
+  c->h_pc = pc;
+  int rc = 0;
+  if ((rc = upload(c, pc, &dc.pc)) || (rc = upload(c, twf, &dc.tw_fwd)) ||
+      (rc = upload(c, twi, &dc.tw_inv)) || (rc = upload(c, cw, &dc.cword)) ||
+      (rc = upload(c, gar, &dc.garner)) || (rc = upload(c, Pf, &dc.Pfull)) ||
+      (rc = upload(c, Ph, &dc.Phalf))) {
+    fhesi_ctx_destroy(c);
+    return rc;
+  }
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  const char *ev = getenv("FHESI_CHUNK");
+  if (ev && atoi(ev) > 0) c->chunk = (u32)atoi(ev);
+  ev = getenv("FHESI_NO_FUSED");
+  if (ev && atoi(ev) > 0) c->use_fused = false;
+  if (!fused_supported(dc)) c->use_fused = false;
+  if (c->use_fused) {
+    rc = fused_configure();
+    if (rc) {
+      fhesi_ctx_destroy(c);
+      return fail(FHESI_ERR_CUDA, "cudaFuncSetAttribute failed for the fused kernels");
+    }
+  }
+  *out = c;
+  return 0;
+}
+
+void fhesi_ctx_destroy(fhesi_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void *p : c->tables) cudaFree(p);
+  if (c->scratch.ptr) cudaFree(c->scratch.ptr);
+  if (c->stage.ptr) cudaFree(c->stage.ptr);
+  if (c->work.ptr) cudaFree(c->work.ptr);
+  prof_clear(c);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+int fhesi_ctx_info(const fhesi_ctx *c, fhesi_info *out) {
+  if (!c || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  *out = c->info;
+  return 0;
+}
+int fhesi_ctx_set_stream(fhesi_ctx *c, void *s) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return 0;
+}
+int fhesi_sync(fhesi_ctx *c) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int fhesi_malloc(fhesi_ctx *c, size_t bytes, void **d) {
+  if (!c || !d) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMalloc(d, bytes ? bytes : 16));
+  return 0;
+}
+int fhesi_free(fhesi_ctx *c, void *d) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d));
+  return 0;
+}
+int fhesi_h2d(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int fhesi_d2h(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+size_t fhesi_ct_bytes(const fhesi_ctx *c, uint32_t parts) {
+  return c ? (size_t)parts * c->info.n * c->info.W * 4 : 0;
+}
+size_t fhesi_tprod_bytes(const fhesi_ctx *c, uint32_t parts) {
+  return c ? (size_t)parts * c->info.Lt * c->info.N * 4 : 0;
+}
+
+static int scratch(fhesi_ctx *c, size_t bytes, u32 **p) {
+  if (c->scratch.cap < bytes) {
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->scratch.ptr) CK(cudaFree(c->scratch.ptr));
+    c->scratch.ptr = nullptr;
+    c->scratch.cap = 0;
+    CK(cudaMalloc(&c->scratch.ptr, bytes));
+    c->scratch.cap = bytes;
+  }
+  *p = (u32 *)c->scratch.ptr;
+  return 0;
+}
+static inline size_t al(size_t words) { return (words + 63) & ~(size_t)63; }
+
+// ---------------------------------------------------------------------------------------
+// launch helpers for the generic kernels
+// ---------------------------------------------------------------------------------------
+static int launch_fwd(fhesi_ctx *c, const void *src, u32 src_mode, u32 Win, u32 scale_mode, u32 L,
+                      u32 *dst, size_t npolys) {
+  if (!npolys) return 0;
+  FwdArgs a{src, Win, L, src_mode, scale_mode, dst};
+  const DevCtx &dc = c->dc;
+  dim3 grid((unsigned)npolys, L), block(dc.N / 2 < 32 ? 32 : dc.N / 2);
+  KL(c, k_fwd, grid, block, dc.N * 4, dc, a);
+  CKL();
+  return 0;
+}
+static int launch_inv(fhesi_ctx *c, const u32 *src, u32 L, u32 *dst, size_t npolys,
+                      const int *e = nullptr, const u32 *msg = nullptr) {
+  if (!npolys) return 0;
+  InvArgs a{src, L, dst, e, msg};
+  const DevCtx &dc = c->dc;
+  dim3 grid((unsigned)npolys, L), block(dc.N / 2 < 32 ? 32 : dc.N / 2);
+  KL(c, k_inv, grid, block, (dc.N + dc.h) * 4, dc, a);
+  CKL();
+  return 0;
+}
+template <int ML>
+static void launch_crt_t(fhesi_ctx *c, const CrtArgs &a) {
+  const int B = 128;
+  unsigned g = (unsigned)((a.total + B - 1) / B);
+  KL(c, k_crt<ML>, g, B, ML * B * 4, c->dc, a);
+}
+static int launch_crt(fhesi_ctx *c, const u32 *res, u32 L, u32 mode, u32 *out, u32 Wout,
+                      size_t npolys) {
+  if (!npolys) return 0;
+  CrtArgs a{res, L, mode, out, Wout, npolys * c->dc.n};
+  // DECRYPT multiplies by p_pt before the shift: two words of head-room
+  u32 need = L + (mode == CRT_DECRYPT ? 2 : 0);
+  if (need <= 8) launch_crt_t<8>(c, a);
+  else if (need <= 12) launch_crt_t<12>(c, a);
+  else if (need <= 20) launch_crt_t<20>(c, a);
+  else if (need <= 28) launch_crt_t<28>(c, a);
+  else if (need <= 36) launch_crt_t<36>(c, a);
+  else launch_crt_t<42>(c, a);
+  CKL();
+  return 0;
+}
+static inline unsigned nblk(size_t total, int B = 256) { return (unsigned)((total + B - 1) / B); }
+
+// ---------------------------------------------------------------------------------------
+// keys
+// ---------------------------------------------------------------------------------------
+int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uint32_t parts,
+                     fhesi_ksw **out) {
+  if (!c || !h_b || !h_A || !out || parts < 1 || parts > 3)
+    return fail(FHESI_ERR_INVALID, "fhesi_ksw_create: bad argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const u32 K = parts * I.D, Lk = I.Lk;
+  const size_t polyw = (size_t)I.n * I.W;
+  // interleave to [K][2] so that one transform launch writes [K*2][Lk][N]
+  std::vector<u32> h((size_t)K * 2 * polyw);
+  for (u32 k = 0; k < K; ++k) {
+    memcpy(&h[((size_t)k * 2 + 0) * polyw], h_b + (size_t)k * polyw, polyw * 4);
+    memcpy(&h[((size_t)k * 2 + 1) * polyw], h_A + (size_t)k * polyw, polyw * 4);
+  }
+  u32 *d_in = nullptr, *d_tmp = nullptr, *d_key = nullptr;
+  CK(cudaMalloc(&d_in, h.size() * 4));
+  CK(cudaMalloc(&d_tmp, (size_t)K * 2 * Lk * I.N * 4));
+  CK(cudaMalloc(&d_key, (size_t)K * 2 * Lk * I.N * 4));
+  CK(cudaMemcpyAsync(d_in, h.data(), h.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  int rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2);
+  if (rc) return rc;
+  // [K*2][Lk][N] -> [Lk][K*2][N]
+  KL(c, k_transpose_key, nblk((size_t)K * 2 * Lk * I.N), 256, 0, d_tmp, d_key, K * 2, Lk, I.N);
+  CKL();
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_in));
+  CK(cudaFree(d_tmp));
+  fhesi_ksw *k = new fhesi_ksw{c, d_key, parts};
+  *out = k;
+  return 0;
+}
+void fhesi_ksw_destroy(fhesi_ksw *k) {
+  if (!k) return;
+  cudaSetDevice(k->ctx->device);
+  cudaStreamSynchronize(k->ctx->stream);
+  cudaFree(k->d_key);
+  delete k;
+}
+int fhesi_key_create(fhesi_ctx *c, const uint32_t *h_polys, uint32_t parts, fhesi_key **out) {
+  if (!c || !h_polys || !out || parts < 1 || parts > 3)
+    return fail(FHESI_ERR_INVALID, "fhesi_key_create: bad argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const size_t polyw = (size_t)I.n * I.W;
+  u32 *d_in = nullptr, *d_tmp = nullptr, *d_key = nullptr;
+  CK(cudaMalloc(&d_in, parts * polyw * 4));
+  CK(cudaMalloc(&d_tmp, (size_t)parts * I.Le * I.N * 4));
+  CK(cudaMalloc(&d_key, (size_t)parts * I.Le * I.N * 4));
+  CK(cudaMemcpyAsync(d_in, h_polys, parts * polyw * 4, cudaMemcpyHostToDevice, c->stream));
+  int rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, I.Le, d_tmp, parts);
+  if (rc) return rc;
+  KL(c, k_transpose_key, nblk((size_t)parts * I.Le * I.N), 256, 0, d_tmp, d_key, parts, I.Le, I.N);
+  CKL();
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_in));
+  CK(cudaFree(d_tmp));
+  *out = new fhesi_key{c, d_key, parts};
+  return 0;
+}
+void fhesi_key_destroy(fhesi_key *k) {
+  if (!k) return;
+  cudaSetDevice(k->ctx->device);
+  cudaStreamSynchronize(k->ctx->stream);
+  cudaFree(k->d_key);
+  delete k;
+}
+
+// ---------------------------------------------------------------------------------------
+// coefficient-domain ops
+// ---------------------------------------------------------------------------------------
+int fhesi_ct_add_dev(fhesi_ctx *c, uint32_t *io, const uint32_t *other, uint32_t parts, size_t count) {
+  if (!c || !io || !other) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  size_t ncoef = count * parts * c->info.n;
+  if (!ncoef) return 0;
+  KL(c, k_ct_add, nblk(ncoef), 256, 0, c->dc, io, other, ncoef);
+  CKL();
+  return 0;
+}
+int fhesi_ct_sum_dev(fhesi_ctx *c, const uint32_t *in, uint32_t *out, uint32_t parts, size_t count) {
+  if (!c || !in || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  size_t per = (size_t)parts * c->info.n;
+  KL(c, k_ct_sum, nblk(per, 64), 64, 0, c->dc, in, out, per, (u32)count);
+  CKL();
+  return 0;
+}
+int fhesi_ct_mul_scalar_dev(fhesi_ctx *c, uint32_t *io, int64_t l, uint32_t parts, size_t count) {
+  if (!c || !io) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  size_t ncoef = count * parts * c->info.n;
+  if (!ncoef) return 0;
+  u64 mag = l < 0 ? (u64)0 - (u64)l : (u64)l;
+  KL(c, k_ct_mul_scalar, nblk(ncoef, 128), 128, 0, c->dc, io, mag, l < 0, ncoef);
+  CKL();
+  return 0;
+}
+int fhesi_reduce_wide_dev(fhesi_ctx *c, const uint32_t *in, uint32_t Win, uint32_t *out,
+                          uint32_t parts, size_t count) {
+  if (!c || !in || !out || Win < c->info.W) return fail(FHESI_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  size_t ncoef = count * parts * c->info.n;
+  if (!ncoef) return 0;
+  KL(c, k_reduce_wide, nblk(ncoef), 256, 0, c->dc, in, Win, out, ncoef);
+  CKL();
+  return 0;
+}
+int fhesi_ct_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uint32_t k,
+                           uint32_t *out, size_t count) {
+  if (!c || !in || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  const fhesi_info &I = c->info;
+  u64 a = k % I.m, b = I.m;
+  while (b) { u64 t = a % b; a = b; b = t; }
+  if (a != 1) return fail(FHESI_ERR_INVALID, "DoubleCRT::automorph: k not in Zm*");
+  CK(cudaSetDevice(c->device));
+  const u32 h = I.m / 2;
+  std::vector<u32> tab(h, 0xFFFFFFFFu);
+  for (u32 i = 0; i < I.n; ++i) {
+    u32 e = (u32)(((u64)i * k) % I.m), neg = 0;
+    if (e >= h) { e -= h; neg = 1; }
+    tab[e] = (i << 1) | neg;
+  }
+  u32 *d_tab = nullptr;
+  size_t npolys = count * parts;
+  CK(cudaMalloc(&d_tab, h * 4));
+  CK(cudaMemcpyAsync(d_tab, tab.data(), h * 4, cudaMemcpyHostToDevice, c->stream));
+  if (npolys) KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, out, npolys);
+  CKL();
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_tab));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// tensor-form ops
+// ---------------------------------------------------------------------------------------
+int fhesi_ct_tensor_dev(fhesi_ctx *c, const uint32_t *a, uint32_t pa, const uint32_t *b, uint32_t pb,
+                        uint32_t *tprod, size_t count, int accumulate) {
+  if (!c || !a || !b || !tprod || pa < 1 || pa > 3 || pb < 1 || pb > 3)
+    return fail(FHESI_ERR_INVALID, "fhesi_ct_tensor_dev: bad argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const size_t per = (size_t)I.Lt * I.N;
+  const u32 po = pa + pb - 1;
+  const size_t CH = c->chunk;
+  u32 *s = nullptr;
+  size_t na = al(CH * pa * per), nb_ = al(CH * pb * per), nacc = al(po * per);
+  int rc = scratch(c, (na + nb_ + nacc) * 4, &s);
+  if (rc) return rc;
+  u32 *sA = s, *sB = s + na, *sAcc = sB + nb_;
+  if (accumulate) CK(cudaMemsetAsync(tprod, 0, po * per * 4, c->stream));
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    if ((rc = launch_fwd(c, a + off * pa * I.n * I.W, SRC_POLY, I.W, SC_TENSOR, I.Lt, sA, cnt * pa))) return rc;
+    if ((rc = launch_fwd(c, b + off * pb * I.n * I.W, SRC_POLY, I.W, SC_NONE, I.Lt, sB, cnt * pb))) return rc;
+    TensArgs t{sA, sB, pa, pb, I.Lt, accumulate ? sAcc : tprod + off * po * per, (u32)cnt, accumulate};
+    size_t total = accumulate ? per : per * cnt;
+    KL(c, k_tensor_pw, nblk(total), 256, 0, c->dc, t);
+    CKL();
+    if (accumulate) {
+      KL(c, k_tprod_add, nblk(po * per), 256, 0, c->dc, tprod, sAcc, I.Lt, po * per);
+      CKL();
+    }
+  }
+  return 0;
+}
+int fhesi_tprod_add_dev(fhesi_ctx *c, uint32_t *io, const uint32_t *other, uint32_t parts, size_t count) {
+  if (!c || !io || !other) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  size_t total = count * parts * c->info.Lt * c->info.N;
+  if (!total) return 0;
+  KL(c, k_tprod_add, nblk(total), 256, 0, c->dc, io, other, c->info.Lt, total);
+  CKL();
+  return 0;
+}
+int fhesi_tprod_mul_scalar_dev(fhesi_ctx *c, uint32_t *io, int64_t l, uint32_t parts, size_t count) {
+  if (!c || !io) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  size_t total = count * parts * I.Lt * I.N;
+  if (!total) return 0;
+  std::vector<u32> sc(I.Lt);
+  for (u32 i = 0; i < I.Lt; ++i) {
+    i64 q = I.primes[i];
+    i64 r = l % q;
+    if (r < 0) r += q;
+    sc[i] = (u32)h_mulmod((u64)r, c->h_pc[i].r1, (u64)q);
+  }
+  u32 *d_sc = nullptr;
+  CK(cudaMalloc(&d_sc, I.Lt * 4));
+  CK(cudaMemcpyAsync(d_sc, sc.data(), I.Lt * 4, cudaMemcpyHostToDevice, c->stream));
+  KL(c, k_tprod_mul_scalar, nblk(total), 256, 0, c->dc, io, d_sc, I.Lt, total);
+  CKL();
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d_sc));
+  return 0;
+}
+int fhesi_tprod_reduce_gathered_dev(fhesi_ctx *c, const uint32_t *g, uint32_t world, uint32_t parts,
+                                    uint32_t *out) {
+  if (!c || !g || !out || !world) return fail(FHESI_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  size_t per = (size_t)parts * c->info.Lt * c->info.N;
+  KL(c, k_tprod_reduce_world, nblk(per), 256, 0, c->dc, g, world, c->info.Lt, per, out);
+  CKL();
+  return 0;
+}
+int fhesi_scaledown_dev(fhesi_ctx *c, const uint32_t *tprod, uint32_t parts, uint32_t *out, size_t count) {
+  if (!c || !tprod || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const size_t CH = c->chunk;
+  u32 *s = nullptr;
+  int rc = scratch(c, al(CH * parts * I.Lt * I.n) * 4, &s);
+  if (rc) return rc;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    if ((rc = launch_inv(c, tprod + off * parts * I.Lt * I.N, I.Lt, s, cnt * parts))) return rc;
+    if ((rc = launch_crt(c, s, I.Lt, CRT_SCALEDOWN, out + off * parts * I.n * I.W, I.W, cnt * parts))) return rc;
+  }
+  return 0;
+}
+
+// generic key switch on already scaled-down parts
+static int keyswitch_generic(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, u32 *out, size_t count) {
+  const fhesi_info &I = c->info;
+  const u32 K = ksw->parts * I.D, Lk = I.Lk;
+  const size_t per = (size_t)Lk * I.N;
+  const size_t CH = c->chunk;
+  size_t nd = al(CH * K * per), no = al(CH * 2 * per), nr = al(CH * 2 * Lk * I.n);
+  u32 *s = nullptr;
+  int rc = scratch(c, (nd + no + nr) * 4, &s);
+  if (rc) return rc;
+  u32 *sD = s, *sO = s + nd, *sR = sO + no;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    if ((rc = launch_fwd(c, in + off * ksw->parts * I.n * I.W, SRC_DIGIT, I.W, SC_NONE, Lk, sD, cnt * K))) return rc;
+    DotArgs d{sD, ksw->d_key, K, 2, Lk, sO, (u32)cnt};
+    KL(c, k_dot, nblk(per * cnt), 256, 0, c->dc, d);
+    CKL();
+    if ((rc = launch_inv(c, sO, Lk, sR, cnt * 2))) return rc;
+    if ((rc = launch_crt(c, sR, Lk, CRT_REDUCE_Q, out + off * 2 * I.n * I.W, I.W, cnt * 2))) return rc;
+  }
+  return 0;
+}
+int fhesi_keyswitch_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *in, uint32_t *out, size_t count) {
+  if (!c || !ksw || !in || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  if (ksw->ctx != c) return fail(FHESI_ERR_INVALID, "key-switch matrix belongs to another context");
+  CK(cudaSetDevice(c->device));
+  if (c->use_fused) return fused_keyswitch(c, ksw, in, out, count);
+  return keyswitch_generic(c, ksw, in, out, count);
+}
+
+int fhesi_mult_relin_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *a, const uint32_t *b,
+                         uint32_t *out, size_t count) {
+  if (!c || !ksw || !a || !b || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  if (ksw->ctx != c) return fail(FHESI_ERR_INVALID, "key-switch matrix belongs to another context");
+  if (ksw->parts != 3) return fail(FHESI_ERR_INVALID, "mult_relin needs the s^2 -> s matrix (3 source parts)");
+  CK(cudaSetDevice(c->device));
+  if (c->use_fused) return fused_mult_relin(c, ksw, a, b, out, count);
+  const fhesi_info &I = c->info;
+  // generic composition: tensor -> ScaleDown -> key switch, chunked through HBM scratch
+  const size_t CH = c->chunk;
+  const size_t ctw = (size_t)I.n * I.W;
+  const size_t nt = al(CH * 3 * I.Lt * I.N), nc = al(CH * 3 * ctw);
+  if (c->work.cap < (nt + nc) * 4) {
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->work.ptr) CK(cudaFree(c->work.ptr));
+    c->work.ptr = nullptr;
+    c->work.cap = 0;
+    CK(cudaMalloc(&c->work.ptr, (nt + nc) * 4));
+    c->work.cap = (nt + nc) * 4;
+  }
+  u32 *d_t = (u32 *)c->work.ptr, *d_c = d_t + nt;
+  int rc = 0;
+  for (size_t off = 0; off < count && !rc; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    rc = fhesi_ct_tensor_dev(c, a + off * 2 * ctw, 2, b + off * 2 * ctw, 2, d_t, cnt, 0);
+    if (!rc) rc = fhesi_scaledown_dev(c, d_t, 3, d_c, cnt);
+    if (!rc) rc = keyswitch_generic(c, ksw, d_c, out + off * 2 * ctw, cnt);
+  }
+  return rc;
+}
+int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_a, const uint32_t *h_b,
+                          uint32_t *h_out, size_t count) {
+  if (!c || !ksw || !h_a || !h_b || !h_out) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = count * fhesi_ct_bytes(c, 2);
+  if (c->stage.cap < 3 * bytes + 64) {  // grow-only staging area, reused across calls
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->stage.ptr) CK(cudaFree(c->stage.ptr));
+    c->stage.ptr = nullptr;
+    c->stage.cap = 0;
+    CK(cudaMalloc(&c->stage.ptr, 3 * bytes + 64));
+    c->stage.cap = 3 * bytes + 64;
+  }
+  char *d = (char *)c->stage.ptr;
+  u32 *da = (u32 *)d, *db = (u32 *)(d + bytes), *dout = (u32 *)(d + 2 * bytes);
+  CK(cudaMemcpyAsync(da, h_a, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(db, h_b, bytes, cudaMemcpyHostToDevice, c->stream));
+  int rc = fhesi_mult_relin_dev(c, ksw, da, db, dout, count);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_out, dout, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Encrypt / Decrypt
+// ---------------------------------------------------------------------------------------
+int fhesi_encrypt_dev(fhesi_ctx *c, const fhesi_key *pk, const uint32_t *msg, const uint8_t *r,
+                      const int32_t *e, uint32_t *out, size_t count) {
+  if (!c || !pk || !msg || !r || !e || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  if (pk->ctx != c || pk->parts != 2) return fail(FHESI_ERR_INVALID, "bad public key");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const u32 Le = I.Le;
+  const size_t per = (size_t)Le * I.N, CH = c->chunk;
+  size_t n1 = al(CH * per), n2 = al(CH * 2 * per), n3 = al(CH * 2 * Le * I.n);
+  u32 *s = nullptr;
+  int rc = scratch(c, (n1 + n2 + n3) * 4, &s);
+  if (rc) return rc;
+  u32 *sR = s, *sO = s + n1, *sC = sO + n2;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    if ((rc = launch_fwd(c, r + off * I.n, SRC_U8, 0, SC_NONE, Le, sR, cnt))) return rc;
+    // out[b][j] = NTT(r_b) . pk_j : K = 1 input, J = 2 outputs; key layout [Le][1][2][N]
+    DotArgs d{sR, pk->d_key, 1, 2, Le, sO, (u32)cnt};
+    KL(c, k_dot, nblk(per * cnt), 256, 0, c->dc, d);
+    CKL();
+    if ((rc = launch_inv(c, sO, Le, sC, cnt * 2, e + off * 2 * I.n, msg + off * I.n))) return rc;
+    if ((rc = launch_crt(c, sC, Le, CRT_REDUCE_Q, out + off * 2 * I.n * I.W, I.W, cnt * 2))) return rc;
+  }
+  return 0;
+}
+int fhesi_decrypt_dev(fhesi_ctx *c, const fhesi_key *sk, const uint32_t *in, uint32_t parts,
+                      uint32_t *msg, size_t count) {
+  if (!c || !sk || !in || !msg) return fail(FHESI_ERR_INVALID, "null argument");
+  if (sk->ctx != c || parts < sk->parts) return fail(FHESI_ERR_INVALID, "bad secret key / part count");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const u32 Le = I.Le, K = sk->parts;
+  const size_t per = (size_t)Le * I.N, CH = c->chunk;
+  size_t n1 = al(CH * K * per), n2 = al(CH * per), n3 = al(CH * Le * I.n), n4 = al(CH * K * I.n * I.W);
+  u32 *s = nullptr;
+  int rc = scratch(c, (n1 + n2 + n3 + n4) * 4, &s);
+  if (rc) return rc;
+  u32 *sF = s, *sO = s + n1, *sC = sO + n2, *sIn = sC + n3;
+  const size_t ctw = (size_t)I.n * I.W;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    const u32 *src = in + off * parts * ctw;
+    if (parts != K) {  // compact the first K parts of each ciphertext
+      CK(cudaMemcpy2DAsync(sIn, K * ctw * 4, src, parts * ctw * 4, K * ctw * 4, cnt,
+                           cudaMemcpyDeviceToDevice, c->stream));
+      src = sIn;
+    }
+    if ((rc = launch_fwd(c, src, SRC_POLY, I.W, SC_NONE, Le, sF, cnt * K))) return rc;
+    DotArgs d{sF, sk->d_key, K, 1, Le, sO, (u32)cnt};  // key layout [Le][K][1][N]
+    KL(c, k_dot, nblk(per * cnt), 256, 0, c->dc, d);
+    CKL();
+    if ((rc = launch_inv(c, sO, Le, sC, cnt))) return rc;
+    if ((rc = launch_crt(c, sC, Le, CRT_DECRYPT, msg + off * I.n, 1, cnt))) return rc;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// reference-chain rows (key export parity)
+// ---------------------------------------------------------------------------------------
+int fhesi_ref_rows_host(fhesi_ctx *c, const uint32_t *h_poly, uint32_t Win, const uint64_t *primes,
+                        const uint64_t *roots, uint32_t L, int64_t *h_rows) {
+  if (!c || !h_poly || !primes || !roots || !h_rows || !L || !Win)
+    return fail(FHESI_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  std::vector<u64> pinv(L), r2(L), zeta(L);
+  for (u32 l = 0; l < L; ++l) {
+    u64 q = primes[l];
+    if (!(q & 1) || q >> 62) return fail(FHESI_ERR_INVALID, "reference primes must be odd and < 2^62");
+    u64 inv = 1;
+    for (int it = 0; it < 6; ++it) inv *= 2 - q * inv;
+    pinv[l] = 0 - inv;
+    u64 R = (u64)(((unsigned __int128)1 << 64) % q);
+    r2[l] = h_mulmod(R, R, q);
+    zeta[l] = h_mulmod(roots[l] % q, roots[l] % q, q);
+  }
+  std::vector<u32> units;
+  for (u32 i = 0; i < I.m; ++i) {
+    u32 a = i, b = I.m;
+    while (b) { u32 t = a % b; a = b; b = t; }
+    if (a == 1) units.push_back(i);
+  }
+  char *d = nullptr;
+  size_t o_poly = 0, o_p = o_poly + al((size_t)I.n * Win) * 4, o_pi = o_p + L * 8, o_r2 = o_pi + L * 8,
+         o_z = o_r2 + L * 8, o_u = o_z + L * 8, o_rows = o_u + al(I.n) * 4, tot = o_rows + (size_t)L * I.n * 8;
+  CK(cudaMalloc(&d, tot));
+  CK(cudaMemcpyAsync(d + o_poly, h_poly, (size_t)I.n * Win * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + o_p, primes, L * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + o_pi, pinv.data(), L * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + o_r2, r2.data(), L * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + o_z, zeta.data(), L * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + o_u, units.data(), I.n * 4, cudaMemcpyHostToDevice, c->stream));
+  RefRowArgs a{(const u32 *)(d + o_poly), Win, L, (const u64 *)(d + o_p), (const u64 *)(d + o_pi),
+               (const u64 *)(d + o_r2), (const u64 *)(d + o_z), (const u32 *)(d + o_u), (i64 *)(d + o_rows)};
+  dim3 grid((I.n + 127) / 128, L);
+  KL(c, k_ref_rows, grid, 128, 0, c->dc, a);
+  CKL();
+  CK(cudaMemcpyAsync(h_rows, d + o_rows, (size_t)L * I.n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch accounting and per-kernel event profiler
+// ---------------------------------------------------------------------------------------
+static void prof_clear(fhesi_ctx *c) {
+  for (auto &r : c->prof_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof_recs.clear();
+  c->prof_names.clear();
+}
+int fhesi_profile_enable(fhesi_ctx *c, int on) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  prof_clear(c);
+  c->prof_on = on != 0;
+  c->launches = 0;
+  return 0;
+}
+int fhesi_profile_launches(fhesi_ctx *c, uint64_t *launches) {
+  if (!c || !launches) return fail(FHESI_ERR_INVALID, "null argument");
+  *launches = c->launches;
+  return 0;
+}
+int fhesi_profile_report(fhesi_ctx *c, char *buf, size_t cap) {
+  if (!c || !buf || !cap) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<double> ms(c->prof_names.size(), 0.0);
+  std::vector<uint64_t> cnt(c->prof_names.size(), 0);
+  for (auto &r : c->prof_recs) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      ms[r.id] += t;
+      cnt[r.id]++;
+    }
+  }
+  std::string out;
+  for (size_t i = 0; i < ms.size(); ++i) {
+    char line[256];
+    snprintf(line, sizeof line, "%s %llu %.6f\n", c->prof_names[i].c_str(), (unsigned long long)cnt[i], ms[i]);
+    out += line;
+  }
+  if (out.size() + 1 > cap) return fail(FHESI_ERR_INVALID, "report buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// modmul peak
+// ---------------------------------------------------------------------------------------
+int fhesi_modmul_peak(fhesi_ctx *c, int word_bits, double *out) {
+  if (!c || !out || (word_bits != 32 && word_bits != 64)) return fail(FHESI_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  void *d = nullptr;
+  CK(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, c->stream));
+    if (word_bits == 32)
+      KL(c, k_peak32, blocks, threads, 0, (u32 *)d, c->h_pc[0].p, c->h_pc[0].pinv, iters);
+    else
+      KL(c, k_peak64, blocks, threads, 0, (u64 *)d, 1152921504606820681ull, 0x9d1c9a1c8c4a3b47ull | 1, iters);
+    CKL();
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *out = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
+  return 0;
+}

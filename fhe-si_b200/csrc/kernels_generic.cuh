@@ -1,0 +1,684 @@
+// kernels_generic.cuh -- the general (any N = 2^k, any part count) CUDA path.
+//
+// These kernels are the building blocks behind every C-ABI entry point; the fused N=1024
+// kernels in kernels_fused.cuh replace the hot sequence (tensor -> ScaleDown -> key switch)
+// but produce bit-identical results and share the data layouts defined here.
+//
+// Reference map:
+//   k_fwd        a2/a4  Cmodulus::FFT / DoubleCRT(const ZZX&)      CModulus.cpp:90-107, DoubleCRT.cpp:244-257
+//   k_inv        a3     Cmodulus::iFFT (incl. rem by Phi_m)        CModulus.cpp:110-132
+//   k_crt        a7/a9/a12/a15  toPoly + intVecCRT + ScaleDown / Reduce / Decrypt rounding
+//                                DoubleCRT.cpp:349-398, NumbTh.cpp:307-335, Ciphertext.cpp:194-218,
+//                                Util.cpp:3-26, FHE-SI.cpp:111-118
+//   k_tensor_pw  a5/a8  DoubleCRT::Op(MulMod/AddMod) in the tensor  Ciphertext.cpp:179-186
+//   k_dot        a11    DotProduct(keySwitchMatrix[i], byteDecomp)  Util.h:80-98, FHE-SI.cpp:251-257
+//   k_fwd(DIGIT) a10    ByteDecomp fused into the transform's load  Ciphertext.cpp:82-121
+#pragma once
+#include "modarith.cuh"
+
+struct PrimeConst {
+  u32 p, pinv;      // prime, -p^-1 mod 2^32
+  u32 r1, r2;       // R mod p, R^2 mod p
+  u32 ninv_r;       // N^-1 * R      : mont(x, .) = x / N            (plain)
+  u32 ninv_r2;      // N^-1 * R^2    : mont(x, .) = x / N * R        (key form)
+  u32 tensor_c;     // p_pt * N^-1 * R^2 : mont(x, .) = x * p_pt / N * R
+  u32 ptxt_r;       // p_pt * R
+  u32 scale_r;      // floor(q / p_pt) * R
+  u32 pad[7];
+};
+
+struct DevCtx {
+  u32 n, N, logN, W, logQ, D, dbits, h;  // h = m/2 (X^h = -1 mod Phi_m), n = h-1
+  u32 Lmax, CW;                           // CW = row length of cword
+  u32 ptxt;                               // plaintext modulus p
+  const PrimeConst *pc;                   // [Lmax]
+  const u32 *tw_fwd, *tw_inv;             // [Lmax][N]  Montgomery form
+  const u32 *cword;                       // [Lmax][CW] 2^(32k) * R mod p
+  const u32 *garner;                      // [Lmax][Lmax] garner[j][i] = p_i^-1 * R mod p_j (i<j)
+  const u32 *Pfull, *Phalf;               // [Lmax+1][Lmax]  words of prod_{i<l} p_i and its half
+};
+
+// Storage order of transform-domain vectors: position i of the in-place DIF output.
+__device__ __forceinline__ u32 store_index(u32 i) { return i; }
+
+// ---------------------------------------------------------------------------------------
+// shared-memory radix-2 NTT, one butterfly per thread per stage
+// ---------------------------------------------------------------------------------------
+// forward: decimation in frequency, natural order in, bit-reversed ("position") order out.
+__device__ __forceinline__ void ntt_fwd_smem(u32 *x, const u32 *__restrict__ tw, u32 N, u32 p,
+                                             u32 pinv) {
+  const u32 p2 = 2 * p;
+  for (u32 h = N >> 1; h >= 1; h >>= 1) {
+    for (u32 b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
+      u32 j = b & (h - 1);
+      u32 i = ((b - j) << 1) | j;
+      u32 X = x[i], Y = x[i + h];
+      u32 w = __ldg(tw + h + j);
+      x[i] = csub(X + Y, p2);
+      x[i + h] = mont_mul(X + p2 - Y, w, p, pinv);
+    }
+    __syncthreads();
+  }
+}
+// inverse: decimation in time with the inverse root; position order in, natural order out,
+// unscaled (the factor 1/N is folded into the constants that produced the input).
+__device__ __forceinline__ void ntt_inv_smem(u32 *x, const u32 *__restrict__ itw, u32 N, u32 p,
+                                             u32 pinv) {
+  const u32 p2 = 2 * p;
+  for (u32 h = 1; h < N; h <<= 1) {
+    for (u32 b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
+      u32 j = b & (h - 1);
+      u32 i = ((b - j) << 1) | j;
+      u32 X = x[i];
+      u32 T = mont_mul(x[i + h], __ldg(itw + h + j), p, pinv);
+      x[i] = csub(X + T, p2);
+      x[i + h] = csub(X + p2 - T, p2);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// residue of one coefficient
+// ---------------------------------------------------------------------------------------
+// two's-complement multiword (Win words) -> [0, 2p)
+__device__ __forceinline__ u32 residue_from_words(const u32 *__restrict__ w, u32 Win,
+                                                  const u32 *__restrict__ cw, u32 p, u32 pinv) {
+  const u32 p2 = 2 * p;
+  u32 r = 0, top = 0;
+  for (u32 k = 0; k < Win; ++k) {
+    top = w[k];
+    r = csub(r + mont_mul(top, __ldg(cw + k), p, pinv), p2);
+  }
+  if (top >> 31) r = csub(r + p2 - mont_mul(1u, __ldg(cw + Win), p, pinv), p2);
+  return r;
+}
+// digit d (dbits wide, little-endian) of the non-negative residue mod 2^logQ
+// (Ciphertext::ByteDecompPart, Ciphertext.cpp:92-103)
+__device__ __forceinline__ u32 digit_from_words(const u32 *__restrict__ w, u32 W, u32 logQ,
+                                                u32 dbits, u32 d) {
+  u32 o = dbits * d;
+  u32 wi = o >> 5, sh = o & 31;
+  u32 lo = w[wi];
+  u32 hi = (wi + 1 < W) ? w[wi + 1] : 0u;
+  u32 v = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+  u32 valid = min(dbits, logQ - o);
+  return v & ((1u << valid) - 1u);
+}
+
+enum { SRC_POLY = 0, SRC_DIGIT = 1, SRC_U8 = 2, SRC_I32 = 3, SRC_U32 = 4 };
+enum { SC_NONE = 0, SC_TENSOR = 1, SC_KEYFORM = 2, SC_NINV = 3 };
+
+struct FwdArgs {
+  const void *src;
+  u32 Win;       // SRC_POLY: words per coefficient
+  u32 L;         // number of primes (prefix of the chain)
+  u32 src_mode, scale_mode;
+  u32 *dst;      // [npolys][L][N]
+};
+
+// grid (npolys, L), block N/2.  dynamic smem: N words.
+__global__ void k_fwd(DevCtx c, FwdArgs a) {
+  FHESI_SMEM(sm);
+  u32 *x = sm;
+  const u32 q = blockIdx.x, l = blockIdx.y;
+  const PrimeConst pc = c.pc[l];
+  const u32 p = pc.p, pinv = pc.pinv;
+  u32 sc = 0;
+  if (a.scale_mode == SC_TENSOR) sc = pc.tensor_c;
+  else if (a.scale_mode == SC_KEYFORM) sc = pc.ninv_r2;
+  else if (a.scale_mode == SC_NINV) sc = pc.ninv_r;
+  for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) {
+    u32 r = 0;
+    if (i < c.n) {
+      switch (a.src_mode) {
+        case SRC_POLY:
+          r = residue_from_words((const u32 *)a.src + ((size_t)q * c.n + i) * a.Win, a.Win,
+                                 c.cword + (size_t)l * c.CW, p, pinv);
+          break;
+        case SRC_DIGIT: {
+          u32 sp = q / c.D, d = q - sp * c.D;
+          r = digit_from_words((const u32 *)a.src + ((size_t)sp * c.n + i) * c.W, c.W, c.logQ,
+                               c.dbits, d);
+          break;
+        }
+        case SRC_U8: r = ((const uint8_t *)a.src)[(size_t)q * c.n + i]; break;
+        case SRC_I32: {
+          int v = ((const int *)a.src)[(size_t)q * c.n + i];
+          r = v < 0 ? p - ((u32)(-v)) % p : ((u32)v) % p;
+          break;
+        }
+        default: r = ((const u32 *)a.src)[(size_t)q * c.n + i] % p; break;
+      }
+      if (a.scale_mode != SC_NONE) r = mont_mul(r, sc, p, pinv);
+    }
+    x[i] = r;
+  }
+  __syncthreads();
+  ntt_fwd_smem(x, c.tw_fwd + (size_t)l * c.N, c.N, p, pinv);
+  u32 *dst = a.dst + ((size_t)q * a.L + l) * c.N;
+  for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) dst[store_index(i)] = full_reduce(x[i], p);
+}
+
+// Phi_m reduction for m = 2h, h odd prime: X^h = -1 and Phi_m = sum_{i<h} (-1)^i X^i.
+// x: N unreduced-product coefficients in [0,2p) (zero beyond 2n-2); writes n residues in [0,p).
+// y: scratch of h words.
+template <class F>
+__device__ __forceinline__ void phim_reduce_store(const u32 *x, u32 *y, u32 N, u32 h, u32 p,
+                                                  F store) {
+  const u32 p2 = 2 * p, n = h - 1;
+  for (u32 r = threadIdx.x; r < h; r += blockDim.x) {
+    u32 v = x[r];
+    if (r + h < N) v = csub(v + p2 - x[r + h], p2);
+    y[r] = v;
+  }
+  __syncthreads();
+  const u32 top = y[n];
+  for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+    u32 v = (i & 1) ? y[i] + top : y[i] + p2 - top;
+    store(i, full_reduce(v, p));
+  }
+}
+
+struct InvArgs {
+  const u32 *src;  // [npolys][L][N]
+  u32 L;
+  u32 *dst;        // [npolys][L][n]
+  // Encrypt addend (FHE-SI.cpp:24-31): + p_pt*e[q][i] + (q even ? floor(q/p_pt)*msg[q/2][i] : 0)
+  const int *e;
+  const u32 *msg;
+};
+
+// grid (npolys, L), block N/2.  dynamic smem: N + h words.
+__global__ void k_inv(DevCtx c, InvArgs a) {
+  FHESI_SMEM(sm);
+  u32 *x = sm, *y = sm + c.N;
+  const u32 q = blockIdx.x, l = blockIdx.y;
+  const PrimeConst pc = c.pc[l];
+  const u32 p = pc.p, pinv = pc.pinv;
+  const u32 *src = a.src + ((size_t)q * a.L + l) * c.N;
+  for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) x[i] = src[store_index(i)];
+  __syncthreads();
+  ntt_inv_smem(x, c.tw_inv + (size_t)l * c.N, c.N, p, pinv);
+  u32 *dst = a.dst + ((size_t)q * a.L + l) * c.n;
+  const int *e = a.e ? a.e + (size_t)q * c.n : nullptr;
+  const u32 *msg = (a.msg && !(q & 1)) ? a.msg + (size_t)(q >> 1) * c.n : nullptr;
+  phim_reduce_store(x, y, c.N, c.h, p, [&](u32 i, u32 v) {
+    if (e) {
+      int ev = e[i];
+      u32 er = ev < 0 ? p - ((u32)(-ev)) % p : ((u32)ev) % p;
+      v = csub(v + csub(mont_mul(er, pc.ptxt_r, p, pinv), p), p);
+      if (msg) v = csub(v + csub(mont_mul(msg[i] % p, pc.scale_r, p, pinv), p), p);
+    }
+    dst[i] = v;
+  });
+}
+
+// ---------------------------------------------------------------------------------------
+// pointwise kernels in the transform domain
+// ---------------------------------------------------------------------------------------
+struct TensArgs {
+  const u32 *A;  // [count][pa][L][N]  scaled by tensor_c (Montgomery form of p_pt*a/N)
+  const u32 *B;  // [count][pb][L][N]  plain
+  u32 pa, pb, L;
+  u32 *out;      // [count or 1][pa+pb-1][L][N]
+  u32 count;
+  int accumulate;
+};
+// one thread per (b, l, e); with accumulate, one thread per (l, e) looping over b.
+__global__ void k_tensor_pw(DevCtx c, TensArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per = (size_t)a.L * c.N;
+  size_t total = a.accumulate ? per : per * a.count;
+  if (idx >= total) return;
+  u32 b0 = a.accumulate ? 0 : (u32)(idx / per);
+  u32 b1 = a.accumulate ? a.count : b0 + 1;
+  size_t le = idx % per;
+  u32 l = (u32)(le / c.N);
+  const PrimeConst pc = c.pc[l];
+  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
+  const u32 po = a.pa + a.pb - 1;
+  u32 acc[5] = {0, 0, 0, 0, 0};
+  for (u32 b = b0; b < b1; ++b) {
+    u32 av[3], bv[3];
+    for (u32 i = 0; i < a.pa; ++i) av[i] = a.A[((size_t)b * a.pa + i) * per + le];
+    for (u32 j = 0; j < a.pb; ++j) bv[j] = a.B[((size_t)b * a.pb + j) * per + le];
+    for (u32 i = 0; i < a.pa; ++i)
+      for (u32 j = 0; j < a.pb; ++j)
+        acc[i + j] = csub(acc[i + j] + mont_mul(av[i], bv[j], p, pinv), p2);
+  }
+  for (u32 k = 0; k < po; ++k) a.out[((size_t)b0 * po + k) * per + le] = csub(acc[k], p);
+}
+
+struct DotArgs {
+  const u32 *in;   // [count][K][L][N] plain
+  const u32 *key;  // [L][K][J][N]     key form (value * R / N)
+  u32 K, J, L;
+  u32 *out;        // [count][J][L][N]
+  u32 count;
+};
+__global__ void k_dot(DevCtx c, DotArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per = (size_t)a.L * c.N;
+  if (idx >= per * a.count) return;
+  u32 b = (u32)(idx / per);
+  size_t le = idx % per;
+  u32 l = (u32)(le / c.N), e = (u32)(le % c.N);
+  const PrimeConst pc = c.pc[l];
+  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
+  u64 acc[2] = {0, 0};
+  u32 ts[2] = {0, 0};
+  for (u32 k = 0; k < a.K; ++k) {
+    u32 v = a.in[((size_t)b * a.K + k) * per + le];
+    const u32 *kp = a.key + (((size_t)l * a.K + k) * a.J) * c.N + e;
+    for (u32 j = 0; j < a.J; ++j) acc[j] += (u64)v * kp[(size_t)j * c.N];
+    if ((k & 3) == 3 || k + 1 == a.K) {
+      for (u32 j = 0; j < a.J; ++j) {
+        ts[j] = csub(ts[j] + mont_red64(acc[j], p, pinv), p2);
+        acc[j] = 0;
+      }
+    }
+  }
+  for (u32 j = 0; j < a.J; ++j) a.out[((size_t)b * a.J + j) * per + le] = csub(ts[j], p);
+}
+
+// io += other (mod p_l) / io *= scalar, over [count][parts][L][N]
+__global__ void k_tprod_add(DevCtx c, u32 *io, const u32 *other, u32 L, size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  u32 l = (u32)((idx / c.N) % L);
+  u32 p = c.pc[l].p;
+  io[idx] = csub(io[idx] + other[idx], p);
+}
+// scal[l] = (scalar mod p_l) * R mod p_l
+__global__ void k_tprod_mul_scalar(DevCtx c, u32 *io, const u32 *scal, u32 L, size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  u32 l = (u32)((idx / c.N) % L);
+  const PrimeConst pc = c.pc[l];
+  io[idx] = csub(mont_mul(io[idx], scal[l], pc.p, pc.pinv), pc.p);
+}
+// out[part][l][e] = sum_w in[w][part][l][e]  (multi-GPU combine after all-gather)
+__global__ void k_tprod_reduce_world(DevCtx c, const u32 *in, u32 world, u32 L, size_t per,
+                                     u32 *out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per) return;
+  u32 l = (u32)((idx / c.N) % L);
+  u32 p = c.pc[l].p;
+  u32 s = 0;
+  for (u32 w = 0; w < world; ++w) s = csub(s + in[(size_t)w * per + idx], p);
+  out[idx] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// CRT: Garner mixed radix -> multiword -> centre -> mode-specific rounding
+// ---------------------------------------------------------------------------------------
+enum { CRT_REDUCE_Q = 0, CRT_SCALEDOWN = 1, CRT_DECRYPT = 2, CRT_WIDE = 3 };
+
+struct CrtArgs {
+  const u32 *res;  // [npolys][L][n]
+  u32 L, mode;
+  u32 *out;        // REDUCE_Q/SCALEDOWN: [npolys][n][W]; DECRYPT: [npolys][n]; WIDE: [npolys][n][Wout]
+  u32 Wout;
+  size_t total;    // npolys * n
+};
+
+// dynamic smem: ML * blockDim.x words (only used for the runtime-offset shifts)
+template <int ML>
+__global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
+  FHESI_SMEM(sm);
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < a.total;
+  const size_t poly = active ? idx / c.n : 0;
+  const u32 coef = active ? (u32)(idx % c.n) : 0;
+  const int L = (int)a.L;
+  u32 v[ML];
+#pragma unroll
+  for (int j = 0; j < ML; ++j)
+    v[j] = (active && j < L) ? a.res[((size_t)poly * L + j) * c.n + coef] : 0u;
+    // mixed-radix digits: v_j = (..((r_j - v_0)/p_0 - v_1)/p_1 ..)/p_{j-1} mod p_j
+#pragma unroll
+  for (int j = 1; j < ML; ++j) {
+    if (j < L) {
+      const PrimeConst pc = c.pc[j];
+      const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
+      const u32 *g = c.garner + (size_t)j * c.Lmax;
+      u32 t = v[j];
+#pragma unroll
+      for (int i = 0; i < j; ++i) t = mont_mul(t + p2 - v[i], __ldg(g + i), p, pinv);
+      v[j] = csub(t, p);
+    }
+  }
+  // x = v_0 + p_0 (v_1 + p_1 (v_2 + ...)), Horner from the top, ML words
+  u32 acc[ML];
+#pragma unroll
+  for (int k = 0; k < ML; ++k) acc[k] = 0;
+#pragma unroll
+  for (int i = ML - 1; i >= 0; --i) {
+    if (i < L) {
+      const u32 p = c.pc[i].p;
+      u64 carry = v[i];
+#pragma unroll
+      for (int k = 0; k < ML; ++k) {
+        u64 t = (u64)acc[k] * p + carry;
+        acc[k] = (u32)t;
+        carry = t >> 32;
+      }
+    }
+  }
+  // centre: if x > P/2 then x -= P   (DoubleCRT.cpp:375-376, NumbTh.cpp:316-318)
+  {
+    const u32 *Ph = c.Phalf + (size_t)L * c.Lmax;
+    const u32 *Pf = c.Pfull + (size_t)L * c.Lmax;
+    bool gt = false, decided = false;
+#pragma unroll
+    for (int k = ML - 1; k >= 0; --k) {
+      u32 ph = (k < (int)c.Lmax) ? __ldg(Ph + k) : 0u;
+      if (!decided && acc[k] != ph) {
+        gt = acc[k] > ph;
+        decided = true;
+      }
+    }
+    if (gt) {
+      u32 borrow = 0;
+#pragma unroll
+      for (int k = 0; k < ML; ++k) {
+        u32 pf = (k < (int)c.Lmax) ? __ldg(Pf + k) : 0u;
+        u64 t = (u64)acc[k] - pf - borrow;
+        acc[k] = (u32)t;
+        borrow = (u32)(t >> 63);
+      }
+    }
+  }
+  const u32 W = c.W, logQ = c.logQ;
+  if (a.mode == CRT_WIDE) {
+    if (active) {
+      u32 *o = a.out + idx * a.Wout;
+      u32 sign = (acc[ML - 1] >> 31) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+      for (int k = 0; k < ML; ++k)
+        if (k < (int)a.Wout) o[k] = acc[k];
+      for (u32 k = ML; k < a.Wout; ++k) o[k] = sign;
+    }
+    return;
+  }
+  if (a.mode == CRT_REDUCE_Q) {
+    if (active) {
+      u32 *o = a.out + idx * W;
+      const u32 tb = (logQ - 1) & 31;  // sign bit position inside the top word
+#pragma unroll
+      for (int k = 0; k < ML; ++k) {
+        if (k < (int)W) {
+          u32 w = acc[k];
+          if (k == (int)W - 1 && tb != 31) w = (u32)((int)(w << (31 - tb)) >> (31 - tb));
+          o[k] = w;
+        }
+      }
+    }
+    return;
+  }
+  // SCALEDOWN: y = (x + q/2) >> logQ, keep logQ bits centred   (Ciphertext.cpp:206-213)
+  // DECRYPT:   y = (p_pt*x + q/2) >> logQ, then mod p_pt       (FHE-SI.cpp:111-118)
+  if (a.mode == CRT_DECRYPT) {
+    u64 carry = 0;
+    const u32 pt = c.ptxt;
+    // two's complement multiply by a small positive constant: multiply magnitude-agnostic
+    // works mod 2^(32 ML) because acc is already sign-extended over ML words.
+#pragma unroll
+    for (int k = 0; k < ML; ++k) {
+      u64 t = (u64)acc[k] * pt + carry;
+      acc[k] = (u32)t;
+      carry = t >> 32;
+    }
+  }
+  {  // += 2^(logQ-1)
+    const u32 hw = (logQ - 1) >> 5, hb = (logQ - 1) & 31;
+    u32 carry = 0;
+#pragma unroll
+    for (int k = 0; k < ML; ++k) {
+      u32 add = (k == (int)hw) ? (1u << hb) : 0u;
+      u64 t = (u64)acc[k] + add + carry;
+      acc[k] = (u32)t;
+      carry = (u32)(t >> 32);
+    }
+  }
+  // runtime-offset funnel shift through shared memory (column per thread)
+  u32 *col = sm + threadIdx.x;
+  const u32 stride = blockDim.x;
+#pragma unroll
+  for (int k = 0; k < ML; ++k) col[k * stride] = acc[k];
+  const u32 sign = (acc[ML - 1] >> 31) ? 0xFFFFFFFFu : 0u;
+  const u32 ws = logQ >> 5, bs = logQ & 31;
+  auto word_at = [&](u32 k) -> u32 { return k < (u32)ML ? col[k * stride] : sign; };
+  if (!active) return;
+  if (a.mode == CRT_SCALEDOWN) {
+    u32 *o = a.out + idx * W;
+    const u32 tb = (logQ - 1) & 31;
+    for (u32 k = 0; k < W; ++k) {
+      u32 lo = word_at(ws + k), hi = word_at(ws + k + 1);
+      u32 w = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
+      if (k == W - 1 && tb != 31) w = (u32)((int)(w << (31 - tb)) >> (31 - tb));
+      o[k] = w;
+    }
+  } else {  // DECRYPT: |y| < 2^62 by construction (x < 2^(logQ+20), p_pt < 2^31)
+    u32 w0, w1;
+    {
+      u32 a0 = word_at(ws), a1 = word_at(ws + 1), a2 = word_at(ws + 2);
+      w0 = bs ? ((a0 >> bs) | (a1 << (32 - bs))) : a0;
+      w1 = bs ? ((a1 >> bs) | (a2 << (32 - bs))) : a1;
+    }
+    i64 y = (i64)(((u64)w1 << 32) | w0);
+    i64 r = y % (i64)c.ptxt;
+    if (r < 0) r += c.ptxt;
+    a.out[idx] = (u32)r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// coefficient-domain multiword kernels (one thread per coefficient)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 sext_top(u32 w, u32 logQ) {
+  const u32 tb = (logQ - 1) & 31;
+  return tb == 31 ? w : (u32)((int)(w << (31 - tb)) >> (31 - tb));
+}
+// io = Reduce(io + other)   (Ciphertext.cpp:128-131)
+__global__ void k_ct_add(DevCtx c, u32 *io, const u32 *other, size_t ncoef) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ncoef) return;
+  u32 *a = io + idx * c.W;
+  const u32 *b = other + idx * c.W;
+  u32 carry = 0;
+  for (u32 k = 0; k < c.W; ++k) {
+    u64 t = (u64)a[k] + b[k] + carry;
+    carry = (u32)(t >> 32);
+    a[k] = (k == c.W - 1) ? sext_top((u32)t, c.logQ) : (u32)t;
+  }
+}
+// out = Reduce(sum_b in[b])  over a batch; per = parts*n coefficients per ciphertext
+__global__ void k_ct_sum(DevCtx c, const u32 *in, u32 *out, size_t per, u32 count) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per) return;
+  u32 acc[17];
+  for (u32 k = 0; k < c.W; ++k) acc[k] = 0;
+  for (u32 b = 0; b < count; ++b) {
+    const u32 *s = in + ((size_t)b * per + idx) * c.W;
+    u32 carry = 0;
+    for (u32 k = 0; k < c.W; ++k) {
+      u64 t = (u64)acc[k] + s[k] + carry;
+      acc[k] = (u32)t;
+      carry = (u32)(t >> 32);
+    }
+  }
+  u32 *o = out + idx * c.W;
+  for (u32 k = 0; k < c.W; ++k) o[k] = (k == c.W - 1) ? sext_top(acc[k], c.logQ) : acc[k];
+}
+// io = Reduce(io * l)   (Ciphertext.cpp:21-27); l given as sign + magnitude
+__global__ void k_ct_mul_scalar(DevCtx c, u32 *io, u64 mag, int neg, size_t ncoef) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ncoef) return;
+  u32 *a = io + idx * c.W;
+  u32 x[17], r[17];
+  const u32 W = c.W;
+  u32 borrow = neg ? 1u : 0u;  // two's complement negate: ~x + 1
+  for (u32 k = 0; k < W; ++k) {
+    u32 w = neg ? ~a[k] : a[k];
+    u64 t = (u64)w + borrow;
+    x[k] = (u32)t;
+    borrow = (u32)(t >> 32);
+    r[k] = 0;
+  }
+  const u32 m0 = (u32)mag, m1 = (u32)(mag >> 32);
+  u64 carry = 0;
+  for (u32 k = 0; k < W; ++k) {
+    u64 t = (u64)x[k] * m0 + carry;
+    r[k] = (u32)t;
+    carry = t >> 32;
+  }
+  carry = 0;
+  for (u32 k = 0; k + 1 < W; ++k) {
+    u64 t = (u64)x[k] * m1 + r[k + 1] + carry;
+    r[k + 1] = (u32)t;
+    carry = t >> 32;
+  }
+  for (u32 k = 0; k < W; ++k) a[k] = (k == W - 1) ? sext_top(r[k], c.logQ) : r[k];
+}
+// Reduce of a wide ([..][Win]) poly into [..][W]
+__global__ void k_reduce_wide(DevCtx c, const u32 *in, u32 Win, u32 *out, size_t ncoef) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ncoef) return;
+  const u32 *a = in + idx * Win;
+  u32 *o = out + idx * c.W;
+  for (u32 k = 0; k < c.W; ++k) o[k] = (k == c.W - 1) ? sext_top(a[k], c.logQ) : a[k];
+}
+// a(X) -> a(X^k) mod Phi_m in coefficient form (m = 2h): a signed permutation into h slots
+// followed by the Phi_m fold.  tab[e] = (source index << 1 | negate) or 0xFFFFFFFF if slot e
+// receives nothing.  out is [..][n][W+1] (not reduced mod q; Ciphertext.cpp:54-59).
+__global__ void k_automorph(DevCtx c, const u32 *in, const u32 *tab, u32 *out, size_t npolys) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npolys * c.n) return;
+  size_t poly = idx / c.n;
+  u32 j = (u32)(idx % c.n);
+  const u32 W = c.W, Wo = W + 1;
+  const u32 *base = in + poly * c.n * W;
+  u32 tj = tab[j], tt = tab[c.n];
+  // w_j = v_j - (-1)^j v_n
+  u32 neg_top = (j & 1) ? 0u : 1u;  // subtract top when j even
+  u32 borrow_a = 0, borrow_b = 0;
+  u32 *o = out + idx * Wo;
+  // term A = +-in[tj>>1], term B = -+(...)in[tt>>1]; add as sign-extended (W+1)-word values
+  u32 ca = (tj != 0xFFFFFFFFu && (tj & 1)) ? 1u : 0u;          // negate A
+  u32 cb = (tt != 0xFFFFFFFFu && ((tt & 1) ^ neg_top)) ? 1u : 0u;  // negate B
+  borrow_a = ca;
+  borrow_b = cb;
+  u32 c2 = 0;
+  for (u32 k = 0; k < Wo; ++k) {
+    u32 wa = 0, wb = 0;
+    if (tj != 0xFFFFFFFFu) {
+      const u32 *s = base + (size_t)(tj >> 1) * W;
+      wa = k < W ? s[k] : ((s[W - 1] >> 31) ? 0xFFFFFFFFu : 0u);
+      if (ca) wa = ~wa;
+      u64 t = (u64)wa + borrow_a;
+      wa = (u32)t;
+      borrow_a = (u32)(t >> 32);
+    }
+    if (tt != 0xFFFFFFFFu) {
+      const u32 *s = base + (size_t)(tt >> 1) * W;
+      wb = k < W ? s[k] : ((s[W - 1] >> 31) ? 0xFFFFFFFFu : 0u);
+      if (cb) wb = ~wb;
+      u64 t = (u64)wb + borrow_b;
+      wb = (u32)t;
+      borrow_b = (u32)(t >> 32);
+    }
+    u64 t = (u64)wa + wb + c2;
+    o[k] = (u32)t;
+    c2 = (u32)(t >> 32);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// reference-chain DoubleCRT rows (64-bit primes, direct evaluation; setup/export time only)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 mont_mul64(u64 a, u64 b, u64 p, u64 pinv) {
+  u64 lo = a * b, hi = __umul64hi(a, b);
+  u64 m = lo * pinv;
+  u64 mh = __umul64hi(m, p);
+  u64 r = hi + mh + (lo != 0);
+  return r >= p ? r - p : r;
+}
+struct RefRowArgs {
+  const u32 *poly;   // [n][Win]
+  u32 Win, L;
+  const u64 *prime;  // [L] p, and per-prime constants below
+  const u64 *pinv;   // -p^-1 mod 2^64
+  const u64 *r2;     // 2^128 mod p
+  const u64 *zeta;   // m-th root (root^2), plain
+  const u32 *units;  // [n]
+  i64 *rows;         // [L][n]
+};
+// grid (ceil(n/128), L): thread = one unit j of one prime
+__global__ void k_ref_rows(DevCtx c, RefRowArgs a) {
+  u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 l = blockIdx.y;
+  if (j >= c.n) return;
+  const u64 p = a.prime[l], pinv = a.pinv[l], r2 = a.r2[l];
+  const u64 one_m = mont_mul64(1, r2, p, pinv);
+  const u64 two32_m = mont_mul64(1ull << 32, r2, p, pinv);
+  // x = zeta^{u_j} in Montgomery form
+  u64 base = mont_mul64(a.zeta[l], r2, p, pinv), x = one_m;
+  for (u32 e = a.units[j]; e; e >>= 1) {
+    if (e & 1) x = mont_mul64(x, base, p, pinv);
+    base = mont_mul64(base, base, p, pinv);
+  }
+  u64 acc = 0;  // Horner over coefficients, high to low, Montgomery form
+  for (int i = (int)c.n - 1; i >= 0; --i) {
+    const u32 *w = a.poly + (size_t)i * a.Win;
+    // coefficient mod p: Horner over words (top word signed)
+    u64 r = 0;
+    for (int k = (int)a.Win - 1; k >= 0; --k) {
+      r = mont_mul64(r, two32_m, p, pinv);
+      u64 wk = mont_mul64((u64)w[k], r2, p, pinv);
+      r += wk;
+      if (r >= p) r -= p;
+    }
+    if (w[a.Win - 1] >> 31) {  // subtract 2^(32 Win)
+      u64 t = one_m;
+      for (u32 k = 0; k < a.Win; ++k) t = mont_mul64(t, two32_m, p, pinv);
+      r = r >= t ? r - t : r + p - t;
+    }
+    acc = mont_mul64(acc, x, p, pinv) + r;
+    if (acc >= p) acc -= p;
+  }
+  a.rows[(size_t)l * c.n + j] = (i64)mont_mul64(acc, 1, p, pinv);
+}
+
+// ---------------------------------------------------------------------------------------
+// modmul peak microbenchmarks: register-resident, ILP 8
+// ---------------------------------------------------------------------------------------
+__global__ void k_peak32(u32 *out, u32 p, u32 pinv, int iters) {
+  u32 x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = (threadIdx.x * 8 + k + blockIdx.x) % p;
+  u32 w = 123456789u % p;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = mont_mul(x[k], w, p, pinv);
+  }
+  u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s ^= x[k];
+  if (s == 0xFFFFFFFFu) out[0] = s;
+}
+__global__ void k_peak64(u64 *out, u64 p, u64 pinv, int iters) {
+  u64 x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = (threadIdx.x * 8 + k + blockIdx.x) % p;
+  u64 w = 1234567890123ull % p;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = mont_mul64(x[k], w, p, pinv);
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s ^= x[k];
+  if (s == ~0ull) out[0] = s;
+}

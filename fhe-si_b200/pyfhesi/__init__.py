@@ -1,0 +1,291 @@
+"""pyfhesi -- thin ctypes binding of include/fhesi.h (libfhesi_b200.so).
+
+Plumbing only: the product is the CUDA library.  The binding never computes anything on
+the CPU; if the CUDA library is missing or no GPU is usable it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(os.path.dirname(_HERE), "libfhesi_b200.so")
+FHESI_MAX_PRIMES = 40
+
+
+class FhesiError(RuntimeError):
+    pass
+
+
+class Info(C.Structure):
+    _fields_ = [("m", C.c_uint32), ("n", C.c_uint32), ("logQ", C.c_uint32), ("W", C.c_uint32),
+                ("decompSize", C.c_uint32), ("D", C.c_uint32), ("N", C.c_uint32), ("Lt", C.c_uint32),
+                ("Lk", C.c_uint32), ("Le", C.c_uint32), ("p", C.c_uint64), ("xi", C.c_uint64),
+                ("primes", C.c_uint32 * FHESI_MAX_PRIMES), ("device", C.c_int)]
+
+
+# every symbol include/fhesi.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_SZ = C.c_size_t
+_U32 = C.c_uint32
+SYMBOLS = {
+    "fhesi_last_error": (C.c_char_p, []),
+    "fhesi_version": (C.c_char_p, []),
+    "fhesi_ctx_create": (C.c_int, [_U32, _U32, C.c_uint64, _U32, C.c_uint64, C.c_int, C.POINTER(_P)]),
+    "fhesi_ctx_destroy": (None, [_P]),
+    "fhesi_ctx_info": (C.c_int, [_P, C.POINTER(Info)]),
+    "fhesi_ctx_set_stream": (C.c_int, [_P, _P]),
+    "fhesi_sync": (C.c_int, [_P]),
+    "fhesi_malloc": (C.c_int, [_P, _SZ, C.POINTER(_P)]),
+    "fhesi_free": (C.c_int, [_P, _P]),
+    "fhesi_h2d": (C.c_int, [_P, _P, _P, _SZ]),
+    "fhesi_d2h": (C.c_int, [_P, _P, _P, _SZ]),
+    "fhesi_ct_bytes": (_SZ, [_P, _U32]),
+    "fhesi_tprod_bytes": (_SZ, [_P, _U32]),
+    "fhesi_ksw_create": (C.c_int, [_P, _P, _P, _U32, C.POINTER(_P)]),
+    "fhesi_ksw_destroy": (None, [_P]),
+    "fhesi_key_create": (C.c_int, [_P, _P, _U32, C.POINTER(_P)]),
+    "fhesi_key_destroy": (None, [_P]),
+    "fhesi_mult_relin_dev": (C.c_int, [_P, _P, _P, _P, _P, _SZ]),
+    "fhesi_mult_relin_host": (C.c_int, [_P, _P, _P, _P, _P, _SZ]),
+    "fhesi_ct_add_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),
+    "fhesi_ct_sum_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),
+    "fhesi_ct_mul_scalar_dev": (C.c_int, [_P, _P, C.c_int64, _U32, _SZ]),
+    "fhesi_ct_tensor_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _P, _SZ, C.c_int]),
+    "fhesi_tprod_add_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),
+    "fhesi_tprod_mul_scalar_dev": (C.c_int, [_P, _P, C.c_int64, _U32, _SZ]),
+    "fhesi_scaledown_dev": (C.c_int, [_P, _P, _U32, _P, _SZ]),
+    "fhesi_keyswitch_dev": (C.c_int, [_P, _P, _P, _P, _SZ]),
+    "fhesi_encrypt_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _SZ]),
+    "fhesi_decrypt_dev": (C.c_int, [_P, _P, _P, _U32, _P, _SZ]),
+    "fhesi_ct_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
+    "fhesi_reduce_wide_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
+    "fhesi_ref_rows_host": (C.c_int, [_P, _P, _U32, _P, _P, _U32, _P]),
+    "fhesi_tprod_reduce_gathered_dev": (C.c_int, [_P, _P, _U32, _U32, _P]),
+    "fhesi_modmul_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "fhesi_profile_enable": (C.c_int, [_P, C.c_int]),
+    "fhesi_profile_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "fhesi_profile_report": (C.c_int, [_P, C.c_char_p, _SZ]),
+}
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise FhesiError(f"{path} not found: build it with `python fhe-si_b200/build.py` "
+                         "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(a) -> int:
+    """numpy array / torch tensor / int -> raw address."""
+    if a is None:
+        return 0
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class DeviceBuffer:
+    """A cudaMalloc'd buffer owned through the C ABI (fhesi_malloc / fhesi_free)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes = ctx, nbytes
+        p = _P()
+        ctx._ck(ctx.lib.fhesi_malloc(ctx.h, nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr: np.ndarray) -> "DeviceBuffer":
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.ctx._ck(self.ctx.lib.fhesi_h2d(self.ctx.h, self.ptr, arr.ctypes.data, arr.nbytes))
+        return self
+
+    def download(self, shape, dtype=np.uint32) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx._ck(self.ctx.lib.fhesi_d2h(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.fhesi_free(self.ctx.h, self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """FHEcontext image on one GPU: fhesi_ctx_create (FHEContext.h:105-118 +
+    FHEContext.cpp:83-85)."""
+
+    def __init__(self, m: int, logQ: int, p: int, decompSize: int = 3, xi: int = 1, device: int = 0,
+                 lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        h = _P()
+        rc = self.lib.fhesi_ctx_create(m, logQ, p, decompSize, xi, device, C.byref(h))
+        if rc:
+            raise FhesiError(f"fhesi_ctx_create: {self.lib.fhesi_last_error().decode()} (rc={rc})")
+        self.h = h.value
+        self.info = Info()
+        self._ck(self.lib.fhesi_ctx_info(self.h, C.byref(self.info)))
+        i = self.info
+        self.n, self.N, self.W, self.D = i.n, i.N, i.W, i.D
+        self.Lt, self.Lk, self.Le = i.Lt, i.Lk, i.Le
+        self.primes = [i.primes[k] for k in range(i.Lt)]
+
+    def _ck(self, rc: int):
+        if rc:
+            raise FhesiError(f"{self.lib.fhesi_last_error().decode()} (rc={rc})")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fhesi_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing
+    def set_stream(self, stream_ptr: int):
+        self._ck(self.lib.fhesi_ctx_set_stream(self.h, stream_ptr))
+
+    def sync(self):
+        self._ck(self.lib.fhesi_sync(self.h))
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr: np.ndarray) -> DeviceBuffer:
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, max(arr.nbytes, 16)).upload(arr)
+
+    def ct_words(self, parts: int) -> int:
+        return parts * self.n * self.W
+
+    def tprod_words(self, parts: int) -> int:
+        return parts * self.Lt * self.N
+
+    # ---- keys
+    def ksw_create(self, b: np.ndarray, A: np.ndarray, src_parts: int) -> int:
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        A = np.ascontiguousarray(A, dtype=np.uint32)
+        assert b.shape == A.shape == (src_parts * self.D, self.n, self.W)
+        k = _P()
+        self._ck(self.lib.fhesi_ksw_create(self.h, b.ctypes.data, A.ctypes.data, src_parts, C.byref(k)))
+        return k.value
+
+    def key_create(self, polys: np.ndarray) -> int:
+        polys = np.ascontiguousarray(polys, dtype=np.uint32)
+        assert polys.shape[1:] == (self.n, self.W)
+        k = _P()
+        self._ck(self.lib.fhesi_key_create(self.h, polys.ctypes.data, polys.shape[0], C.byref(k)))
+        return k.value
+
+    # ---- ops on device pointers (numpy arrays are NOT accepted here: use *_host or to_device)
+    def mult_relin_dev(self, ksw, a, b, out, count):
+        self._ck(self.lib.fhesi_mult_relin_dev(self.h, ksw, _ptr(a), _ptr(b), _ptr(out), count))
+
+    def mult_relin_host(self, ksw, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        count = a.shape[0]
+        assert a.shape == b.shape == (count, 2, self.n, self.W)
+        out = np.empty_like(a)
+        self._ck(self.lib.fhesi_mult_relin_host(self.h, ksw, a.ctypes.data, b.ctypes.data,
+                                                out.ctypes.data, count))
+        return out
+
+    def ct_add_dev(self, io, other, parts, count):
+        self._ck(self.lib.fhesi_ct_add_dev(self.h, _ptr(io), _ptr(other), parts, count))
+
+    def ct_sum_dev(self, inp, out, parts, count):
+        self._ck(self.lib.fhesi_ct_sum_dev(self.h, _ptr(inp), _ptr(out), parts, count))
+
+    def ct_mul_scalar_dev(self, io, l, parts, count):
+        self._ck(self.lib.fhesi_ct_mul_scalar_dev(self.h, _ptr(io), l, parts, count))
+
+    def ct_tensor_dev(self, a, pa, b, pb, tprod, count, accumulate=False):
+        self._ck(self.lib.fhesi_ct_tensor_dev(self.h, _ptr(a), pa, _ptr(b), pb, _ptr(tprod), count,
+                                              1 if accumulate else 0))
+
+    def tprod_add_dev(self, io, other, parts, count):
+        self._ck(self.lib.fhesi_tprod_add_dev(self.h, _ptr(io), _ptr(other), parts, count))
+
+    def tprod_mul_scalar_dev(self, io, l, parts, count):
+        self._ck(self.lib.fhesi_tprod_mul_scalar_dev(self.h, _ptr(io), l, parts, count))
+
+    def scaledown_dev(self, tprod, parts, out, count):
+        self._ck(self.lib.fhesi_scaledown_dev(self.h, _ptr(tprod), parts, _ptr(out), count))
+
+    def keyswitch_dev(self, ksw, inp, out, count):
+        self._ck(self.lib.fhesi_keyswitch_dev(self.h, ksw, _ptr(inp), _ptr(out), count))
+
+    def encrypt_dev(self, pk, msg, r, e, out, count):
+        self._ck(self.lib.fhesi_encrypt_dev(self.h, pk, _ptr(msg), _ptr(r), _ptr(e), _ptr(out), count))
+
+    def decrypt_dev(self, sk, inp, parts, msg, count):
+        self._ck(self.lib.fhesi_decrypt_dev(self.h, sk, _ptr(inp), parts, _ptr(msg), count))
+
+    def ct_automorph_dev(self, inp, parts, k, out_wide, count):
+        self._ck(self.lib.fhesi_ct_automorph_dev(self.h, _ptr(inp), parts, k, _ptr(out_wide), count))
+
+    def reduce_wide_dev(self, inp, Win, out, parts, count):
+        self._ck(self.lib.fhesi_reduce_wide_dev(self.h, _ptr(inp), Win, _ptr(out), parts, count))
+
+    def tprod_reduce_gathered_dev(self, gathered, world, parts, out):
+        self._ck(self.lib.fhesi_tprod_reduce_gathered_dev(self.h, _ptr(gathered), world, parts, _ptr(out)))
+
+    def ref_rows_host(self, poly: np.ndarray, primes, roots) -> np.ndarray:
+        poly = np.ascontiguousarray(poly, dtype=np.uint32)
+        L = len(primes)
+        pr = np.asarray(primes, dtype=np.uint64)
+        rt = np.asarray(roots, dtype=np.uint64)
+        rows = np.empty((L, self.n), dtype=np.int64)
+        self._ck(self.lib.fhesi_ref_rows_host(self.h, poly.ctypes.data, poly.shape[1], pr.ctypes.data,
+                                              rt.ctypes.data, L, rows.ctypes.data))
+        return rows
+
+    def profile_enable(self, on: bool = True):
+        self._ck(self.lib.fhesi_profile_enable(self.h, 1 if on else 0))
+
+    def launches(self) -> int:
+        v = C.c_uint64()
+        self._ck(self.lib.fhesi_profile_launches(self.h, C.byref(v)))
+        return v.value
+
+    def profile_report(self) -> dict:
+        """kernel name -> (launches, total_ms) since profile_enable(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.fhesi_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
+
+    def modmul_peak(self, word_bits: int) -> float:
+        v = C.c_double()
+        self._ck(self.lib.fhesi_modmul_peak(self.h, word_bits, C.byref(v)))
+        return v.value

@@ -1,0 +1,27 @@
+"""TEST INFRASTRUCTURE ONLY: compile the kernel sources under fhe-si_b200/csrc with g++
+against tests/emu/cuda_emu.h (CUDA threads = OS threads) so that `pytest -m "not gpu"` can
+check kernel logic against the oracle on a GPU-less machine.  The product never loads this."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "fhe-si_b200", "csrc")
+OUT = os.path.join(HERE, "_build", "libfhesi_emu.so")
+
+
+def build_emu(force=False):
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "cuda_emu.h"),
+                                                               os.path.join(ROOT, "include", "fhesi.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = ["g++", "-std=c++20", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-DFHESI_EMU=1",
+           "-include", os.path.join(HERE, "cuda_emu.h"), "-x", "c++", os.path.join(CSRC, "fhesi_lib.cu"),
+           "-o", OUT]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_emu(force=True))

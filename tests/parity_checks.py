@@ -1,0 +1,196 @@
+"""Parity checks shared by the CPU (emulator) and GPU test modules.  Each check runs one
+C-ABI entry point on explicit inputs and compares with the oracle bit for bit."""
+import numpy as np
+
+import fhesi_oracle as O
+from common import Scenario, assert_ct_equal
+
+
+def check_mult_relin(sc: Scenario, count=2, host=False, random_inputs=False):
+    if random_inputs:
+        A, B = sc.random_cts(count), sc.random_cts(count)
+    else:
+        _, cts = sc.fresh(2 * count)
+        A, B = cts[:count], cts[count:]
+    out = sc.dev_mult_relin(A, B, host=host)
+    for i in range(count):
+        want = O.mult_relin(sc.ks, A[i], B[i])
+        assert_ct_equal(sc, out[i], want, f"mult_relin[{i}]")
+
+
+def check_pieces(sc: Scenario, count=2):
+    """tensor -> (tprod add) -> ScaleDown -> key switch as separate calls, plus decrypt."""
+    d = sc.dev
+    msgs, cts = sc.fresh(2 * count)
+    A, B = cts[:count], cts[count:]
+    da, db = d.to_device(sc.pack_cts(A)), d.to_device(sc.pack_cts(B))
+    dt = d.alloc(count * d.tprod_words(3) * 4)
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, count)
+    # c*c + c*c in tensor form (Test_AddMul.cpp:73-75 adds tProd-form ciphertexts)
+    dt2 = d.alloc(count * d.tprod_words(3) * 4)
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt2.ptr, count)
+    d.tprod_add_dev(dt2.ptr, dt.ptr, 3, count)
+    dc = d.alloc(count * d.ct_words(3) * 4)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, count)
+    d.sync()
+    c3 = dc.download((count, 3, d.n, d.W))
+    wants = []
+    for i in range(count):
+        w = A[i].copy().mul(B[i])
+        w2 = w.copy().add(w)
+        w.scale_down()
+        assert_ct_equal(sc, c3[i], w, f"scaledown[{i}]")
+        wants.append((w, w2))
+    d.scaledown_dev(dt2.ptr, 3, dc.ptr, count)
+    d.sync()
+    c3b = dc.download((count, 3, d.n, d.W))
+    for i in range(count):
+        assert_ct_equal(sc, c3b[i], wants[i][1].copy().scale_down(), f"tprod_add+scaledown[{i}]")
+    # key switch of the scaled-down 3-part ciphertexts, then decrypt
+    dc.upload(c3)
+    do = d.alloc(count * d.ct_words(2) * 4)
+    d.keyswitch_dev(sc.ksw, dc.ptr, do.ptr, count)
+    dm = d.alloc(count * d.n * 4)
+    d.decrypt_dev(sc.dsk, do.ptr, 2, dm.ptr, count)
+    d.sync()
+    o2 = do.download((count, 2, d.n, d.W))
+    dec = dm.download((count, d.n))
+    for i in range(count):
+        w = O.apply_key_switch(sc.ks, wants[i][0])
+        assert_ct_equal(sc, o2[i], w, f"keyswitch[{i}]")
+        m = O.decrypt(sc.sk, w)
+        assert dec[i].tolist() == m, f"decrypt[{i}]"
+        prod = [c % sc.p for c in sc.octx.ring.mul(msgs[i], msgs[count + i])]
+        assert m == prod, "homomorphic product"  # Test_AddMul.cpp:84-86 identity
+
+
+def check_tensor_accumulate(sc: Scenario, count=3):
+    """sum_i a_i * b_i in tensor form (Matrix.cpp:80-97), then ScaleDown."""
+    d = sc.dev
+    _, cts = sc.fresh(2 * count)
+    A, B = cts[:count], cts[count:]
+    da, db = d.to_device(sc.pack_cts(A)), d.to_device(sc.pack_cts(B))
+    dt = d.alloc(d.tprod_words(3) * 4)
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, count, accumulate=True)
+    dc = d.alloc(d.ct_words(3) * 4)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.sync()
+    got = dc.download((3, d.n, d.W))
+    acc = A[0].copy().mul(B[0])
+    for i in range(1, count):
+        acc.add(A[i].copy().mul(B[i]))
+    assert_ct_equal(sc, got, acc.scale_down(), "tensor accumulate")
+
+
+def check_encrypt_decrypt(sc: Scenario, count=2):
+    d = sc.dev
+    n = d.n
+    rng = sc.rng
+    msgs = [[rng.random_bnd(sc.p) for _ in range(n)] for _ in range(count)]
+    rs = [[rng.random_bnd(2) for _ in range(n)] for _ in range(count)]
+    es = [[O.sample_gaussian(rng, n, sc.octx.stdev) for _ in range(2)] for _ in range(count)]
+    dmsg = d.to_device(np.array(msgs, dtype=np.uint32))
+    dr = d.to_device(np.array(rs, dtype=np.uint8))
+    de = d.to_device(np.array(es, dtype=np.int32))
+    dout = d.alloc(count * d.ct_words(2) * 4)
+    d.encrypt_dev(sc.dpk, dmsg.ptr, dr.ptr, de.ptr, dout.ptr, count)
+    dm = d.alloc(count * n * 4)
+    d.decrypt_dev(sc.dsk, dout.ptr, 2, dm.ptr, count)
+    d.sync()
+    got = dout.download((count, 2, n, d.W))
+    dec = dm.download((count, n))
+    for i in range(count):
+        want = O.encrypt(sc.pk, msgs[i], rs[i], es[i])
+        assert_ct_equal(sc, got[i], want, f"encrypt[{i}]")
+        assert dec[i].tolist() == msgs[i], f"decrypt(encrypt)[{i}]"
+
+
+def check_coeff_ops(sc: Scenario, count=3):
+    """+=, batch sum, *= long, >>= and Reduce in coefficient form."""
+    d = sc.dev
+    A, B = sc.random_cts(count), sc.random_cts(count)
+    pa = sc.pack_cts(A)
+    da, db = d.to_device(pa), d.to_device(sc.pack_cts(B))
+    d.ct_add_dev(da.ptr, db.ptr, 2, count)
+    d.sync()
+    got = da.download(pa.shape)
+    for i in range(count):
+        assert_ct_equal(sc, got[i], A[i].copy().add(B[i]), f"ct_add[{i}]")
+    # batch sum
+    da.upload(pa)
+    ds = d.alloc(d.ct_words(2) * 4)
+    d.ct_sum_dev(da.ptr, ds.ptr, 2, count)
+    d.sync()
+    acc = A[0].copy()
+    for i in range(1, count):
+        acc.add(A[i])
+    assert_ct_equal(sc, ds.download((2, d.n, d.W)), acc, "ct_sum")
+    # scalar multiply, positive and negative
+    for l in (7, -3, 123456789012345):
+        da.upload(pa)
+        d.ct_mul_scalar_dev(da.ptr, l, 2, count)
+        d.sync()
+        got = da.download(pa.shape)
+        for i in range(count):
+            assert_ct_equal(sc, got[i], A[i].copy().mul_scalar(l), f"ct_mul_scalar {l} [{i}]")
+    # automorphism (not reduced mod q) and Reduce
+    units = sc.octx.ring.units
+    for k in (units[1], units[len(units) // 2], units[-1]):
+        da.upload(pa)
+        dw = d.alloc(count * 2 * d.n * (d.W + 1) * 4)
+        d.ct_automorph_dev(da.ptr, 2, k, dw.ptr, count)
+        dr = d.alloc(count * d.ct_words(2) * 4)
+        d.reduce_wide_dev(dw.ptr, d.W + 1, dr.ptr, 2, count)
+        d.sync()
+        wide = dw.download((count, 2, d.n, d.W + 1))
+        red = dr.download(pa.shape)
+        for i in range(count):
+            want = A[i].copy().automorph(k)
+            for part in range(2):
+                assert O.unpack_poly_words(wide[i, part]) == want.parts[part], f"automorph k={k} [{i}]"
+                assert O.unpack_poly_words(red[i, part]) == O.reduce_poly(want.parts[part], sc.logq)
+
+
+def check_tprod_scalar(sc: Scenario):
+    d = sc.dev
+    _, cts = sc.fresh(2)
+    da, db = d.to_device(sc.pack_cts(cts[:1])), d.to_device(sc.pack_cts(cts[1:]))
+    dt = d.alloc(d.tprod_words(3) * 4)
+    dc = d.alloc(d.ct_words(3) * 4)
+    for l in (9, -2):
+        d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, 1)
+        d.tprod_mul_scalar_dev(dt.ptr, l, 3, 1)
+        d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+        d.sync()
+        want = cts[0].copy().mul(cts[1]).mul_scalar(l).scale_down()
+        assert_ct_equal(sc, dc.download((3, d.n, d.W)), want, f"tprod *= {l}")
+
+
+def check_ref_rows(sc: Scenario):
+    """DoubleCRT rows on the reference chain (key export parity)."""
+    a = O.sample_random(sc.rng, sc.octx.q, sc.octx.phim)
+    rows = sc.dev.ref_rows_host(O.pack_poly_words(a, sc.logq), sc.octx.primes, sc.octx.roots)
+    want = O.dcrt_rows(sc.octx, a)
+    assert rows.tolist() == want
+
+
+def check_gathered_reduce(sc: Scenario, world=3):
+    d = sc.dev
+    _, cts = sc.fresh(2 * world)
+    bufs = []
+    acc = None
+    for w in range(world):
+        da, db = d.to_device(sc.pack_cts([cts[2 * w]])), d.to_device(sc.pack_cts([cts[2 * w + 1]]))
+        dt = d.alloc(d.tprod_words(3) * 4)
+        d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, 1)
+        d.sync()
+        bufs.append(dt.download((3, d.Lt, d.N)))
+        t = cts[2 * w].copy().mul(cts[2 * w + 1])
+        acc = t if acc is None else acc.add(t)
+    dg = d.to_device(np.stack(bufs))
+    do = d.alloc(d.tprod_words(3) * 4)
+    d.tprod_reduce_gathered_dev(dg.ptr, world, 3, do.ptr)
+    dc = d.alloc(d.ct_words(3) * 4)
+    d.scaledown_dev(do.ptr, 3, dc.ptr, 1)
+    d.sync()
+    assert_ct_equal(sc, dc.download((3, d.n, d.W)), acc.scale_down(), "gathered reduce")

@@ -1,0 +1,48 @@
+"""The C-ABI library loads and exports every symbol include/fhesi.h declares (no compute
+calls without a GPU), and fails loudly -- no CPU fallback -- when no device is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "fhesi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fhesi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    import pyfhesi
+    assert declared_symbols() == sorted(pyfhesi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    lib = ctypes.CDLL(cuda_lib)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_built_for_sm100a(cuda_lib):
+    import pyfhesi
+    lib = pyfhesi.load_library(cuda_lib)
+    assert b"sm_100a" in lib.fhesi_version()
+
+
+def test_no_cpu_fallback_without_gpu(cuda_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import pyfhesi
+    with pytest.raises(pyfhesi.FhesiError):
+        pyfhesi.Context(22, 80, 23, lib_path=cuda_lib)
+
+
+def test_bad_parameters_rejected(emu_lib):
+    import pyfhesi
+    for args in ((21, 80, 23), (24, 80, 23), (22, 4, 23), (22, 80, 1)):
+        with pytest.raises(pyfhesi.FhesiError):
+            pyfhesi.Context(*args, lib_path=emu_lib)

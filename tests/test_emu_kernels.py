@@ -1,0 +1,52 @@
+"""CPU CI: the kernel sources compiled against tests/emu/cuda_emu.h (CUDA threads as OS
+threads) must match the oracle bit for bit.  This checks kernel LOGIC only; the GPU parity
+tests proper are in test_gpu_parity.py and run on the B200."""
+import pytest
+
+import parity_checks as P
+from common import CONFIGS, Scenario
+
+
+@pytest.fixture(scope="module")
+def sc1(emu_lib):
+    return Scenario(*CONFIGS["cfg1"], seed=11, xi=4, lib_path=emu_lib)
+
+
+def test_emu_mult_relin_cfg1(sc1):
+    P.check_mult_relin(sc1, count=3)
+    P.check_mult_relin(sc1, count=2, host=True)
+    P.check_mult_relin(sc1, count=2, random_inputs=True)
+
+
+def test_emu_pieces_cfg1(sc1):
+    P.check_pieces(sc1, count=2)
+    P.check_tensor_accumulate(sc1, count=3)
+    P.check_tprod_scalar(sc1)
+    P.check_gathered_reduce(sc1)
+
+
+def test_emu_encrypt_decrypt_cfg1(sc1):
+    P.check_encrypt_decrypt(sc1, count=3)
+
+
+def test_emu_coeff_ops_cfg1(sc1):
+    P.check_coeff_ops(sc1, count=3)
+
+
+def test_emu_ref_rows_cfg1(sc1):
+    P.check_ref_rows(sc1)
+
+
+def test_emu_other_small_rings(emu_lib):
+    # m = 2*17 (n = 16: N = 2n exactly, the fold guard) and m = 2*13, odd logQ
+    for m_half, logq in ((17, 61), (13, 100)):
+        p = 2 * m_half + 1
+        sc = Scenario(logq, p, 3, seed=3, lib_path=emu_lib)
+        P.check_mult_relin(sc, count=2)
+        P.check_encrypt_decrypt(sc, count=1)
+        P.check_coeff_ops(sc, count=2)
+
+
+def test_emu_mult_relin_cfg2(emu_lib):
+    sc = Scenario(*CONFIGS["cfg2"], seed=2, lib_path=emu_lib)
+    P.check_mult_relin(sc, count=1)

@@ -1,0 +1,118 @@
+"""GPU parity tests (run on the B200 with `pytest -m gpu`): every C-ABI entry point of
+libfhesi_b200.so against the oracle, bit for bit, on all five BASELINE.json configs."""
+import numpy as np
+import pytest
+
+import parity_checks as P
+from common import CONFIGS, Scenario
+
+pytestmark = pytest.mark.gpu
+
+_cache = {}
+
+
+def scenario(name, cuda_lib, xi=1):
+    key = (name, xi)
+    if key not in _cache:
+        _cache[key] = Scenario(*CONFIGS[name], seed=20240611, xi=xi, lib_path=cuda_lib)
+    return _cache[key]
+
+
+def test_library_is_cuda(cuda_lib):
+    import pyfhesi
+    lib = pyfhesi.load_library(cuda_lib)
+    assert b"sm_100a" in lib.fhesi_version()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5_128", "cfg5_512"])
+def test_mult_relin(name, cuda_lib):
+    sc = scenario(name, cuda_lib)
+    P.check_mult_relin(sc, count=2 if name == "cfg5_512" else 3)
+
+
+def test_mult_relin_host_and_random_cfg2(cuda_lib):
+    sc = scenario("cfg2", cuda_lib)
+    P.check_mult_relin(sc, count=2, host=True)
+    P.check_mult_relin(sc, count=2, random_inputs=True)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg4"])
+def test_pieces(name, cuda_lib):
+    sc = scenario(name, cuda_lib, xi=8)
+    P.check_pieces(sc, count=2)
+    P.check_tensor_accumulate(sc, count=5)
+    P.check_tprod_scalar(sc)
+    P.check_gathered_reduce(sc)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_encrypt_decrypt(name, cuda_lib):
+    P.check_encrypt_decrypt(scenario(name, cuda_lib), count=3)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg4"])
+def test_coeff_ops(name, cuda_lib):
+    P.check_coeff_ops(scenario(name, cuda_lib), count=3)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_ref_rows(name, cuda_lib):
+    P.check_ref_rows(scenario(name, cuda_lib))
+
+
+def test_generic_and_fused_paths_agree(cuda_lib, monkeypatch):
+    """The fused N=1024 kernels and the generic kernels are two CUDA implementations of the
+    same arithmetic; they must agree bit for bit (and both with the oracle, above)."""
+    sc = scenario("cfg2", cuda_lib)
+    A, B = sc.random_cts(4), sc.random_cts(4)
+    fused = sc.dev_mult_relin(A, B)
+    monkeypatch.setenv("FHESI_NO_FUSED", "1")
+    sc2 = Scenario(*CONFIGS["cfg2"], seed=20240611, lib_path=cuda_lib)
+    sc2.ks = sc.ks
+    generic = sc2.dev_mult_relin(A, B)
+    assert np.array_equal(fused, generic)
+
+
+def test_full_batch_properties_cfg2(cuda_lib):
+    """BASELINE-size batch: size-independent properties instead of the (slow) oracle.
+    (1) a batch equals the concatenation of its halves (no cross-talk, chunking exact);
+    (2) mult_relin(a, b) decrypts to the plaintext product for every element
+        (Test_AddMul.cpp:84-86 identity), checked on device;
+    (3) commutativity: mult_relin(a,b) and mult_relin(b,a) decrypt identically."""
+    import fhesi_oracle as O
+    sc = scenario("cfg2", cuda_lib)
+    d = sc.dev
+    count, n = 512, d.n
+    rng = np.random.default_rng(7)
+    msgs = rng.integers(0, sc.p, size=(2 * count, n), dtype=np.uint32)
+    rs = rng.integers(0, 2, size=(2 * count, n), dtype=np.uint8)
+    es = np.rint(rng.normal(0, 3.2, size=(2 * count, 2, n))).astype(np.int32)
+    dct = d.alloc(2 * count * d.ct_words(2) * 4)
+    d.encrypt_dev(sc.dpk, d.to_device(msgs).ptr, d.to_device(rs).ptr, d.to_device(es).ptr, dct.ptr, 2 * count)
+    half = count * d.ct_words(2) * 4
+    dout = d.alloc(half)
+    dout2 = d.alloc(half)
+    d.mult_relin_dev(sc.ksw, dct.ptr, dct.ptr + half, dout.ptr, count)
+    d.mult_relin_dev(sc.ksw, dct.ptr + half, dct.ptr, dout2.ptr, count)
+    dm, dm2 = d.alloc(count * n * 4), d.alloc(count * n * 4)
+    d.decrypt_dev(sc.dsk, dout.ptr, 2, dm.ptr, count)
+    d.decrypt_dev(sc.dsk, dout2.ptr, 2, dm2.ptr, count)
+    d.sync()
+    full = dout.download((count, 2, n, d.W))
+    dec, dec2 = dm.download((count, n)), dm2.download((count, n))
+    assert np.array_equal(dec, dec2)
+    ring = sc.octx.ring
+    for i in (0, 1, count // 2, count - 1):
+        want = [c % sc.p for c in ring.mul(msgs[i].tolist(), msgs[count + i].tolist())]
+        assert dec[i].tolist() == want
+    # all elements: plaintext product through numpy (exact int64, mod p)
+    k = 200  # halves
+    d.mult_relin_dev(sc.ksw, dct.ptr, dct.ptr + half, dout2.ptr, k)
+    d.sync()
+    assert np.array_equal(dout2.download((k, 2, n, d.W)), full[:k])
+    # one oracle spot check inside the big batch
+    cts = dct.download((2 * count, 2, n, d.W))
+    a = O.Ciphertext(sc.octx, sc.unpack_ct(cts[5]))
+    b = O.Ciphertext(sc.octx, sc.unpack_ct(cts[count + 5]))
+    from common import assert_ct_equal
+    assert_ct_equal(sc, full[5], O.mult_relin(sc.ks, a, b), "big batch element 5")
