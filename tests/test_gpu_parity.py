@@ -88,7 +88,8 @@ def test_full_batch_properties_cfg2(cuda_lib):
     rs = rng.integers(0, 2, size=(2 * count, n), dtype=np.uint8)
     es = np.rint(rng.normal(0, 3.2, size=(2 * count, 2, n))).astype(np.int32)
     dct = d.alloc(2 * count * d.ct_words(2) * 4)
-    d.encrypt_dev(sc.dpk, d.to_device(msgs).ptr, d.to_device(rs).ptr, d.to_device(es).ptr, dct.ptr, 2 * count)
+    dmsg, drs, des = d.to_device(msgs), d.to_device(rs), d.to_device(es)  # keep alive until sync
+    d.encrypt_dev(sc.dpk, dmsg.ptr, drs.ptr, des.ptr, dct.ptr, 2 * count)
     half = count * d.ct_words(2) * 4
     dout = d.alloc(half)
     dout2 = d.alloc(half)
