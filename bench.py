@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- batched ciphertext mult+relinearise throughput (BASELINE.json metric).
+
+A step is one pass of the hot path (c = a; c *= b; ks.ApplyKeySwitch(c), Test_AddMul.cpp:59-66)
+over one batch of B independent fresh ciphertext pairs per GPU at the cfg2 parameters
+(logQ=256, p=1019, g=3 -- g=2 is not in Z_1018^*).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...             # CPU arm: the reference algorithm
+
+Under torchrun (N>1) every rank drives its own GPU over its own disjoint batch (no data-path
+collective: the units are independent); time is the max over ranks.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fhe-si_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+SEED = 20240611
+CFG = {"logQ": 256, "p": 1019, "g": 3}
+METRIC = "ciphertext mult+relin/sec at logQ=256"
+
+# canonical algorithmic work per op (SURVEY.md §8d / BASELINE.md §5), 64-bit modmul-equivalents
+CANON_MODMUL = {128: 1_759_670, 256: 5_514_040, 512: 17_824_284, 80: 14_322, 100: 1_248_160, 176: 3_022_054}
+
+
+def algorithmic_bytes_per_op(n, logq):
+    return 6 * n * (logq // 8)  # read 2 ct x 2 parts, write 2 parts (SURVEY.md §8d B_min)
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: oracle/ref_restate.c, the reference algorithm restated in C (kind = "port")
+# ---------------------------------------------------------------------------------------
+def _cpu_setup(logq, p, g, faithful=False):
+    import fhesi_oracle as O
+    import ref_port
+    octx = O.Context(p - 1, logq, p, g).setup_si()
+    rng = O.Rng(SEED)
+    sk = O.SecKey.generate(octx, rng)
+    pk = O.PubKey.generate(sk, rng)
+    ks = O.KeySwitch.init_s2(sk, rng)
+    port = ref_port.RefPort(octx, faithful=faithful)
+    port.set_key_switch(ks)
+    pack = lambda ct: np.stack([O.pack_poly_words(x, logq) for x in ct.parts])
+    msgs = [[rng.random_bnd(p) for _ in range(octx.phim)] for _ in range(2)]
+    a, b = (pack(O.encrypt_rng(pk, m, rng)) for m in msgs)
+    out = port.mult_relin(a, b)  # warm-up op: cached Rb tables exist, as in the reference
+    return port, a, b, out
+
+
+def _cpu_worker(args):
+    logq, p, g, nops, faithful = args
+    port, a, b, _ = _cpu_setup(logq, p, g, faithful)
+    t = time.perf_counter()
+    for _ in range(nops):
+        port.mult_relin(a, b)
+    return time.perf_counter() - t
+
+
+def cpu_baseline_single_core(logq, p, g, budget_s=12.0):
+    """1 core, table-bug-fixed and faithful variants."""
+    port, a, b, _ = _cpu_setup(logq, p, g, False)
+    t = time.perf_counter()
+    port.mult_relin(a, b)
+    one = time.perf_counter() - t
+    nops = max(2, min(64, int(budget_s / max(one, 1e-6))))
+    t = time.perf_counter()
+    for _ in range(nops):
+        port.mult_relin(a, b)
+    fixed = nops / (time.perf_counter() - t)
+    port.lib.ref_set_faithful(port.h, 1)
+    nf = max(1, nops // 6)
+    t = time.perf_counter()
+    for _ in range(nf):
+        port.mult_relin(a, b)
+    faithful = nf / (time.perf_counter() - t)
+    return {"value": fixed, "unit": "ops/s", "cores": 1, "kind": "port",
+            "sample": f"{nops} mult+relin ops at logQ={logq} p={p} (oracle/ref_restate.c: m-point Bluestein "
+                      f"N=2^{(2 * (p - 1) - 1).bit_length()}, incremental bigint CRT), tables cached",
+            "faithful_table_bug_ops_per_s": faithful, "faithful_sample_ops": nf}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    logq, p, g = CFG["logQ"], CFG["p"], CFG["g"]
+    # size one step to ~4 s of wall time
+    port, a, b, _ = _cpu_setup(logq, p, g)
+    t = time.perf_counter()
+    port.mult_relin(a, b)
+    one = time.perf_counter() - t
+    per_worker = max(1, int(4.0 / one))
+    ctxm = mp.get_context("fork")
+    times = []
+    with ctxm.Pool(cores) as pool:
+        for s in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            pool.map(_cpu_worker, [(logq, p, g, per_worker, False)] * cores)
+            dt = time.perf_counter() - t
+            if s >= args.warmup:
+                times.append(dt)
+    ops_per_step = per_worker * cores
+    ms = 1e3 * sum(times) / len(times)
+    value = ops_per_step / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "ops/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": workload_name(), "ops_per_step": ops_per_step,
+                   "note": "each step includes per-process context+key-matrix set-up (~0.3 s)"},
+        "cpu_baseline": {"value": value, "unit": "ops/s", "cores": cores, "kind": "port",
+                         "sample": f"{ops_per_step} ops/step over {cores} processes, oracle/ref_restate.c "
+                                   "(the NTL build cannot be compiled in this image)"},
+        "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name():
+    return (f"cfg2: TestAddMul logQ={CFG['logQ']} p={CFG['p']} g={CFG['g']} (m=1018, phi(m)=508, D=11), "
+            "batched c=a; c*=b; ApplyKeySwitch(c) on fresh encryptions")
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import build as fhesi_build
+    import fhesi_oracle as O
+    import pyfhesi
+    lib_path = fhesi_build.build()
+    logq, p, g = CFG["logQ"], CFG["p"], CFG["g"]
+    octx = O.Context(p - 1, logq, p, g).setup_si()
+    rng = O.Rng(SEED)
+    sk = O.SecKey.generate(octx, rng)
+    pk = O.PubKey.generate(sk, rng)
+    ks = O.KeySwitch.init_s2(sk, rng)
+    pack = lambda polys: np.stack([O.pack_poly_words(a, logq) for a in polys])
+
+    dev = pyfhesi.Context(p - 1, logq, p, 3, 1, local_rank, lib_path=lib_path)
+    # one explicit (non-default) stream for the library's kernels AND the timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    dev.set_stream(stream.cuda_stream)
+    ksw = dev.ksw_create(pack(ks.b), pack([O.reduce_poly(a, logq) for a in ks.A]), 3)
+    dpk = dev.key_create(pack(pk.pk))
+    dsk = dev.key_create(pack(sk.s))
+    n, W = dev.n, dev.W
+    B = args.batch
+
+    # synthetic operands: 2B fresh encryptions per rank, made on the device from explicit randomness
+    nrng = np.random.default_rng(SEED + rank)
+    msgs = nrng.integers(0, p, size=(2 * B, n), dtype=np.uint32)
+    rs = nrng.integers(0, 2, size=(2 * B, n), dtype=np.uint8)
+    es = np.rint(nrng.normal(0.0, 3.2, size=(2 * B, 2, n))).astype(np.int32)
+    ct_words = 2 * n * W
+    d_ct = torch.empty((2 * B, ct_words), dtype=torch.int32, device="cuda")
+    d_out = torch.empty((B, ct_words), dtype=torch.int32, device="cuda")
+    t_msgs, t_rs, t_es = (torch.from_numpy(x).cuda() for x in (msgs.view(np.int32), rs, es))
+    dev.encrypt_dev(dpk, t_msgs, t_rs, t_es, d_ct, 2 * B)
+    torch.cuda.synchronize()
+    d_a, d_b = d_ct[:B], d_ct[B:]
+
+    def step():
+        dev.mult_relin_dev(ksw, d_a, d_b, d_out, B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness guard inside the bench: element 0 against the oracle, all via decrypt
+    step()
+    torch.cuda.synchronize()
+    h_ct = d_ct.cpu().numpy().view(np.uint32).reshape(2 * B, 2, n, W)
+    h_out = d_out.cpu().numpy().view(np.uint32).reshape(B, 2, n, W)
+    if rank == 0:
+        a0 = O.Ciphertext(octx, [O.unpack_poly_words(h_ct[0, i]) for i in range(2)])
+        b0 = O.Ciphertext(octx, [O.unpack_poly_words(h_ct[B, i]) for i in range(2)])
+        want = O.mult_relin(ks, a0, b0)
+        got = [O.unpack_poly_words(h_out[0, i]) for i in range(2)]
+        assert got == want.parts, "bench: device result differs from the oracle"
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = dev.launches()
+    prof = dev.profile_report()
+    dev.profile_enable(False)
+    sampler.stop_flag = True
+    sampler.join()
+
+    # ---- e2e: pinned host buffers -> H2D -> hot path -> D2H, all inside the timed region
+    h_a = torch.from_numpy(h_ct[:B].view(np.int32).reshape(B, ct_words).copy()).pin_memory()
+    h_b = torch.from_numpy(h_ct[B:].view(np.int32).reshape(B, ct_words).copy()).pin_memory()
+    h_o = torch.empty((B, ct_words), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        dev._ck(dev.lib.fhesi_mult_relin_host(dev.h, ksw, h_a.data_ptr(), h_b.data_ptr(), h_o.data_ptr(), B))
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    e2e_steps = max(2, args.steps // 2)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), 0.0)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, e2e_wall_ms) / e2e_steps  # host-blocking call: wall clock is the honest one
+    assert np.array_equal(h_o.numpy().view(np.uint32).reshape(B, 2, n, W), h_out), "e2e result differs"
+
+    ms_step = ms_total / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = t.tolist()
+    value = world * B / (ms_step * 1e-3)
+    e2e_value = world * B / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak32 = dev.modmul_peak(32)
+        peak64 = dev.modmul_peak(64)
+        # dominant kernel by measured device time, with its algorithmic modmuls per launch
+        work_all = kernel_work_per_op(dev)
+        work = {k: v for k, v in work_all.items() if k in prof}  # kernels that actually ran
+        top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
+        tname, (tcnt, tms) = top
+        share = tms / max(sum(v[1] for v in prof.values()), 1e-9)
+        ops_timed = B * args.steps
+        alg_per_launch = work.get(tname, 0) * ops_timed / max(tcnt, 1)
+        avg_launch_s = tms * 1e-3 / max(tcnt, 1)
+        achieved = alg_per_launch / max(avg_launch_s, 1e-12)
+        canon = CANON_MODMUL[logq]
+        roofline = {
+            "bound": "int32-modmul (integer pipe; SURVEY.md §8d -- HBM does not bind)",
+            "kernel": tname, "kernel_share_of_step": share,
+            "achieved": achieved / 1e9, "peak": peak32 / 1e9, "unit": "Gmodmul/s (32-bit Montgomery)",
+            "frac": achieved / peak32, "traffic": None,
+            "peak_source": "measured in this run: fhesi_modmul_peak(32), register-resident ILP-8 all-SM",
+            "algorithmic_modmul_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+            "whole_op": {
+                "executed_modmul32_per_op": sum(work.values()),
+                "frac_of_peak32": (value / world) * sum(work.values()) / peak32,
+                "canonical_modmul64_eq_per_op": canon,
+                "canonical_achieved_Gmodmul_s": (value / world) * canon / 1e9,
+                "peak64_Gmodmul_s": peak64 / 1e9,
+                "canonical_frac_of_peak64": (value / world) * canon / peak64,
+            },
+            "hbm": {"algorithmic_bytes_per_op": algorithmic_bytes_per_op(n, logq),
+                    "achieved_GBs": (value / world) * algorithmic_bytes_per_op(n, logq) / 1e9,
+                    "peak_GBs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "frac": (value / world) * algorithmic_bytes_per_op(n, logq) / 1e9 / hbm_peak},
+            "per_kernel_ms": {k: {"launches": v[0], "ms": v[1]} for k, v in sorted(prof.items())},
+        }
+        cpu = cpu_baseline_single_core(logq, p, g) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "ops/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(), "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"independent ciphertext shards x{world}, no data-path collective",
+                       "l2": f"inputs {2 * B * ct_words * 4 / 2**20:.0f} MiB per step > 126 MB L2",
+                       "chain": f"{dev.Lt} x 30-bit primes (tensor), {dev.Lk} (key switch), N={dev.N}",
+                       "seed": SEED},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_words * 4,
+                    "d2h_bytes_per_step": B * ct_words * 4, "ms_per_step": e2e_ms,
+                    "api": "fhesi_mult_relin_host (pinned host buffers)"},
+            "gpu_launches": launches,
+            "clocks": sampler.result(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_work_per_op(dev):
+    """Algorithmic 32-bit modmuls per mult+relin op, by kernel (DESIGN.md "work accounting"):
+    butterflies (N/2 log2 N per transform) + pointwise products + Garner products."""
+    N, n, D = dev.N, dev.n, dev.D
+    Lt, Lk = dev.Lt, dev.Lk
+    bf = (N // 2) * int(math.log2(N))
+    garner = lambda L: L * (L - 1) // 2
+    return {
+        "k_fwd": (4 * Lt + 3 * D * Lk) * bf,
+        "k_inv": (3 * Lt + 2 * Lk) * bf,
+        "k_tensor_pw": 4 * Lt * N,
+        "k_dot": 2 * 3 * D * Lk * N,
+        "k_crt<ML>": 3 * n * garner(Lt) + 2 * n * garner(Lk),
+        # fused path (kernels_fused.cuh)
+        "k_fused_tensor": (4 * Lt) * bf + 4 * Lt * N + 3 * Lt * bf,
+        "k_fused_keyswitch": (3 * D * Lk) * bf + 2 * 3 * D * Lk * N + 2 * Lk * bf,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=2048, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
