@@ -137,7 +137,7 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   fhesi_ctx *c = new fhesi_ctx();
   c->device = device;
   const u32 n = h - 1;
-  u32 N = 2;
+  u32 N = 16;  // store_index() needs N >= 16
   while (N < 2 * n - 1) N <<= 1;
   if (N > 2048) {
     delete c;
@@ -545,6 +545,17 @@ int fhesi_ct_tensor_dev(fhesi_ctx *c, const uint32_t *a, uint32_t pa, const uint
   const size_t per = (size_t)I.Lt * I.N;
   const u32 po = pa + pb - 1;
   const size_t CH = c->chunk;
+  if (c->use_fused && pa == 2 && pb == 2 && !accumulate) {
+    const size_t ctw = (size_t)I.n * I.W, GY = 32768;  // gridDim.y limit
+    for (size_t off = 0; off < count; off += GY) {
+      size_t cnt = count - off < GY ? count - off : GY;
+      FusedTprodArgs t{a + off * 2 * ctw, b + off * 2 * ctw, tprod + off * 3 * per, I.Lt};
+      dim3 grid(I.Lt, (unsigned)cnt);
+      KL(c, k_fused_tprod, grid, 512, FT_SMEM_WORDS * 4, c->dc, t);
+      CKL();
+    }
+    return 0;
+  }
   u32 *s = nullptr;
   size_t na = al(CH * pa * per), nb_ = al(CH * pb * per), nacc = al(po * per);
   int rc = scratch(c, (na + nb_ + nacc) * 4, &s);
@@ -644,6 +655,59 @@ static int keyswitch_generic(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, 
   }
   return 0;
 }
+// ---------------------------------------------------------------------------------------
+// fused N=1024 path (kernels_fused.cuh)
+// ---------------------------------------------------------------------------------------
+static int fused_ks_from_digits(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *digits, u32 *res, u32 *out,
+                                size_t cnt) {
+  const fhesi_info &I = c->info;
+  FusedKsArgs k{digits, ksw->d_key, res, ksw->parts * I.D, I.Lk, (u32)cnt};
+  dim3 grid(I.Lk, (unsigned)((cnt + KG - 1) / KG));
+  KL(c, k_fused_keyswitch, grid, KG * 128, FK_SMEM_WORDS * 4, c->dc, k);
+  CKL();
+  return launch_crt(c, res, I.Lk, CRT_REDUCE_Q, out, I.W, cnt * 2);
+}
+static int fused_keyswitch(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, u32 *out, size_t count) {
+  const fhesi_info &I = c->info;
+  const u32 K = ksw->parts * I.D;
+  const size_t CH = c->chunk;
+  size_t nd = al(CH * K * I.n), nr = al(CH * 2 * I.Lk * I.n);
+  u32 *s = nullptr;
+  int rc = scratch(c, (nd + nr) * 4, &s);
+  if (rc) return rc;
+  u32 *sD = s, *sR = s + nd;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    size_t npolys = cnt * ksw->parts;
+    KL(c, k_digits, nblk(npolys * I.n), 256, 0, c->dc, in + off * ksw->parts * I.n * I.W, sD, npolys);
+    CKL();
+    if ((rc = fused_ks_from_digits(c, ksw, sD, sR, out + off * 2 * I.n * I.W, cnt))) return rc;
+  }
+  return 0;
+}
+static int fused_mult_relin(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *a, const u32 *b, u32 *out,
+                            size_t count) {
+  const fhesi_info &I = c->info;
+  const u32 K = 3 * I.D;
+  const size_t CH = c->chunk;
+  const size_t ctw = (size_t)I.n * I.W;
+  size_t n1 = al(CH * 3 * I.Lt * I.n), nd = al(CH * K * I.n), n2 = al(CH * 2 * I.Lk * I.n);
+  u32 *s = nullptr;
+  int rc = scratch(c, (n1 + nd + n2) * 4, &s);
+  if (rc) return rc;
+  u32 *sR1 = s, *sD = s + n1, *sR2 = sD + nd;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    FusedTensorArgs t{a + off * 2 * ctw, b + off * 2 * ctw, sR1, I.Lt};
+    dim3 grid(I.Lt, (unsigned)cnt);
+    KL(c, k_fused_tensor, grid, 512, FT_SMEM_WORDS * 4, c->dc, t);
+    CKL();
+    if ((rc = launch_crt(c, sR1, I.Lt, CRT_SCALEDOWN_DIGITS, sD, I.W, cnt * 3))) return rc;
+    if ((rc = fused_ks_from_digits(c, ksw, sD, sR2, out + off * 2 * ctw, cnt))) return rc;
+  }
+  return 0;
+}
+
 int fhesi_keyswitch_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *in, uint32_t *out, size_t count) {
   if (!c || !ksw || !in || !out) return fail(FHESI_ERR_INVALID, "null argument");
   if (ksw->ctx != c) return fail(FHESI_ERR_INVALID, "key-switch matrix belongs to another context");

@@ -38,8 +38,12 @@ struct DevCtx {
   const u32 *Pfull, *Phalf;               // [Lmax+1][Lmax]  words of prod_{i<l} p_i and its half
 };
 
-// Storage order of transform-domain vectors: position i of the in-place DIF output.
-__device__ __forceinline__ u32 store_index(u32 i) { return i; }
+// Storage order of transform-domain vectors.  Position i of the in-place DIF output lives at
+// store_index(i): inside every block of 16 positions the 8 even ones come first, then the 8
+// odd ones.  This is the natural register order of the fused N=1024 kernels
+// (kernels_fused.cuh: thread t, register r <-> storage index 8t + r), which lets them read
+// key tiles with 128-bit loads; pointwise kernels do not care.  Needs N >= 16.
+__device__ __forceinline__ u32 store_index(u32 i) { return (i & ~15u) | ((i & 1u) << 3) | ((i >> 1) & 7u); }
 
 // ---------------------------------------------------------------------------------------
 // shared-memory radix-2 NTT, one butterfly per thread per stage
@@ -313,12 +317,13 @@ __global__ void k_tprod_reduce_world(DevCtx c, const u32 *in, u32 world, u32 L, 
 // ---------------------------------------------------------------------------------------
 // CRT: Garner mixed radix -> multiword -> centre -> mode-specific rounding
 // ---------------------------------------------------------------------------------------
-enum { CRT_REDUCE_Q = 0, CRT_SCALEDOWN = 1, CRT_DECRYPT = 2, CRT_WIDE = 3 };
+enum { CRT_REDUCE_Q = 0, CRT_SCALEDOWN = 1, CRT_DECRYPT = 2, CRT_WIDE = 3, CRT_SCALEDOWN_DIGITS = 4 };
 
 struct CrtArgs {
   const u32 *res;  // [npolys][L][n]
   u32 L, mode;
   u32 *out;        // REDUCE_Q/SCALEDOWN: [npolys][n][W]; DECRYPT: [npolys][n]; WIDE: [npolys][n][Wout]
+                   // SCALEDOWN_DIGITS: [npolys][D][n] -- ScaleDown fused with ByteDecomp
   u32 Wout;
   size_t total;    // npolys * n
 };
@@ -451,6 +456,19 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
   const u32 ws = logQ >> 5, bs = logQ & 31;
   auto word_at = [&](u32 k) -> u32 { return k < (u32)ML ? col[k * stride] : sign; };
   if (!active) return;
+  if (a.mode == CRT_SCALEDOWN_DIGITS) {
+    // digit d of the non-negative residue mod q of y = (x + q/2) >> logQ: bits
+    // [logQ + d*dbits, +dbits) of the shifted sum, clipped at 2*logQ  (Ciphertext.cpp:92-103)
+    for (u32 d = 0; d < c.D; ++d) {
+      const u32 o = logQ + c.dbits * d;
+      const u32 wi = o >> 5, sh = o & 31;
+      u32 lo = word_at(wi), hi = word_at(wi + 1);
+      u32 v = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+      const u32 valid = min(c.dbits, logQ - c.dbits * d);
+      a.out[((size_t)poly * c.D + d) * c.n + coef] = v & ((1u << valid) - 1u);
+    }
+    return;
+  }
   if (a.mode == CRT_SCALEDOWN) {
     u32 *o = a.out + idx * W;
     const u32 tb = (logQ - 1) & 31;
