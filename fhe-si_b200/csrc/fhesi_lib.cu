@@ -47,7 +47,8 @@ struct fhesi_ctx {
   std::vector<void *> tables;  // device allocations owned by the context
   Arena scratch;
   std::vector<PrimeConst> h_pc;
-  u32 chunk = 128;  // ciphertexts per pass through the scratch arena
+  u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
+  u32 fused_chunk = 2048; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
   // launch accounting / per-kernel CUDA-event profiler (bench.py "roofline", "gpu_launches")
   uint64_t launches = 0;
@@ -180,6 +181,8 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   const u32 CW = W + 2;
   std::vector<PrimeConst> pc(L);
   std::vector<u32> twf((size_t)L * N), twi((size_t)L * N), cw((size_t)L * CW), gar((size_t)L * L, 0);
+  std::vector<uint2> twsf((size_t)L * N), twsi((size_t)L * N);
+  std::vector<u32> cwr((size_t)L * 2 * CW);
   // floor(2^logQ / p_pt) mod q needs 2^logQ mod p_pt
   const u64 rem_q = h_powmod(2, logQ, p_pt);
   for (u32 l = 0; l < L; ++l) {
@@ -210,6 +213,9 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
       for (u32 j = 0; j < hh; ++j) {
         twf[(size_t)l * N + hh + j] = (u32)a;
         twi[(size_t)l * N + hh + j] = (u32)b;
+        const u64 ap = h_mulmod(a, h_invmod(R, q), q), bp = h_mulmod(b, h_invmod(R, q), q);  // plain
+        twsf[(size_t)l * N + hh + j] = make_uint2((u32)ap, (u32)((ap << 32) / q));
+        twsi[(size_t)l * N + hh + j] = make_uint2((u32)bp, (u32)((bp << 32) / q));
         a = h_mulmod(a, step, q);
         b = h_mulmod(b, istep, q);
       }
@@ -219,6 +225,19 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
     for (u32 k = 0; k < CW; ++k) {
       cw[(size_t)l * CW + k] = (u32)t;
       t = h_mulmod(t, R, q);
+    }
+    twsf[(size_t)l * N] = twsi[(size_t)l * N] = make_uint2(1u, (u32)((1ull << 32) / q));
+    for (u32 v = 0; v < 2; ++v) {
+      const u64 sv = v ? h_mulmod(h_mulmod(p_pt % q, ninv, q), R, q) : 1;
+      u64 c2 = h_mulmod(R, sv, q);  // 2^(32k) * R * s_v
+      for (u32 k = 0; k < CW; ++k) {
+        // entry W holds the correction for a negative top word: p - 2^(32W) * s_v (no extra R:
+        // it is added after the Montgomery reduction)
+        cwr[((size_t)l * 2 + v) * CW + k] = (u32)c2;
+        c2 = h_mulmod(c2, R, q);
+      }
+      const u64 topc = h_mulmod(h_powmod(2, 32ull * W, q), sv, q);
+      cwr[((size_t)l * 2 + v) * CW + W] = (u32)((q - topc) % q);
     }
     for (u32 i = 0; i < l; ++i)
       gar[(size_t)l * L + i] = (u32)h_mulmod(h_invmod(primes[i] % q, q), R, q);
@@ -253,7 +272,8 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   if ((rc = upload(c, pc, &dc.pc)) || (rc = upload(c, twf, &dc.tw_fwd)) ||
       (rc = upload(c, twi, &dc.tw_inv)) || (rc = upload(c, cw, &dc.cword)) ||
       (rc = upload(c, gar, &dc.garner)) || (rc = upload(c, Pf, &dc.Pfull)) ||
-      (rc = upload(c, Ph, &dc.Phalf))) {
+      (rc = upload(c, Ph, &dc.Phalf)) || (rc = upload(c, twsf, &dc.tws_fwd)) ||
+      (rc = upload(c, twsi, &dc.tws_inv)) || (rc = upload(c, cwr, &dc.cwr))) {
     fhesi_ctx_destroy(c);
     return rc;
   }
@@ -261,6 +281,8 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   c->stream = c->own_stream;
   const char *ev = getenv("FHESI_CHUNK");
   if (ev && atoi(ev) > 0) c->chunk = (u32)atoi(ev);
+  ev = getenv("FHESI_FUSED_CHUNK");
+  if (ev && atoi(ev) > 0) c->fused_chunk = (u32)atoi(ev);
   ev = getenv("FHESI_NO_FUSED");
   if (ev && atoi(ev) > 0) c->use_fused = false;
   if (!fused_supported(dc)) c->use_fused = false;
@@ -546,12 +568,12 @@ int fhesi_ct_tensor_dev(fhesi_ctx *c, const uint32_t *a, uint32_t pa, const uint
   const u32 po = pa + pb - 1;
   const size_t CH = c->chunk;
   if (c->use_fused && pa == 2 && pb == 2 && !accumulate) {
-    const size_t ctw = (size_t)I.n * I.W, GY = 32768;  // gridDim.y limit
+    const size_t ctw = (size_t)I.n * I.W, GY = 65536;  // keeps gridDim.y below its limit
     for (size_t off = 0; off < count; off += GY) {
       size_t cnt = count - off < GY ? count - off : GY;
-      FusedTprodArgs t{a + off * 2 * ctw, b + off * 2 * ctw, tprod + off * 3 * per, I.Lt};
-      dim3 grid(I.Lt, (unsigned)cnt);
-      KL(c, k_fused_tprod, grid, 512, FT_SMEM_WORDS * 4, c->dc, t);
+      FusedTensorArgs t{a + off * 2 * ctw, b + off * 2 * ctw, tprod + off * 3 * per, I.Lt, (u32)cnt, 1, 1};
+      dim3 grid(I.Lt, (unsigned)((cnt + KG - 1) / KG));
+      KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
       CKL();
     }
     return 0;
@@ -663,14 +685,14 @@ static int fused_ks_from_digits(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *d
   const fhesi_info &I = c->info;
   FusedKsArgs k{digits, ksw->d_key, res, ksw->parts * I.D, I.Lk, (u32)cnt};
   dim3 grid(I.Lk, (unsigned)((cnt + KG - 1) / KG));
-  KL(c, k_fused_keyswitch, grid, KG * 128, FK_SMEM_WORDS * 4, c->dc, k);
+  KL(c, k_fused_keyswitch, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, k);
   CKL();
   return launch_crt(c, res, I.Lk, CRT_REDUCE_Q, out, I.W, cnt * 2);
 }
 static int fused_keyswitch(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, u32 *out, size_t count) {
   const fhesi_info &I = c->info;
   const u32 K = ksw->parts * I.D;
-  const size_t CH = c->chunk;
+  const size_t CH = c->fused_chunk;
   size_t nd = al(CH * K * I.n), nr = al(CH * 2 * I.Lk * I.n);
   u32 *s = nullptr;
   int rc = scratch(c, (nd + nr) * 4, &s);
@@ -689,7 +711,7 @@ static int fused_mult_relin(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *a, co
                             size_t count) {
   const fhesi_info &I = c->info;
   const u32 K = 3 * I.D;
-  const size_t CH = c->chunk;
+  const size_t CH = c->fused_chunk;
   const size_t ctw = (size_t)I.n * I.W;
   size_t n1 = al(CH * 3 * I.Lt * I.n), nd = al(CH * K * I.n), n2 = al(CH * 2 * I.Lk * I.n);
   u32 *s = nullptr;
@@ -698,9 +720,10 @@ static int fused_mult_relin(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *a, co
   u32 *sR1 = s, *sD = s + n1, *sR2 = sD + nd;
   for (size_t off = 0; off < count; off += CH) {
     size_t cnt = count - off < CH ? count - off : CH;
-    FusedTensorArgs t{a + off * 2 * ctw, b + off * 2 * ctw, sR1, I.Lt};
-    dim3 grid(I.Lt, (unsigned)cnt);
-    KL(c, k_fused_tensor, grid, 512, FT_SMEM_WORDS * 4, c->dc, t);
+    const u32 opg = cnt >= 4096 ? 4 : (cnt >= 1024 ? 2 : 1);  // ops per group: amortise the table fill
+    FusedTensorArgs t{a + off * 2 * ctw, b + off * 2 * ctw, sR1, I.Lt, (u32)cnt, opg, 0};
+    dim3 grid(I.Lt, (unsigned)((cnt + KG * opg - 1) / (KG * opg)));
+    KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
     CKL();
     if ((rc = launch_crt(c, sR1, I.Lt, CRT_SCALEDOWN_DIGITS, sD, I.W, cnt * 3))) return rc;
     if ((rc = fused_ks_from_digits(c, ksw, sD, sR2, out + off * 2 * ctw, cnt))) return rc;

@@ -38,106 +38,134 @@ __device__ __forceinline__ void fhesi_group_sync(unsigned g) {
 #endif
 
 #define FN 1024u
-#define FPADN 1152u  // FN + 2*(FN>>4)
-__device__ __forceinline__ u32 fpad(u32 i) { return i + ((i >> 4) << 1); }
+#define FPADN 1152u  // FN + 128
+// exchange 1 (pass-1 <-> pass-2 ownership): 16 words of padding per 128; exchange 2
+// (pass-2 <-> pass-3 ownership): 2 words per 16.  Both are bank-conflict free on both sides.
+__device__ __forceinline__ u32 fpad1(u32 i) { return i + ((i >> 7) << 4); }
+__device__ __forceinline__ u32 fpad2(u32 i) { return i + ((i >> 4) << 1); }
 
-struct Tw21 {
-  u32 a[7], b[7], c[7];
-};
-// tw: the prime's [N] table (forward or inverse), index h + j (kernels_generic.cuh)
-__device__ __forceinline__ void load_tw21(Tw21 &w, const u32 *__restrict__ tw, u32 tg) {
-  const u32 lo = tg & 15, b0 = tg & 1;
+// Shoup multiplication by a fixed w: (w, floor(w 2^32 / p)); any x < 2^32 -> [0, 2p)
+__device__ __forceinline__ u32 mulw(u32 x, uint2 w, u32 p) { return x * w.x - __umulhi(x, w.y) * p; }
+
+// The 21 twiddles a thread needs live in shared memory as tws[s * 128 + tg], s = 0..20
+// (0-6 pass 1, 7-13 pass 2, 14-20 pass 3); one table per direction, shared by the CTA.
+#define FTW_WORDS (21u * 128u * 2u)
+__device__ __forceinline__ u32 tw_index(u32 s, u32 t) {
+  if (s < 4) return 512 + s * 128 + t;
+  if (s < 6) return 256 + (s - 4) * 128 + t;
+  if (s == 6) return 128 + t;
+  const u32 lo = t & 15, b0 = t & 1;
+  if (s < 11) return 64 + (s - 7) * 16 + lo;
+  if (s < 13) return 32 + (s - 11) * 16 + lo;
+  if (s == 13) return 16 + lo;
+  if (s < 18) return 8 + (s - 14) * 2 + b0;
+  if (s < 20) return 4 + (s - 18) * 2 + b0;
+  return 2 + b0;
+}
+__device__ __forceinline__ void fill_tw_table(uint2 *tws, const uint2 *__restrict__ table) {
+  for (u32 e = threadIdx.x; e < 21u * 128u; e += blockDim.x) tws[e] = __ldg(table + tw_index(e >> 7, e & 127));
+}
+
+#define GSW(X, Y, W)                          \
+  do {                                        \
+    u32 s_ = (X) + (Y), d_ = (X) + p2 - (Y);  \
+    (X) = csub(s_, p2);                       \
+    (Y) = mulw(d_, (W), p);                   \
+  } while (0)
+#define CTW(X, Y, W)                          \
+  do {                                        \
+    u32 t_ = mulw((Y), (W), p);               \
+    u32 s_ = (X) + t_, d_ = (X) + p2 - t_;    \
+    (X) = csub(s_, p2);                       \
+    (Y) = csub(d_, p2);                       \
+  } while (0)
+
+// three DIF stages on the 8 registers, twiddles tw[0..3], tw[4..5], tw[6] (stride 128 apart)
+__device__ __forceinline__ void dif8(u32 *x, const uint2 *tw, u32 p) {
+  const u32 p2 = 2 * p;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    w.a[j] = __ldg(tw + 512 + j * 128 + tg);
-    w.b[j] = __ldg(tw + 64 + j * 16 + lo);
-    w.c[j] = __ldg(tw + 8 + j * 2 + b0);
+    const uint2 w = tw[j * 128];
+    GSW(x[j], x[j + 4], w);
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    w.a[4 + j] = __ldg(tw + 256 + j * 128 + tg);
-    w.b[4 + j] = __ldg(tw + 32 + j * 16 + lo);
-    w.c[4 + j] = __ldg(tw + 4 + j * 2 + b0);
+    const uint2 w = tw[(4 + j) * 128];
+    GSW(x[j], x[j + 2], w);
+    GSW(x[j + 4], x[j + 6], w);
   }
-  w.a[6] = __ldg(tw + 128 + tg);
-  w.b[6] = __ldg(tw + 16 + lo);
-  w.c[6] = __ldg(tw + 2 + b0);
+  const uint2 w = tw[6 * 128];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) GSW(x[j], x[j + 1], w);
+}
+__device__ __forceinline__ void dit8(u32 *x, const uint2 *tw, u32 p) {
+  const u32 p2 = 2 * p;
+  {
+    const uint2 w = tw[6 * 128];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) CTW(x[j], x[j + 1], w);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint2 w = tw[(4 + j) * 128];
+    CTW(x[j], x[j + 2], w);
+    CTW(x[j + 4], x[j + 6], w);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint2 w = tw[j * 128];
+    CTW(x[j], x[j + 4], w);
+  }
 }
 
-// Gentleman-Sande butterfly: values in [0,2p) in and out
-#define GS(X, Y, W)                              \
-  do {                                           \
-    u32 s_ = (X) + (Y), d_ = (X) + p2 - (Y);     \
-    (X) = csub(s_, p2);                          \
-    (Y) = mont_mul(d_, (W), p, pinv);            \
-  } while (0)
-// Cooley-Tukey butterfly: values in [0,2p) in and out
-#define CT(X, Y, W)                              \
-  do {                                           \
-    u32 t_ = mont_mul((Y), (W), p, pinv);        \
-    u32 s_ = (X) + t_, d_ = (X) + p2 - t_;       \
-    (X) = csub(s_, p2);                          \
-    (Y) = csub(d_, p2);                          \
-  } while (0)
-
-// three DIF stages on the 8 registers; w[0..3] first stage, w[4..5] second, w[6] third
-__device__ __forceinline__ void dif8(u32 *x, const u32 *w, u32 p, u32 pinv) {
-  const u32 p2 = 2 * p;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) GS(x[j], x[j + 4], w[j]);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    GS(x[j], x[j + 2], w[4 + j]);
-    GS(x[j + 4], x[j + 6], w[4 + j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; j += 2) GS(x[j], x[j + 1], w[6]);
-}
-// the mirror image: three DIT stages, innermost first
-__device__ __forceinline__ void dit8(u32 *x, const u32 *w, u32 p, u32 pinv) {
-  const u32 p2 = 2 * p;
-#pragma unroll
-  for (int j = 0; j < 8; j += 2) CT(x[j], x[j + 1], w[6]);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    CT(x[j], x[j + 2], w[4 + j]);
-    CT(x[j + 4], x[j + 6], w[4 + j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) CT(x[j], x[j + 4], w[j]);
+// per-thread shared-memory offsets of the three ownerships (loop invariant)
+struct XAddr {
+  u32 a1, a2a, a2b, a3;  // pass-1 view of bufA, pass-2 view of bufA, of bufB, pass-3 view of bufB
+};
+__device__ __forceinline__ XAddr make_xaddr(u32 tg) {
+  const u32 hi = tg >> 4, lo = tg & 15, u = tg >> 1, b0 = tg & 1;
+  XAddr r;
+  r.a1 = tg;                    // fpad1(j*128 + tg)          = a1  + 144 j
+  r.a2a = hi * 144 + lo;        // fpad1(hi*128 + j*16 + lo)  = a2a + 16 j
+  r.a2b = hi * 144 + lo;        // fpad2(hi*128 + j*16 + lo)  = a2b + 18 j
+  r.a3 = u * 18 + b0;           // fpad2(u*16 + j*2 + b0)     = a3  + 2 j
+  return r;
 }
 
 // Forward transform of a polynomial whose upper half is zero.  In: x[0..3] = coefficients
-// j*128 + tg (values < 2p; x[4..7] ignored).  Out: x[r] = transform value at storage index
-// tg*8 + r, fully reduced to [0,p).  bufA/bufB: two FPADN-word exchange buffers of the group.
-__device__ __forceinline__ void fwd1024(u32 *x, const Tw21 &w, u32 *bufA, u32 *bufB, u32 g, u32 tg,
-                                        u32 p, u32 pinv) {
+// j*128 + tg (< 2p; x[4..7] ignored).  Out: x[r] = value at storage index tg*8 + r, in [0,p).
+__device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A, u32 *bufA, u32 *bufB,
+                                        u32 g, u32 tg, u32 p) {
   const u32 p2 = 2 * p;
+  const uint2 *tw = twf + tg;
   // pass 1; its first stage sees (X, 0): X stays, the partner becomes X * w
 #pragma unroll
-  for (int j = 0; j < 4; ++j) x[j + 4] = mont_mul(x[j], w.a[j], p, pinv);
+  for (int j = 0; j < 4; ++j) x[j + 4] = mulw(x[j], tw[j * 128], p);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    GS(x[j], x[j + 2], w.a[4 + j]);
-    GS(x[j + 4], x[j + 6], w.a[4 + j]);
+    const uint2 w = tw[(4 + j) * 128];
+    GSW(x[j], x[j + 2], w);
+    GSW(x[j + 4], x[j + 6], w);
+  }
+  {
+    const uint2 w = tw[6 * 128];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) GSW(x[j], x[j + 1], w);
   }
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) GS(x[j], x[j + 1], w.a[6]);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) bufA[fpad(j * 128 + tg)] = x[j];
+  for (int j = 0; j < 8; ++j) bufA[A.a1 + 144 * j] = x[j];
   fhesi_group_sync(g);
-  const u32 hi = tg >> 4, lo = tg & 15;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = bufA[fpad(hi * 128 + j * 16 + lo)];
-  dif8(x, w.b, p, pinv);
+  for (int j = 0; j < 8; ++j) x[j] = bufA[A.a2a + 16 * j];
+  dif8(x, tw + 7 * 128, p);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) bufB[fpad(hi * 128 + j * 16 + lo)] = x[j];
+  for (int j = 0; j < 8; ++j) bufB[A.a2b + 18 * j] = x[j];
   fhesi_group_sync(g);
-  const u32 u = tg >> 1, b0 = tg & 1;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = bufB[fpad(u * 16 + j * 2 + b0)];
-  dif8(x, w.c, p, pinv);
+  for (int j = 0; j < 8; ++j) x[j] = bufB[A.a3 + 2 * j];
+  dif8(x, tw + 14 * 128, p);
   // last stage (position bit 0) across lane pairs, twiddle 1
+  const u32 b0 = tg & 1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     u32 o = __shfl_xor_sync(0xffffffffu, x[j], 1);
@@ -146,32 +174,34 @@ __device__ __forceinline__ void fwd1024(u32 *x, const Tw21 &w, u32 *bufA, u32 *b
   }
 }
 // Inverse transform.  In: x[r] = value at storage index tg*8 + r (< 2p).  Out: the natural
-// order result (unscaled) is written to nat[0..1024) (nat may alias bufA) and the group is
-// synchronised, so every thread may read any coefficient afterwards.
-__device__ __forceinline__ void inv1024(u32 *x, const Tw21 &w, u32 *bufA, u32 *bufB, u32 *nat, u32 g,
-                                        u32 tg, u32 p, u32 pinv) {
+// order result (unscaled, < 2p) is written to nat[0..1024) (nat may alias bufA) and the group
+// is synchronised, so every thread may read any coefficient afterwards.
+__device__ __forceinline__ void inv1024(u32 *x, const uint2 *twi, const XAddr &A, u32 *bufA, u32 *bufB,
+                                        u32 *nat, u32 g, u32 tg, u32 p) {
   const u32 p2 = 2 * p;
-  const u32 u = tg >> 1, b0 = tg & 1, hi = tg >> 4, lo = tg & 15;
+  const uint2 *tw = twi + tg;
+  const u32 b0 = tg & 1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     u32 o = __shfl_xor_sync(0xffffffffu, x[j], 1);
     u32 v = b0 ? o + p2 - x[j] : x[j] + o;
     x[j] = csub(v, p2);
   }
-  dit8(x, w.c, p, pinv);
+  dit8(x, tw + 14 * 128, p);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) bufA[fpad(u * 16 + j * 2 + b0)] = x[j];
+  for (int j = 0; j < 8; ++j) bufB[A.a3 + 2 * j] = x[j];
   fhesi_group_sync(g);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = bufA[fpad(hi * 128 + j * 16 + lo)];
-  dit8(x, w.b, p, pinv);
+  for (int j = 0; j < 8; ++j) x[j] = bufB[A.a2b + 18 * j];
+  dit8(x, tw + 7 * 128, p);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) bufB[fpad(hi * 128 + j * 16 + lo)] = x[j];
+  for (int j = 0; j < 8; ++j) bufA[A.a2a + 16 * j] = x[j];
   fhesi_group_sync(g);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = bufB[fpad(j * 128 + tg)];
-  dit8(x, w.a, p, pinv);
-  // every thread is past its bufA reads (it passed the bufB barrier), so nat may alias bufA
+  for (int j = 0; j < 8; ++j) x[j] = bufA[A.a1 + 144 * j];
+  dit8(x, tw, p);
+  // nat aliases bufA: every thread must be past its bufA reads before anyone writes
+  fhesi_group_sync(g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) nat[j * 128 + tg] = x[j];
   fhesi_group_sync(g);
@@ -197,111 +227,103 @@ __device__ __forceinline__ void phim_store_1024(const u32 *nat, u32 *__restrict_
 
 static bool fused_supported(const DevCtx &dc) { return dc.N == FN && dc.n <= 512; }
 
+// multiword two's complement (W words) -> residue in [0,2p), scaled by s_v (DevCtx::cwr).
+// Lazy: 4 word products are summed in 64 bits (< 2^64) and Montgomery-reduced once.
+__device__ __forceinline__ u32 residue_lazy(const u32 *__restrict__ w, u32 W, const u32 *__restrict__ cw,
+                                            u32 p, u32 pinv) {
+  const u32 p2 = 2 * p;
+  u32 r = 0, top = 0;
+  for (u32 k0 = 0; k0 < W; k0 += 4) {
+    u64 t = 0;
+    if (k0 + 4 <= W && (W & 3) == 0) {
+      const uint4 v = *(const uint4 *)(w + k0);
+      t = (u64)v.x * __ldg(cw + k0) + (u64)v.y * __ldg(cw + k0 + 1) + (u64)v.z * __ldg(cw + k0 + 2) +
+          (u64)v.w * __ldg(cw + k0 + 3);
+      top = v.w;
+    } else {
+      for (u32 k = k0; k < W && k < k0 + 4; ++k) {
+        top = w[k];
+        t += (u64)top * __ldg(cw + k);
+      }
+    }
+    // t < 4 * 2^32 * p.  t - m*p == 0 mod 2^32 with m = t_lo * p^-1; quotient t_hi - hi(m p)
+    const u32 m = (u32)t * (0u - pinv);
+    const u32 th = (u32)(t >> 32), hm = __umulhi(m, p);
+    u32 q = th - hm;
+    if (th < hm) q += p;                   // q in [0, 4p)
+    r = csub(r + csub(q, p2), p2);
+  }
+  if (top >> 31) r = csub(r + __ldg(cw + W), p2);
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------
-// tensor product + inverse transform + Phi_m fold, one CTA per (prime, ciphertext pair)
+// tensor product, one 128-thread group per (prime, ciphertext pair); a group is independent
+// of the other groups of its CTA (they only share the prime's twiddle tables)
 // ---------------------------------------------------------------------------------------
 struct FusedTensorArgs {
   const u32 *a, *b;  // [count][2][n][W]
-  u32 *res;          // [count][3][Lt][n]
-  u32 Lt;
+  u32 *res;          // to_tprod == 0: [count][3][Lt][n]   coefficient residues after the Phi_m fold
+                     // to_tprod == 1: [count][3][Lt][N]   transform-domain tprod
+  u32 Lt, count, ops_per_group, to_tprod;
 };
-#define FT_SMEM_WORDS (4 * 2 * FPADN + 4 * FN)
-__global__ void __launch_bounds__(512, 1) k_fused_tensor(DevCtx c, FusedTensorArgs a) {
+#define KG 4
+#define FUSED_SMEM_WORDS (2 * FTW_WORDS + KG * 2 * FPADN)
+__global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTensorArgs a) {
   FHESI_SMEM(sm);
+  uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
   const u32 l = blockIdx.x;
-  const size_t op = blockIdx.y;
+  fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
+  fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
+  __syncthreads();
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
-  u32 *bufA = sm + g * 2 * FPADN, *bufB = bufA + FPADN;
-  u32 *F = sm + 4 * 2 * FPADN;  // [4][FN] transform images, storage order
-  Tw21 w;
-  load_tw21(w, c.tw_fwd + (size_t)l * FN, tg);
-  // group g transforms a0, a1 (scaled by p_pt / N, Montgomery form) or b0, b1 (plain)
-  const u32 *src = (g < 2 ? a.a + (op * 2 + g) * (size_t)c.n * c.W : a.b + (op * 2 + (g - 2)) * (size_t)c.n * c.W);
-  u32 x[8];
+  u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
+  const XAddr A = make_xaddr(tg);
+  const size_t polyw = (size_t)c.n * c.W;
+  for (u32 it = 0; it < a.ops_per_group; ++it) {
+    const size_t op = ((size_t)blockIdx.y * a.ops_per_group + it) * KG + g;
+    if (op >= a.count) return;  // only group barriers from here on
+    // images of a0, a1 (scaled by p_pt/N, Montgomery form) and b0, b1 (plain), in registers
+    u32 F[4][8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const u32 i = j * 128 + tg;
-    u32 r = 0;
-    if (i < c.n) {
-      r = residue_from_words(src + (size_t)i * c.W, c.W, c.cword + (size_t)l * c.CW, p, pinv);
-      if (g < 2) r = mont_mul(r, pc.tensor_c, p, pinv);
+    for (int q = 0; q < 4; ++q) {
+      const u32 *src = (q < 2 ? a.a : a.b) + (op * 2 + (q & 1)) * polyw;
+      const u32 *cw = c.cwr + ((size_t)l * 2 + (q < 2 ? 1 : 0)) * c.CW;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const u32 i = j * 128 + tg;
+        F[q][j] = i < c.n ? residue_lazy(src + (size_t)i * c.W, c.W, cw, p, pinv) : 0u;
+      }
+      fwd1024(F[q], twf, A, bufA, bufB, g, tg, p);
     }
-    x[j] = r;
-  }
-  fwd1024(x, w, bufA, bufB, g, tg, p, pinv);
+    // tProd[k] = sum_{i+j=k} a_i * b_j   (Ciphertext.cpp:179-186)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) F[g * FN + tg * 8 + j] = x[j];
-  __syncthreads();
-  if (g == 3) return;
-  // tProd[g] = sum_{i+j=g} a_i * b_j   (Ciphertext.cpp:179-186)
-  const u32 *A0 = F, *A1 = F + FN, *B0 = F + 2 * FN, *B1 = F + 3 * FN;
+    for (int k = 0; k < 3; ++k) {
+      u32 y[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const u32 s = tg * 8 + j;
-    u32 v;
-    if (g == 0) v = mont_mul(A0[s], B0[s], p, pinv);
-    else if (g == 2) v = mont_mul(A1[s], B1[s], p, pinv);
-    else v = csub(mont_mul(A0[s], B1[s], p, pinv) + mont_mul(A1[s], B0[s], p, pinv), p2);
-    x[j] = v;
-  }
-  load_tw21(w, c.tw_inv + (size_t)l * FN, tg);
-  inv1024(x, w, bufA, bufB, bufA, g, tg, p, pinv);
-  phim_store_1024(bufA, a.res + ((op * 3 + g) * a.Lt + l) * (size_t)c.n, c.h, tg, p);
-}
-
-// Same forward half, but leaving the tensor in transform-domain (tprod) form:
-// Ciphertext::operator*= without the ScaleDown (Ciphertext.cpp:167-192).
-struct FusedTprodArgs {
-  const u32 *a, *b;  // [count][2][n][W]
-  u32 *tprod;        // [count][3][Lt][N]
-  u32 Lt;
-};
-__global__ void __launch_bounds__(512, 1) k_fused_tprod(DevCtx c, FusedTprodArgs a) {
-  FHESI_SMEM(sm);
-  const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
-  const u32 l = blockIdx.x;
-  const size_t op = blockIdx.y;
-  const PrimeConst pc = c.pc[l];
-  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
-  u32 *bufA = sm + g * 2 * FPADN, *bufB = bufA + FPADN;
-  u32 *F = sm + 4 * 2 * FPADN;
-  Tw21 w;
-  load_tw21(w, c.tw_fwd + (size_t)l * FN, tg);
-  const u32 *src = (g < 2 ? a.a + (op * 2 + g) * (size_t)c.n * c.W : a.b + (op * 2 + (g - 2)) * (size_t)c.n * c.W);
-  u32 x[8];
+      for (int j = 0; j < 8; ++j) {
+        if (k == 0) y[j] = mont_mul(F[0][j], F[2][j], p, pinv);
+        else if (k == 2) y[j] = mont_mul(F[1][j], F[3][j], p, pinv);
+        else y[j] = csub(mont_mul(F[0][j], F[3][j], p, pinv) + mont_mul(F[1][j], F[2][j], p, pinv), p2);
+      }
+      if (a.to_tprod) {
+        u32 *dst = a.res + ((op * 3 + k) * a.Lt + l) * (size_t)FN + tg * 8;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const u32 i = j * 128 + tg;
-    u32 r = 0;
-    if (i < c.n) {
-      r = residue_from_words(src + (size_t)i * c.W, c.W, c.cword + (size_t)l * c.CW, p, pinv);
-      if (g < 2) r = mont_mul(r, pc.tensor_c, p, pinv);
+        for (int j = 0; j < 8; ++j) dst[j] = csub(y[j], p);
+      } else {
+        inv1024(y, twi, A, bufA, bufB, bufA, g, tg, p);
+        phim_store_1024(bufA, a.res + ((op * 3 + k) * a.Lt + l) * (size_t)c.n, c.h, tg, p);
+        fhesi_group_sync(g);  // bufA (nat) is rewritten by the next transform
+      }
     }
-    x[j] = r;
-  }
-  fwd1024(x, w, bufA, bufB, g, tg, p, pinv);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) F[g * FN + tg * 8 + j] = x[j];
-  __syncthreads();
-  if (g == 3) return;
-  const u32 *A0 = F, *A1 = F + FN, *B0 = F + 2 * FN, *B1 = F + 3 * FN;
-  u32 *dst = a.tprod + ((op * 3 + g) * a.Lt + l) * (size_t)FN + tg * 8;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const u32 s = tg * 8 + j;
-    u32 v;
-    if (g == 0) v = mont_mul(A0[s], B0[s], p, pinv);
-    else if (g == 2) v = mont_mul(A1[s], B1[s], p, pinv);
-    else v = csub(mont_mul(A0[s], B1[s], p, pinv) + mont_mul(A1[s], B0[s], p, pinv), p2);
-    dst[j] = csub(v, p);
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// key switch: one 128-thread group per (prime, ciphertext); KG ciphertexts per CTA share the
-// prime's key tiles through L1
+// key switch: one 128-thread group per (prime, ciphertext); the KG ciphertexts of a CTA share
+// the prime's twiddle tables (shared memory) and key tiles (L1)
 // ---------------------------------------------------------------------------------------
 struct FusedKsArgs {
   const u32 *digits;  // [count][K][n]   dbits-wide digits, part-major digit-minor
@@ -309,36 +331,42 @@ struct FusedKsArgs {
   u32 *res;           // [count][2][Lk][n]
   u32 K, Lk, count;
 };
-#define KG 4
-#define FK_SMEM_WORDS (KG * 2 * FPADN)
 __global__ void __launch_bounds__(KG * 128, 1) k_fused_keyswitch(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
+  uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
   const u32 l = blockIdx.x;
+  fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
+  fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
+  __syncthreads();
   const size_t op = (size_t)blockIdx.y * KG + g;
-  if (op >= a.count) return;  // whole group leaves together; only group barriers are used
+  if (op >= a.count) return;  // whole group leaves together; only group barriers from here on
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
-  u32 *bufA = sm + g * 2 * FPADN, *bufB = bufA + FPADN;
-  Tw21 w;
-  load_tw21(w, c.tw_fwd + (size_t)l * FN, tg);
+  u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
+  const XAddr A = make_xaddr(tg);
   u64 acc0[8], acc1[8];
   u32 t0[8], t1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0, t0[j] = t1[j] = 0;
   const u32 *dig = a.digits + op * a.K * (size_t)c.n;
   const u32 *key = a.key + (size_t)l * a.K * 2 * FN + tg * 8;
+  u32 xn[4];  // next digit, prefetched one transform ahead
+#pragma unroll
+  for (int j = 0; j < 4; ++j) xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + j * 128 + tg) : 0u;
   for (u32 k = 0; k < a.K; ++k) {
     u32 x[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const u32 i = j * 128 + tg;
-      x[j] = i < c.n ? __ldg(dig + (size_t)k * c.n + i) : 0u;
+    for (int j = 0; j < 4; ++j) x[j] = xn[j];
+    if (k + 1 < a.K) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + (size_t)(k + 1) * c.n + j * 128 + tg) : 0u;
     }
     const uint4 *kp = (const uint4 *)(key + (size_t)k * 2 * FN);
     const uint4 ka0 = __ldg(kp), ka1 = __ldg(kp + 1);
     const uint4 kb0 = __ldg(kp + FN / 4), kb1 = __ldg(kp + FN / 4 + 1);
-    fwd1024(x, w, bufA, bufB, g, tg, p, pinv);
+    fwd1024(x, twf, A, bufA, bufB, g, tg, p);
     const u32 kb[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
     const u32 kA[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
 #pragma unroll
@@ -355,11 +383,10 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_keyswitch(DevCtx c, Fused
       }
     }
   }
-  load_tw21(w, c.tw_inv + (size_t)l * FN, tg);
-  inv1024(t0, w, bufA, bufB, bufA, g, tg, p, pinv);
+  inv1024(t0, twi, A, bufA, bufB, bufA, g, tg, p);
   phim_store_1024(bufA, a.res + ((op * 2 + 0) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
-  fhesi_group_sync(g);  // bufA is rewritten by the next inverse transform
-  inv1024(t1, w, bufA, bufB, bufA, g, tg, p, pinv);
+  fhesi_group_sync(g);  // bufA (nat) is rewritten by the next inverse transform
+  inv1024(t1, twi, A, bufA, bufB, bufA, g, tg, p);
   phim_store_1024(bufA, a.res + ((op * 2 + 1) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
 }
 
@@ -376,11 +403,9 @@ __global__ void k_digits(DevCtx c, const u32 *in, u32 *out, size_t npolys) {
 
 static int fused_configure() {
   cudaError_t e = cudaFuncSetAttribute(k_fused_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(FT_SMEM_WORDS * 4));
-  if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(k_fused_tprod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FT_SMEM_WORDS * 4));
+                                       (int)(FUSED_SMEM_WORDS * 4));
   if (e != cudaSuccess) return -1;
   e = cudaFuncSetAttribute(k_fused_keyswitch, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(FK_SMEM_WORDS * 4));
+                           (int)(FUSED_SMEM_WORDS * 4));
   return e == cudaSuccess ? 0 : -1;
 }

@@ -36,6 +36,13 @@ struct DevCtx {
   const u32 *cword;                       // [Lmax][CW] 2^(32k) * R mod p
   const u32 *garner;                      // [Lmax][Lmax] garner[j][i] = p_i^-1 * R mod p_j (i<j)
   const u32 *Pfull, *Phalf;               // [Lmax+1][Lmax]  words of prod_{i<l} p_i and its half
+  // Shoup tables for the fused kernels: (w, floor(w * 2^32 / p)), plain (non-Montgomery) w
+  const uint2 *tws_fwd, *tws_inv;         // [Lmax][N] same index h + j as tw_fwd / tw_inv
+  // multiword -> residue constants: cwr[l][v][k] = 2^(32k) * R * s_v mod p for k < W, and
+  // cwr[l][v][W] = p - (2^(32W) * s_v mod p); s_0 = 1 (plain result after Montgomery
+  // reduction), s_1 = p_pt / N * R (Montgomery form of the tensor's left operand)
+  const u32 *cwr;                         // [Lmax][2][CW]
+  u32 pad_;
 };
 
 // Storage order of transform-domain vectors.  Position i of the in-place DIF output lives at
@@ -363,11 +370,14 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
     if (i < L) {
       const u32 p = c.pc[i].p;
       u64 carry = v[i];
+      // before this step acc < prod_{i<j<L} p_j < 2^(30 (ML-1-i)): only ML-i words can change
 #pragma unroll
       for (int k = 0; k < ML; ++k) {
-        u64 t = (u64)acc[k] * p + carry;
-        acc[k] = (u32)t;
-        carry = t >> 32;
+        if (k <= ML - 1 - i) {
+          u64 t = (u64)acc[k] * p + carry;
+          acc[k] = (u32)t;
+          carry = t >> 32;
+        }
       }
     }
   }

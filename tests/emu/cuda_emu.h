@@ -131,6 +131,10 @@ inline T __shfl_sync(unsigned, T v, int src_lane) {
 struct uint4 {
   unsigned x, y, z, w;
 };
+struct uint2 {
+  unsigned x, y;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
 // named barrier over the 128-thread group `g` of the block (bar.sync g+1, 128 on the GPU)
