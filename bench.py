@@ -303,8 +303,12 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak32 = dev.modmul_peak(32)
+        peak_mont32 = dev.modmul_peak(32)
         peak64 = dev.modmul_peak(64)
+        pipes = {name: dev.pipe_peak(kind) for kind, name in
+                 enumerate(["imad_lo32", "imad_wide64", "imad_hi32", "shoup_modmul32", "alu_csub", "dfma"])}
+        # roofline denominator: the faster of the two 32-bit modular-product formulations
+        peak32 = max(peak_mont32, pipes["shoup_modmul32"])
         # dominant kernel by measured device time, with its algorithmic modmuls per launch
         work_all = kernel_work_per_op(dev)
         work = {k: v for k, v in work_all.items() if k in prof}  # kernels that actually ran
@@ -321,7 +325,10 @@ def run_ours(args, rank, local_rank, world):
             "kernel": tname, "kernel_share_of_step": share,
             "achieved": achieved / 1e9, "peak": peak32 / 1e9, "unit": "Gmodmul/s (32-bit Montgomery)",
             "frac": achieved / peak32, "traffic": None,
-            "peak_source": "measured in this run: fhesi_modmul_peak(32), register-resident ILP-8 all-SM",
+            "peak_source": "measured in this run: max(fhesi_modmul_peak(32) Montgomery, fhesi_pipe_peak(3) Shoup), "
+                           "register-resident ILP-8 chains on all SMs",
+            "peak_montgomery32_Gmodmul_s": peak_mont32 / 1e9,
+            "pipe_peaks_Gops_s": {k: v / 1e9 for k, v in pipes.items()},
             "algorithmic_modmul_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
             "whole_op": {
                 "executed_modmul32_per_op": sum(work.values()),
@@ -375,8 +382,9 @@ def kernel_work_per_op(dev):
         "k_dot": 2 * 3 * D * Lk * N,
         "k_crt<ML>": 3 * n * garner(Lt) + 2 * n * garner(Lk),
         # fused path (kernels_fused.cuh)
-        "k_fused_tensor": (4 * Lt) * bf + 4 * Lt * N + 3 * Lt * bf,
-        "k_fused_keyswitch": (3 * D * Lk) * bf + 2 * 3 * D * Lk * N + 2 * Lk * bf,
+        "k_residues": 4 * n * Lt * dev.W,
+        "k_fused_tensor": 7 * Lt * bf + 4 * Lt * N,
+        "k_fused_keyswitch": (3 * D + 2) * Lk * bf + 2 * 3 * D * Lk * N,
     }
 
 

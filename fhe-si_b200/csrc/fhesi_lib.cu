@@ -56,6 +56,9 @@ struct fhesi_ctx {
   std::vector<std::string> prof_names;
   std::vector<ProfRec> prof_recs;
   Arena stage;  // device staging for the *_host entry points
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the host pipeline
+  std::vector<cudaEvent_t> pipe_events;
+  u32 pipe_chunk = 512;
   Arena work;   // tprod / scaled-down intermediates of the generic mult_relin composition
 };
 static void prof_clear(fhesi_ctx *c);
@@ -283,6 +286,8 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   if (ev && atoi(ev) > 0) c->chunk = (u32)atoi(ev);
   ev = getenv("FHESI_FUSED_CHUNK");
   if (ev && atoi(ev) > 0) c->fused_chunk = (u32)atoi(ev);
+  ev = getenv("FHESI_PIPE_CHUNK");
+  if (ev && atoi(ev) > 0) c->pipe_chunk = (u32)atoi(ev);
   ev = getenv("FHESI_NO_FUSED");
   if (ev && atoi(ev) > 0) c->use_fused = false;
   if (!fused_supported(dc)) c->use_fused = false;
@@ -306,6 +311,9 @@ void fhesi_ctx_destroy(fhesi_ctx *c) {
   if (c->stage.ptr) cudaFree(c->stage.ptr);
   if (c->work.ptr) cudaFree(c->work.ptr);
   prof_clear(c);
+  for (auto e : c->pipe_events) cudaEventDestroy(e);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -418,6 +426,21 @@ static int launch_crt(fhesi_ctx *c, const u32 *res, u32 L, u32 mode, u32 *out, u
   return 0;
 }
 static inline unsigned nblk(size_t total, int B = 256) { return (unsigned)((total + B - 1) / B); }
+
+// k_residues + k_fused_tensor over one chunk; resid: scratch of cnt*4*Lt*n words
+static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *resid, u32 *out, size_t cnt,
+                               int to_tprod) {
+  const fhesi_info &I = c->info;
+  ResidueArgs r{a, b, resid, I.Lt, cnt};
+  KL(c, k_residues, nblk(cnt * 4 * I.n, 128), 128, I.Lt * 2 * c->dc.CW * 4, c->dc, r);
+  CKL();
+  const u32 opg = cnt >= 4096 ? 4 : (cnt >= 1024 ? 2 : 1);  // ops per group: amortise the table fill
+  FusedTensorArgs t{resid, out, I.Lt, (u32)cnt, opg, (u32)to_tprod};
+  dim3 grid(I.Lt, (unsigned)((cnt + KG * opg - 1) / (KG * opg)));
+  KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
+  CKL();
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------
 // keys
@@ -568,13 +591,16 @@ int fhesi_ct_tensor_dev(fhesi_ctx *c, const uint32_t *a, uint32_t pa, const uint
   const u32 po = pa + pb - 1;
   const size_t CH = c->chunk;
   if (c->use_fused && pa == 2 && pb == 2 && !accumulate) {
-    const size_t ctw = (size_t)I.n * I.W, GY = 65536;  // keeps gridDim.y below its limit
-    for (size_t off = 0; off < count; off += GY) {
-      size_t cnt = count - off < GY ? count - off : GY;
-      FusedTensorArgs t{a + off * 2 * ctw, b + off * 2 * ctw, tprod + off * 3 * per, I.Lt, (u32)cnt, 1, 1};
-      dim3 grid(I.Lt, (unsigned)((cnt + KG - 1) / KG));
-      KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
-      CKL();
+    const size_t ctw = (size_t)I.n * I.W;
+    size_t FC = c->fused_chunk;
+    if (count < FC) FC = count ? count : 1;
+    u32 *sres = nullptr;
+    int rc2 = scratch(c, al(FC * 4 * I.Lt * I.n) * 4, &sres);
+    if (rc2) return rc2;
+    for (size_t off = 0; off < count; off += FC) {
+      size_t cnt = count - off < FC ? count - off : FC;
+      if ((rc2 = launch_fused_tensor(c, a + off * 2 * ctw, b + off * 2 * ctw, sres, tprod + off * 3 * per, cnt, 1)))
+        return rc2;
     }
     return 0;
   }
@@ -711,20 +737,18 @@ static int fused_mult_relin(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *a, co
                             size_t count) {
   const fhesi_info &I = c->info;
   const u32 K = 3 * I.D;
-  const size_t CH = c->fused_chunk;
+  size_t CH = c->fused_chunk;
   const size_t ctw = (size_t)I.n * I.W;
-  size_t n1 = al(CH * 3 * I.Lt * I.n), nd = al(CH * K * I.n), n2 = al(CH * 2 * I.Lk * I.n);
+  if (count < CH) CH = count ? count : 1;
+  size_t n0 = al(CH * 4 * I.Lt * I.n), n1 = al(CH * 3 * I.Lt * I.n), nd = al(CH * K * I.n),
+         n2 = al(CH * 2 * I.Lk * I.n);
   u32 *s = nullptr;
-  int rc = scratch(c, (n1 + nd + n2) * 4, &s);
+  int rc = scratch(c, (n0 + n1 + nd + n2) * 4, &s);
   if (rc) return rc;
-  u32 *sR1 = s, *sD = s + n1, *sR2 = sD + nd;
+  u32 *sR0 = s, *sR1 = s + n0, *sD = sR1 + n1, *sR2 = sD + nd;
   for (size_t off = 0; off < count; off += CH) {
     size_t cnt = count - off < CH ? count - off : CH;
-    const u32 opg = cnt >= 4096 ? 4 : (cnt >= 1024 ? 2 : 1);  // ops per group: amortise the table fill
-    FusedTensorArgs t{a + off * 2 * ctw, b + off * 2 * ctw, sR1, I.Lt, (u32)cnt, opg, 0};
-    dim3 grid(I.Lt, (unsigned)((cnt + KG * opg - 1) / (KG * opg)));
-    KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
-    CKL();
+    if ((rc = launch_fused_tensor(c, a + off * 2 * ctw, b + off * 2 * ctw, sR0, sR1, cnt, 0))) return rc;
     if ((rc = launch_crt(c, sR1, I.Lt, CRT_SCALEDOWN_DIGITS, sD, I.W, cnt * 3))) return rc;
     if ((rc = fused_ks_from_digits(c, ksw, sD, sR2, out + off * 2 * ctw, cnt))) return rc;
   }
@@ -769,11 +793,15 @@ int fhesi_mult_relin_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *a, 
   }
   return rc;
 }
+// Host-buffer entry point.  The batch is cut into pipeline chunks: chunk i+1 is uploaded on a
+// copy stream while chunk i computes on the context's stream and chunk i-1 is downloaded on a
+// second copy stream, so PCIe in both directions overlaps the kernels.
 int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_a, const uint32_t *h_b,
                           uint32_t *h_out, size_t count) {
   if (!c || !ksw || !h_a || !h_b || !h_out) return fail(FHESI_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
-  const size_t bytes = count * fhesi_ct_bytes(c, 2);
+  if (!count) return 0;
+  const size_t ctb = fhesi_ct_bytes(c, 2), bytes = count * ctb;
   if (c->stage.cap < 3 * bytes + 64) {  // grow-only staging area, reused across calls
     CK(cudaStreamSynchronize(c->stream));
     if (c->stage.ptr) CK(cudaFree(c->stage.ptr));
@@ -782,13 +810,37 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
     CK(cudaMalloc(&c->stage.ptr, 3 * bytes + 64));
     c->stage.cap = 3 * bytes + 64;
   }
+  if (!c->h2d_stream) {
+    CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  }
+  const size_t PC = c->pipe_chunk;
+  const size_t nchunks = (count + PC - 1) / PC;
+  while (c->pipe_events.size() < 2 * nchunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->pipe_events.push_back(e);
+  }
   char *d = (char *)c->stage.ptr;
-  u32 *da = (u32 *)d, *db = (u32 *)(d + bytes), *dout = (u32 *)(d + 2 * bytes);
-  CK(cudaMemcpyAsync(da, h_a, bytes, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(db, h_b, bytes, cudaMemcpyHostToDevice, c->stream));
-  int rc = fhesi_mult_relin_dev(c, ksw, da, db, dout, count);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h_out, dout, bytes, cudaMemcpyDeviceToHost, c->stream));
+  char *da = d, *db = d + bytes, *dout = d + 2 * bytes;
+  // the copy stream must not overtake work already queued on the compute stream
+  CK(cudaEventRecord(c->pipe_events[0], c->stream));
+  CK(cudaStreamWaitEvent(c->h2d_stream, c->pipe_events[0], 0));
+  for (size_t ci = 0; ci < nchunks; ++ci) {
+    const size_t off = ci * PC, cnt = count - off < PC ? count - off : PC;
+    cudaEvent_t ev_in = c->pipe_events[2 * ci], ev_done = c->pipe_events[2 * ci + 1];
+    CK(cudaMemcpyAsync(da + off * ctb, (const char *)h_a + off * ctb, cnt * ctb, cudaMemcpyHostToDevice, c->h2d_stream));
+    CK(cudaMemcpyAsync(db + off * ctb, (const char *)h_b + off * ctb, cnt * ctb, cudaMemcpyHostToDevice, c->h2d_stream));
+    CK(cudaEventRecord(ev_in, c->h2d_stream));
+    CK(cudaStreamWaitEvent(c->stream, ev_in, 0));
+    int rc = fhesi_mult_relin_dev(c, ksw, (const u32 *)(da + off * ctb), (const u32 *)(db + off * ctb),
+                                  (u32 *)(dout + off * ctb), cnt);
+    if (rc) return rc;
+    CK(cudaEventRecord(ev_done, c->stream));
+    CK(cudaStreamWaitEvent(c->d2h_stream, ev_done, 0));
+    CK(cudaMemcpyAsync((char *)h_out + off * ctb, dout + off * ctb, cnt * ctb, cudaMemcpyDeviceToHost, c->d2h_stream));
+  }
+  CK(cudaStreamSynchronize(c->d2h_stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -952,6 +1004,45 @@ int fhesi_profile_report(fhesi_ctx *c, char *buf, size_t cap) {
 // ---------------------------------------------------------------------------------------
 // modmul peak
 // ---------------------------------------------------------------------------------------
+template <int KIND>
+static void launch_pipe(fhesi_ctx *c, int blocks, int threads, void *d, int iters) {
+  FHESI_LAUNCH(k_pipe<KIND>, blocks, threads, 0, c->stream, (u32 *)d, c->h_pc[0].p, iters);
+}
+int fhesi_pipe_peak(fhesi_ctx *c, int kind, double *out) {
+  if (!c || !out || kind < 0 || kind > 5) return fail(FHESI_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  void *d = nullptr;
+  CK(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, c->stream));
+    switch (kind) {
+      case 0: launch_pipe<0>(c, blocks, threads, d, iters); break;
+      case 1: launch_pipe<1>(c, blocks, threads, d, iters); break;
+      case 2: launch_pipe<2>(c, blocks, threads, d, iters); break;
+      case 3: launch_pipe<3>(c, blocks, threads, d, iters); break;
+      case 4: launch_pipe<4>(c, blocks, threads, d, iters); break;
+      default: launch_pipe<5>(c, blocks, threads, d, iters); break;
+    }
+    CKL();
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *out = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
+  return 0;
+}
 int fhesi_modmul_peak(fhesi_ctx *c, int word_bits, double *out) {
   if (!c || !out || (word_bits != 32 && word_bits != 64)) return fail(FHESI_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(c->device));

@@ -258,11 +258,78 @@ __device__ __forceinline__ u32 residue_lazy(const u32 *__restrict__ w, u32 W, co
 }
 
 // ---------------------------------------------------------------------------------------
+// multiword -> residues for all tensor primes, one thread per coefficient (the `conv(in, x)`
+// of Cmodulus::FFT, CModulus.cpp:96).  a-parts come out scaled by p_pt/N in Montgomery form.
+// in a, b: [count][2][n][W] -> out [count][4][Lt][n]  (poly order a0, a1, b0, b1)
+// ---------------------------------------------------------------------------------------
+struct ResidueArgs {
+  const u32 *a, *b;
+  u32 *out;
+  u32 Lt;
+  size_t count;
+};
+__global__ void __launch_bounds__(128) k_residues(DevCtx c, ResidueArgs a) {
+  FHESI_SMEM(sm);  // cwr table of the first Lt primes: [Lt][2][CW]
+  const u32 tabw = a.Lt * 2 * c.CW;
+  for (u32 e = threadIdx.x; e < tabw; e += blockDim.x) sm[e] = __ldg(c.cwr + e);
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = a.count * 4 * c.n;
+  if (idx >= total) return;
+  const u32 i = (u32)(idx % c.n);
+  const size_t pq = idx / c.n;  // op * 4 + q
+  const u32 q = (u32)(pq & 3);
+  const size_t op = pq >> 2;
+  const u32 W = c.W;
+  const u32 *src = (q < 2 ? a.a : a.b) + ((op * 2 + (q & 1)) * c.n + i) * (size_t)W;
+  u32 w[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = 0;
+  if ((W & 3) == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 4)
+      if ((u32)k < W) {
+        const uint4 v = *(const uint4 *)(src + k);
+        w[k] = v.x, w[k + 1] = v.y, w[k + 2] = v.z, w[k + 3] = v.w;
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if ((u32)k < W) w[k] = src[k];
+  }
+  const bool neg = (src[W - 1] >> 31) != 0;
+  const u32 v = q < 2 ? 1u : 0u;
+  u32 *dst = a.out + pq * a.Lt * (size_t)c.n + i;
+  for (u32 l = 0; l < a.Lt; ++l) {
+    const PrimeConst pc = c.pc[l];
+    const u32 p = pc.p, p2 = 2 * p, ipinv = 0u - pc.pinv;
+    const u32 *cw = sm + (l * 2 + v) * c.CW;
+    u32 r = 0;
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0 += 4) {
+      if ((u32)k0 < W) {
+        // words beyond W are zero, so a partial last group needs no special case
+        const u64 t = (u64)w[k0] * cw[k0] + (u64)w[k0 + 1] * (k0 + 1 < (int)W ? cw[k0 + 1] : 0u) +
+                      (u64)w[k0 + 2] * (k0 + 2 < (int)W ? cw[k0 + 2] : 0u) +
+                      (u64)w[k0 + 3] * (k0 + 3 < (int)W ? cw[k0 + 3] : 0u);
+        const u32 m = (u32)t * ipinv;
+        const u32 th = (u32)(t >> 32), hm = __umulhi(m, p);
+        u32 qv = th - hm;
+        if (th < hm) qv += p;  // [0, 4p)
+        r = csub(r + csub(qv, p2), p2);
+      }
+    }
+    if (neg) r = csub(r + cw[W], p2);
+    dst[(size_t)l * c.n] = csub(r, p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // tensor product, one 128-thread group per (prime, ciphertext pair); a group is independent
 // of the other groups of its CTA (they only share the prime's twiddle tables)
 // ---------------------------------------------------------------------------------------
 struct FusedTensorArgs {
-  const u32 *a, *b;  // [count][2][n][W]
+  const u32 *resin;  // [count][4][Lt][n]   residues of a0, a1 (scaled), b0, b1 from k_residues
   u32 *res;          // to_tprod == 0: [count][3][Lt][n]   coefficient residues after the Phi_m fold
                      // to_tprod == 1: [count][3][Lt][N]   transform-domain tprod
   u32 Lt, count, ops_per_group, to_tprod;
@@ -281,20 +348,24 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTen
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
   u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
   const XAddr A = make_xaddr(tg);
-  const size_t polyw = (size_t)c.n * c.W;
   for (u32 it = 0; it < a.ops_per_group; ++it) {
     const size_t op = ((size_t)blockIdx.y * a.ops_per_group + it) * KG + g;
     if (op >= a.count) return;  // only group barriers from here on
     // images of a0, a1 (scaled by p_pt/N, Montgomery form) and b0, b1 (plain), in registers
     u32 F[4][8];
+    const u32 *rin = a.resin + ((op * 4) * a.Lt + l) * (size_t)c.n;
+    const size_t qstride = (size_t)a.Lt * c.n;
+    u32 xn[4];  // next polynomial's coefficients, prefetched one transform ahead
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xn[j] = (j * 128 + tg < c.n) ? __ldg(rin + j * 128 + tg) : 0u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const u32 *src = (q < 2 ? a.a : a.b) + (op * 2 + (q & 1)) * polyw;
-      const u32 *cw = c.cwr + ((size_t)l * 2 + (q < 2 ? 1 : 0)) * c.CW;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const u32 i = j * 128 + tg;
-        F[q][j] = i < c.n ? residue_lazy(src + (size_t)i * c.W, c.W, cw, p, pinv) : 0u;
+      for (int j = 0; j < 4; ++j) F[q][j] = xn[j];
+      if (q < 3) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          xn[j] = (j * 128 + tg < c.n) ? __ldg(rin + (q + 1) * qstride + j * 128 + tg) : 0u;
       }
       fwd1024(F[q], twf, A, bufA, bufB, g, tg, p);
     }

@@ -696,6 +696,37 @@ __global__ void k_peak32(u32 *out, u32 p, u32 pinv, int iters) {
   for (int k = 0; k < 8; ++k) s ^= x[k];
   if (s == 0xFFFFFFFFu) out[0] = s;
 }
+// single-instruction-class chains: which pipe costs what (DESIGN.md "integer pipe model")
+//  kind 0: 32x32->lo32 multiply-add   1: 32x32->64 multiply-add   2: hi32 multiply
+//  kind 3: Shoup product x*w - hi(x*w')*p   4: conditional subtract (ALU)   5: fp64 FMA
+template <int KIND>
+__global__ void k_pipe(u32 *out, u32 p, int iters) {
+  u32 x[8];
+  u64 y[8];
+  double z[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    x[k] = (threadIdx.x * 8 + k + blockIdx.x) | 1u;
+    y[k] = x[k];
+    z[k] = (double)x[k];
+  }
+  const u32 w = 0x2468ace1u % p, wq = (u32)(((u64)w << 32) / p);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (KIND == 0) x[k] = x[k] * w + p;
+      else if (KIND == 1) y[k] = (u64)(u32)y[k] * w + y[k];
+      else if (KIND == 2) x[k] = __umulhi(x[k], wq) + w;
+      else if (KIND == 3) x[k] = x[k] * w - __umulhi(x[k], wq) * p;
+      else if (KIND == 4) x[k] = csub(x[k] + w, p);
+      else z[k] = z[k] * 1.0000001 + 0.5;
+    }
+  }
+  u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s ^= x[k] ^ (u32)y[k] ^ (u32)(y[k] >> 32) ^ (u32)z[k];
+  if (s == 0xFFFFFFFFu) out[0] = s;
+}
 __global__ void k_peak64(u64 *out, u64 p, u64 pinv, int iters) {
   u64 x[8];
 #pragma unroll

@@ -66,6 +66,7 @@ SYMBOLS = {
     "fhesi_ref_rows_host": (C.c_int, [_P, _P, _U32, _P, _P, _U32, _P]),
     "fhesi_tprod_reduce_gathered_dev": (C.c_int, [_P, _P, _U32, _U32, _P]),
     "fhesi_modmul_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "fhesi_pipe_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "fhesi_profile_enable": (C.c_int, [_P, C.c_int]),
     "fhesi_profile_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "fhesi_profile_report": (C.c_int, [_P, C.c_char_p, _SZ]),
@@ -284,6 +285,11 @@ class Context:
             name, cnt, ms = line.rsplit(" ", 2)
             out[name] = (int(cnt), float(ms))
         return out
+
+    def pipe_peak(self, kind: int) -> float:
+        v = C.c_double()
+        self._ck(self.lib.fhesi_pipe_peak(self.h, kind, C.byref(v)))
+        return v.value
 
     def modmul_peak(self, word_bits: int) -> float:
         v = C.c_double()

@@ -173,6 +173,10 @@ int fhesi_tprod_reduce_gathered_dev(fhesi_ctx *ctx, const uint32_t *d_gathered, 
 /* ---- measurement helpers (bench.py): register-resident Montgomery-multiply peak, in
  * modmul/s, for word size 32 or 64 (SURVEY.md §8d "modmul_peak"). */
 int fhesi_modmul_peak(fhesi_ctx *ctx, int word_bits, double *modmul_per_s);
+/* Single-instruction-class throughput, ops/s over the whole GPU: kind 0 = 32x32->lo32
+ * multiply-add, 1 = 32x32->64 multiply-add, 2 = hi32 multiply, 3 = Shoup modular product
+ * (the butterfly multiply of the fused kernels), 4 = conditional subtract (ALU), 5 = fp64 FMA. */
+int fhesi_pipe_peak(fhesi_ctx *ctx, int kind, double *ops_per_s);
 
 /* Launch accounting and a per-kernel CUDA-event profiler: with profiling on, every kernel
  * launch is bracketed by events on the context's stream.  fhesi_profile_report writes one
