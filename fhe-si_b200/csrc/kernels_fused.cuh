@@ -49,71 +49,78 @@ __device__ __forceinline__ u32 mulw(u32 x, uint2 w, u32 p) { return x * w.x - __
 
 // The 21 twiddles a thread needs live in shared memory as tws[s * 128 + tg], s = 0..20
 // (0-6 pass 1, 7-13 pass 2, 14-20 pass 3); one table per direction, shared by the CTA.
-#define FTW_WORDS (21u * 128u * 2u)
-__device__ __forceinline__ u32 tw_index(u32 s, u32 t) {
-  if (s < 4) return 512 + s * 128 + t;
-  if (s < 6) return 256 + (s - 4) * 128 + t;
-  if (s == 6) return 128 + t;
-  const u32 lo = t & 15, b0 = t & 1;
-  if (s < 11) return 64 + (s - 7) * 16 + lo;
-  if (s < 13) return 32 + (s - 11) * 16 + lo;
-  if (s == 13) return 16 + lo;
-  if (s < 18) return 8 + (s - 14) * 2 + b0;
-  if (s < 20) return 4 + (s - 18) * 2 + b0;
-  return 2 + b0;
-}
+#define FTW_P2 (7u * 128u)            // entry offset of the pass-2 block
+#define FTW_P3 (7u * 128u + 7u * 16u) // entry offset of the pass-3 block
+#define FTW_ENTRIES (7u * 128u + 7u * 16u + 7u * 2u)
+#define FTW_WORDS (FTW_ENTRIES * 2u + 4u)  // uint2 entries, padded to a 16-byte multiple
+// tws layout: pass 1: [s][tg] (s < 7, 128 per row); pass 2: [s][lo] (16 per row); pass 3: [s][b0]
 __device__ __forceinline__ void fill_tw_table(uint2 *tws, const uint2 *__restrict__ table) {
-  for (u32 e = threadIdx.x; e < 21u * 128u; e += blockDim.x) tws[e] = __ldg(table + tw_index(e >> 7, e & 127));
+  for (u32 e = threadIdx.x; e < FTW_ENTRIES; e += blockDim.x) {
+    u32 idx;
+    if (e < FTW_P2) {
+      const u32 s = e >> 7, t = e & 127;
+      idx = s < 4 ? 512 + s * 128 + t : (s < 6 ? 256 + (s - 4) * 128 + t : 128 + t);
+    } else if (e < FTW_P3) {
+      const u32 s = (e - FTW_P2) >> 4, lo = (e - FTW_P2) & 15;
+      idx = s < 4 ? 64 + s * 16 + lo : (s < 6 ? 32 + (s - 4) * 16 + lo : 16 + lo);
+    } else {
+      const u32 s = (e - FTW_P3) >> 1, b0 = (e - FTW_P3) & 1;
+      idx = s < 4 ? 8 + s * 2 + b0 : (s < 6 ? 4 + (s - 4) * 2 + b0 : 2 + b0);
+    }
+    tws[e] = __ldg(table + idx);
+  }
 }
 
 #define GSW(X, Y, W)                          \
   do {                                        \
-    u32 s_ = (X) + (Y), d_ = (X) + p2 - (Y);  \
+    u32 s_ = add_alu((X), (Y)), d_ = (X) + p2 - (Y);  \
     (X) = csub(s_, p2);                       \
     (Y) = mulw(d_, (W), p);                   \
   } while (0)
 #define CTW(X, Y, W)                          \
   do {                                        \
     u32 t_ = mulw((Y), (W), p);               \
-    u32 s_ = (X) + t_, d_ = (X) + p2 - t_;    \
+    u32 s_ = add_alu((X), t_), d_ = (X) + p2 - t_;    \
     (X) = csub(s_, p2);                       \
     (Y) = csub(d_, p2);                       \
   } while (0)
 
 // three DIF stages on the 8 registers, twiddles tw[0..3], tw[4..5], tw[6] (stride 128 apart)
+template <int ST>
 __device__ __forceinline__ void dif8(u32 *x, const uint2 *tw, u32 p) {
   const u32 p2 = 2 * p;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint2 w = tw[j * 128];
+    const uint2 w = tw[j * ST];
     GSW(x[j], x[j + 4], w);
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const uint2 w = tw[(4 + j) * 128];
+    const uint2 w = tw[(4 + j) * ST];
     GSW(x[j], x[j + 2], w);
     GSW(x[j + 4], x[j + 6], w);
   }
-  const uint2 w = tw[6 * 128];
+  const uint2 w = tw[6 * ST];
 #pragma unroll
   for (int j = 0; j < 8; j += 2) GSW(x[j], x[j + 1], w);
 }
+template <int ST>
 __device__ __forceinline__ void dit8(u32 *x, const uint2 *tw, u32 p) {
   const u32 p2 = 2 * p;
   {
-    const uint2 w = tw[6 * 128];
+    const uint2 w = tw[6 * ST];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) CTW(x[j], x[j + 1], w);
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const uint2 w = tw[(4 + j) * 128];
+    const uint2 w = tw[(4 + j) * ST];
     CTW(x[j], x[j + 2], w);
     CTW(x[j + 4], x[j + 6], w);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint2 w = tw[j * 128];
+    const uint2 w = tw[j * ST];
     CTW(x[j], x[j + 4], w);
   }
 }
@@ -157,19 +164,19 @@ __device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A
   fhesi_group_sync(g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufA[A.a2a + 16 * j];
-  dif8(x, tw + 7 * 128, p);
+  dif8<16>(x, twf + FTW_P2 + (tg & 15), p);
 #pragma unroll
   for (int j = 0; j < 8; ++j) bufB[A.a2b + 18 * j] = x[j];
   fhesi_group_sync(g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufB[A.a3 + 2 * j];
-  dif8(x, tw + 14 * 128, p);
+  dif8<2>(x, twf + FTW_P3 + (tg & 1), p);
   // last stage (position bit 0) across lane pairs, twiddle 1
   const u32 b0 = tg & 1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     u32 o = __shfl_xor_sync(0xffffffffu, x[j], 1);
-    u32 v = b0 ? o + p2 - x[j] : x[j] + o;
+    u32 v = b0 ? o + p2 - x[j] : add_alu(x[j], o);
     x[j] = csub(csub(v, p2), p);
   }
 }
@@ -184,22 +191,22 @@ __device__ __forceinline__ void inv1024(u32 *x, const uint2 *twi, const XAddr &A
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     u32 o = __shfl_xor_sync(0xffffffffu, x[j], 1);
-    u32 v = b0 ? o + p2 - x[j] : x[j] + o;
+    u32 v = b0 ? o + p2 - x[j] : add_alu(x[j], o);
     x[j] = csub(v, p2);
   }
-  dit8(x, tw + 14 * 128, p);
+  dit8<2>(x, twi + FTW_P3 + (tg & 1), p);
 #pragma unroll
   for (int j = 0; j < 8; ++j) bufB[A.a3 + 2 * j] = x[j];
   fhesi_group_sync(g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufB[A.a2b + 18 * j];
-  dit8(x, tw + 7 * 128, p);
+  dit8<16>(x, twi + FTW_P2 + (tg & 15), p);
 #pragma unroll
   for (int j = 0; j < 8; ++j) bufA[A.a2a + 16 * j] = x[j];
   fhesi_group_sync(g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufA[A.a1 + 144 * j];
-  dit8(x, tw, p);
+  dit8<128>(x, tw, p);
   // nat aliases bufA: every thread must be past its bufA reads before anyone writes
   fhesi_group_sync(g);
 #pragma unroll

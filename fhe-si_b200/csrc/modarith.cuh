@@ -36,6 +36,16 @@ FHESI_HD u32 mont_red64(u64 t, u32 p, u32 pinv) {
   u64 u = t + (u64)m * p;
   return (u32)(u >> 32);
 }
+// a + b forced onto the ALU pipe (VIADDMNMX).  ptxas otherwise turns many plain adds into
+// IMAD.IADD, which occupies the integer-multiply pipe -- the pipe that bounds these kernels
+// (profiles/r01_summary_v4.md).
+FHESI_HD u32 add_alu(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+  return __viaddmax_u32(a, b, 0u);
+#else
+  return a + b;
+#endif
+}
 // x in [0, 2*c) -> [0, c) by one conditional subtract (unsigned-min trick).
 FHESI_HD u32 csub(u32 x, u32 c) {
   u32 y = x - c;
