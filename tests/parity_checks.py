@@ -194,3 +194,71 @@ def check_gathered_reduce(sc: Scenario, world=3):
     d.scaledown_dev(do.ptr, 3, dc.ptr, 1)
     d.sync()
     assert_ct_equal(sc, dc.download((3, d.n, d.W)), acc.scale_down(), "gathered reduce")
+
+
+def check_golden(name, lib_path, device=0):
+    """Run the committed golden inputs (tests/golden/golden.json, made by make_golden.py from
+    the oracle) through the C ABI and compare the Export bytes of every output."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+    import pyfhesi
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "golden.json")))
+    g = gold["configs"][name]
+    P = g["params"]
+    logq, p = P["logQ"], P["p"]
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ctx, sk, pk, ks, msgs, rand, cts = mg.scenario(logq, p, P["g"], gold["seed"])
+    if "cts" in g:  # full vectors: take every input from the fixture, not from the RNG
+        imp = lambda h: O.import_zzx(bytes.fromhex(h), 0, ctx.phim)[0]
+        sk = O.SecKey(ctx, [imp(h) for h in g["sk"]])
+        pk = O.PubKey(ctx, [imp(h) for h in g["pk"]])
+        ks = O.KeySwitch(ctx, [imp(h) for h in g["ksw_b"]], [imp(h) for h in g["ksw_A"]])
+        cts = [O.import_ciphertext(ctx, bytes.fromhex(h))[0] for h in g["cts"]]
+    d = pyfhesi.Context(p - 1, logq, p, 3, 1, device, lib_path=lib_path)
+    pack = lambda polys: np.stack([O.pack_poly_words(a, logq) for a in polys])
+    n, W = d.n, d.W
+    ksw = d.ksw_create(pack(ks.b), pack([O.reduce_poly(a, logq) for a in ks.A]), 3)
+    dsk = d.key_create(pack(sk.s))
+    da, db = d.to_device(pack(cts[0].parts)[None]), d.to_device(pack(cts[1].parts)[None])
+    unpack = lambda arr: O.Ciphertext(ctx, [O.unpack_poly_words(arr[i]) for i in range(arr.shape[0])])
+    got = {}
+    # add
+    dx = d.to_device(pack(cts[0].parts)[None])
+    d.ct_add_dev(dx.ptr, db.ptr, 2, 1)
+    d.sync()
+    got["add"] = O.export_ciphertext(unpack(dx.download((2, n, W))))
+    # tensor, ScaleDown
+    dt = d.alloc(d.tprod_words(3) * 4)
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, 1)
+    dc = d.alloc(d.ct_words(3) * 4)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.sync()
+    got["tensor_scaledown"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
+    # mult+relin, decrypt, square
+    do = d.alloc(d.ct_words(2) * 4)
+    d.mult_relin_dev(ksw, da.ptr, db.ptr, do.ptr, 1)
+    dm = d.alloc(n * 4)
+    d.decrypt_dev(dsk, do.ptr, 2, dm.ptr, 1)
+    do2 = d.alloc(d.ct_words(2) * 4)
+    d.mult_relin_dev(ksw, do.ptr, do.ptr, do2.ptr, 1)
+    d.sync()
+    got["mult_relin"] = O.export_ciphertext(unpack(do.download((2, n, W))))
+    got["decrypt_mult_relin"] = O.export_zzx(dm.download((n,)).tolist())
+    got["square_relin"] = O.export_ciphertext(unpack(do2.download((2, n, W))))
+    # scalar, automorphism (not reduced mod q)
+    dx.upload(pack(cts[0].parts)[None])
+    d.ct_mul_scalar_dev(dx.ptr, -7, 2, 1)
+    dw = d.alloc(2 * n * (W + 1) * 4)
+    d.ct_automorph_dev(da.ptr, 2, 3, dw.ptr, 1)
+    d.sync()
+    got["mul_scalar_m7"] = O.export_ciphertext(unpack(dx.download((2, n, W))))
+    got["automorph_3"] = O.export_ciphertext(unpack(dw.download((2, n, W + 1))))
+    if "out" in g:
+        assert {k: v.hex() for k, v in got.items()} == g["out"]
+    else:
+        assert {k: hashlib.sha256(v).hexdigest() for k, v in got.items()} == g["out_sha256"]

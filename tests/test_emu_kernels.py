@@ -37,6 +37,10 @@ def test_emu_ref_rows_cfg1(sc1):
     P.check_ref_rows(sc1)
 
 
+def test_emu_golden_cfg1(emu_lib):
+    P.check_golden("cfg1", emu_lib)
+
+
 def test_emu_other_small_rings(emu_lib):
     # m = 2*17 (n = 16: N = 2n exactly, the fold guard) and m = 2*13, odd logQ
     for m_half, logq in ((17, 61), (13, 100)):

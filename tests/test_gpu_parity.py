@@ -60,6 +60,11 @@ def test_ref_rows(name, cuda_lib):
     P.check_ref_rows(scenario(name, cuda_lib))
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4"])
+def test_golden_vectors(name, cuda_lib):
+    P.check_golden(name, cuda_lib)
+
+
 def test_generic_and_fused_paths_agree(cuda_lib, monkeypatch):
     """The fused N=1024 kernels and the generic kernels are two CUDA implementations of the
     same arithmetic; they must agree bit for bit (and both with the oracle, above)."""
