@@ -360,6 +360,12 @@ int fhesi_d2h(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
+int fhesi_d2d(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
 size_t fhesi_ct_bytes(const fhesi_ctx *c, uint32_t parts) {
   return c ? (size_t)parts * c->info.n * c->info.W * 4 : 0;
 }
@@ -575,6 +581,36 @@ int fhesi_ct_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uin
   CKL();
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaFree(d_tab));
+  return 0;
+}
+
+// every part times one plaintext polynomial: key-form transform of the parts, plain transform of
+// the plaintext, pointwise product, inverse transform, CRT + Reduce
+int fhesi_ct_mul_plain_dev(fhesi_ctx *c, uint32_t *io, const uint32_t *plain, uint32_t parts, size_t count) {
+  if (!c || !io || !plain || parts < 1 || parts > 3) return fail(FHESI_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const u32 Le = I.Le;
+  const size_t per = (size_t)Le * I.N, CH = c->chunk;
+  size_t n1 = al(CH * parts * per), n2 = al(per), n3 = al(CH * parts * Le * I.n);
+  u32 *s = nullptr;
+  int rc = scratch(c, (n1 + n2 + n1 + n3) * 4, &s);
+  if (rc) return rc;
+  u32 *sA = s, *sP = s + n1, *sO = sP + n2, *sR = sO + n1;
+  if ((rc = launch_fwd(c, plain, SRC_U32, 0, SC_NONE, Le, sP, 1))) return rc;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    u32 *cur = io + off * parts * I.n * I.W;
+    if ((rc = launch_fwd(c, cur, SRC_POLY, I.W, SC_KEYFORM, Le, sA, cnt * parts))) return rc;
+    // out[q] = A[q] * P : a 1x1 "tensor" per part, the plaintext image broadcast (count 1 each)
+    for (size_t q = 0; q < cnt * parts; ++q) {
+      TensArgs t{sA + q * per, sP, 1, 1, Le, sO + q * per, 1, 0};
+      KL(c, k_tensor_pw, nblk(per), 256, 0, c->dc, t);
+      CKL();
+    }
+    if ((rc = launch_inv(c, sO, Le, sR, cnt * parts))) return rc;
+    if ((rc = launch_crt(c, sR, Le, CRT_REDUCE_Q, cur, I.W, cnt * parts))) return rc;
+  }
   return 0;
 }
 

@@ -43,6 +43,8 @@ SYMBOLS = {
     "fhesi_free": (C.c_int, [_P, _P]),
     "fhesi_h2d": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_d2h": (C.c_int, [_P, _P, _P, _SZ]),
+    "fhesi_d2d": (C.c_int, [_P, _P, _P, _SZ]),
+    "fhesi_ct_mul_plain_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),
     "fhesi_ct_bytes": (_SZ, [_P, _U32]),
     "fhesi_tprod_bytes": (_SZ, [_P, _U32]),
     "fhesi_ksw_create": (C.c_int, [_P, _P, _P, _U32, C.POINTER(_P)]),
@@ -226,6 +228,9 @@ class Context:
 
     def ct_mul_scalar_dev(self, io, l, parts, count):
         self._ck(self.lib.fhesi_ct_mul_scalar_dev(self.h, _ptr(io), l, parts, count))
+
+    def ct_mul_plain_dev(self, io, plain, parts, count):
+        self._ck(self.lib.fhesi_ct_mul_plain_dev(self.h, _ptr(io), _ptr(plain), parts, count))
 
     def ct_tensor_dev(self, a, pa, b, pb, tprod, count, accumulate=False):
         self._ck(self.lib.fhesi_ct_tensor_dev(self.h, _ptr(a), pa, _ptr(b), pb, _ptr(tprod), count,

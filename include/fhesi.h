@@ -79,6 +79,7 @@ int fhesi_malloc(fhesi_ctx *ctx, size_t bytes, void **dptr);
 int fhesi_free(fhesi_ctx *ctx, void *dptr);
 int fhesi_h2d(fhesi_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int fhesi_d2h(fhesi_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int fhesi_d2d(fhesi_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
 size_t fhesi_ct_bytes(const fhesi_ctx *ctx, uint32_t parts);    /* parts*n*W*4      */
 size_t fhesi_tprod_bytes(const fhesi_ctx *ctx, uint32_t parts); /* parts*Lt*N*4     */
 
@@ -115,6 +116,12 @@ int fhesi_ct_sum_dev(fhesi_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint
                      size_t count);
 /* CiphertextPart::operator*=(long) (Ciphertext.cpp:21-27): io = Reduce(io * l). */
 int fhesi_ct_mul_scalar_dev(fhesi_ctx *ctx, uint32_t *d_io, int64_t l, uint32_t parts, size_t count);
+
+/* CiphertextPart::operator*=(const ZZX&) (Ciphertext.cpp:29-36, 246-250): every part of io times
+ * the same plaintext polynomial mod Phi_m, then Reduce.  plain: DEVICE uint32 [n], coefficients
+ * in [0, 2^29) (to_ZZX of a ZZ_pX).  io: [count][parts][n][W]. */
+int fhesi_ct_mul_plain_dev(fhesi_ctx *ctx, uint32_t *d_io, const uint32_t *d_plain, uint32_t parts,
+                           size_t count);
 
 /* Ciphertext::operator*=(const Ciphertext&) (Ciphertext.cpp:167-192): tensor product into
  * tprod form.  a: [count][pa][n][W], b: [count][pb][n][W], out: [count][pa+pb-1][Lt][N].

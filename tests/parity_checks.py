@@ -262,3 +262,17 @@ def check_golden(name, lib_path, device=0):
         assert {k: v.hex() for k, v in got.items()} == g["out"]
     else:
         assert {k: hashlib.sha256(v).hexdigest() for k, v in got.items()} == g["out_sha256"]
+
+
+def check_mul_plain(sc: Scenario, count=2):
+    """Ciphertext *= ZZX in coefficient form (Ciphertext.cpp:246-250)."""
+    d = sc.dev
+    A = sc.random_cts(count)
+    pt = [sc.rng.random_bnd(sc.p) for _ in range(d.n)]
+    da = d.to_device(sc.pack_cts(A))
+    dp = d.to_device(np.array(pt, dtype=np.uint32))
+    d.ct_mul_plain_dev(da.ptr, dp.ptr, 2, count)
+    d.sync()
+    got = da.download((count, 2, d.n, d.W))
+    for i in range(count):
+        assert_ct_equal(sc, got[i], A[i].copy().mul_plain(pt), f"ct *= plain [{i}]")

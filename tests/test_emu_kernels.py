@@ -31,6 +31,7 @@ def test_emu_encrypt_decrypt_cfg1(sc1):
 
 def test_emu_coeff_ops_cfg1(sc1):
     P.check_coeff_ops(sc1, count=3)
+    P.check_mul_plain(sc1, count=2)
 
 
 def test_emu_ref_rows_cfg1(sc1):

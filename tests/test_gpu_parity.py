@@ -53,6 +53,7 @@ def test_encrypt_decrypt(name, cuda_lib):
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg4"])
 def test_coeff_ops(name, cuda_lib):
     P.check_coeff_ops(scenario(name, cuda_lib), count=3)
+    P.check_mul_plain(scenario(name, cuda_lib), count=2)
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2"])
