@@ -1,0 +1,3 @@
+// NTL/ZZX.h -- client-facing include name; everything lives in ntl_shim.h
+#pragma once
+#include "../ntl_shim.h"

@@ -1,0 +1,1033 @@
+// fhesi_host.cpp -- bodies of the reference-named classes (fhesi_host.h) over the C ABI.
+// Compiled with g++ into libfhesi_host.so and linked against libfhesi_b200.so (or, in GPU-less
+// CI, against the kernel-logic emulator build of the same sources, tests/emu).
+#include "fhesi_host.h"
+
+#include <map>
+
+FHEcontext *activeContext = NULL;
+
+static void Check(int rc, const char *what) {
+  if (rc) {
+    std::cerr << what << ": " << fhesi_last_error() << std::endl;
+    std::abort();
+  }
+}
+
+// ------------------------------------------------------------------------------- number theory
+ZZX Cyclotomic(long N) {  // NumbTh.cpp:142-159
+  std::map<long, std::vector<long long>> phi;
+  phi[1] = {-1, 1};
+  for (long d = 2; d <= N; ++d) {
+    if (N % d) continue;
+    std::vector<long long> num(d + 1, 0);
+    num[0] = -1, num[d] = 1;
+    for (long e = 1; e < d; ++e) {
+      if (d % e) continue;
+      const std::vector<long long> &b = phi[e];
+      std::vector<long long> q(num.size() - b.size() + 1, 0);
+      for (long i = (long)q.size() - 1; i >= 0; --i) {
+        long long c = num[i + b.size() - 1] / b.back();
+        q[i] = c;
+        for (size_t j = 0; j < b.size(); ++j) num[i + j] -= c * b[j];
+      }
+      num = q;
+    }
+    phi[d] = num;
+  }
+  ZZX r;
+  const std::vector<long long> &c = phi[N];
+  r.rep.v.resize(c.size());
+  for (size_t i = 0; i < c.size(); ++i) r.rep.v[i] = ZZ((long)c[i]);
+  r.normalize();
+  return r;
+}
+
+void PAlgebra::init(unsigned mm, unsigned gen) {
+  if (m == mm) return;
+  m = mm;
+  g = gen;
+  zmsIdx.assign(m, -1);
+  long idx = 0;
+  for (unsigned i = 0; i < m; i++)
+    if (GCD(i, m) == 1) zmsIdx[i] = idx++;
+  phim = idx;
+  Phi_mX = Cyclotomic(m);
+}
+
+// a mod Phi_m for m = 2h (h odd prime): X^h = -1, Phi_m = sum (-1)^i X^i; generic otherwise
+static void RemPhim(ZZX &a, const PAlgebra &zms) {
+  const unsigned m = zms.M(), n = zms.phiM(), h = m / 2;
+  if (deg(a) < (long)n) return;
+  if (m % 2 == 0 && n == h - 1) {
+    std::vector<ZZ> v(h);
+    for (long i = 0; i <= deg(a); ++i) {
+      if (a.rep.v[i].is_zero()) continue;
+      if ((i / h) & 1) v[i % h] -= a.rep.v[i];
+      else v[i % h] += a.rep.v[i];
+    }
+    ZZ top = v[n];
+    a.rep.v.assign(n, ZZ());
+    for (unsigned i = 0; i < n; ++i) a.rep.v[i] = (i & 1) ? v[i] + top : v[i] - top;
+    a.normalize();
+  } else {
+    rem(a, a, zms.PhimX());
+  }
+}
+// a * b mod Phi_m; shift-and-add when one operand is sparse/tiny (secret keys are ternary)
+static ZZX MulModPhim(const ZZX &a, const ZZX &b, const PAlgebra &zms) {
+  auto small = [](const ZZX &x) {
+    for (auto &c : x.rep.v)
+      if (c.mag.size() > 1) return false;
+    return true;
+  };
+  const ZZX *big = &a, *sm = &b;
+  if (!small(b) && small(a)) big = &b, sm = &a;
+  ZZX r;
+  if (small(*sm)) {
+    r.rep.v.assign(big->rep.v.size() + sm->rep.v.size(), ZZ());
+    for (size_t j = 0; j < sm->rep.v.size(); ++j) {
+      const ZZ &c = sm->rep.v[j];
+      if (c.is_zero()) continue;
+      bool unit = c.mag.size() == 1 && c.mag[0] == 1;
+      for (size_t i = 0; i < big->rep.v.size(); ++i) {
+        if (big->rep.v[i].is_zero()) continue;
+        if (unit) {
+          if (c.neg) r.rep.v[i + j] -= big->rep.v[i];
+          else r.rep.v[i + j] += big->rep.v[i];
+        } else {
+          r.rep.v[i + j] += big->rep.v[i] * c;
+        }
+      }
+    }
+    r.normalize();
+  } else {
+    r = a * b;
+  }
+  RemPhim(r, zms);
+  return r;
+}
+
+// ------------------------------------------------------------------------------- Util / samplers
+void Reduce(ZZ &val, unsigned logQ, bool positive) {  // Util.cpp:3-26
+  ZZ q = ZZ(1L) << (long)logQ;
+  val %= q;  // non-negative
+  if (!positive && val >= (q >> 1)) val -= q;
+}
+void ReduceCoefficients(ZZX &poly, unsigned logQ, bool positive) {
+  for (long i = 0; i <= deg(poly); i++) Reduce(poly.rep[i], logQ, positive);
+  poly.normalize();
+}
+void SampleRandom(ZZX &poly, const ZZ &modulus, unsigned d) {  // Util.cpp:49-56
+  ZZ offset = modulus / 2;
+  poly.rep.v.assign(d, ZZ());
+  for (unsigned i = 0; i < d; i++) poly.rep.v[i] = RandomBnd(modulus) - offset;
+  poly.normalize();
+}
+void sampleHWt(ZZX &poly, long Hwt, long n) {  // NumbTh.cpp:340-359
+  if (n <= 0) n = deg(poly) + 1;
+  if (n <= 0) return;
+  poly.rep.v.assign(n, ZZ());
+  if (Hwt > n) Hwt = n;
+  long i = 0;
+  while (i < Hwt) {
+    long u = RandomBnd(n);
+    if (poly.rep.v[u].is_zero()) {
+      long b = 2 * to_long(RandomBits_ZZ(1)) - 1;
+      poly.rep.v[u] = ZZ(b);
+      i++;
+    }
+  }
+  poly.normalize();
+}
+void sampleSmall(ZZX &poly, long n) {  // NumbTh.cpp:361-375
+  if (n <= 0) n = deg(poly) + 1;
+  if (n <= 0) return;
+  poly.rep.v.assign(n, ZZ());
+  for (long i = 0; i < n; i++) {
+    long u = to_long(RandomBits_ZZ(2));
+    if (u & 1) poly.rep.v[i] = ZZ((long)(u & 2) - 1);
+  }
+  poly.normalize();
+}
+void sampleGaussian(ZZX &poly, long n, double stdev) {  // NumbTh.cpp:377-404
+  static double const Pi = 4.0 * atan(1.0);
+  static long const bignum = 0xfffffff;
+  if (n <= 0) n = deg(poly) + 1;
+  if (n <= 0) return;
+  poly.rep.v.assign(n, ZZ());
+  for (long i = 0; i < n; i += 2) {
+    double r1 = (1 + RandomBnd(bignum)) / ((double)bignum + 1);
+    double r2 = (1 + RandomBnd(bignum)) / ((double)bignum + 1);
+    double theta = 2 * Pi * r1;
+    double rr = sqrt(-2.0 * std::log(r2)) * stdev;
+    assert(rr < 8 * stdev);
+    poly.rep.v[i] = ZZ((long)floor(rr * cos(theta) + 0.5));
+    if (i + 1 < n) poly.rep.v[i + 1] = ZZ((long)floor(rr * sin(theta) + 0.5));
+  }
+  poly.normalize();
+}
+
+// ------------------------------------------------------------------------------- PlaintextSpace
+void PlaintextSpace::Init(const ZZX &PhiX, const ZZ &pp, unsigned gen) {
+  generator = gen;
+  Init(PhiX, pp);
+}
+void PlaintextSpace::Init(const ZZX &PhiX, const ZZ &pp) {
+  ZZ_p::init(pp);
+  p = pp;
+  const long P = to_long(pp), n = deg(PhiX);
+  totalSlots = usableSlots = 0;
+  roots.clear();
+  basis.clear();
+  if (m == 0 || !ProbPrime(P) || (P - 1) % m != 0) return;  // no linear slots: packing unavailable
+  // primitive m-th root of unity mod p
+  std::vector<long> fs;
+  for (long t = m, d = 2; t > 1; ++d)
+    if (t % d == 0) {
+      fs.push_back(d);
+      while (t % d == 0) t /= d;
+    }
+  long rho = 0;
+  for (long x = 2; !rho; ++x) {
+    long r = PowerMod(x, (P - 1) / m, P);
+    bool ok = true;
+    for (long f : fs)
+      if (PowerMod(r, m / f, P) == 1) ok = false;
+    if (ok) rho = r;
+  }
+  // slot j <-> rho^(g^j): the order PlaintextSpace::ReorderSlots (PlaintextSpace.cpp:87-110)
+  // produces, up to its arbitrary starting factor
+  long e = 1;
+  for (long j = 0; j < n; ++j) {
+    roots.push_back(PowerMod(rho, e, P));
+    e = MulMod(e, generator % m, m);
+    if (e == 1 && j + 1 < n) break;
+  }
+  if ((long)roots.size() != n) {
+    roots.clear();
+    return;  // generator does not generate Z_m^* (the reference asserts here)
+  }
+  totalSlots = n;
+  usableSlots = 1;
+  for (unsigned t = totalSlots; t > 1; t >>= 1) usableSlots <<= 1;
+  // CRT idempotents: basis_j = Phi/(X - r_j) / Phi'(r_j)
+  std::vector<long> phi(n + 1);
+  for (long i = 0; i <= n; ++i) phi[i] = to_long(coeff(PhiX, i) % pp);
+  basis.assign(n, std::vector<long>(n));
+  for (long j = 0; j < n; ++j) {
+    std::vector<long> &b = basis[j];
+    long r = roots[j], carry = phi[n];
+    for (long i = n - 1; i >= 0; --i) {  // synthetic division by (X - r)
+      b[i] = carry;
+      carry = AddMod(phi[i], MulMod(carry, r, P), P);
+    }
+    long d = 0;
+    for (long i = n - 1; i >= 0; --i) d = AddMod(MulMod(d, r, P), b[i], P);
+    long di = InvMod(d, P);
+    for (long i = 0; i < n; ++i) b[i] = MulMod(b[i], di, P);
+  }
+}
+void PlaintextSpace::EmbedInSlots(ZZ_pX &embedded, const vector<ZZ_pX> &msgs, bool onlyUsable) const {
+  if (!totalSlots) Error("PlaintextSpace: slots need a prime p = 1 mod m and a generator of Z_m^*");
+  const long P = to_long(p), n = totalSlots;
+  std::vector<unsigned __int128> acc(n, 0);
+  unsigned msgInd = 0;
+  for (unsigned i = 0; i < totalSlots && msgInd < msgs.size(); i++) {
+    if (onlyUsable && i >= usableSlots) break;
+    const ZZ_pX &mi = msgs[msgInd++];
+    long c = eval(mi, ZZ_p(roots[i])).v;  // a slot only sees the message modulo its factor X - r_i
+    if (!c) continue;
+    for (long k = 0; k < n; ++k) acc[k] += (unsigned __int128)basis[i][k] * c;
+  }
+  embedded.rep.v.assign(n, ZZ_p());
+  for (long k = 0; k < n; ++k) embedded.rep.v[k].v = (long)(acc[k] % (unsigned long)P);
+  embedded.normalize();
+}
+void PlaintextSpace::DecodeSlot(ZZ_pX &val, const ZZ_pX &msg, unsigned ind) const {
+  if (!totalSlots) Error("PlaintextSpace: slots need a prime p = 1 mod m and a generator of Z_m^*");
+  val = to_ZZ_pX(eval(msg, ZZ_p(roots[ind])));
+}
+void PlaintextSpace::DecodeSlots(vector<ZZ_pX> &msgBatch, const ZZ_pX &msg, bool onlyUsable) const {
+  msgBatch.resize(totalSlots);
+  for (unsigned i = 0; i < totalSlots; i++) {
+    if (onlyUsable && i >= usableSlots) break;
+    DecodeSlot(msgBatch[i], msg, i);
+  }
+}
+
+// ------------------------------------------------------------------------------- FHEcontext
+void FHEcontext::Init(unsigned m, unsigned lq, const ZZ &p, unsigned generator, unsigned ds) {
+  stdev = 3.2;
+  zMstar.init(m, generator);
+  logQ = lq;
+  modulusQ = ZZ(1L) << (long)lq;
+  decompSize = ds;
+  ndigits = (lq + 8 * ds - 1) / (8 * ds);
+  ptxtSpace.m = m;
+  ptxtSpace.Init(zMstar.PhimX(), p, generator);
+}
+FHEcontext::~FHEcontext() {
+  if (dev) fhesi_ctx_destroy(dev);
+  if (activeContext == this) activeContext = NULL;
+}
+static long RootOfUnity2m(long p, long m) {  // deterministic (CModulus.cpp:66-76 picks at random)
+  long e = 2 * m;
+  std::vector<long> fs;
+  for (long t = e, d = 2; t > 1; ++d)
+    if (t % d == 0) {
+      fs.push_back(d);
+      while (t % d == 0) t /= d;
+    }
+  for (long x = 2;; ++x) {
+    long r = PowerMod(x, (p - 1) / e, p);
+    bool ok = true;
+    for (long f : fs)
+      if (PowerMod(r, e / f, p) == 1) ok = false;
+    if (ok) return r;
+  }
+}
+void FHEcontext::AddPrime(long p, bool special, long root) {  // FHEContext.cpp:30-43
+  long twoM = 2 * zMstar.M();
+  assert(ProbPrime(p) && p % twoM == 1 && !inChain(p));
+  CmodulusInfo mo;
+  mo.q = p;
+  mo.root = root ? root : RootOfUnity2m(p, zMstar.M());
+  long i = moduli.size();
+  moduli.push_back(mo);
+  if (special) specialPrimes.insert(i);
+  else ctxtPrimes.insert(i);
+}
+double AddPrimesBySize(FHEcontext &context, double totalSize, bool special) {  // FHEContext.cpp:88-115
+  if (!context.zMstar.M() || context.zMstar.M() > (1 << 20)) Error("AddModuli1: m undefined or larger than 2^20");
+  long p = (1UL << NTL_SP_NBITS) - 1;
+  long twoM = 2 * context.zMstar.M();
+  p -= (p % twoM);
+  p += twoM + 1;
+  bool lastPrime = false;
+  double sizeLeft = totalSize;
+  while (sizeLeft > 0.0) {
+    if (sizeLeft < std::log((double)p) && !lastPrime) {
+      lastPrime = true;
+      p = ceil(exp(sizeLeft));
+      p -= (p % twoM) - 1;
+      twoM = -twoM;
+    }
+    do { p -= twoM; } while (!ProbPrime(p));
+    if (!context.inChain(p)) {
+      context.AddPrime(p, special);
+      sizeLeft -= std::log((double)p);
+    }
+  }
+  return totalSize - sizeLeft;
+}
+void FHEcontext::SetUpSIContext(long xi) {  // FHEContext.cpp:83-85
+  xiHint = xi < 1 ? 1 : xi;
+  AddPrimesBySize(*this, NTL::log(modulusQ) * 2 + NTL::log(ModulusP()) + std::log((double)zMstar.phiM()) * 2 +
+                             std::log(2.0) + std::log((double)xiHint), false);
+}
+fhesi_ctx *FHEcontext::Dev() const {
+  if (!dev) {
+    Check(fhesi_ctx_create(zMstar.M(), logQ, (uint64_t)to_long(ModulusP()), decompSize, (uint64_t)xiHint, device, &dev),
+          "fhesi_ctx_create");
+    devXi = xiHint;
+  }
+  return dev;
+}
+void FHEcontext::ExportSIContext(ofstream &out) {  // FHEContext.cpp:45-60
+  unsigned m = zMstar.M(), g = Generator();
+  Export(out, m);
+  Export(out, logQ);
+  Export(out, ModulusP());
+  Export(out, g);
+  Export(out, decompSize);
+  uint32_t size = moduli.size();
+  Export(out, size);
+  for (auto &mo : moduli) {
+    long q = mo.q, root = mo.root;
+    Export(out, q);
+    Export(out, root);
+  }
+}
+void FHEcontext::ImportSIContext(ifstream &in) {  // FHEContext.cpp:62-81
+  unsigned m, lq, generator, ds;
+  ZZ p;
+  Import(in, m);
+  Import(in, lq);
+  Import(in, p);
+  Import(in, generator);
+  Import(in, ds);
+  Init(m, lq, p, generator, ds);
+  uint32_t size;
+  Import(in, size);
+  long q, root;
+  for (unsigned i = 0; i < size; i++) {
+    Import(in, q);
+    Import(in, root);
+    AddPrime(q, false, root);
+  }
+}
+ostream &operator<<(ostream &os, const FHEcontext &context) {
+  os << "logQ: " << context.logQ << endl << "p: " << context.ModulusP() << endl
+     << "g: " << context.Generator() << endl << "primes: [";
+  for (auto &mo : context.moduli) os << mo.q << ", ";
+  return os << "]" << endl;
+}
+
+// ------------------------------------------------------------------------------- word packing
+static void PackZZ(uint32_t *w, const ZZ &c, unsigned W) {  // two's complement, W words
+  for (unsigned k = 0; k < W; ++k) w[k] = k < c.mag.size() ? c.mag[k] : 0u;
+  if (c.neg) {
+    uint64_t carry = 1;
+    for (unsigned k = 0; k < W; ++k) {
+      carry += (uint32_t)~w[k];
+      w[k] = (uint32_t)carry;
+      carry >>= 32;
+    }
+  }
+}
+static ZZ UnpackZZ(const uint32_t *w, unsigned W) {
+  ZZ c;
+  bool neg = w[W - 1] >> 31;
+  c.mag.assign(w, w + W);
+  if (neg) {
+    uint64_t carry = 1;
+    for (unsigned k = 0; k < W; ++k) {
+      carry += (uint32_t)~c.mag[k];
+      c.mag[k] = (uint32_t)carry;
+      carry >>= 32;
+    }
+  }
+  c.neg = neg;
+  c.trim();
+  return c;
+}
+static std::vector<uint32_t> PackPoly(const ZZX &a, unsigned n, unsigned W) {
+  std::vector<uint32_t> w((size_t)n * W, 0);
+  for (long i = 0; i <= deg(a) && i < (long)n; ++i) PackZZ(&w[(size_t)i * W], a.rep.v[i], W);
+  return w;
+}
+static ZZX UnpackPoly(const uint32_t *w, unsigned n, unsigned W) {
+  ZZX a;
+  a.rep.v.resize(n);
+  for (unsigned i = 0; i < n; ++i) a.rep.v[i] = UnpackZZ(w + (size_t)i * W, W);
+  a.normalize();
+  return a;
+}
+
+// ------------------------------------------------------------------------------- DoubleCRT
+DoubleCRT::DoubleCRT() : context(*activeContext) {}
+DoubleCRT::DoubleCRT(const FHEcontext &c) : context(c) {}
+DoubleCRT::DoubleCRT(const ZZX &p) : context(*activeContext), poly(p) { wrap(); }
+DoubleCRT::DoubleCRT(const ZZX &p, const FHEcontext &c) : context(c), poly(p) { wrap(); }
+void DoubleCRT::wrap() {  // the matrix represents the polynomial modulo the chain product, centred
+  RemPhim(poly, context.zMstar);
+  ZZ P = context.productOfPrimes(), half = P / 2;
+  for (auto &c : poly.rep.v) {
+    if (c > half || c < -half) {
+      c %= P;
+      if (c > half) c -= P;
+    }
+  }
+  poly.normalize();
+}
+DoubleCRT &DoubleCRT::operator=(const DoubleCRT &o) {
+  if (&context != &o.context) Error("DoubleCRT assigment: incompatible contexts");
+  poly = o.poly;
+  return *this;
+}
+DoubleCRT &DoubleCRT::operator=(const ZZX &p) { poly = p; wrap(); return *this; }
+DoubleCRT &DoubleCRT::operator=(const ZZ &num) { poly = to_ZZX(num); wrap(); return *this; }
+DoubleCRT &DoubleCRT::operator+=(const DoubleCRT &o) {
+  if (&context != &o.context) Error("DoubleCRT::Op: incompatible objects");
+  poly += o.poly;
+  wrap();
+  return *this;
+}
+DoubleCRT &DoubleCRT::operator-=(const DoubleCRT &o) {
+  if (&context != &o.context) Error("DoubleCRT::Op: incompatible objects");
+  poly -= o.poly;
+  wrap();
+  return *this;
+}
+DoubleCRT &DoubleCRT::operator*=(const DoubleCRT &o) {
+  if (&context != &o.context) Error("DoubleCRT::Op: incompatible objects");
+  poly = MulModPhim(poly, o.poly, context.zMstar);
+  wrap();
+  return *this;
+}
+DoubleCRT &DoubleCRT::operator+=(const ZZ &c) {  // adds c to every evaluation = to the constant term
+  SetCoeff(poly, 0, coeff(poly, 0) + c);
+  wrap();
+  return *this;
+}
+DoubleCRT &DoubleCRT::operator*=(const ZZ &c) { poly *= c; wrap(); return *this; }
+void DoubleCRT::toPoly(ZZX &p, bool positive) const {
+  p = poly;
+  if (positive) {
+    ZZ P = context.productOfPrimes();
+    for (auto &c : p.rep.v)
+      if (c < 0L) c += P;
+  }
+  p.normalize();
+}
+void DoubleCRT::automorph(long k) {  // DoubleCRT.cpp:439-465 in coefficient form
+  const PAlgebra &z = context.zMstar;
+  if (!z.inZmStar(k)) Error("DoubleCRT::automorph: k not in Zm*");
+  const long m = z.M();
+  ZZX r;
+  r.rep.v.assign(m, ZZ());
+  for (long i = 0; i <= deg(poly); ++i) r.rep.v[MulMod(i, k, m)] += poly.rep.v[i];
+  r.normalize();
+  poly = r;
+  // fold modulo X^m - 1 happened above; now modulo Phi_m
+  if (m % 2 == 0 && z.phiM() == (unsigned)(m / 2 - 1)) {
+    ZZX t;  // X^(m/2) = -1
+    const long h = m / 2;
+    t.rep.v.assign(h, ZZ());
+    for (long i = 0; i <= deg(poly); ++i) {
+      if (i >= h) t.rep.v[i - h] -= poly.rep.v[i];
+      else t.rep.v[i] += poly.rep.v[i];
+    }
+    t.normalize();
+    poly = t;
+  }
+  wrap();
+}
+vector<vector<long>> DoubleCRT::getRows() const {
+  const unsigned n = context.zMstar.phiM(), L = context.numPrimes();
+  unsigned Win = (unsigned)((NumBits(context.productOfPrimes()) + 32) / 32) + 1;
+  std::vector<uint32_t> words = PackPoly(poly, n, Win);
+  std::vector<uint64_t> primes(L), roots(L);
+  for (unsigned i = 0; i < L; ++i) primes[i] = context.ithPrime(i), roots[i] = context.ithModulus(i).root;
+  std::vector<int64_t> flat((size_t)L * n);
+  Check(fhesi_ref_rows_host(context.Dev(), words.data(), Win, primes.data(), roots.data(), L, flat.data()),
+        "fhesi_ref_rows_host");
+  vector<vector<long>> rows(L, vector<long>(n));
+  for (unsigned i = 0; i < L; ++i)
+    for (unsigned j = 0; j < n; ++j) rows[i][j] = flat[(size_t)i * n + j];
+  return rows;
+}
+void DoubleCRT::setRows(const vector<vector<long>> &rows) {
+  // Cmodulus::iFFT per prime (CModulus.cpp:110-132), then DoubleCRT::toPoly's incremental CRT
+  // (DoubleCRT.cpp:349-398, NumbTh.cpp:307-335); import-time only
+  const PAlgebra &z = context.zMstar;
+  const long m = z.M(), n = z.phiM();
+  std::vector<long> units;
+  for (long i = 0; i < m; ++i)
+    if (z.inZmStar(i)) units.push_back(i);
+  std::vector<long> phi(n + 1);
+  std::vector<ZZ> acc(n);
+  ZZ prod(1L);
+  for (size_t l = 0; l < rows.size(); ++l) {
+    const long q = context.ithPrime(l), root = context.ithModulus(l).root;
+    const long zinv = InvMod(MulMod(root, root, q), q), minv = InvMod(m % q, q);
+    for (long i = 0; i <= n; ++i) phi[i] = to_long(coeff(z.PhimX(), i) % ZZ(q));
+    std::vector<long> c(m), zpow(m);
+    zpow[0] = 1;
+    for (long t = 1; t < m; ++t) zpow[t] = MulMod(zpow[t - 1], zinv, q);
+    for (long t = 0; t < m; ++t) {
+      unsigned __int128 s = 0;
+      for (long j = 0; j < n; ++j) s += (unsigned __int128)rows[l][j] * zpow[(units[j] * t) % m];
+      c[t] = MulMod((long)(s % (unsigned long)q), minv, q);
+    }
+    for (long i = m - 1; i >= n; --i) {
+      long ci = c[i];
+      if (!ci) continue;
+      for (long j = 0; j <= n; ++j) c[i - n + j] = SubMod(c[i - n + j], MulMod(ci, phi[j], q), q);
+    }
+    if (l == 0) {
+      for (long j = 0; j < n; ++j) acc[j] = ZZ(c[j] > q / 2 ? c[j] - q : c[j]);
+      prod = ZZ(q);
+    } else {
+      const long pinv = InvMod(rem(prod, q), q), qh = q / 2;
+      for (long j = 0; j < n; ++j) {
+        long d = MulMod(SubMod(c[j], rem(acc[j], q), q), pinv, q);
+        if (d > qh) d -= q;
+        acc[j] += prod * ZZ(d);
+      }
+      prod *= ZZ(q);
+    }
+  }
+  poly.rep.v = acc;
+  poly.normalize();
+}
+
+// ------------------------------------------------------------------------------- Ciphertext
+DevBuf::DevBuf(fhesi_ctx *c, size_t b) : ctx(c), bytes(b) {
+  void *p = nullptr;
+  Check(fhesi_malloc(c, b, &p), "fhesi_malloc");
+  ptr = (uint32_t *)p;
+}
+DevBuf::~DevBuf() {
+  if (ptr) fhesi_free(ctx, ptr);
+}
+Ciphertext::Ciphertext(const FHESIPubKey &pk) : context(&pk.GetContext()) {}
+Ciphertext::Ciphertext(const Ciphertext &o)
+    : context(o.context), nparts(o.nparts), wordsPer(o.wordsPer), scaledUp(o.scaledUp), hostStale(o.hostStale),
+      parts(o.parts) {
+  if (o.buf) {
+    buf = make_shared<DevBuf>(o.buf->ctx, o.buf->bytes);
+    Check(fhesi_d2d(buf->ctx, buf->ptr, o.buf->ptr, buf->bytes), "fhesi_d2d");
+  }
+}
+Ciphertext &Ciphertext::operator=(const Ciphertext &o) {
+  if (this == &o) return *this;
+  context = o.context;
+  nparts = o.nparts, wordsPer = o.wordsPer, scaledUp = o.scaledUp, hostStale = o.hostStale;
+  parts = o.parts;
+  buf.reset();
+  if (o.buf) {
+    buf = make_shared<DevBuf>(o.buf->ctx, o.buf->bytes);
+    Check(fhesi_d2d(buf->ctx, buf->ptr, o.buf->ptr, buf->bytes), "fhesi_d2d");
+  }
+  return *this;
+}
+void Ciphertext::Alloc(unsigned np, unsigned words) {
+  fhesi_ctx *d = context->Dev();
+  nparts = np, wordsPer = words;
+  buf = make_shared<DevBuf>(d, (size_t)np * context->zMstar.phiM() * words * 4);
+}
+void Ciphertext::Initialize(unsigned n, const FHEcontext &c) {
+  context = &c;
+  Clear();
+  if (n) {
+    Alloc(n, c.Words());
+    std::vector<uint32_t> z(buf->bytes / 4, 0);
+    Check(fhesi_h2d(buf->ctx, buf->ptr, z.data(), buf->bytes), "fhesi_h2d");
+  }
+  hostStale = true;
+}
+void Ciphertext::Clear() {
+  buf.reset();
+  nparts = 0, wordsPer = 0, scaledUp = false, hostStale = false;
+  parts.clear();
+}
+void Ciphertext::SyncHost() const {
+  Ciphertext *self = const_cast<Ciphertext *>(this);
+  if (!hostStale) return;
+  self->parts.clear();
+  if (!scaledUp && buf) {
+    const unsigned n = context->zMstar.phiM();
+    std::vector<uint32_t> w(buf->bytes / 4);
+    Check(fhesi_d2h(buf->ctx, w.data(), buf->ptr, buf->bytes), "fhesi_d2h");
+    for (unsigned i = 0; i < nparts; ++i) {
+      CiphertextPart part(*context);
+      part.poly = UnpackPoly(&w[(size_t)i * n * wordsPer], n, wordsPer);
+      self->parts.push_back(part);
+    }
+  }
+  hostStale = false;
+}
+void Ciphertext::UploadHost() {  // after Import / a write through operator[]
+  const unsigned n = context->zMstar.phiM(), W = context->Words();
+  Alloc(parts.size(), W + 1);  // head-room word: imported parts need not be reduced
+  std::vector<uint32_t> w;
+  for (auto &p : parts) {
+    std::vector<uint32_t> pw = PackPoly(p.poly, n, W + 1);
+    w.insert(w.end(), pw.begin(), pw.end());
+  }
+  if (!w.empty()) Check(fhesi_h2d(buf->ctx, buf->ptr, w.data(), w.size() * 4), "fhesi_h2d");
+  scaledUp = false;
+  hostStale = false;
+}
+void Ciphertext::EnsureReduced() {
+  if (scaledUp || !buf || wordsPer == context->Words()) return;
+  const unsigned W = context->Words();
+  auto nb = make_shared<DevBuf>(buf->ctx, (size_t)nparts * context->zMstar.phiM() * W * 4);
+  Check(fhesi_reduce_wide_dev(buf->ctx, buf->ptr, wordsPer, nb->ptr, nparts, 1), "fhesi_reduce_wide_dev");
+  buf = nb;
+  wordsPer = W;
+  hostStale = true;
+}
+CiphertextPart Ciphertext::GetPart(unsigned ind) const {
+  SyncHost();
+  return parts[ind];
+}
+CiphertextPart &Ciphertext::operator[](unsigned ind) {
+  SyncHost();
+  return parts[ind];
+}
+Ciphertext &Ciphertext::operator+=(const Ciphertext &o) {  // Ciphertext.cpp:123-145
+  assert(scaledUp == o.scaledUp);
+  if (!o.buf || o.nparts == 0) return *this;
+  if (!buf || nparts == 0) return *this = o;
+  fhesi_ctx *d = context->Dev();
+  const unsigned n = context->zMstar.phiM();
+  Ciphertext tmp(*context);
+  const Ciphertext *rhs = &o;
+  if (!scaledUp) {
+    EnsureReduced();
+    if (o.wordsPer != context->Words()) {
+      tmp = o;
+      tmp.EnsureReduced();
+      rhs = &tmp;
+    }
+  }
+  const size_t partBytes = scaledUp ? fhesi_tprod_bytes(d, 1) : (size_t)n * wordsPer * 4;
+  if (rhs->nparts > nparts) {  // "parts.push_back(other.parts[i])" for the missing ones
+    auto nb = make_shared<DevBuf>(d, partBytes * rhs->nparts);
+    Check(fhesi_d2d(d, nb->ptr, buf->ptr, partBytes * nparts), "fhesi_d2d");
+    Check(fhesi_d2d(d, (char *)nb->ptr + partBytes * nparts, (char *)rhs->buf->ptr + partBytes * nparts,
+                    partBytes * (rhs->nparts - nparts)), "fhesi_d2d");
+    unsigned common = nparts;
+    buf = nb;
+    nparts = rhs->nparts;
+    if (scaledUp) Check(fhesi_tprod_add_dev(d, buf->ptr, rhs->buf->ptr, common, 1), "fhesi_tprod_add_dev");
+    else Check(fhesi_ct_add_dev(d, buf->ptr, rhs->buf->ptr, common, 1), "fhesi_ct_add_dev");
+  } else {
+    if (scaledUp) Check(fhesi_tprod_add_dev(d, buf->ptr, rhs->buf->ptr, rhs->nparts, 1), "fhesi_tprod_add_dev");
+    else Check(fhesi_ct_add_dev(d, buf->ptr, rhs->buf->ptr, rhs->nparts, 1), "fhesi_ct_add_dev");
+  }
+  Check(fhesi_sync(d), "fhesi_sync");  // tmp / rhs buffers may be released on return
+  hostStale = true;
+  return *this;
+}
+Ciphertext &Ciphertext::operator+=(const ZZX &other) {  // Ciphertext.cpp:147-161
+  if (scaledUp) Error("Ciphertext += ZZX on a tensor-form ciphertext is not supported: ScaleDown first");
+  EnsureReduced();
+  fhesi_ctx *d = context->Dev();
+  const unsigned n = context->zMstar.phiM(), W = context->Words();
+  ZZX sc = other;
+  for (long i = 0; i <= deg(sc); i++) {
+    sc.rep[i] <<= (long)context->logQ;
+    sc.rep[i] /= context->ModulusP();
+    Reduce(sc.rep[i], context->logQ);
+  }
+  std::vector<uint32_t> w = PackPoly(sc, n, W);
+  DevBuf t(d, w.size() * 4);
+  Check(fhesi_h2d(d, t.ptr, w.data(), w.size() * 4), "fhesi_h2d");
+  Check(fhesi_ct_add_dev(d, buf->ptr, t.ptr, 1, 1), "fhesi_ct_add_dev");
+  Check(fhesi_sync(d), "fhesi_sync");
+  hostStale = true;
+  return *this;
+}
+Ciphertext &Ciphertext::operator*=(const Ciphertext &o) {  // Ciphertext.cpp:167-192
+  if (scaledUp || o.scaledUp) Error("Ciphertext *= : operands must not be in tensor form (Ciphertext.cpp:169-176)");
+  fhesi_ctx *d = context->Dev();
+  Ciphertext rhs(o);  // also covers self-multiplication
+  EnsureReduced();
+  rhs.EnsureReduced();
+  const unsigned po = nparts + rhs.nparts - 1;
+  auto nb = make_shared<DevBuf>(d, fhesi_tprod_bytes(d, po));
+  Check(fhesi_ct_tensor_dev(d, buf->ptr, nparts, rhs.buf->ptr, rhs.nparts, nb->ptr, 1, 0), "fhesi_ct_tensor_dev");
+  Check(fhesi_sync(d), "fhesi_sync");
+  buf = nb;
+  nparts = po;
+  wordsPer = 0;
+  scaledUp = true;
+  parts.clear();
+  hostStale = true;
+  return *this;
+}
+Ciphertext &Ciphertext::operator*=(long l) {  // Ciphertext.cpp:233-244
+  if (!buf) return *this;
+  fhesi_ctx *d = context->Dev();
+  if (!scaledUp) {
+    EnsureReduced();
+    Check(fhesi_ct_mul_scalar_dev(d, buf->ptr, l, nparts, 1), "fhesi_ct_mul_scalar_dev");
+  } else {
+    Check(fhesi_tprod_mul_scalar_dev(d, buf->ptr, l, nparts, 1), "fhesi_tprod_mul_scalar_dev");
+  }
+  hostStale = true;
+  return *this;
+}
+Ciphertext &Ciphertext::operator*=(const ZZX &other) {  // Ciphertext.cpp:246-258
+  if (scaledUp) Error("Ciphertext *= ZZX on a tensor-form ciphertext is not supported: ScaleDown first");
+  if (!buf) return *this;
+  EnsureReduced();
+  fhesi_ctx *d = context->Dev();
+  const unsigned n = context->zMstar.phiM();
+  std::vector<uint32_t> pt(n, 0);
+  const ZZ &P = context->ModulusP();
+  for (long i = 0; i <= deg(other) && i < (long)n; ++i) pt[i] = (uint32_t)to_long(other.rep.v[i] % P);
+  // NOTE: the reference multiplies by `other` as an integer polynomial; callers pass to_ZZX of a
+  // ZZ_pX (coefficients in [0,p)), for which reducing mod p is the identity.
+  DevBuf t(d, n * 4);
+  Check(fhesi_h2d(d, t.ptr, pt.data(), n * 4), "fhesi_h2d");
+  Check(fhesi_ct_mul_plain_dev(d, buf->ptr, t.ptr, nparts, 1), "fhesi_ct_mul_plain_dev");
+  Check(fhesi_sync(d), "fhesi_sync");
+  hostStale = true;
+  return *this;
+}
+Ciphertext &Ciphertext::operator>>=(long k) {  // Ciphertext.cpp:264-275
+  if (scaledUp) Error("Ciphertext >>= on a tensor-form ciphertext is not supported: ScaleDown first");
+  if (!buf) return *this;
+  EnsureReduced();
+  fhesi_ctx *d = context->Dev();
+  const unsigned n = context->zMstar.phiM(), W = context->Words();
+  auto nb = make_shared<DevBuf>(d, (size_t)nparts * n * (W + 1) * 4);
+  Check(fhesi_ct_automorph_dev(d, buf->ptr, nparts, (uint32_t)k, nb->ptr, 1), "fhesi_ct_automorph_dev");
+  buf = nb;
+  wordsPer = W + 1;
+  hostStale = true;
+  return *this;
+}
+void Ciphertext::ScaleDown() {  // Ciphertext.cpp:194-218
+  if (!scaledUp) return;
+  fhesi_ctx *d = context->Dev();
+  auto nb = make_shared<DevBuf>(d, fhesi_ct_bytes(d, nparts));
+  Check(fhesi_scaledown_dev(d, buf->ptr, nparts, nb->ptr, 1), "fhesi_scaledown_dev");
+  Check(fhesi_sync(d), "fhesi_sync");
+  buf = nb;
+  wordsPer = context->Words();
+  scaledUp = false;
+  hostStale = true;
+}
+ostream &operator<<(ostream &os, const Ciphertext &c) {
+  Ciphertext t(c);
+  t.ScaleDown();
+  t.SyncHost();
+  for (unsigned i = 0; i < t.size(); i++) os << t.parts[i] << ", ";
+  return os;
+}
+
+// ------------------------------------------------------------------------------- keys
+void FHESISecKey::Init(const FHEcontext &c) {  // FHE-SI.cpp:86-91
+  sKeys.assign(2, DoubleCRT(c));
+  sKeys[0] = 1;
+  sKeys[1].sampleHWt(64);
+  devKey.reset();
+}
+static shared_ptr<fhesi_key> UploadKey(const FHEcontext &c, const vector<DoubleCRT> &rep) {
+  const unsigned n = c.zMstar.phiM(), W = c.Words();
+  std::vector<uint32_t> w;
+  for (auto &d : rep) {
+    ZZX p;
+    d.toPoly(p);
+    ReduceCoefficients(p, c.logQ);
+    std::vector<uint32_t> pw = PackPoly(p, n, W);
+    w.insert(w.end(), pw.begin(), pw.end());
+  }
+  fhesi_key *k = nullptr;
+  Check(fhesi_key_create(c.Dev(), w.data(), rep.size(), &k), "fhesi_key_create");
+  return shared_ptr<fhesi_key>(k, [](fhesi_key *p) { fhesi_key_destroy(p); });
+}
+void FHESISecKey::Decrypt(Plaintext &ptxt, const Ciphertext &ct) const {  // FHE-SI.cpp:93-119
+  if (!devKey) devKey = UploadKey(context, sKeys);
+  Ciphertext c(ct);
+  c.ScaleDown();
+  c.EnsureReduced();
+  if (c.size() < sKeys.size()) Error("Decrypt: ciphertext has fewer parts than the secret key");
+  fhesi_ctx *d = context.Dev();
+  const unsigned n = context.zMstar.phiM();
+  DevBuf m(d, n * 4);
+  Check(fhesi_decrypt_dev(d, devKey.get(), c.buf->ptr, c.size(), m.ptr, 1), "fhesi_decrypt_dev");
+  std::vector<uint32_t> h(n);
+  Check(fhesi_d2h(d, h.data(), m.ptr, n * 4), "fhesi_d2h");
+  ptxt.message.rep.v.assign(n, ZZ_p());
+  for (unsigned i = 0; i < n; ++i) ptxt.message.rep.v[i].v = h[i];
+  ptxt.message.normalize();
+}
+void FHESISecKey::Export(ofstream &out) const { ::Export(out, sKeys); }
+void FHESISecKey::Import(ifstream &in) { ::Import(in, sKeys); devKey.reset(); }
+
+void FHESIPubKey::Init(const FHESISecKey &secKey) {  // FHE-SI.cpp:42-62
+  ZZX c0, c1;
+  sampleGaussian(c0, context.zMstar.phiM(), context.stdev);
+  SampleRandom(c1, context.modulusQ, context.zMstar.phiM());
+  ZZX s;
+  secKey.GetRepresentation()[1].toPoly(s);
+  c0 += MulModPhim(s, c1, context.zMstar);
+  c1 *= -1;
+  ReduceCoefficients(c0, context.logQ);
+  ReduceCoefficients(c1, context.logQ);
+  publicKey.clear();
+  publicKey.push_back(DoubleCRT(c0, context));
+  publicKey.push_back(DoubleCRT(c1, context));
+  devKey.reset();
+}
+void FHESIPubKey::Encrypt(Ciphertext &ctxt, const Plaintext &ptxt) const {  // FHE-SI.cpp:10-36
+  if (!devKey) devKey = UploadKey(context, publicKey);
+  fhesi_ctx *d = context.Dev();
+  const unsigned n = context.zMstar.phiM();
+  std::vector<uint8_t> r(n);
+  for (unsigned i = 0; i < n; i++) r[i] = (uint8_t)RandomBnd(2L);        // :14-17
+  std::vector<int32_t> e(2 * n, 0);
+  for (unsigned i = 0; i < 2; ++i) {                                       // :24, one draw per part
+    ZZX g;
+    sampleGaussian(g, n, context.stdev);
+    for (long j = 0; j <= deg(g); ++j) e[i * n + j] = (int32_t)to_long(g.rep.v[j]);
+  }
+  std::vector<uint32_t> msg(n, 0);
+  for (long j = 0; j <= deg(ptxt.message) && j < (long)n; ++j) msg[j] = (uint32_t)ptxt.message.rep.v[j].v;
+  DevBuf dm(d, n * 4), dr(d, n), de(d, 2 * n * 4);
+  Check(fhesi_h2d(d, dm.ptr, msg.data(), n * 4), "fhesi_h2d");
+  Check(fhesi_h2d(d, dr.ptr, r.data(), n), "fhesi_h2d");
+  Check(fhesi_h2d(d, de.ptr, e.data(), 2 * n * 4), "fhesi_h2d");
+  ctxt.context = &context;
+  ctxt.Clear();
+  ctxt.Alloc(2, context.Words());
+  Check(fhesi_encrypt_dev(d, devKey.get(), dm.ptr, (const uint8_t *)dr.ptr, (const int32_t *)de.ptr, ctxt.buf->ptr, 1),
+        "fhesi_encrypt_dev");
+  Check(fhesi_sync(d), "fhesi_sync");
+  ctxt.hostStale = true;
+}
+void FHESIPubKey::Export(ofstream &out) const { ::Export(out, publicKey); }
+void FHESIPubKey::Import(ifstream &in) { ::Import(in, publicKey); devKey.reset(); }
+
+void KeySwitchSI::Init(const FHESISecKey &src, const FHESISecKey &dst) {  // FHE-SI.cpp:153-209
+  const vector<DoubleCRT> &s = src.GetRepresentation();
+  vector<ZZX> sCoeff(s.size());
+  for (size_t i = 0; i < s.size(); i++) s[i].toPoly(sCoeff[i]);
+  ZZX t;
+  dst.GetRepresentation()[1].toPoly(t);
+  const size_t n = src.GetSize();
+  vector<DoubleCRT> A, b;
+  for (unsigned i = 0; i < n; i++) {
+    for (unsigned j = 0; j < context.ndigits; j++) {
+      ZZX poly;
+      SampleRandom(poly, context.modulusQ, context.zMstar.phiM());
+      ZZX bCoeff = MulModPhim(poly, t, context.zMstar);
+      ZZX err;
+      sampleGaussian(err, context.zMstar.phiM(), context.stdev);
+      bCoeff += err;
+      bCoeff += sCoeff[i];
+      for (long k = 0; k <= deg(sCoeff[i]); k++) sCoeff[i].rep[k] <<= (long)(8 * context.decompSize);
+      ReduceCoefficients(bCoeff, context.logQ);
+      poly *= -1;  // A = -poly, not reduced (FHE-SI.cpp:178-180)
+      A.push_back(DoubleCRT(poly, context));
+      b.push_back(DoubleCRT(bCoeff, context));
+    }
+  }
+  keySwitchMatrix.resize(2);
+  keySwitchMatrix[0] = b;
+  keySwitchMatrix[1] = A;
+  devKsw.reset();
+}
+void KeySwitchSI::InitS2(const FHESISecKey &s) {  // FHE-SI.cpp:211-227
+  vector<DoubleCRT> sKeys = s.GetRepresentation();
+  vector<DoubleCRT> tKeys;
+  tKeys.assign(sKeys.size() * 2 - 1, sKeys[1]);
+  tKeys[0] = sKeys[0];
+  for (unsigned i = 2; i < tKeys.size(); i++) tKeys[i] *= tKeys[i - 1];
+  FHESISecKey tensoredKey(s.GetContext(), FHESISecKey::Empty());
+  tensoredKey.UpdateRepresentation(tKeys);
+  Init(tensoredKey, s);
+}
+void KeySwitchSI::InitAutomorph(const FHESISecKey &s, unsigned k) {  // FHE-SI.cpp:229-239
+  vector<DoubleCRT> sKeys = s.GetRepresentation();
+  FHESISecKey automorphedKey(s.GetContext(), FHESISecKey::Empty());
+  for (unsigned i = 0; i < sKeys.size(); i++) sKeys[i].automorph(k);
+  automorphedKey.UpdateRepresentation(sKeys);
+  Init(automorphedKey, s);
+}
+const fhesi_ksw *KeySwitchSI::Dev() const {
+  if (!devKsw) {
+    const unsigned n = context.zMstar.phiM(), W = context.Words();
+    std::vector<uint32_t> wb, wA;
+    for (int r = 0; r < 2; ++r) {
+      for (auto &d : keySwitchMatrix[r]) {
+        ZZX p;
+        d.toPoly(p);
+        ReduceCoefficients(p, context.logQ);  // only the value mod q matters
+        std::vector<uint32_t> pw = PackPoly(p, n, W);
+        (r ? wA : wb).insert((r ? wA : wb).end(), pw.begin(), pw.end());
+      }
+    }
+    fhesi_ksw *k = nullptr;
+    Check(fhesi_ksw_create(context.Dev(), wb.data(), wA.data(), keySwitchMatrix[0].size() / context.ndigits, &k),
+          "fhesi_ksw_create");
+    devKsw = shared_ptr<fhesi_ksw>(k, [](fhesi_ksw *p) { fhesi_ksw_destroy(p); });
+  }
+  return devKsw.get();
+}
+void KeySwitchSI::ApplyKeySwitch(Ciphertext &ctxt) const {  // FHE-SI.cpp:241-260
+  ctxt.ScaleDown();
+  ctxt.EnsureReduced();
+  if (keySwitchMatrix.size() != 2 || ctxt.size() * context.ndigits != keySwitchMatrix[0].size())
+    Error("ApplyKeySwitch: ciphertext size does not match the key-switch matrix");
+  fhesi_ctx *d = context.Dev();
+  auto nb = make_shared<DevBuf>(d, fhesi_ct_bytes(d, 2));
+  Check(fhesi_keyswitch_dev(d, Dev(), ctxt.buf->ptr, nb->ptr, 1), "fhesi_keyswitch_dev");
+  Check(fhesi_sync(d), "fhesi_sync");
+  ctxt.buf = nb;
+  ctxt.nparts = 2;
+  ctxt.hostStale = true;
+}
+void KeySwitchSI::Export(ofstream &out) const { ::Export(out, keySwitchMatrix); }
+void KeySwitchSI::Import(ifstream &in) { ::Import(in, keySwitchMatrix); devKsw.reset(); }
+
+// ------------------------------------------------------------------------------- Serialization
+void Export(ofstream &out, const ZZ &val) {  // Serialization.cpp:3-13
+  uint32_t nBytes = NumBytes(val);
+  out.write((char *)&nBytes, sizeof(uint32_t));
+  bool neg = (val < 0L);
+  out.write((char *)&neg, sizeof(bool));
+  std::vector<unsigned char> data(nBytes + 1);
+  BytesFromZZ(data.data(), val, nBytes);
+  out.write((char *)data.data(), nBytes);
+}
+void Import(ifstream &in, ZZ &val) {
+  uint32_t nBytes;
+  in.read((char *)&nBytes, sizeof(uint32_t));
+  bool neg;
+  in.read((char *)&neg, sizeof(bool));
+  std::vector<unsigned char> data(nBytes + 1);
+  in.read((char *)data.data(), nBytes);
+  ZZFromBytes(val, data.data(), nBytes);
+  if (neg) val *= -1;
+}
+void Export(ofstream &out, const ZZX &poly) {  // Serialization.cpp:29-36
+  int32_t degree = deg(poly);
+  out.write((char *)&degree, sizeof(int32_t));
+  for (int i = 0; i <= degree; i++) Export(out, poly.rep[i]);
+}
+void Import(ifstream &in, ZZX &poly) {
+  poly = ZZX::zero();
+  int32_t degree;
+  in.read((char *)&degree, sizeof(int32_t));
+  if (degree == -1) return;
+  poly.rep.v.resize(degree + 1);
+  for (int i = 0; i <= degree; i++) Import(in, poly.rep.v[i]);
+  poly.normalize();
+}
+void Export(ofstream &out, const vec_long &vec) {  // Serialization.cpp:83-89
+  uint32_t len = vec.length();
+  Export(out, len);
+  for (long i = 0; i < vec.length(); i++) Export(out, vec[i]);
+}
+void Import(ifstream &in, vec_long &vec) {
+  uint32_t size;
+  Import(in, size);
+  vec.SetLength(size);
+  for (uint32_t i = 0; i < size; i++) Import(in, vec[i]);
+}
+void Export(ofstream &out, const DoubleCRT &poly) {  // Serialization.cpp:56-65
+  vector<vector<long>> rows = poly.getRows();
+  uint32_t size = rows.size();
+  Export(out, size);
+  for (long i = 0; i < (long)rows.size(); ++i) {
+    Export(out, i);
+    vec_long v;
+    v.v = rows[i];
+    Export(out, v);
+  }
+}
+void Import(ifstream &in, DoubleCRT &poly) {
+  uint32_t size;
+  Import(in, size);
+  vector<vector<long>> rows(size);
+  for (unsigned i = 0; i < size; i++) {
+    long key;
+    Import(in, key);
+    vec_long v;
+    Import(in, v);
+    if (key < 0 || key >= (long)size) Error("Import(DoubleCRT): bad row index");
+    rows[key] = v.v;
+  }
+  poly.setRows(rows);
+}
+void Export(ofstream &out, const CiphertextPart &part) { Export(out, part.poly); }
+void Import(ifstream &in, CiphertextPart &part) { Import(in, part.poly); }
+void Export(ofstream &out, const Ciphertext &ctxt) {  // Serialization.cpp:109-114
+  Ciphertext copy = ctxt;
+  copy.ScaleDown();
+  copy.SyncHost();
+  Export(out, copy.parts);
+}
+void Import(ifstream &in, Ciphertext &ctxt) {
+  ctxt.Clear();
+  Import(in, ctxt.parts);
+  ctxt.UploadHost();
+}

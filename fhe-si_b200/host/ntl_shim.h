@@ -771,6 +771,8 @@ inline void random(ZZ_pX &x, long n) {
 }
 inline ZZ_pX to_ZZ_pX(long c) { ZZ_pX r; SetCoeff(r, 0, ZZ_p(c)); return r; }
 inline ZZ_pX to_ZZ_pX(int c) { return to_ZZ_pX((long)c); }
+inline ZZ_pX to_ZZ_pX(unsigned c) { return to_ZZ_pX((long)c); }
+inline ZZ_pX to_ZZ_pX(unsigned long c) { return to_ZZ_pX((long)(c % (unsigned long)ZZ_p::mod())); }
 inline ZZ_pX to_ZZ_pX(const ZZ_p &c) { ZZ_pX r; SetCoeff(r, 0, c); return r; }
 inline ZZ_pX to_ZZ_pX(const ZZ &c) { return to_ZZ_pX(to_ZZ_p(c)); }
 inline const ZZ_pX &to_ZZ_pX(const ZZ_pX &a) { return a; }

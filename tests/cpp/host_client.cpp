@@ -1,0 +1,117 @@
+// host_client.cpp -- a client of the reference's C++ API (our own code, written against the
+// class surface of SURVEY.md §8b) used by tests/test_host_cpp.py.  It follows the draw order of
+// tests/golden/make_golden.py::scenario so that, with the shared SplitMix64 stream, every file
+// it writes must equal the oracle's golden bytes.
+//
+//   host_client <logQ> <p> <g> <seed> <outdir>
+#include <fstream>
+#include <string>
+
+#include "Ciphertext.h"
+#include "DoubleCRT.h"
+#include "FHE-SI.h"
+#include "FHEContext.h"
+#include "Plaintext.h"
+#include "Serialization.h"
+
+template <typename T>
+static void Save(const std::string &path, const T &v) {
+  std::ofstream out(path, std::ios::binary);
+  Export(out, v);
+}
+
+int main(int argc, char **argv) {
+  if (argc < 6) return 2;
+  unsigned logQ = atoi(argv[1]), p = atoi(argv[2]), g = atoi(argv[3]);
+  long long seed = atoll(argv[4]);
+  std::string dir = argv[5];
+
+  FHEcontext context(p - 1, logQ, p, g, 3);
+  activeContext = &context;
+  context.SetUpSIContext();
+  {
+    std::ofstream out(dir + "/context.bin", std::ios::binary);
+    context.ExportSIContext(out);
+  }
+  SetSeed(to_ZZ((long)seed));
+  FHESISecKey secretKey(context);
+  const FHESIPubKey &publicKey(secretKey);
+  KeySwitchSI keySwitch(secretKey);
+
+  long phim = context.zMstar.phiM();
+  ZZ_pX m[2];
+  for (int k = 0; k < 2; ++k) {
+    m[k].rep.SetLength(phim);
+    for (long i = 0; i < phim; i++) m[k].rep[i] = to_ZZ_p(RandomBnd((long)p));
+    m[k].normalize();
+  }
+  Plaintext pt0(context, m[0]), pt1(context, m[1]);
+  Ciphertext a(publicKey), b(publicKey);
+  publicKey.Encrypt(a, pt0);
+  publicKey.Encrypt(b, pt1);
+  Save(dir + "/ct0.bin", a);
+  Save(dir + "/ct1.bin", b);
+
+  Ciphertext sum = a;
+  sum += b;
+  Save(dir + "/add.bin", sum);
+
+  Ciphertext t = a;
+  t *= b;
+  Save(dir + "/tensor_scaledown.bin", t);  // Export applies ScaleDown
+
+  Ciphertext mr = a;
+  mr *= b;
+  keySwitch.ApplyKeySwitch(mr);
+  Save(dir + "/mult_relin.bin", mr);
+
+  Plaintext dec;
+  secretKey.Decrypt(dec, mr);
+  Save(dir + "/decrypt_mult_relin.bin", to_ZZX(dec.message));
+
+  Ciphertext sq = mr;
+  sq *= mr;
+  keySwitch.ApplyKeySwitch(sq);
+  Save(dir + "/square_relin.bin", sq);
+
+  Ciphertext sc = a;
+  sc *= -7;
+  Save(dir + "/mul_scalar_m7.bin", sc);
+
+  Ciphertext au = a;
+  au >>= 3;
+  Save(dir + "/automorph_3.bin", au);
+
+  // keys as DoubleCRT rows over the reference chain (Serialization.cpp:56-65)
+  {
+    std::ofstream out(dir + "/pk.bin", std::ios::binary);
+    publicKey.Export(out);
+  }
+  // round trip: import the ciphertext and the public key again, re-export, compare in Python
+  {
+    std::ifstream in(dir + "/mult_relin.bin", std::ios::binary);
+    Ciphertext back;
+    Import(in, back);
+    Save(dir + "/mult_relin_roundtrip.bin", back);
+    std::ifstream kin(dir + "/pk.bin", std::ios::binary);
+    FHESIPubKey pk2(context);
+    pk2.Import(kin);
+    std::ofstream kout(dir + "/pk_roundtrip.bin", std::ios::binary);
+    pk2.Export(kout);
+    // an imported key must still encrypt: decrypt(encrypt_pk2(m0)) == m0
+    Ciphertext c2(pk2);
+    pk2.Encrypt(c2, pt0);
+    Plaintext d2;
+    secretKey.Decrypt(d2, c2);
+    if (!(d2.message == m[0])) return 3;
+  }
+  // the identities of Test_AddMul.cpp:84-86, for good measure
+  Plaintext dsum;
+  secretKey.Decrypt(dsum, sum);
+  if (!(dsum.message == m[0] + m[1])) return 4;
+  ZZ_pX prod = m[0] * m[1];
+  rem(prod, prod, to_ZZ_pX(context.zMstar.PhimX()));
+  if (!(dec.message == prod)) return 5;
+  std::cout << "host_client ok" << std::endl;
+  return 0;
+}
