@@ -528,7 +528,7 @@ void DoubleCRT::setRows(const vector<vector<long>> &rows) {
     for (long t = 1; t < m; ++t) zpow[t] = MulMod(zpow[t - 1], zinv, q);
     for (long t = 0; t < m; ++t) {
       unsigned __int128 s = 0;
-      for (long j = 0; j < n; ++j) s += (unsigned __int128)rows[l][j] * zpow[(units[j] * t) % m];
+      for (long j = 0; j < n; ++j) s += (unsigned long)MulMod(rows[l][j], zpow[(units[j] * t) % m], q);
       c[t] = MulMod((long)(s % (unsigned long)q), minv, q);
     }
     for (long i = m - 1; i >= n; --i) {
