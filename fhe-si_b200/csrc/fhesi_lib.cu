@@ -50,6 +50,7 @@ struct fhesi_ctx {
   u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
   u32 fused_chunk = 2048; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
+  bool tfree = false;  // every prime satisfies 3D (p/2)^2 < 2^63 (single-accumulator key switch)
   // launch accounting / per-kernel CUDA-event profiler (bench.py "roofline", "gpu_launches")
   uint64_t launches = 0;
   bool prof_on = false;
@@ -89,7 +90,8 @@ static void prof_end(fhesi_ctx *c) {
   } while (0)
 struct fhesi_ksw {
   fhesi_ctx *ctx;
-  u32 *d_key;  // [Lk][parts*D][2][N] key form
+  u32 *d_key;      // [Lk][parts*D][2][N] key form, residues in [0,p)
+  u32 *d_key_bal;  // same, balanced residues (fused T-free path); NULL if unused
   u32 parts;
 };
 struct fhesi_key {
@@ -158,7 +160,18 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   std::vector<u32> primes;
   double bits = 0;
   u32 Lt = 0, Lk = 0, Le = 0;
-  for (u64 q = ((1ull << 30) - 1) / N * N + 1; q > (1ull << 29) && Lt == 0; q -= N) {
+  // T-free key switch (kernels_fused.cuh): with balanced residues the 3D-term inner product fits a
+  // signed 64-bit accumulator if 3D (p/2)^2 < 2^63.  Start the chain below that cap when it costs
+  // no extra prime at logQ <= 256 (cap ~ 2^29.98 for D = 11); otherwise keep 30-bit primes.
+  u64 start = (1ull << 30) - 1;
+  {
+    const double cap = std::floor(std::sqrt(std::ldexp(1.0, 65) / (3.0 * D))) - 1;
+    if (cap > 1.02 * std::ldexp(1.0, 29)) {
+      if (cap < (double)start) start = (u64)cap;
+      c->tfree = true;
+    }
+  }
+  for (u64 q = start / N * N + 1; q > (1ull << 29) && Lt == 0; q -= N) {
     if (q >= (1ull << 30) || !h_is_prime(q)) continue;
     primes.push_back((u32)q);
     bits += std::log2((double)q);
@@ -478,7 +491,15 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaFree(d_in));
   CK(cudaFree(d_tmp));
-  fhesi_ksw *k = new fhesi_ksw{c, d_key, parts};
+  u32 *d_bal = nullptr;
+  if (c->use_fused && c->tfree) {
+    const size_t total = (size_t)K * 2 * Lk * I.N;
+    CK(cudaMalloc(&d_bal, total * 4));
+    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_key, d_bal, K * 2, total);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  fhesi_ksw *k = new fhesi_ksw{c, d_key, d_bal, parts};
   *out = k;
   return 0;
 }
@@ -487,6 +508,7 @@ void fhesi_ksw_destroy(fhesi_ksw *k) {
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   cudaFree(k->d_key);
+  if (k->d_key_bal) cudaFree(k->d_key_bal);
   delete k;
 }
 int fhesi_key_create(fhesi_ctx *c, const uint32_t *h_polys, uint32_t parts, fhesi_key **out) {
@@ -745,9 +767,11 @@ static int keyswitch_generic(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, 
 static int fused_ks_from_digits(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *digits, u32 *res, u32 *out,
                                 size_t cnt) {
   const fhesi_info &I = c->info;
-  FusedKsArgs k{digits, ksw->d_key, res, ksw->parts * I.D, I.Lk, (u32)cnt};
-  dim3 grid(I.Lk, (unsigned)((cnt + KG - 1) / KG));
-  KL(c, k_fused_keyswitch, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, k);
+  const bool tfree = c->tfree && ksw->d_key_bal;
+  FusedKsArgs k{digits, tfree ? ksw->d_key_bal : ksw->d_key, res, ksw->parts * I.D, I.Lk, (u32)cnt};
+  dim3 grid(I.Lk, (unsigned)((cnt + KSG - 1) / KSG));
+  if (tfree) KL(c, k_fused_keyswitch<true>, grid, KSG * 128, KS_SMEM_WORDS * 4, c->dc, k);
+  else KL(c, k_fused_keyswitch<false>, grid, KSG * 128, KS_SMEM_WORDS * 4, c->dc, k);
   CKL();
   return launch_crt(c, res, I.Lk, CRT_REDUCE_Q, out, I.W, cnt * 2);
 }

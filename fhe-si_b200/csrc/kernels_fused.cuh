@@ -405,11 +405,17 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTen
 // ---------------------------------------------------------------------------------------
 struct FusedKsArgs {
   const u32 *digits;  // [count][K][n]   dbits-wide digits, part-major digit-minor
-  const u32 *key;     // [Lk][K][2][N]   key form, storage order
+  const u32 *key;     // [Lk][K][2][N]   key form, storage order; TFREE: balanced (int32 in (-p/2, p/2])
   u32 *res;           // [count][2][Lk][n]
   u32 K, Lk, count;
 };
-__global__ void __launch_bounds__(KG * 128, 1) k_fused_keyswitch(DevCtx c, FusedKsArgs a) {
+// G transform groups (ciphertexts) per CTA.  TFREE: every prime satisfies K * (p/2)^2 < 2^63, so
+// the whole inner product of balanced residues fits one signed 64-bit accumulator and no
+// intermediate reduction (nor its 16 partial-sum registers) is needed.
+#define KSG 6
+#define KS_SMEM_WORDS (2 * FTW_WORDS + KSG * 2 * FPADN)
+template <bool TFREE>
+__global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
@@ -417,10 +423,10 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_keyswitch(DevCtx c, Fused
   fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
   fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
   __syncthreads();
-  const size_t op = (size_t)blockIdx.y * KG + g;
+  const size_t op = (size_t)blockIdx.y * KSG + g;
   if (op >= a.count) return;  // whole group leaves together; only group barriers from here on
   const PrimeConst pc = c.pc[l];
-  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
+  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p, half = p >> 1;
   u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
   const XAddr A = make_xaddr(tg);
   u64 acc0[8], acc1[8];
@@ -441,24 +447,43 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_keyswitch(DevCtx c, Fused
       for (int j = 0; j < 4; ++j)
         xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + (size_t)(k + 1) * c.n + j * 128 + tg) : 0u;
     }
+    fwd1024(x, twf, A, bufA, bufB, g, tg, p);
     const uint4 *kp = (const uint4 *)(key + (size_t)k * 2 * FN);
     const uint4 ka0 = __ldg(kp), ka1 = __ldg(kp + 1);
     const uint4 kb0 = __ldg(kp + FN / 4), kb1 = __ldg(kp + FN / 4 + 1);
-    fwd1024(x, twf, A, bufA, bufB, g, tg, p);
     const u32 kb[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
     const u32 kA[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc0[j] += (u64)x[j] * kb[j];
-      acc1[j] += (u64)x[j] * kA[j];
-    }
-    if ((k & 7) == 7 || k + 1 == a.K) {  // <= 8 products of < p^2 each: the sum stays < 2^63
+    if (TFREE) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        t0[j] = csub(t0[j] + csub(mont_red64(acc0[j], p, pinv), p2), p2);
-        t1[j] = csub(t1[j] + csub(mont_red64(acc1[j], p, pinv), p2), p2);
-        acc0[j] = acc1[j] = 0;
+        const int xb = (int)x[j] - (x[j] > half ? (int)p : 0);  // balanced residue
+        acc0[j] += (u64)((i64)xb * (int)kb[j]);
+        acc1[j] += (u64)((i64)xb * (int)kA[j]);
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc0[j] += (u64)x[j] * kb[j];
+        acc1[j] += (u64)x[j] * kA[j];
+      }
+      if ((k & 7) == 7 || k + 1 == a.K) {  // <= 8 products of < p^2 each: the sum stays < 2^63
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          t0[j] = csub(t0[j] + csub(mont_red64(acc0[j], p, pinv), p2), p2);
+          t1[j] = csub(t1[j] + csub(mont_red64(acc1[j], p, pinv), p2), p2);
+          acc0[j] = acc1[j] = 0;
+        }
+      }
+    }
+  }
+  if (TFREE) {  // |sum| < 2^63: reduce the magnitude, then restore the sign
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const i64 s0 = (i64)acc0[j], s1 = (i64)acc1[j];
+      u32 r0 = csub(mont_red64((u64)(s0 < 0 ? -s0 : s0), p, pinv), p2);
+      u32 r1 = csub(mont_red64((u64)(s1 < 0 ? -s1 : s1), p, pinv), p2);
+      t0[j] = s0 < 0 ? csub(p2 - r0, p2) : r0;
+      t1[j] = s1 < 0 ? csub(p2 - r1, p2) : r1;
     }
   }
   inv1024(t0, twi, A, bufA, bufB, bufA, g, tg, p);
@@ -466,6 +491,14 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_keyswitch(DevCtx c, Fused
   fhesi_group_sync(g);  // bufA (nat) is rewritten by the next inverse transform
   inv1024(t1, twi, A, bufA, bufB, bufA, g, tg, p);
   phim_store_1024(bufA, a.res + ((op * 2 + 1) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+}
+// key form [0,p) -> balanced (-p/2, p/2], same layout [L][P][N]
+__global__ void k_balance_key(DevCtx c, const u32 *in, u32 *out, u32 P, size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const u32 l = (u32)(idx / ((size_t)P * c.N));
+  const u32 p = c.pc[l].p, v = in[idx];
+  out[idx] = v > (p >> 1) ? v - p : v;
 }
 
 // ByteDecomp (Ciphertext.cpp:82-121) of coefficient-form parts into the digit layout above:
@@ -483,7 +516,10 @@ static int fused_configure() {
   cudaError_t e = cudaFuncSetAttribute(k_fused_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(FUSED_SMEM_WORDS * 4));
   if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(k_fused_keyswitch, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(FUSED_SMEM_WORDS * 4));
+  e = cudaFuncSetAttribute(k_fused_keyswitch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(KS_SMEM_WORDS * 4));
+  if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(k_fused_keyswitch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(KS_SMEM_WORDS * 4));
   return e == cudaSuccess ? 0 : -1;
 }
