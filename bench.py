@@ -311,7 +311,8 @@ def run_ours(args, rank, local_rank, world):
         peak32 = max(peak_mont32, pipes["shoup_modmul32"])
         # dominant kernel by measured device time, with its algorithmic modmuls per launch
         work_all = kernel_work_per_op(dev)
-        work = {k: v for k, v in work_all.items() if k in prof}  # kernels that actually ran
+        # kernels that actually ran (template instances report as name<...>)
+        work = {k: work_all[k.split("<")[0]] for k in prof if k.split("<")[0] in work_all}
         top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
         tname, (tcnt, tms) = top
         share = tms / max(sum(v[1] for v in prof.values()), 1e-9)
@@ -380,7 +381,7 @@ def kernel_work_per_op(dev):
         "k_inv": (3 * Lt + 2 * Lk) * bf,
         "k_tensor_pw": 4 * Lt * N,
         "k_dot": 2 * 3 * D * Lk * N,
-        "k_crt<ML>": 3 * n * garner(Lt) + 2 * n * garner(Lk),
+        "k_crt": 3 * n * garner(Lt) + 2 * n * garner(Lk),
         # fused path (kernels_fused.cuh)
         "k_residues": 4 * n * Lt * dev.W,
         "k_fused_tensor": 7 * Lt * bf + 4 * Lt * N,

@@ -47,6 +47,7 @@ struct fhesi_ctx {
   std::vector<void *> tables;  // device allocations owned by the context
   Arena scratch;
   std::vector<PrimeConst> h_pc;
+  std::vector<u32> h_garner, h_Pfull, h_Phalf;  // host copies for the by-value CRT tables
   u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
   u32 fused_chunk = 2048; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
@@ -284,6 +285,9 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   dc.n = n; dc.N = N; dc.logN = ilog2_ceil(N); dc.W = W; dc.logQ = logQ; dc.D = D; dc.dbits = dbits;
   dc.h = h; dc.Lmax = L; dc.CW = CW; dc.ptxt = (u32)p_pt;
   c->h_pc = pc;
+  c->h_garner = gar;
+  c->h_Pfull = Pf;
+  c->h_Phalf = Ph;
   int rc = 0;
   if ((rc = upload(c, pc, &dc.pc)) || (rc = upload(c, twf, &dc.tw_fwd)) ||
       (rc = upload(c, twi, &dc.tw_inv)) || (rc = upload(c, cw, &dc.cword)) ||
@@ -427,7 +431,19 @@ template <int ML>
 static void launch_crt_t(fhesi_ctx *c, const CrtArgs &a) {
   const int B = 128;
   unsigned g = (unsigned)((a.total + B - 1) / B);
-  KL(c, k_crt<ML>, g, B, ML * B * 4, c->dc, a);
+  CrtTables<ML> T;
+  memset(&T, 0, sizeof T);
+  const u32 L = a.L, LM = c->dc.Lmax;
+  for (u32 j = 0; j < L && j < (u32)ML; ++j) {
+    T.p[j] = c->h_pc[j].p;
+    T.pinv[j] = c->h_pc[j].pinv;
+    for (u32 i = 0; i < j; ++i) T.garner[j][i] = c->h_garner[(size_t)j * LM + i];
+  }
+  for (u32 k = 0; k < LM && k < (u32)ML; ++k) {
+    T.Pfull[k] = c->h_Pfull[(size_t)L * LM + k];
+    T.Phalf[k] = c->h_Phalf[(size_t)L * LM + k];
+  }
+  KL(c, k_crt<ML>, g, B, ML * B * 4, c->dc, a, T);
 }
 static int launch_crt(fhesi_ctx *c, const u32 *res, u32 L, u32 mode, u32 *out, u32 Wout,
                       size_t npolys) {
@@ -451,7 +467,7 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
                                int to_tprod) {
   const fhesi_info &I = c->info;
   ResidueArgs r{a, b, resid, I.Lt, cnt};
-  KL(c, k_residues, nblk(cnt * 4 * I.n, 128), 128, I.Lt * 2 * c->dc.CW * 4, c->dc, r);
+  KL(c, k_residues, nblk(cnt * 4 * I.n, 128), 128, (I.Lt * 2 * c->dc.CW + 2 * I.Lt) * 4, c->dc, r);
   CKL();
   const u32 opg = cnt >= 4096 ? 4 : (cnt >= 1024 ? 2 : 1);  // ops per group: amortise the table fill
   FusedTensorArgs t{resid, out, I.Lt, (u32)cnt, opg, (u32)to_tprod};

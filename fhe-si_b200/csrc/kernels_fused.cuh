@@ -276,9 +276,13 @@ struct ResidueArgs {
   size_t count;
 };
 __global__ void __launch_bounds__(128) k_residues(DevCtx c, ResidueArgs a) {
-  FHESI_SMEM(sm);  // cwr table of the first Lt primes: [Lt][2][CW]
+  FHESI_SMEM(sm);  // cwr table of the first Lt primes: [Lt][2][CW], then (p, p^-1) per prime
   const u32 tabw = a.Lt * 2 * c.CW;
   for (u32 e = threadIdx.x; e < tabw; e += blockDim.x) sm[e] = __ldg(c.cwr + e);
+  for (u32 e = threadIdx.x; e < a.Lt; e += blockDim.x) {
+    sm[tabw + 2 * e] = c.pc[e].p;
+    sm[tabw + 2 * e + 1] = 0u - c.pc[e].pinv;
+  }
   __syncthreads();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = a.count * 4 * c.n;
@@ -307,9 +311,9 @@ __global__ void __launch_bounds__(128) k_residues(DevCtx c, ResidueArgs a) {
   const bool neg = (src[W - 1] >> 31) != 0;
   const u32 v = q < 2 ? 1u : 0u;
   u32 *dst = a.out + pq * a.Lt * (size_t)c.n + i;
+#pragma unroll 2
   for (u32 l = 0; l < a.Lt; ++l) {
-    const PrimeConst pc = c.pc[l];
-    const u32 p = pc.p, p2 = 2 * p, ipinv = 0u - pc.pinv;
+    const u32 p = sm[tabw + 2 * l], p2 = 2 * p, ipinv = sm[tabw + 2 * l + 1];
     const u32 *cw = sm + (l * 2 + v) * c.CW;
     u32 r = 0;
 #pragma unroll

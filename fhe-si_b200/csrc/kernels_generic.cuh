@@ -335,9 +335,19 @@ struct CrtArgs {
   size_t total;    // npolys * n
 };
 
+// Per-launch constants passed BY VALUE: they sit in the kernel-parameter constant bank, and since
+// every loop below is fully unrolled with compile-time indices they become immediate constant
+// operands -- no loads at all (the first version fetched them with dependent __ldg's and stalled
+// on long_scoreboard for 7 of every 8 issue slots, profiles/r01_summary_v6.md).
+template <int ML>
+struct CrtTables {
+  u32 p[ML], pinv[ML];
+  u32 garner[ML][ML];   // [j][i] = p_i^-1 * R mod p_j for i < j
+  u32 Pfull[ML], Phalf[ML];  // words of prod_{i<L} p_i and of its half
+};
 // dynamic smem: ML * blockDim.x words (only used for the runtime-offset shifts)
 template <int ML>
-__global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
+__global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a, const __grid_constant__ CrtTables<ML> T) {
   FHESI_SMEM(sm);
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = idx < a.total;
@@ -352,12 +362,10 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
 #pragma unroll
   for (int j = 1; j < ML; ++j) {
     if (j < L) {
-      const PrimeConst pc = c.pc[j];
-      const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
-      const u32 *g = c.garner + (size_t)j * c.Lmax;
+      const u32 p = T.p[j], pinv = T.pinv[j], p2 = 2 * p;
       u32 t = v[j];
 #pragma unroll
-      for (int i = 0; i < j; ++i) t = mont_mul(t + p2 - v[i], __ldg(g + i), p, pinv);
+      for (int i = 0; i < j; ++i) t = mont_mul(t + p2 - v[i], T.garner[j][i], p, pinv);
       v[j] = csub(t, p);
     }
   }
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
 #pragma unroll
   for (int i = ML - 1; i >= 0; --i) {
     if (i < L) {
-      const u32 p = c.pc[i].p;
+      const u32 p = T.p[i];
       u64 carry = v[i];
       // before this step acc < prod_{i<j<L} p_j < 2^(30 (ML-1-i)): only ML-i words can change
 #pragma unroll
@@ -383,12 +391,10 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
   }
   // centre: if x > P/2 then x -= P   (DoubleCRT.cpp:375-376, NumbTh.cpp:316-318)
   {
-    const u32 *Ph = c.Phalf + (size_t)L * c.Lmax;
-    const u32 *Pf = c.Pfull + (size_t)L * c.Lmax;
     bool gt = false, decided = false;
 #pragma unroll
     for (int k = ML - 1; k >= 0; --k) {
-      u32 ph = (k < (int)c.Lmax) ? __ldg(Ph + k) : 0u;
+      u32 ph = T.Phalf[k];
       if (!decided && acc[k] != ph) {
         gt = acc[k] > ph;
         decided = true;
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a) {
       u32 borrow = 0;
 #pragma unroll
       for (int k = 0; k < ML; ++k) {
-        u32 pf = (k < (int)c.Lmax) ? __ldg(Pf + k) : 0u;
+        u32 pf = T.Pfull[k];
         u64 t = (u64)acc[k] - pf - borrow;
         acc[k] = (u32)t;
         borrow = (u32)(t >> 63);

@@ -27,6 +27,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __grid_constant__
 
 struct dim3 {
   unsigned x, y, z;
