@@ -345,7 +345,7 @@ struct FusedTensorArgs {
                      // to_tprod == 1: [count][3][Lt][N]   transform-domain tprod
   u32 Lt, count, ops_per_group, to_tprod;
 };
-#define KG 4
+#define KG 6
 #define FUSED_SMEM_WORDS (2 * FTW_WORDS + KG * 2 * FPADN)
 __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTensorArgs a) {
   FHESI_SMEM(sm);
