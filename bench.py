@@ -130,7 +130,8 @@ def run_reference(args, rank, world):
 
 
 def workload_name():
-    return (f"cfg2: TestAddMul logQ={CFG['logQ']} p={CFG['p']} g={CFG['g']} (m=1018, phi(m)=508, D=11), "
+    return (f"{'cfg2' if CFG['logQ'] == 256 else 'cfg5'}: TestAddMul logQ={CFG['logQ']} p={CFG['p']} g={CFG['g']} "
+            f"(m=1018, phi(m)=508, D={(CFG['logQ'] + 23) // 24}), "
             "batched c=a; c*=b; ApplyKeySwitch(c) on fresh encryptions")
 
 
@@ -397,7 +398,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2048, help="ciphertext pairs per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--logq", type=int, default=256, choices=[128, 256, 512],
+                    help="BASELINE config 5 sweep; the headline metric is quoted at 256")
     args = ap.parse_args()
+    CFG["logQ"] = args.logq
+    global METRIC
+    METRIC = f"ciphertext mult+relin/sec at logQ={args.logq}"
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,7 @@ struct fhesi_ctx {
   Arena scratch;
   std::vector<PrimeConst> h_pc;
   std::vector<u32> h_garner, h_Pfull, h_Phalf;  // host copies for the by-value CRT tables
+  std::map<std::pair<int, u32>, std::vector<unsigned char>> crt_tables;
   u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
   u32 fused_chunk = 2048; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
@@ -431,18 +433,27 @@ template <int ML>
 static void launch_crt_t(fhesi_ctx *c, const CrtArgs &a) {
   const int B = 128;
   unsigned g = (unsigned)((a.total + B - 1) / B);
-  CrtTables<ML> T;
-  memset(&T, 0, sizeof T);
-  const u32 L = a.L, LM = c->dc.Lmax;
-  for (u32 j = 0; j < L && j < (u32)ML; ++j) {
-    T.p[j] = c->h_pc[j].p;
-    T.pinv[j] = c->h_pc[j].pinv;
-    for (u32 i = 0; i < j; ++i) T.garner[j][i] = c->h_garner[(size_t)j * LM + i];
+  // the by-value table for (ML, L) is built once per context and cached
+  std::vector<unsigned char> &raw = c->crt_tables[std::make_pair(ML, a.L)];
+  if (raw.empty()) {
+    raw.assign(sizeof(CrtTables<ML>), 0);
+    CrtTables<ML> &T = *reinterpret_cast<CrtTables<ML> *>(raw.data());
+    const u32 L = a.L, LM = c->dc.Lmax;
+    for (u32 j = 0; j < L && j < (u32)ML; ++j) {
+      T.p[j] = c->h_pc[j].p;
+      T.pinv[j] = c->h_pc[j].pinv;
+      for (u32 i = 0; i < j; ++i) {
+        const u64 q = c->h_pc[j].p, gi = h_invmod(c->h_pc[i].p % q, q);
+        T.garner[j][i] = (u32)gi;
+        T.garnerq[j][i] = (u32)((gi << 32) / q);
+      }
+    }
+    for (u32 k = 0; k < LM && k < (u32)ML; ++k) {
+      T.Pfull[k] = c->h_Pfull[(size_t)L * LM + k];
+      T.Phalf[k] = c->h_Phalf[(size_t)L * LM + k];
+    }
   }
-  for (u32 k = 0; k < LM && k < (u32)ML; ++k) {
-    T.Pfull[k] = c->h_Pfull[(size_t)L * LM + k];
-    T.Phalf[k] = c->h_Phalf[(size_t)L * LM + k];
-  }
+  const CrtTables<ML> &T = *reinterpret_cast<const CrtTables<ML> *>(raw.data());
   KL(c, k_crt<ML>, g, B, ML * B * 4, c->dc, a, T);
 }
 static int launch_crt(fhesi_ctx *c, const u32 *res, u32 L, u32 mode, u32 *out, u32 Wout,

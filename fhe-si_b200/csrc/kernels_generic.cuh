@@ -342,7 +342,8 @@ struct CrtArgs {
 template <int ML>
 struct CrtTables {
   u32 p[ML], pinv[ML];
-  u32 garner[ML][ML];   // [j][i] = p_i^-1 * R mod p_j for i < j
+  u32 garner[ML][ML];   // [j][i] = p_i^-1 mod p_j for i < j (plain), and its Shoup quotient
+  u32 garnerq[ML][ML];  // floor(garner * 2^32 / p_j)
   u32 Pfull[ML], Phalf[ML];  // words of prod_{i<L} p_i and of its half
 };
 // dynamic smem: ML * blockDim.x words (only used for the runtime-offset shifts)
@@ -362,10 +363,13 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a, const __grid_c
 #pragma unroll
   for (int j = 1; j < ML; ++j) {
     if (j < L) {
-      const u32 p = T.p[j], pinv = T.pinv[j], p2 = 2 * p;
+      const u32 p = T.p[j], p2 = 2 * p;
       u32 t = v[j];
 #pragma unroll
-      for (int i = 0; i < j; ++i) t = mont_mul(t + p2 - v[i], T.garner[j][i], p, pinv);
+      for (int i = 0; i < j; ++i) {  // Shoup product: any 32-bit input -> [0, 2p)
+        const u32 d = t + p2 - v[i];
+        t = d * T.garner[j][i] - __umulhi(d, T.garnerq[j][i]) * p;
+      }
       v[j] = csub(t, p);
     }
   }
