@@ -62,7 +62,7 @@ struct fhesi_ctx {
   Arena stage;  // device staging for the *_host entry points
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the host pipeline
   std::vector<cudaEvent_t> pipe_events;
-  u32 pipe_chunk = 512;
+  u32 pipe_chunk = 256;
   Arena work;   // tprod / scaled-down intermediates of the generic mult_relin composition
 };
 static void prof_clear(fhesi_ctx *c);
