@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Encrypted least-squares regression with the data points sharded across GPUs
+(BASELINE.json config 4).
+
+The reference has no multi-file / multi-process driver (Test_Regression.cpp takes one file and
+sizes logQ from that file's N), so this is new code.  It follows Regression.h:102-149 and
+Matrix.cpp:80-97,149-262 for the circuit:
+
+  data phase   every rank encrypts its own blocks of 256 data points and accumulates its
+               partial sums of X_i*y and X_i*X_j in tensor form (d + d(d+1)/2 = 14 sums, d = 4)
+  exchange     one all-gather of the partial sums + modular add (pyfhesi.sharded)
+  serial tail  key switch + slot sums by rotations, adjugate inverse with a key switch after
+               every product level, adj * X^T y, masking noise -- replicated on every rank
+
+Parameters come from the GLOBAL N: logQ by Test_Regression.cpp:107-108, xi = max(blocks, d).
+Prints the reference's phase names and one JSON line; checks the decrypted theta*det and det
+against the plaintext computation mod p.
+
+  python apps/regression_sharded.py --dim 4 --points 100000                      # 1 GPU
+  python -m torch.distributed.run --nproc-per-node 8 ... apps/regression_sharded.py --dim 4 --points 100000
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fhe-si_b200"), os.path.join(ROOT, "scripts"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------
+# plaintext slots for p = 1 mod m (PlaintextSpace.cpp:22-134): slot j <-> root rho^(g^j)
+# ---------------------------------------------------------------------------------------
+class Slots:
+    def __init__(self, m, p, g, phi):
+        self.p, n = p, len(phi) - 1
+        fs = [f for f in range(2, m + 1) if m % f == 0 and all(f % q for q in range(2, f))]
+        x = 2
+        while True:
+            rho = pow(x, (p - 1) // m, p)
+            if all(pow(rho, m // f, p) != 1 for f in fs):
+                break
+            x += 1
+        self.roots, e = [], 1
+        for _ in range(n):
+            self.roots.append(pow(rho, e, p))
+            e = e * g % m
+        assert len(set(self.roots)) == n, "g does not generate Z_m^* (SURVEY.md §0.4)"
+        self.total, self.usable = n, 1 << (n.bit_length() - 1)
+        basis = np.zeros((n, n), dtype=np.int64)
+        for j, r in enumerate(self.roots):
+            b, carry = [0] * n, phi[n] % p
+            for i in range(n - 1, -1, -1):
+                b[i] = carry
+                carry = (phi[i] + carry * r) % p
+            d = 0
+            for i in range(n - 1, -1, -1):
+                d = (d * r + b[i]) % p
+            di = pow(d, p - 2, p)
+            basis[j] = [(v * di) % p for v in b]
+        self.basis = basis
+
+    def embed(self, values):
+        """EmbedInSlots(msgs, onlyUsable=True): values -> polynomial coefficients mod p."""
+        v = np.zeros(self.total, dtype=np.int64)
+        v[:len(values)] = np.asarray(values, dtype=np.int64) % self.p
+        return (v @ self.basis) % self.p
+
+    def decode0(self, coeffs):
+        acc = 0
+        for c in reversed(list(coeffs)):
+            acc = (acc * self.roots[0] + int(c)) % self.p
+        return acc
+
+
+# ---------------------------------------------------------------------------------------
+# a device-resident ciphertext (value semantics, like the reference's Ciphertext)
+# ---------------------------------------------------------------------------------------
+class Ct:
+    def __init__(self, env, buf, parts, scaled_up=False):
+        self.env, self.buf, self.parts, self.scaled_up = env, buf, parts, scaled_up
+
+    def copy(self):
+        return Ct(self.env, self.buf.clone(), self.parts, self.scaled_up)
+
+    def mul(self, other):  # Ciphertext::operator*=  -> tensor form
+        e = self.env
+        out = e.empty(e.dev.tprod_words(self.parts + other.parts - 1))
+        e.dev.ct_tensor_dev(self.buf, self.parts, other.buf, other.parts, out, 1)
+        return Ct(e, out, self.parts + other.parts - 1, True)
+
+    def add_(self, other):
+        assert self.scaled_up == other.scaled_up and self.parts == other.parts
+        (self.env.dev.tprod_add_dev if self.scaled_up else self.env.dev.ct_add_dev)(self.buf, other.buf, self.parts, 1)
+        return self
+
+    def neg_(self):
+        (self.env.dev.tprod_mul_scalar_dev if self.scaled_up else self.env.dev.ct_mul_scalar_dev)(self.buf, -1, self.parts, 1)
+        return self
+
+    def keyswitch_(self, ksw):  # KeySwitchSI::ApplyKeySwitch
+        e = self.env
+        if self.scaled_up:
+            c = e.empty(e.dev.ct_words(self.parts))
+            e.dev.scaledown_dev(self.buf, self.parts, c, 1)
+            self.buf, self.scaled_up = c, False
+        out = e.empty(e.dev.ct_words(2))
+        e.dev.keyswitch_dev(ksw, self.buf, out, 1)
+        self.buf, self.parts = out, 2
+        return self
+
+    def rotate_(self, k, ksw):  # tmp >>= k; autoKeySwitch.ApplyKeySwitch(tmp)
+        e, d = self.env, self.env.dev
+        wide = e.empty(self.parts * d.n * (d.W + 1))
+        d.ct_automorph_dev(self.buf, self.parts, k, wide, 1)
+        red = e.empty(d.ct_words(self.parts))
+        d.reduce_wide_dev(wide, d.W + 1, red, self.parts, 1)
+        self.buf = red
+        return self.keyswitch_(ksw)
+
+
+class Env:
+    def __init__(self, dev, device):
+        self.dev, self.device = dev, device
+
+    def empty(self, words):
+        return torch.empty(int(words), dtype=torch.int32, device=self.device)
+
+
+def determinant(M, rows, cols, reduce):
+    """Matrix<T>::Determinant (Matrix.cpp:223-262): Laplace expansion along the first free row,
+    products summed in tensor form, one `reduce` (key switch) per level."""
+    row = rows[0]
+    if len(rows) == 1:
+        return M[row][cols[0]].copy()
+    det, negative = None, False
+    for col in cols:
+        tmp = M[row][col].copy()
+        if negative:
+            tmp.neg_()
+        negative = not negative
+        minor = determinant(M, rows[1:], [c for c in cols if c != col], reduce)
+        tmp = tmp.mul(minor)
+        det = tmp if det is None else det.add_(tmp)
+    reduce(det)
+    return det
+
+
+def plaintext_regression(rows, labels, p):
+    """RegressPT (Regression.h:191-214): theta*det = adj(X^T X) X^T y and det, exact, mod p."""
+    d = len(rows[0])
+    A = [[sum(r[i] * r[j] for r in rows) for j in range(d)] for i in range(d)]
+    b = [sum(r[i] * l for r, l in zip(rows, labels)) for i in range(d)]
+
+    def det(M):
+        if len(M) == 1:
+            return M[0][0]
+        return sum((-1) ** j * M[0][j] * det([r[:j] + r[j + 1:] for r in M[1:]]) for j in range(len(M)))
+    if d == 1:
+        return [b[0] % p], A[0][0] % p
+    adj = [[(-1) ** (i + j) * det([r[:i] + r[i + 1:] for k, r in enumerate(A) if k != j]) for j in range(d)]
+           for i in range(d)]
+    theta = [sum(adj[i][k] * b[k] for k in range(d)) % p for i in range(d)]
+    return theta, det(A) % p
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dim", dest="d", type=int, default=4)
+    ap.add_argument("--points", dest="n", type=int, default=100000)
+    ap.add_argument("--prime", dest="p", type=int, default=1019)
+    ap.add_argument("--gen", dest="g", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--lib", default=None, help="C-ABI library (default: the in-tree CUDA build)")
+    ap.add_argument("--cpu-tensors", action="store_true", help="host tensors + gloo (emulator tests only)")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    device = "cpu" if args.cpu_tensors else f"cuda:{local}"
+    if not args.cpu_tensors:
+        torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("gloo" if args.cpu_tensors else "nccl")
+
+    import fhesi_oracle as O
+    import pyfhesi
+    from generate_random_data import generate
+    from pyfhesi.sharded import shard_bounds
+    if args.lib is None:
+        import build as fhesi_build
+        args.lib = fhesi_build.build()
+    p, g, d, N = args.p, args.g, args.d, args.n
+    m = p - 1
+    t_start = time.perf_counter()
+
+    rows, labels = generate(d, N, args.seed)            # every rank derives the same global data set
+    nslots = (p - 1) // 2 - 1
+    block = 1 << (nslots.bit_length() - 1)              # Test_Regression.cpp:86-91
+    nblocks = (N + block - 1) // block
+    xi = max(nblocks, d)
+    lgq = 4.5 * math.log(nslots) + max(1, d - 1) * (math.log(1280) + 2 * math.log(nslots) + math.log(xi))
+    logq = int(math.ceil(lgq / math.log(2) + 24.7))     # Test_Regression.cpp:107-108
+
+    # ---- Setup: context, keys (host, oracle classes), upload
+    octx = O.Context(m, logq, p, g).setup_si(xi)
+    rng = O.Rng(args.seed)
+    sk = O.SecKey.generate(octx, rng)
+    pk = O.PubKey.generate(sk, rng)
+    ks = O.KeySwitch.init_s2(sk, rng)
+    slots = Slots(m, p, g, octx.ring.PhimX)
+    rot_k, k, ns = [], g % m, slots.usable
+    while ns > 1:                                       # Regression.h:70-81
+        rot_k.append(k)
+        ns >>= 1
+        k = k * k % m
+    rot_ks = [O.KeySwitch.init_automorph(sk, kk, rng) for kk in rot_k]
+    dev = pyfhesi.Context(m, logq, p, 3, xi, 0 if args.cpu_tensors else local, lib_path=args.lib)
+    if not args.cpu_tensors:
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        dev.set_stream(stream.cuda_stream)
+    env = Env(dev, device)
+    pack = lambda polys: np.stack([O.pack_poly_words(a, logq) for a in polys])
+    ksw = dev.ksw_create(pack(ks.b), pack([O.reduce_poly(a, logq) for a in ks.A]), 3)
+    rot_ksw = [dev.ksw_create(pack(r.b), pack([O.reduce_poly(a, logq) for a in r.A]), 2) for r in rot_ks]
+    dpk, dsk = dev.key_create(pack(pk.pk)), dev.key_create(pack(sk.s))
+    t_setup = time.perf_counter()
+
+    # ---- Batch + Encryption of this rank's blocks (BatchData, Regression.h:43-66; AddData :83-95)
+    lo, hi = shard_bounds(nblocks, rank, world)
+    nb = hi - lo
+    n = dev.n
+    msgs = np.zeros((max(nb, 1) * (d + 1), n), dtype=np.uint32)
+    for bi in range(nb):
+        blk = slice((lo + bi) * block, min(N, (lo + bi + 1) * block))
+        for j in range(d):
+            msgs[bi * (d + 1) + j] = slots.embed([r[j] for r in rows[blk]])
+        msgs[bi * (d + 1) + d] = slots.embed(labels[blk])
+    t_batch = time.perf_counter()
+    nrng = np.random.default_rng(args.seed + 1000 + rank)
+    cnt = nb * (d + 1)
+    r_bits = nrng.integers(0, 2, size=(max(cnt, 1), n), dtype=np.uint8)
+    e_gauss = np.rint(nrng.normal(0.0, 3.2, size=(max(cnt, 1), 2, n))).astype(np.int32)
+    cts = env.empty(max(cnt, 1) * dev.ct_words(2)).view(max(cnt, 1), -1)
+    to_dev = lambda a: torch.from_numpy(a).to(device)
+    if cnt:
+        dev.encrypt_dev(dpk, to_dev(msgs.view(np.int32)), to_dev(r_bits), to_dev(e_gauss), cts, cnt)
+    dev.sync()
+    t_enc = time.perf_counter()
+
+    # ---- data phase: partial sums in tensor form (Matrix.cpp:80-97, 149-173), then one exchange
+    cw = dev.ct_words(2)
+    col = lambda j: cts.view(max(nb, 1), d + 1, cw)[:nb, j].contiguous()
+    pairs = [(i, d) for i in range(d)] + [(i, j) for i in range(d) for j in range(i, d)]
+    po_words = dev.tprod_words(3)
+    partial = torch.zeros((len(pairs), po_words), dtype=torch.int32, device=device)
+    for idx, (i, j) in enumerate(pairs):
+        if nb:
+            dev.ct_tensor_dev(col(i), 2, col(j), 2, partial[idx], nb, accumulate=True)
+    dev.sync()
+    if world > 1:
+        gathered = torch.empty((world,) + tuple(partial.shape), dtype=torch.int32, device=device)
+        dist.all_gather([gathered[w] for w in range(world)], partial)
+        total = torch.empty_like(partial)
+        dev.tprod_reduce_gathered_dev(gathered, world, 3 * len(pairs), total)
+        dev.sync()
+    else:
+        total = partial
+    t_data = time.perf_counter()
+
+    # ---- serial tail, replicated (Regression.h:106-148)
+    def reduce(ct):
+        ct.keyswitch_(ksw)
+
+    def process(ct):  # ApplyKeySwitch + SumBatchedData (Regression.h:166-178)
+        ct.keyswitch_(ksw)
+        for kk, rk in zip(rot_k, rot_ksw):
+            tmp = ct.copy().rotate_(kk, rk)
+            ct.add_(tmp)
+        return ct
+    sums = [process(Ct(env, total[i].clone(), 3, True)) for i in range(len(pairs))]
+    xty = sums[:d]
+    xtx = [[None] * d for _ in range(d)]
+    it = iter(sums[d:])
+    for i in range(d):
+        for j in range(i, d):
+            xtx[i][j] = next(it)
+            xtx[j][i] = xtx[i][j]
+    if d == 1:
+        det, theta = xtx[0][0], [xty[0]]
+    else:
+        idx = list(range(d))
+        adj = [[None] * d for _ in range(d)]
+        for i in range(d):                                # Matrix::Invert, Matrix.cpp:181-213
+            for j in range(d):
+                c = determinant(xtx, [r for r in idx if r != i], [c_ for c_ in idx if c_ != j], reduce)
+                adj[j][i] = c.neg_() if (i + j) % 2 == 1 else c
+        det = None
+        for i in range(d):
+            tmp = xtx[0][i].copy().mul(adj[i][0])
+            det = tmp if det is None else det.add_(tmp)
+        reduce(det)
+        theta = []
+        for i in range(d):                                # dataCopy *= last; MapAll(KS)
+            acc = None
+            for kx in range(d):
+                tmp = adj[i][kx].copy().mul(xty[kx])
+                acc = tmp if acc is None else acc.add_(tmp)
+            reduce(acc)
+            theta.append(acc)
+    # masking noise in every slot but the first (Regression.h:180-189)
+    for ct in theta + [det]:
+        vals = [0] + [int(v) for v in nrng.integers(0, p, size=slots.total - 1)]
+        v = np.zeros(slots.total, dtype=np.int64)
+        v[:] = vals
+        noise_msg = ((v @ slots.basis) % p).astype(np.uint32)[None]
+        nz = env.empty(dev.ct_words(2))
+        dev.encrypt_dev(dpk, to_dev(noise_msg.view(np.int32)),
+                        to_dev(nrng.integers(0, 2, size=(1, n), dtype=np.uint8)),
+                        to_dev(np.rint(nrng.normal(0.0, 3.2, size=(1, 2, n))).astype(np.int32)), nz, 1)
+        ct.add_(Ct(env, nz, 2))
+    dev.sync()
+    t_reg = time.perf_counter()
+
+    # ---- Decryption
+    out = []
+    for ct in theta + [det]:
+        mbuf = torch.empty(n, dtype=torch.int32, device=device)
+        dev.decrypt_dev(dsk, ct.buf, 2, mbuf, 1)
+        dev.sync()
+        out.append(slots.decode0(mbuf.cpu().numpy().view(np.uint32)))
+    t_dec = time.perf_counter()
+
+    want_theta, want_det = plaintext_regression(rows, labels, p)
+    ok = out[:-1] == want_theta and out[-1] == want_det
+    if rank == 0:
+        print(f"Setup time: {t_setup - t_start:.3f}\nBatch time: {t_batch - t_setup:.3f}\n"
+              f"Encryption time: {t_enc - t_batch:.3f}\nRegression time: {t_reg - t_enc:.3f} "
+              f"(data phase + exchange {t_data - t_enc:.3f})\nDecryption time: {t_dec - t_reg:.3f}\n"
+              f"Total time: {t_dec - t_start:.3f}")
+        print(json.dumps({
+            "metric": f"Test_Regression N={N} d={d} wall time", "unit": "s", "higher_is_better": False,
+            "value": t_dec - t_start, "n_gpus": world, "correct": ok,
+            "phases_s": {"setup": t_setup - t_start, "batch": t_batch - t_setup, "encryption": t_enc - t_batch,
+                         "data_phase_and_exchange": t_data - t_enc, "serial_tail": t_reg - t_data,
+                         "decryption": t_dec - t_reg},
+            "config": {"p": p, "g": g, "logQ": logq, "xi": xi, "blocks": nblocks, "block_size": block,
+                       "chain": f"{dev.Lt}/{dev.Lk}", "blocks_per_rank": nb},
+            "theta_det": out, "expected": want_theta + [want_det]}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not ok:
+        raise SystemExit(f"rank {rank}: decrypted regression differs from the plaintext computation: {out} "
+                         f"vs {want_theta + [want_det]}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,45 @@
+"""apps/regression_sharded.py end to end (BASELINE config 4 at toy size): encrypted regression
+with blocks sharded over 2 gloo ranks, kernels in the test emulator; the decrypted theta*det and
+det must equal the plaintext computation mod p.  The GPU run uses the same script over NCCL."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_app(extra, nproc, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "apps", "regression_sharded.py")] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)
+
+
+def test_sharded_regression_world2_emu(emu_lib):
+    out = run_app(["--dim", "2", "--points", "20", "--prime", "23", "--gen", "7", "--lib", emu_lib, "--cpu-tensors"],
+                  2, 29600 + os.getpid() % 300)
+    assert out["correct"] and out["n_gpus"] == 2 and out["config"]["blocks"] == 3
+    assert out["theta_det"] == out["expected"]
+
+
+def test_data_generator_is_seeded_and_formatted(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from generate_random_data import generate, main
+    a, b = generate(4, 50, 7), generate(4, 50, 7)
+    assert a == b and len(a[0]) == 50 and all(-100 <= v <= 100 for r in a[0] for v in r)
+    assert main(["x", str(tmp_path / "d"), "4", "50", "8", "--seed", "7"]) == 0
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 8  # README:82-84 split
+    first = open(tmp_path / files[0]).read().splitlines()
+    assert first[0] == "4 7" and len(first) == 8 and len(first[1].split()) == 5
+
+
+@pytest.mark.gpu
+def test_regression_cfg_small_gpu(cuda_lib):
+    out = run_app(["--dim", "3", "--points", "2000"], 1, 29700 + os.getpid() % 200)
+    assert out["correct"], out
