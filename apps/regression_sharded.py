@@ -232,6 +232,11 @@ def main():
     ksw = dev.ksw_create(pack(ks.b), pack([O.reduce_poly(a, logq) for a in ks.A]), 3)
     rot_ksw = [dev.ksw_create(pack(r.b), pack([O.reduce_poly(a, logq) for a in r.A]), 2) for r in rot_ks]
     dpk, dsk = dev.key_create(pack(pk.pk)), dev.key_create(pack(sk.s))
+    if world > 1:  # create the communicator now: NCCL's lazy init is set-up cost, not data-phase time
+        warm = torch.zeros(8, dtype=torch.int32, device=device)
+        dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
+        if not args.cpu_tensors:
+            torch.cuda.synchronize()
     t_setup = time.perf_counter()
 
     # ---- Batch + Encryption of this rank's blocks (BatchData, Regression.h:43-66; AddData :83-95)
