@@ -354,7 +354,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": workload_name(), "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"independent ciphertext shards x{world}, no data-path collective",
                        "l2": f"inputs {2 * B * ct_words * 4 / 2**20:.0f} MiB per step > 126 MB L2",
-                       "chain": f"{dev.Lt} x 30-bit primes (tensor), {dev.Lk} (key switch), N={dev.N}",
+                       "chain": f"{dev.Lt} x 30-bit primes (tensor), {dev.Lk} (key switch"
+                                + (f", {dev.Ls} with split keys" if dev.Ls else "") + f"), N={dev.N}",
                        "seed": SEED},
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -382,11 +383,13 @@ def kernel_work_per_op(dev):
         "k_inv": (3 * Lt + 2 * Lk) * bf,
         "k_tensor_pw": 4 * Lt * N,
         "k_dot": 2 * 3 * D * Lk * N,
-        "k_crt": 3 * n * garner(Lt) + 2 * n * garner(Lk),
+        "k_crt": 3 * n * garner(Lt) + (0 if dev.Ls else 2 * n * garner(Lk)),
         # fused path (kernels_fused.cuh)
         "k_residues": 4 * n * Lt * dev.W,
         "k_fused_tensor": 7 * Lt * bf + 4 * Lt * N,
         "k_fused_keyswitch": (3 * D + 2) * Lk * bf + 2 * 3 * D * Lk * N,
+        "k_fused_keyswitch_split": (3 * D + 4) * dev.Ls * bf + 4 * 3 * D * dev.Ls * N,
+        "k_crt_split": 2 * n * 2 * garner(dev.Ls),
     }
 
 

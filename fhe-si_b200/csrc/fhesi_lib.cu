@@ -95,6 +95,7 @@ struct fhesi_ksw {
   fhesi_ctx *ctx;
   u32 *d_key;      // [Lk][parts*D][2][N] key form, residues in [0,p)
   u32 *d_key_bal;  // same, balanced residues (fused T-free path); NULL if unused
+  u32 *d_key_split;  // [Ls][parts*D][4][N] balanced key form of (b_lo, b_hi, A_lo, A_hi); NULL if unused
   u32 parts;
 };
 struct fhesi_key {
@@ -190,10 +191,24 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   if (Lk > Lt) Lk = Lt;
   if (Le > Lt) Le = Lt;
   const u32 L = Lt;
+  // split-key key switch: halves of 32*ws bits (kernels_fused.cuh).  Needs W >= 2 and the
+  // single-accumulator bound; inner products are non-negative and must stay below P_s / 2.
+  u32 Ls = 0, ws = 0;
+  if (c->tfree && W >= 2 && N == 1024) {
+    ws = (W + 1) / 2;
+    const double need_s = dbits + 32.0 * ws + lg2n + std::log2(3.0 * D) + 1 + 0.1;
+    double b2 = 0;
+    for (u32 i = 0; i < L && !Ls; ++i) {
+      b2 += std::log2((double)primes[i]);
+      if (b2 >= need_s) Ls = i + 1;
+    }
+    if (!Ls || Ls >= Lk) Ls = 0, ws = 0;
+  }
 
   fhesi_info &I = c->info;
   I.m = m; I.n = n; I.logQ = logQ; I.W = W; I.decompSize = decompSize; I.D = D; I.N = N;
   I.Lt = Lt; I.Lk = Lk; I.Le = Le; I.p = p_pt; I.xi = xi; I.device = device;
+  I.Ls = Ls; I.split_words = ws;
   for (u32 i = 0; i < L; ++i) I.primes[i] = primes[i];
 
   // per-prime constants and tables
@@ -307,6 +322,8 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   if (ev && atoi(ev) > 0) c->fused_chunk = (u32)atoi(ev);
   ev = getenv("FHESI_PIPE_CHUNK");
   if (ev && atoi(ev) > 0) c->pipe_chunk = (u32)atoi(ev);
+  ev = getenv("FHESI_NO_SPLIT");
+  if (ev && atoi(ev) > 0) c->info.Ls = 0, c->info.split_words = 0;
   ev = getenv("FHESI_NO_FUSED");
   if (ev && atoi(ev) > 0) c->use_fused = false;
   if (!fused_supported(dc)) c->use_fused = false;
@@ -429,16 +446,14 @@ static int launch_inv(fhesi_ctx *c, const u32 *src, u32 L, u32 *dst, size_t npol
   CKL();
   return 0;
 }
+// the by-value table for (ML, L) is built once per context and cached
 template <int ML>
-static void launch_crt_t(fhesi_ctx *c, const CrtArgs &a) {
-  const int B = 128;
-  unsigned g = (unsigned)((a.total + B - 1) / B);
-  // the by-value table for (ML, L) is built once per context and cached
-  std::vector<unsigned char> &raw = c->crt_tables[std::make_pair(ML, a.L)];
+static const CrtTables<ML> &crt_tables(fhesi_ctx *c, u32 L) {
+  std::vector<unsigned char> &raw = c->crt_tables[std::make_pair(ML, L)];
   if (raw.empty()) {
     raw.assign(sizeof(CrtTables<ML>), 0);
     CrtTables<ML> &T = *reinterpret_cast<CrtTables<ML> *>(raw.data());
-    const u32 L = a.L, LM = c->dc.Lmax;
+    const u32 LM = c->dc.Lmax;
     for (u32 j = 0; j < L && j < (u32)ML; ++j) {
       T.p[j] = c->h_pc[j].p;
       T.pinv[j] = c->h_pc[j].pinv;
@@ -453,8 +468,31 @@ static void launch_crt_t(fhesi_ctx *c, const CrtArgs &a) {
       T.Phalf[k] = c->h_Phalf[(size_t)L * LM + k];
     }
   }
-  const CrtTables<ML> &T = *reinterpret_cast<const CrtTables<ML> *>(raw.data());
+  return *reinterpret_cast<const CrtTables<ML> *>(raw.data());
+}
+template <int ML>
+static void launch_crt_t(fhesi_ctx *c, const CrtArgs &a) {
+  const int B = 128;
+  unsigned g = (unsigned)((a.total + B - 1) / B);
+  const CrtTables<ML> &T = crt_tables<ML>(c, a.L);
   KL(c, k_crt<ML>, g, B, ML * B * 4, c->dc, a, T);
+}
+template <int ML>
+static void launch_crt_split_t(fhesi_ctx *c, const CrtSplitArgs &a) {
+  const int B = 128;
+  unsigned g = (unsigned)((a.total + B - 1) / B);
+  const CrtTables<ML> &T = crt_tables<ML>(c, a.L);
+  KL(c, k_crt_split<ML>, g, B, 2 * ML * B * 4, c->dc, a, T);
+}
+static int launch_crt_split(fhesi_ctx *c, const u32 *res, u32 L, u32 *out, size_t npolys) {
+  if (!npolys) return 0;
+  CrtSplitArgs a{res, L, c->info.split_words, out, npolys * c->dc.n};
+  if (L <= 8) launch_crt_split_t<8>(c, a);
+  else if (L <= 12) launch_crt_split_t<12>(c, a);
+  else if (L <= 20) launch_crt_split_t<20>(c, a);
+  else return fail(FHESI_ERR_UNSUPPORTED, "split CRT: too many primes");
+  CKL();
+  return 0;
 }
 static int launch_crt(fhesi_ctx *c, const u32 *res, u32 L, u32 mode, u32 *out, u32 Wout,
                       size_t npolys) {
@@ -526,7 +564,41 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
     CKL();
     CK(cudaStreamSynchronize(c->stream));
   }
-  fhesi_ksw *k = new fhesi_ksw{c, d_key, d_bal, parts};
+  u32 *d_split = nullptr;
+  if (c->use_fused && c->tfree && I.Ls) {
+    // K mod q (non-negative) = lo + 2^(32 ws) hi, each half as a non-negative W-word polynomial
+    const u32 ws = I.split_words, W = I.W, Ls = I.Ls, tb = I.logQ & 31;
+    std::vector<u32> hs((size_t)K * 4 * polyw, 0);
+    for (u32 k = 0; k < K; ++k)
+      for (u32 r = 0; r < 2; ++r) {
+        const u32 *src = (r ? h_A : h_b) + (size_t)k * polyw;
+        u32 *lo = &hs[((size_t)k * 4 + 2 * r) * polyw], *hi = lo + polyw;
+        for (u32 i = 0; i < I.n; ++i)
+          for (u32 w = 0; w < W; ++w) {
+            u32 v = src[(size_t)i * W + w];
+            if (w == W - 1 && tb) v &= (1u << tb) - 1;  // two's complement -> residue in [0, q)
+            if (w < ws) lo[(size_t)i * W + w] = v;
+            else hi[(size_t)i * W + (w - ws)] = v;
+          }
+      }
+    u32 *d_in2 = nullptr, *d_tmp2 = nullptr, *d_t2 = nullptr;
+    const size_t total = (size_t)K * 4 * Ls * I.N;
+    CK(cudaMalloc(&d_in2, hs.size() * 4));
+    CK(cudaMalloc(&d_tmp2, total * 4));
+    CK(cudaMalloc(&d_t2, total * 4));
+    CK(cudaMalloc(&d_split, total * 4));
+    CK(cudaMemcpyAsync(d_in2, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_fwd(c, d_in2, SRC_POLY, W, SC_KEYFORM, Ls, d_tmp2, (size_t)K * 4))) return rc;
+    KL(c, k_transpose_key, nblk(total), 256, 0, d_tmp2, d_t2, K * 4, Ls, I.N);
+    CKL();
+    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_t2, d_split, K * 4, total);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d_in2));
+    CK(cudaFree(d_tmp2));
+    CK(cudaFree(d_t2));
+  }
+  fhesi_ksw *k = new fhesi_ksw{c, d_key, d_bal, d_split, parts};
   *out = k;
   return 0;
 }
@@ -536,6 +608,7 @@ void fhesi_ksw_destroy(fhesi_ksw *k) {
   cudaStreamSynchronize(k->ctx->stream);
   cudaFree(k->d_key);
   if (k->d_key_bal) cudaFree(k->d_key_bal);
+  if (k->d_key_split) cudaFree(k->d_key_split);
   delete k;
 }
 int fhesi_key_create(fhesi_ctx *c, const uint32_t *h_polys, uint32_t parts, fhesi_key **out) {
@@ -794,6 +867,13 @@ static int keyswitch_generic(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, 
 static int fused_ks_from_digits(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *digits, u32 *res, u32 *out,
                                 size_t cnt) {
   const fhesi_info &I = c->info;
+  if (I.Ls && ksw->d_key_split) {  // split-key path: res holds [cnt][4][Ls][n]
+    FusedKsArgs k{digits, ksw->d_key_split, res, ksw->parts * I.D, I.Ls, (u32)cnt};
+    dim3 grid(I.Ls, (unsigned)((cnt + KSS - 1) / KSS));
+    KL(c, k_fused_keyswitch_split, grid, KSS * 128, KSS_SMEM_WORDS * 4, c->dc, k);
+    CKL();
+    return launch_crt_split(c, res, I.Ls, out, cnt * 2);
+  }
   const bool tfree = c->tfree && ksw->d_key_bal;
   FusedKsArgs k{digits, tfree ? ksw->d_key_bal : ksw->d_key, res, ksw->parts * I.D, I.Lk, (u32)cnt};
   dim3 grid(I.Lk, (unsigned)((cnt + KSG - 1) / KSG));
@@ -806,7 +886,8 @@ static int fused_keyswitch(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, u3
   const fhesi_info &I = c->info;
   const u32 K = ksw->parts * I.D;
   const size_t CH = c->fused_chunk;
-  size_t nd = al(CH * K * I.n), nr = al(CH * 2 * I.Lk * I.n);
+  const size_t rw = (size_t)(2 * I.Lk > 4 * I.Ls ? 2 * I.Lk : 4 * I.Ls);
+  size_t nd = al(CH * K * I.n), nr = al(CH * rw * I.n);
   u32 *s = nullptr;
   int rc = scratch(c, (nd + nr) * 4, &s);
   if (rc) return rc;
@@ -827,8 +908,9 @@ static int fused_mult_relin(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *a, co
   size_t CH = c->fused_chunk;
   const size_t ctw = (size_t)I.n * I.W;
   if (count < CH) CH = count ? count : 1;
+  const size_t rw = (size_t)(2 * I.Lk > 4 * I.Ls ? 2 * I.Lk : 4 * I.Ls);
   size_t n0 = al(CH * 4 * I.Lt * I.n), n1 = al(CH * 3 * I.Lt * I.n), nd = al(CH * K * I.n),
-         n2 = al(CH * 2 * I.Lk * I.n);
+         n2 = al(CH * rw * I.n);
   u32 *s = nullptr;
   int rc = scratch(c, (n0 + n1 + nd + n2) * 4, &s);
   if (rc) return rc;

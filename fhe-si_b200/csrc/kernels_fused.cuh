@@ -496,6 +496,78 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
   inv1024(t1, twi, A, bufA, bufB, bufA, g, tg, p);
   phim_store_1024(bufA, a.res + ((op * 2 + 1) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
 }
+// ---------------------------------------------------------------------------------------
+// split-key key switch.  Every key polynomial K (mod q) is stored as two non-negative halves,
+// K = K_lo + 2^(32 ws) K_hi, so each inner product sum_k digit_k * K_half,k is bounded by
+// ~2^(24 + 32 ws) * 3D * 2n instead of 2^(24 + logQ): it needs Ls ~ 0.6 Lk primes.  The 3D digit
+// transforms -- the dominant cost -- are shared by the four accumulators (b_lo, b_hi, A_lo, A_hi),
+// so forward transforms drop from 3D*Lk to 3D*Ls (330 -> 198 at logQ = 256) for 20 % more
+// multiply-accumulates.  Requires the single-accumulator (TFREE) bound.
+// key: [Ls][K][4][N] balanced;  res: [count][4][Ls][n] in the order b_lo, b_hi, A_lo, A_hi.
+// ---------------------------------------------------------------------------------------
+#define KSS 4
+#define KSS_SMEM_WORDS (2 * FTW_WORDS + KSS * 2 * FPADN)
+__global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c, FusedKsArgs a) {
+  FHESI_SMEM(sm);
+  uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
+  const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
+  const u32 l = blockIdx.x;
+  fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
+  fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
+  __syncthreads();
+  const size_t op = (size_t)blockIdx.y * KSS + g;
+  if (op >= a.count) return;
+  const PrimeConst pc = c.pc[l];
+  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p, half = p >> 1;
+  u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
+  const XAddr A = make_xaddr(tg);
+  u64 acc[4][8];
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[h][j] = 0;
+  const u32 *dig = a.digits + op * a.K * (size_t)c.n;
+  const u32 *key = a.key + (size_t)l * a.K * 4 * FN + tg * 8;
+  u32 xn[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + j * 128 + tg) : 0u;
+  for (u32 k = 0; k < a.K; ++k) {
+    u32 x[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = xn[j];
+    if (k + 1 < a.K) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + (size_t)(k + 1) * c.n + j * 128 + tg) : 0u;
+    }
+    fwd1024(x, twf, A, bufA, bufB, g, tg, p);
+    int xb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xb[j] = (int)x[j] - (x[j] > half ? (int)p : 0);
+    const uint4 *kp = (const uint4 *)(key + (size_t)k * 4 * FN);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const uint4 k0 = __ldg(kp + h * (FN / 4)), k1 = __ldg(kp + h * (FN / 4) + 1);
+      const u32 kv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[h][j] += (u64)((i64)xb[j] * (int)kv[j]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    u32 t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const i64 s0 = (i64)acc[h][j];
+      const u32 r0 = csub(mont_red64((u64)(s0 < 0 ? -s0 : s0), p, pinv), p2);
+      t[j] = s0 < 0 ? csub(p2 - r0, p2) : r0;
+    }
+    inv1024(t, twi, A, bufA, bufB, bufA, g, tg, p);
+    phim_store_1024(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+    fhesi_group_sync(g);  // bufA (nat) is rewritten by the next inverse transform
+  }
+}
+
 // key form [0,p) -> balanced (-p/2, p/2], same layout [L][P][N]
 __global__ void k_balance_key(DevCtx c, const u32 *in, u32 *out, u32 P, size_t total) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -525,5 +597,8 @@ static int fused_configure() {
   if (e != cudaSuccess) return -1;
   e = cudaFuncSetAttribute(k_fused_keyswitch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(KS_SMEM_WORDS * 4));
+  if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(k_fused_keyswitch_split, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(KSS_SMEM_WORDS * 4));
   return e == cudaSuccess ? 0 : -1;
 }

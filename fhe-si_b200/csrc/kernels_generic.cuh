@@ -324,6 +324,10 @@ __global__ void k_tprod_reduce_world(DevCtx c, const u32 *in, u32 world, u32 L, 
 // ---------------------------------------------------------------------------------------
 // CRT: Garner mixed radix -> multiword -> centre -> mode-specific rounding
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 sext_top(u32 w, u32 logQ) {
+  const u32 tb = (logQ - 1) & 31;
+  return tb == 31 ? w : (u32)((int)(w << (31 - tb)) >> (31 - tb));
+}
 enum { CRT_REDUCE_Q = 0, CRT_SCALEDOWN = 1, CRT_DECRYPT = 2, CRT_WIDE = 3, CRT_SCALEDOWN_DIGITS = 4 };
 
 struct CrtArgs {
@@ -512,13 +516,103 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a, const __grid_c
   }
 }
 
+// CRT for the split-key key switch: two non-negative values lo, hi < P/2 (Ls primes each) ->
+// Reduce(lo + 2^(32 ws) hi).  res: [npolys][2][L][n];  out: [npolys][n][W].
+struct CrtSplitArgs {
+  const u32 *res;
+  u32 L, ws;
+  u32 *out;
+  size_t total;  // npolys * n
+};
+template <int ML>
+__global__ void __launch_bounds__(128) k_crt_split(DevCtx c, CrtSplitArgs a, const __grid_constant__ CrtTables<ML> T) {
+  FHESI_SMEM(sm);  // 2 * ML * blockDim.x words
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < a.total;
+  const size_t poly = active ? idx / c.n : 0;
+  const u32 coef = active ? (u32)(idx % c.n) : 0;
+  const int L = (int)a.L;
+  const u32 stride = blockDim.x;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    u32 v[ML];
+#pragma unroll
+    for (int j = 0; j < ML; ++j)
+      v[j] = (active && j < L) ? a.res[(((size_t)poly * 2 + hf) * L + j) * c.n + coef] : 0u;
+#pragma unroll
+    for (int j = 1; j < ML; ++j) {
+      if (j < L) {
+        const u32 p = T.p[j], p2 = 2 * p;
+        u32 t = v[j];
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+          const u32 d = t + p2 - v[i];
+          t = d * T.garner[j][i] - __umulhi(d, T.garnerq[j][i]) * p;
+        }
+        v[j] = csub(t, p);
+      }
+    }
+    u32 acc[ML];
+#pragma unroll
+    for (int k = 0; k < ML; ++k) acc[k] = 0;
+#pragma unroll
+    for (int i = ML - 1; i >= 0; --i) {
+      if (i < L) {
+        const u32 p = T.p[i];
+        u64 carry = v[i];
+#pragma unroll
+        for (int k = 0; k < ML; ++k) {
+          if (k <= ML - 1 - i) {
+            u64 t = (u64)acc[k] * p + carry;
+            acc[k] = (u32)t;
+            carry = t >> 32;
+          }
+        }
+      }
+    }
+    // the Phi_m fold makes the sums signed: centre at P/2 like every other toPoly
+    {
+      bool gt = false, decided = false;
+#pragma unroll
+      for (int k = ML - 1; k >= 0; --k) {
+        const u32 ph = T.Phalf[k];
+        if (!decided && acc[k] != ph) {
+          gt = acc[k] > ph;
+          decided = true;
+        }
+      }
+      if (gt) {
+        u32 borrow = 0;
+#pragma unroll
+        for (int k = 0; k < ML; ++k) {
+          u64 t = (u64)acc[k] - T.Pfull[k] - borrow;
+          acc[k] = (u32)t;
+          borrow = (u32)(t >> 63);
+        }
+      }
+    }
+    u32 *col = sm + (size_t)hf * ML * stride + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < ML; ++k) col[k * stride] = acc[k];
+  }
+  if (!active) return;
+  const u32 *lo = sm + threadIdx.x, *hi = sm + (size_t)ML * stride + threadIdx.x;
+  const u32 slo = (lo[(ML - 1) * stride] >> 31) ? 0xFFFFFFFFu : 0u;
+  const u32 shi = (hi[(ML - 1) * stride] >> 31) ? 0xFFFFFFFFu : 0u;
+  u32 *o = a.out + idx * c.W;
+  u32 carry = 0;
+  for (u32 k = 0; k < c.W; ++k) {
+    const u32 a0 = k < (u32)ML ? lo[k * stride] : slo;
+    const u32 a1 = k >= a.ws ? ((k - a.ws < (u32)ML) ? hi[(k - a.ws) * stride] : shi) : 0u;
+    const u64 t = (u64)a0 + a1 + carry;
+    carry = (u32)(t >> 32);
+    o[k] = (k == c.W - 1) ? sext_top((u32)t, c.logQ) : (u32)t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // coefficient-domain multiword kernels (one thread per coefficient)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 sext_top(u32 w, u32 logQ) {
-  const u32 tb = (logQ - 1) & 31;
-  return tb == 31 ? w : (u32)((int)(w << (31 - tb)) >> (31 - tb));
-}
 // io = Reduce(io + other)   (Ciphertext.cpp:128-131)
 __global__ void k_ct_add(DevCtx c, u32 *io, const u32 *other, size_t ncoef) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -24,7 +24,8 @@ class Info(C.Structure):
     _fields_ = [("m", C.c_uint32), ("n", C.c_uint32), ("logQ", C.c_uint32), ("W", C.c_uint32),
                 ("decompSize", C.c_uint32), ("D", C.c_uint32), ("N", C.c_uint32), ("Lt", C.c_uint32),
                 ("Lk", C.c_uint32), ("Le", C.c_uint32), ("p", C.c_uint64), ("xi", C.c_uint64),
-                ("primes", C.c_uint32 * FHESI_MAX_PRIMES), ("device", C.c_int)]
+                ("primes", C.c_uint32 * FHESI_MAX_PRIMES), ("device", C.c_int), ("Ls", C.c_uint32),
+                ("split_words", C.c_uint32)]
 
 
 # every symbol include/fhesi.h declares: name -> (restype, argtypes)
@@ -152,7 +153,7 @@ class Context:
         self._ck(self.lib.fhesi_ctx_info(self.h, C.byref(self.info)))
         i = self.info
         self.n, self.N, self.W, self.D = i.n, i.N, i.W, i.D
-        self.Lt, self.Lk, self.Le = i.Lt, i.Lk, i.Le
+        self.Lt, self.Lk, self.Le, self.Ls = i.Lt, i.Lk, i.Le, i.Ls
         self.primes = [i.primes[k] for k in range(i.Lt)]
 
     def _ck(self, rc: int):

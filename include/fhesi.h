@@ -57,6 +57,8 @@ typedef struct fhesi_info {
   uint64_t p, xi;
   uint32_t primes[FHESI_MAX_PRIMES];     /* the library's own chain (30-bit, = 1 mod N)  */
   int device;
+  uint32_t Ls, split_words;              /* split-key key switch: primes used, words in the low half
+                                            (0 = not used); see DESIGN.md "split keys"          */
 } fhesi_info;
 
 const char *fhesi_last_error(void);
