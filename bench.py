@@ -326,7 +326,9 @@ def run_ours(args, rank, local_rank, world):
             "bound": "int32-modmul (integer pipe; SURVEY.md §8d -- HBM does not bind)",
             "kernel": tname, "kernel_share_of_step": share,
             "achieved": achieved / 1e9, "peak": peak32 / 1e9, "unit": "Gmodmul/s (32-bit Montgomery)",
-            "frac": achieved / peak32, "traffic": None,
+            "frac": achieved / peak32,
+            "traffic": (NCU_DRAM_BYTES_PER_OP.get((tname or "").split("<")[0]) or 0) * ops_timed / max(tcnt, 1) or None,
+            "traffic_unit": "bytes per launch (ncu dram read+write, per-op figure x ops in one launch)",
             "peak_source": "measured in this run: max(fhesi_modmul_peak(32) Montgomery, fhesi_pipe_peak(3) Shoup), "
                            "register-resident ILP-8 chains on all SMs",
             "peak_montgomery32_Gmodmul_s": peak_mont32 / 1e9,
@@ -369,6 +371,13 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# DRAM traffic per op of each hot kernel, from `ncu --set full` captures (dram__bytes_read.sum +
+# dram__bytes_write.sum over a 2046-op launch, profiles/r01_summary_v9.md); the driver-timed run
+# itself is never profiled.
+NCU_DRAM_BYTES_PER_OP = {"k_fused_keyswitch": 96.9e3, "k_fused_keyswitch_split": 96.9e3, "k_fused_tensor": 237.8e3,
+                         "k_residues": 183.7e3}
 
 
 def kernel_work_per_op(dev):
