@@ -27,7 +27,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fhe-si_b200"), os.path.join(ROOT, "scripts"), ROOT):
+for p in (os.path.join(ROOT, "fhe-si_b200"), os.path.join(ROOT, "scripts"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -190,9 +190,9 @@ def main():
     if world > 1:
         dist.init_process_group("gloo" if args.cpu_tensors else "nccl")
 
-    import fhesi_oracle as O
     import pyfhesi
     from generate_random_data import generate
+    from pyfhesi.hostkeys import keygen
     from pyfhesi.sharded import shard_bounds
     if args.lib is None:
         import build as fhesi_build
@@ -209,29 +209,25 @@ def main():
     lgq = 4.5 * math.log(nslots) + max(1, d - 1) * (math.log(1280) + 2 * math.log(nslots) + math.log(xi))
     logq = int(math.ceil(lgq / math.log(2) + 24.7))     # Test_Regression.cpp:107-108
 
-    # ---- Setup: context, keys (host, oracle classes), upload
-    octx = O.Context(m, logq, p, g).setup_si(xi)
-    rng = O.Rng(args.seed)
-    sk = O.SecKey.generate(octx, rng)
-    pk = O.PubKey.generate(sk, rng)
-    ks = O.KeySwitch.init_s2(sk, rng)
-    slots = Slots(m, p, g, octx.ring.PhimX)
+    # ---- Setup: context, keys (C++ host layer: FHESISecKey/FHESIPubKey/KeySwitchSI), upload
+    assert m % 2 == 0, "m = p - 1 must be 2 * (odd prime)"
+    phi = [(-1) ** i for i in range(m // 2)]           # Phi_m(X) = sum (-1)^i X^i for m = 2p'
+    slots = Slots(m, p, g, phi)
     rot_k, k, ns = [], g % m, slots.usable
     while ns > 1:                                       # Regression.h:70-81
         rot_k.append(k)
         ns >>= 1
         k = k * k % m
-    rot_ks = [O.KeySwitch.init_automorph(sk, kk, rng) for kk in rot_k]
     dev = pyfhesi.Context(m, logq, p, 3, xi, 0 if args.cpu_tensors else local, lib_path=args.lib)
     if not args.cpu_tensors:
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         dev.set_stream(stream.cuda_stream)
     env = Env(dev, device)
-    pack = lambda polys: np.stack([O.pack_poly_words(a, logq) for a in polys])
-    ksw = dev.ksw_create(pack(ks.b), pack([O.reduce_poly(a, logq) for a in ks.A]), 3)
-    rot_ksw = [dev.ksw_create(pack(r.b), pack([O.reduce_poly(a, logq) for a in r.A]), 2) for r in rot_ks]
-    dpk, dsk = dev.key_create(pack(pk.pk)), dev.key_create(pack(sk.s))
+    keys = keygen(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
+    ksw = dev.ksw_create(keys["ks_b"], keys["ks_A"], 3)
+    rot_ksw = [dev.ksw_create(keys["rot_b"][i], keys["rot_A"][i], 2) for i in range(len(rot_k))]
+    dpk, dsk = dev.key_create(keys["pk"]), dev.key_create(keys["sk"])
     if world > 1:  # create the communicator now: NCCL's lazy init is set-up cost, not data-phase time
         warm = torch.zeros(8, dtype=torch.int32, device=device)
         dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)

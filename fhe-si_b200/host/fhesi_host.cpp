@@ -1031,3 +1031,49 @@ void Import(ifstream &in, Ciphertext &ctxt) {
   Import(in, ctxt.parts);
   ctxt.UploadHost();
 }
+
+// ------------------------------------------------------------------------------- C entry: key generation
+// Host-side key generation for callers that drive the C ABI directly (bench.py,
+// apps/regression_sharded.py through ctypes): the same FHESISecKey / FHESIPubKey / KeySwitchSI code
+// paths as the C++ clients, results as `poly`-format words ready for fhesi_key_create /
+// fhesi_ksw_create.  Pure host work; no device is touched.
+extern "C" int fhesih_keygen(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, uint32_t decompSize, uint64_t xi,
+                             uint64_t seed, uint32_t n_rot, const uint32_t *rot_k, uint32_t *sk_words,
+                             uint32_t *pk_words, uint32_t *ks_b, uint32_t *ks_A, uint32_t *rot_b, uint32_t *rot_A) {
+  FHEcontext *saved = activeContext;
+  {
+    FHEcontext context(m, logQ, to_ZZ((unsigned long)p), g, decompSize);
+    activeContext = &context;
+    context.SetUpSIContext((long)xi);
+    SetSeed(ZZ((unsigned long)seed));
+    const unsigned n = context.zMstar.phiM(), W = context.Words(), D = context.ndigits;
+    const size_t pw = (size_t)n * W;
+    auto put = [&](uint32_t *dst, const DoubleCRT &d) {
+      ZZX poly;
+      d.toPoly(poly);
+      ReduceCoefficients(poly, logQ);
+      std::vector<uint32_t> w = PackPoly(poly, n, W);
+      memcpy(dst, w.data(), pw * 4);
+    };
+    FHESISecKey sk(context);
+    FHESIPubKey pk(sk);
+    KeySwitchSI ks(sk);
+    for (int i = 0; i < 2; ++i) {
+      put(sk_words + i * pw, sk.GetRepresentation()[i]);
+      put(pk_words + i * pw, pk.GetRepresentation()[i]);
+    }
+    for (unsigned k = 0; k < 3 * D; ++k) {
+      put(ks_b + k * pw, ks.GetRepresentation()[0][k]);
+      put(ks_A + k * pw, ks.GetRepresentation()[1][k]);
+    }
+    for (uint32_t r = 0; r < n_rot; ++r) {
+      KeySwitchSI rk(sk, rot_k[r]);
+      for (unsigned k = 0; k < 2 * D; ++k) {
+        put(rot_b + ((size_t)r * 2 * D + k) * pw, rk.GetRepresentation()[0][k]);
+        put(rot_A + ((size_t)r * 2 * D + k) * pw, rk.GetRepresentation()[1][k]);
+      }
+    }
+  }
+  activeContext = saved;
+  return 0;
+}

@@ -1,0 +1,43 @@
+"""Key generation for Python callers of the C ABI, through the C++ host layer
+(fhe-si_b200/host: FHESISecKey / FHESIPubKey / KeySwitchSI -- FHE-SI.cpp:42-62,86-91,153-239).
+Returns `poly`-format uint32 arrays ready for Context.key_create / Context.ksw_create."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+
+
+def _host_lib(backend_path: str) -> C.CDLL:
+    sys.path.insert(0, os.path.join(_PKG, "host"))
+    from build_host import build_host
+    C.CDLL(backend_path, mode=C.RTLD_GLOBAL)  # the host library resolves fhesi_* from the backend
+    return C.CDLL(build_host(backend_path))
+
+
+def keygen(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
+    """-> dict(sk [2][n][W], pk [2][n][W], ks_b / ks_A [3D][n][W], rot_b / rot_A [len(rot_k)][2D][n][W])."""
+    from . import DEFAULT_LIB
+    lib = _host_lib(lib_path or DEFAULT_LIB)
+    i = ctx.info
+    n, W, D = ctx.n, ctx.W, ctx.D
+    rot = np.asarray(list(rot_k), dtype=np.uint32)
+    out = {"sk": np.zeros((2, n, W), np.uint32), "pk": np.zeros((2, n, W), np.uint32),
+           "ks_b": np.zeros((3 * D, n, W), np.uint32), "ks_A": np.zeros((3 * D, n, W), np.uint32),
+           "rot_b": np.zeros((max(len(rot), 1), 2 * D, n, W), np.uint32),
+           "rot_A": np.zeros((max(len(rot), 1), 2 * D, n, W), np.uint32)}
+    fn = lib.fhesih_keygen
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32] + \
+        [C.c_void_p] * 7
+    rc = fn(i.m, i.logQ, i.p, g, i.decompSize, i.xi, seed, len(rot), rot.ctypes.data if len(rot) else None,
+            out["sk"].ctypes.data, out["pk"].ctypes.data, out["ks_b"].ctypes.data, out["ks_A"].ctypes.data,
+            out["rot_b"].ctypes.data, out["rot_A"].ctypes.data)
+    if rc:
+        raise RuntimeError(f"fhesih_keygen failed ({rc})")
+    return out
