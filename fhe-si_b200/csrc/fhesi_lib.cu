@@ -748,17 +748,23 @@ int fhesi_ct_tensor_dev(fhesi_ctx *c, const uint32_t *a, uint32_t pa, const uint
   const size_t per = (size_t)I.Lt * I.N;
   const u32 po = pa + pb - 1;
   const size_t CH = c->chunk;
-  if (c->use_fused && pa == 2 && pb == 2 && !accumulate) {
+  if (c->use_fused && pa == 2 && pb == 2) {
     const size_t ctw = (size_t)I.n * I.W;
-    size_t FC = c->fused_chunk;
+    size_t FC = accumulate ? 512 : c->fused_chunk;
     if (count < FC) FC = count ? count : 1;
     u32 *sres = nullptr;
-    int rc2 = scratch(c, al(FC * 4 * I.Lt * I.n) * 4, &sres);
+    const size_t nres = al(FC * 4 * I.Lt * I.n), ntp = accumulate ? al(FC * 3 * per) : 0;
+    int rc2 = scratch(c, (nres + ntp) * 4, &sres);
     if (rc2) return rc2;
+    if (accumulate) CK(cudaMemsetAsync(tprod, 0, 3 * per * 4, c->stream));
     for (size_t off = 0; off < count; off += FC) {
       size_t cnt = count - off < FC ? count - off : FC;
-      if ((rc2 = launch_fused_tensor(c, a + off * 2 * ctw, b + off * 2 * ctw, sres, tprod + off * 3 * per, cnt, 1)))
-        return rc2;
+      u32 *dst = accumulate ? sres + nres : tprod + off * 3 * per;
+      if ((rc2 = launch_fused_tensor(c, a + off * 2 * ctw, b + off * 2 * ctw, sres, dst, cnt, 1))) return rc2;
+      if (accumulate) {  // fold the chunk's tprods into the single running sum
+        KL(c, k_tprod_batch_sum, nblk(3 * per), 256, 0, c->dc, dst, (u32)cnt, I.Lt, 3 * per, tprod);
+        CKL();
+      }
     }
     return 0;
   }

@@ -309,6 +309,16 @@ __global__ void k_tprod_mul_scalar(DevCtx c, u32 *io, const u32 *scal, u32 L, si
   const PrimeConst pc = c.pc[l];
   io[idx] = csub(mont_mul(io[idx], scal[l], pc.p, pc.pinv), pc.p);
 }
+// io[e] += sum_b in[b][e] over a batch of tprods (the data-phase sums of Matrix.cpp:80-97,149-173)
+__global__ void k_tprod_batch_sum(DevCtx c, const u32 *in, u32 count, u32 L, size_t per, u32 *io) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per) return;
+  u32 l = (u32)((idx / c.N) % L);
+  u32 p = c.pc[l].p;
+  u32 s = io[idx];
+  for (u32 b = 0; b < count; ++b) s = csub(s + in[(size_t)b * per + idx], p);
+  io[idx] = s;
+}
 // out[part][l][e] = sum_w in[w][part][l][e]  (multi-GPU combine after all-gather)
 __global__ void k_tprod_reduce_world(DevCtx c, const u32 *in, u32 world, u32 L, size_t per,
                                      u32 *out) {

@@ -74,31 +74,67 @@ static void RemPhim(ZZX &a, const PAlgebra &zms) {
     rem(a, a, zms.PhimX());
   }
 }
-// a * b mod Phi_m; shift-and-add when one operand is sparse/tiny (secret keys are ternary)
+// a * b mod Phi_m.  Secret keys are ternary and sparse (Hamming weight 64), so the products key
+// generation needs are shift-and-add; they run on fixed-width two's-complement word arrays
+// (no allocation per coefficient), which keeps KeySwitchSI::Init at set-up-time cost.
 static ZZX MulModPhim(const ZZX &a, const ZZX &b, const PAlgebra &zms) {
-  auto small = [](const ZZX &x) {
+  auto tiny = [](const ZZX &x) {
     for (auto &c : x.rep.v)
-      if (c.mag.size() > 1) return false;
+      if (c.mag.size() > 1 || (c.mag.size() == 1 && c.mag[0] > 1)) return false;
     return true;
   };
   const ZZX *big = &a, *sm = &b;
-  if (!small(b) && small(a)) big = &b, sm = &a;
+  if (!tiny(b) && tiny(a)) big = &b, sm = &a;
   ZZX r;
-  if (small(*sm)) {
-    r.rep.v.assign(big->rep.v.size() + sm->rep.v.size(), ZZ());
+  if (tiny(*sm) && !big->rep.v.empty() && !sm->rep.v.empty()) {
+    size_t maxw = 1;
+    for (auto &c : big->rep.v) maxw = std::max(maxw, c.mag.size());
+    const size_t Wd = maxw + 2, nb = big->rep.v.size(), len = nb + sm->rep.v.size();
+    std::vector<uint32_t> src(nb * Wd), acc(len * Wd, 0);
+    for (size_t i = 0; i < nb; ++i) {  // two's complement, sign-extended to Wd words
+      const ZZ &c = big->rep.v[i];
+      uint32_t *w = &src[i * Wd];
+      for (size_t k = 0; k < Wd; ++k) w[k] = k < c.mag.size() ? c.mag[k] : 0u;
+      if (c.neg) {
+        uint64_t cy = 1;
+        for (size_t k = 0; k < Wd; ++k) {
+          cy += (uint32_t)~w[k];
+          w[k] = (uint32_t)cy;
+          cy >>= 32;
+        }
+      }
+    }
     for (size_t j = 0; j < sm->rep.v.size(); ++j) {
       const ZZ &c = sm->rep.v[j];
       if (c.is_zero()) continue;
-      bool unit = c.mag.size() == 1 && c.mag[0] == 1;
-      for (size_t i = 0; i < big->rep.v.size(); ++i) {
-        if (big->rep.v[i].is_zero()) continue;
-        if (unit) {
-          if (c.neg) r.rep.v[i + j] -= big->rep.v[i];
-          else r.rep.v[i + j] += big->rep.v[i];
-        } else {
-          r.rep.v[i + j] += big->rep.v[i] * c;
+      for (size_t i = 0; i < nb; ++i) {
+        const uint32_t *w = &src[i * Wd];
+        uint32_t *d = &acc[(i + j) * Wd];
+        uint64_t cy = c.neg ? 1 : 0;
+        for (size_t k = 0; k < Wd; ++k) {
+          cy += (uint64_t)d[k] + (c.neg ? (uint32_t)~w[k] : w[k]);
+          d[k] = (uint32_t)cy;
+          cy >>= 32;
         }
       }
+    }
+    r.rep.v.resize(len);
+    for (size_t i = 0; i < len; ++i) {
+      uint32_t *w = &acc[i * Wd];
+      ZZ c;
+      bool neg = w[Wd - 1] >> 31;
+      if (neg) {
+        uint64_t cy = 1;
+        for (size_t k = 0; k < Wd; ++k) {
+          cy += (uint32_t)~w[k];
+          w[k] = (uint32_t)cy;
+          cy >>= 32;
+        }
+      }
+      c.mag.assign(w, w + Wd);
+      c.neg = neg;
+      c.trim();
+      r.rep.v[i] = c;
     }
     r.normalize();
   } else {
@@ -109,10 +145,37 @@ static ZZX MulModPhim(const ZZX &a, const ZZX &b, const PAlgebra &zms) {
 }
 
 // ------------------------------------------------------------------------------- Util / samplers
-void Reduce(ZZ &val, unsigned logQ, bool positive) {  // Util.cpp:3-26
-  ZZ q = ZZ(1L) << (long)logQ;
-  val %= q;  // non-negative
-  if (!positive && val >= (q >> 1)) val -= q;
+void Reduce(ZZ &val, unsigned logQ, bool positive) {  // Util.cpp:3-26, q = 2^logQ: masks, no division
+  const size_t words = (logQ + 31) / 32, tb = logQ & 31;
+  // |val| mod q
+  if (val.mag.size() > words) val.mag.resize(words);
+  if (tb && val.mag.size() == words) val.mag[words - 1] &= (1u << tb) - 1;
+  bool neg = val.neg;
+  val.neg = false;
+  val.trim();
+  if (neg && !val.mag.empty()) {  // q - r
+    val.mag.resize(words, 0);
+    uint64_t cy = 1;
+    for (size_t k = 0; k < words; ++k) {
+      cy += (uint32_t)~val.mag[k];
+      val.mag[k] = (uint32_t)cy;
+      cy >>= 32;
+    }
+    if (tb) val.mag[words - 1] &= (1u << tb) - 1;
+    val.trim();
+  }
+  if (!positive && val.bits() == logQ) {  // >= q/2: subtract q
+    val.mag.resize(words, 0);
+    uint64_t cy = 1;
+    for (size_t k = 0; k < words; ++k) {
+      cy += (uint32_t)~val.mag[k];
+      val.mag[k] = (uint32_t)cy;
+      cy >>= 32;
+    }
+    if (tb) val.mag[words - 1] &= (1u << tb) - 1;
+    val.neg = true;
+    val.trim();
+  }
 }
 void ReduceCoefficients(ZZX &poly, unsigned logQ, bool positive) {
   for (long i = 0; i <= deg(poly); i++) Reduce(poly.rep[i], logQ, positive);
