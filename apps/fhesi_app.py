@@ -1,0 +1,175 @@
+"""Shared pieces of the application drivers (apps/*.py): plaintext slot packing, a device-resident
+ciphertext with the reference's value semantics, and the set-up that every driver repeats.
+Everything here goes through the C ABI (pyfhesi) and the C++ host layer's key generation; nothing
+imports oracle/."""
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (os.path.join(ROOT, "fhe-si_b200"), os.path.join(ROOT, "scripts"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------
+# plaintext slots for p = 1 mod m (PlaintextSpace.cpp:22-134): slot j <-> root rho^(g^j)
+# ---------------------------------------------------------------------------------------
+class Slots:
+    def __init__(self, m, p, g, phi):
+        self.p, n = p, len(phi) - 1
+        fs = [f for f in range(2, m + 1) if m % f == 0 and all(f % q for q in range(2, f))]
+        x = 2
+        while True:
+            rho = pow(x, (p - 1) // m, p)
+            if all(pow(rho, m // f, p) != 1 for f in fs):
+                break
+            x += 1
+        self.roots, e = [], 1
+        for _ in range(n):
+            self.roots.append(pow(rho, e, p))
+            e = e * g % m
+        assert len(set(self.roots)) == n, "g does not generate Z_m^* (SURVEY.md §0.4)"
+        self.total, self.usable = n, 1 << (n.bit_length() - 1)
+        basis = np.zeros((n, n), dtype=np.int64)
+        for j, r in enumerate(self.roots):
+            b, carry = [0] * n, phi[n] % p
+            for i in range(n - 1, -1, -1):
+                b[i] = carry
+                carry = (phi[i] + carry * r) % p
+            d = 0
+            for i in range(n - 1, -1, -1):
+                d = (d * r + b[i]) % p
+            di = pow(d, p - 2, p)
+            basis[j] = [(v * di) % p for v in b]
+        self.basis = basis
+
+    def embed(self, values):
+        """EmbedInSlots(msgs, onlyUsable=True): values -> polynomial coefficients mod p."""
+        v = np.zeros(self.total, dtype=np.int64)
+        v[:len(values)] = np.asarray(values, dtype=np.int64) % self.p
+        return (v @ self.basis) % self.p
+
+    def decode0(self, coeffs):
+        acc = 0
+        for c in reversed(list(coeffs)):
+            acc = (acc * self.roots[0] + int(c)) % self.p
+        return acc
+
+
+# ---------------------------------------------------------------------------------------
+# a device-resident ciphertext (value semantics, like the reference's Ciphertext)
+# ---------------------------------------------------------------------------------------
+class Ct:
+    def __init__(self, env, buf, parts, scaled_up=False):
+        self.env, self.buf, self.parts, self.scaled_up = env, buf, parts, scaled_up
+
+    def copy(self):
+        return Ct(self.env, self.buf.clone(), self.parts, self.scaled_up)
+
+    def mul(self, other):  # Ciphertext::operator*=  -> tensor form
+        e = self.env
+        out = e.empty(e.dev.tprod_words(self.parts + other.parts - 1))
+        e.dev.ct_tensor_dev(self.buf, self.parts, other.buf, other.parts, out, 1)
+        return Ct(e, out, self.parts + other.parts - 1, True)
+
+    def add_(self, other):
+        assert self.scaled_up == other.scaled_up and self.parts == other.parts
+        (self.env.dev.tprod_add_dev if self.scaled_up else self.env.dev.ct_add_dev)(self.buf, other.buf, self.parts, 1)
+        return self
+
+    def neg_(self):
+        (self.env.dev.tprod_mul_scalar_dev if self.scaled_up else self.env.dev.ct_mul_scalar_dev)(self.buf, -1, self.parts, 1)
+        return self
+
+    def keyswitch_(self, ksw):  # KeySwitchSI::ApplyKeySwitch
+        e = self.env
+        if self.scaled_up:
+            c = e.empty(e.dev.ct_words(self.parts))
+            e.dev.scaledown_dev(self.buf, self.parts, c, 1)
+            self.buf, self.scaled_up = c, False
+        out = e.empty(e.dev.ct_words(2))
+        e.dev.keyswitch_dev(ksw, self.buf, out, 1)
+        self.buf, self.parts = out, 2
+        return self
+
+    def rotate_(self, k, ksw):  # tmp >>= k; autoKeySwitch.ApplyKeySwitch(tmp)
+        e, d = self.env, self.env.dev
+        wide = e.empty(self.parts * d.n * (d.W + 1))
+        d.ct_automorph_dev(self.buf, self.parts, k, wide, 1)
+        red = e.empty(d.ct_words(self.parts))
+        d.reduce_wide_dev(wide, d.W + 1, red, self.parts, 1)
+        self.buf = red
+        return self.keyswitch_(ksw)
+
+
+class Env:
+    def __init__(self, dev, device):
+        self.dev, self.device = dev, device
+
+    def empty(self, words):
+        return torch.empty(int(words), dtype=torch.int32, device=self.device)
+
+
+
+
+def sum_slots(ct, rot_k, rot_ksw):
+    """SumBatchedData (Regression.h:166-178, Statistics.h:146-158): log2(usableSlots) rotate-and-add
+    steps leave the sum of the usable slots in slot 0."""
+    for kk, rk in zip(rot_k, rot_ksw):
+        tmp = ct.copy().rotate_(kk, rk)
+        ct.add_(tmp)
+    return ct
+
+
+def rotation_exponents(g, m, usable):
+    """k = g, g^2, g^4, ... (Regression.h:70-81)."""
+    out, k, ns = [], g % m, usable
+    while ns > 1:
+        out.append(k)
+        ns >>= 1
+        k = k * k % m
+    return out
+
+
+def embed_batch(slots, values, device):
+    """values: int array [count][<= usable] -> uint32 message coefficients [count][n] on `device`
+    (EmbedInSlots for a whole batch: one matrix product with the CRT-idempotent basis; exact in
+    float64 since entries < p < 2^10 and row sums < 2^29)."""
+    cnt, width = values.shape
+    v = torch.zeros((max(cnt, 1), slots.total), dtype=torch.float64, device=device)
+    if cnt:
+        v[:cnt, :width] = torch.from_numpy(np.ascontiguousarray(values % slots.p)).to(device=device, dtype=torch.float64)
+    basis = torch.from_numpy(slots.basis).to(device=device, dtype=torch.float64)
+    return torch.remainder(torch.round(v @ basis).to(torch.int64), slots.p).to(torch.int32).contiguous()
+
+
+def encrypt_batch(env, dpk, d_msgs, count, nrng):
+    """FHESIPubKey::Encrypt over a batch with explicit randomness (FHE-SI.cpp:10-36)."""
+    dev, n = env.dev, env.dev.n
+    cts = env.empty(max(count, 1) * dev.ct_words(2)).view(max(count, 1), -1)
+    if count:
+        r_bits = torch.from_numpy(nrng.integers(0, 2, size=(count, n), dtype=np.uint8)).to(env.device)
+        e = torch.from_numpy(np.rint(nrng.normal(0.0, 3.2, size=(count, 2, n))).astype(np.int32)).to(env.device)
+        dev.encrypt_dev(dpk, d_msgs, r_bits, e, cts, count)
+    return cts
+
+
+def add_mask(env, dpk, slots, ct, nrng):
+    """GenerateNoise (Regression.h:180-189): uniformly random values in every slot but the first."""
+    v = np.zeros((1, slots.total), dtype=np.int64)
+    v[0, 1:] = nrng.integers(0, slots.p, size=slots.total - 1)
+    msg = ((v @ slots.basis) % slots.p).astype(np.int32)
+    nz = encrypt_batch(env, dpk, torch.from_numpy(msg).to(env.device), 1, nrng)
+    return ct.add_(Ct(env, nz[0].contiguous(), 2))
+
+
+def decrypt_slot0(env, dsk, slots, ct):
+    mbuf = torch.empty(env.dev.n, dtype=torch.int32, device=env.device)
+    env.dev.decrypt_dev(dsk, ct.buf, 2, mbuf, 1)
+    env.dev.sync()
+    return slots.decode0(mbuf.cpu().numpy().view(np.uint32))

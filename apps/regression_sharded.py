@@ -27,7 +27,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "fhe-si_b200"), os.path.join(ROOT, "scripts"), ROOT):
+for p in (os.path.join(ROOT, "fhe-si_b200"), os.path.join(ROOT, "scripts"), os.path.join(ROOT, "apps"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -36,103 +36,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-# ---------------------------------------------------------------------------------------
-# plaintext slots for p = 1 mod m (PlaintextSpace.cpp:22-134): slot j <-> root rho^(g^j)
-# ---------------------------------------------------------------------------------------
-class Slots:
-    def __init__(self, m, p, g, phi):
-        self.p, n = p, len(phi) - 1
-        fs = [f for f in range(2, m + 1) if m % f == 0 and all(f % q for q in range(2, f))]
-        x = 2
-        while True:
-            rho = pow(x, (p - 1) // m, p)
-            if all(pow(rho, m // f, p) != 1 for f in fs):
-                break
-            x += 1
-        self.roots, e = [], 1
-        for _ in range(n):
-            self.roots.append(pow(rho, e, p))
-            e = e * g % m
-        assert len(set(self.roots)) == n, "g does not generate Z_m^* (SURVEY.md §0.4)"
-        self.total, self.usable = n, 1 << (n.bit_length() - 1)
-        basis = np.zeros((n, n), dtype=np.int64)
-        for j, r in enumerate(self.roots):
-            b, carry = [0] * n, phi[n] % p
-            for i in range(n - 1, -1, -1):
-                b[i] = carry
-                carry = (phi[i] + carry * r) % p
-            d = 0
-            for i in range(n - 1, -1, -1):
-                d = (d * r + b[i]) % p
-            di = pow(d, p - 2, p)
-            basis[j] = [(v * di) % p for v in b]
-        self.basis = basis
-
-    def embed(self, values):
-        """EmbedInSlots(msgs, onlyUsable=True): values -> polynomial coefficients mod p."""
-        v = np.zeros(self.total, dtype=np.int64)
-        v[:len(values)] = np.asarray(values, dtype=np.int64) % self.p
-        return (v @ self.basis) % self.p
-
-    def decode0(self, coeffs):
-        acc = 0
-        for c in reversed(list(coeffs)):
-            acc = (acc * self.roots[0] + int(c)) % self.p
-        return acc
-
-
-# ---------------------------------------------------------------------------------------
-# a device-resident ciphertext (value semantics, like the reference's Ciphertext)
-# ---------------------------------------------------------------------------------------
-class Ct:
-    def __init__(self, env, buf, parts, scaled_up=False):
-        self.env, self.buf, self.parts, self.scaled_up = env, buf, parts, scaled_up
-
-    def copy(self):
-        return Ct(self.env, self.buf.clone(), self.parts, self.scaled_up)
-
-    def mul(self, other):  # Ciphertext::operator*=  -> tensor form
-        e = self.env
-        out = e.empty(e.dev.tprod_words(self.parts + other.parts - 1))
-        e.dev.ct_tensor_dev(self.buf, self.parts, other.buf, other.parts, out, 1)
-        return Ct(e, out, self.parts + other.parts - 1, True)
-
-    def add_(self, other):
-        assert self.scaled_up == other.scaled_up and self.parts == other.parts
-        (self.env.dev.tprod_add_dev if self.scaled_up else self.env.dev.ct_add_dev)(self.buf, other.buf, self.parts, 1)
-        return self
-
-    def neg_(self):
-        (self.env.dev.tprod_mul_scalar_dev if self.scaled_up else self.env.dev.ct_mul_scalar_dev)(self.buf, -1, self.parts, 1)
-        return self
-
-    def keyswitch_(self, ksw):  # KeySwitchSI::ApplyKeySwitch
-        e = self.env
-        if self.scaled_up:
-            c = e.empty(e.dev.ct_words(self.parts))
-            e.dev.scaledown_dev(self.buf, self.parts, c, 1)
-            self.buf, self.scaled_up = c, False
-        out = e.empty(e.dev.ct_words(2))
-        e.dev.keyswitch_dev(ksw, self.buf, out, 1)
-        self.buf, self.parts = out, 2
-        return self
-
-    def rotate_(self, k, ksw):  # tmp >>= k; autoKeySwitch.ApplyKeySwitch(tmp)
-        e, d = self.env, self.env.dev
-        wide = e.empty(self.parts * d.n * (d.W + 1))
-        d.ct_automorph_dev(self.buf, self.parts, k, wide, 1)
-        red = e.empty(d.ct_words(self.parts))
-        d.reduce_wide_dev(wide, d.W + 1, red, self.parts, 1)
-        self.buf = red
-        return self.keyswitch_(ksw)
-
-
-class Env:
-    def __init__(self, dev, device):
-        self.dev, self.device = dev, device
-
-    def empty(self, words):
-        return torch.empty(int(words), dtype=torch.int32, device=self.device)
+from fhesi_app import Ct, Env, Slots  # noqa: E402
 
 
 def determinant(M, rows, cols, reduce):

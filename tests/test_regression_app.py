@@ -11,9 +11,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_app(extra, nproc, port):
+def run_app(extra, nproc, port, app="regression_sharded.py"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "apps", "regression_sharded.py")] + extra
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "apps", app)] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
@@ -27,6 +27,15 @@ def test_sharded_regression_world2_emu(emu_lib):
     assert out["theta_det"] == out["expected"]
 
 
+def test_sharded_statistics_world2_emu(emu_lib):
+    """BASELINE config 3 at toy size: encrypted mean / covariance over 2 gloo ranks."""
+    out = run_app(["--dim", "2", "--points", "20", "--prime", "23", "--gen", "7", "--lib", emu_lib, "--cpu-tensors"],
+                  2, 29900 + os.getpid() % 90, app="statistics_sharded.py")
+    assert out["correct"] and out["n_gpus"] == 2
+    assert out["mean"] == out["expected"]["mean"] and out["cov_upper"] == out["expected"]["cov_upper"]
+    assert out["N"] == 20 and out["N2"] == out["expected"]["N2"]
+
+
 def test_data_generator_is_seeded_and_formatted(tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     from generate_random_data import generate, main
@@ -37,6 +46,12 @@ def test_data_generator_is_seeded_and_formatted(tmp_path):
     assert len(files) == 8  # README:82-84 split
     first = open(tmp_path / files[0]).read().splitlines()
     assert first[0] == "4 7" and len(first) == 8 and len(first[1].split()) == 5
+
+
+@pytest.mark.gpu
+def test_statistics_cfg3_gpu(cuda_lib):
+    out = run_app(["--dim", "4", "--points", "10000"], 1, 29800 + os.getpid() % 90, app="statistics_sharded.py")
+    assert out["correct"] and out["config"]["logQ"] == 100, out
 
 
 @pytest.mark.gpu
