@@ -395,14 +395,25 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a, const __grid_c
   for (int i = ML - 1; i >= 0; --i) {
     if (i < L) {
       const u32 p = T.p[i];
-      u64 carry = v[i];
-      // before this step acc < prod_{i<j<L} p_j < 2^(30 (ML-1-i)): only ML-i words can change
+      // before this step acc < prod_{i<j<L} p_j < 2^(30 (ML-1-i)): only ML-i words can change.
+      // The ML-i word products are independent (no carry threaded through the multiplier); the
+      // carries ripple through a separate add chain on the ALU pipe.
+      u32 plo[ML], phi[ML];
 #pragma unroll
       for (int k = 0; k < ML; ++k) {
         if (k <= ML - 1 - i) {
-          u64 t = (u64)acc[k] * p + carry;
-          acc[k] = (u32)t;
-          carry = t >> 32;
+          const u64 t = (u64)acc[k] * p;
+          plo[k] = (u32)t;
+          phi[k] = (u32)(t >> 32);
+        }
+      }
+      u64 carry = v[i];
+#pragma unroll
+      for (int k = 0; k < ML; ++k) {
+        if (k <= ML - 1 - i) {
+          carry += (u64)plo[k] + (k > 0 ? phi[k - 1] : 0u);
+          acc[k] = (u32)carry;
+          carry >>= 32;
         }
       }
     }
@@ -569,13 +580,22 @@ __global__ void __launch_bounds__(128) k_crt_split(DevCtx c, CrtSplitArgs a, con
     for (int i = ML - 1; i >= 0; --i) {
       if (i < L) {
         const u32 p = T.p[i];
+        u32 plo[ML], phi[ML];
+#pragma unroll
+        for (int k = 0; k < ML; ++k) {
+          if (k <= ML - 1 - i) {
+            const u64 t = (u64)acc[k] * p;
+            plo[k] = (u32)t;
+            phi[k] = (u32)(t >> 32);
+          }
+        }
         u64 carry = v[i];
 #pragma unroll
         for (int k = 0; k < ML; ++k) {
           if (k <= ML - 1 - i) {
-            u64 t = (u64)acc[k] * p + carry;
-            acc[k] = (u32)t;
-            carry = t >> 32;
+            carry += (u64)plo[k] + (k > 0 ? phi[k - 1] : 0u);
+            acc[k] = (u32)carry;
+            carry >>= 32;
           }
         }
       }
