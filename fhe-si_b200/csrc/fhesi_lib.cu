@@ -39,6 +39,20 @@ struct Arena {
   void *ptr = nullptr;
   size_t cap = 0;
 };
+// a temporary device allocation released on every exit path (cudaFree synchronises implicitly)
+struct DevTmp {
+  void *p = nullptr;
+  ~DevTmp() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  u32 *u() const { return (u32 *)p; }
+  void *release() {
+    void *r = p;
+    p = nullptr;
+    return r;
+  }
+};
 
 struct fhesi_ctx {
   fhesi_info info{};
@@ -50,6 +64,7 @@ struct fhesi_ctx {
   std::vector<PrimeConst> h_pc;
   std::vector<u32> h_garner, h_Pfull, h_Phalf;  // host copies for the by-value CRT tables
   std::map<std::pair<int, u32>, std::vector<unsigned char>> crt_tables;
+  std::map<u32, u32 *> automorph_tabs;  // Galois element -> device permutation table
   u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
   u32 fused_chunk = 2048; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
@@ -543,10 +558,11 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
     memcpy(&h[((size_t)k * 2 + 0) * polyw], h_b + (size_t)k * polyw, polyw * 4);
     memcpy(&h[((size_t)k * 2 + 1) * polyw], h_A + (size_t)k * polyw, polyw * 4);
   }
-  u32 *d_in = nullptr, *d_tmp = nullptr, *d_key = nullptr;
-  CK(cudaMalloc(&d_in, h.size() * 4));
-  CK(cudaMalloc(&d_tmp, (size_t)K * 2 * Lk * I.N * 4));
-  CK(cudaMalloc(&d_key, (size_t)K * 2 * Lk * I.N * 4));
+  DevTmp t_in, t_tmp, t_key, t_bal, t_split;
+  CK(t_in.alloc(h.size() * 4));
+  CK(t_tmp.alloc((size_t)K * 2 * Lk * I.N * 4));
+  CK(t_key.alloc((size_t)K * 2 * Lk * I.N * 4));
+  u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
   CK(cudaMemcpyAsync(d_in, h.data(), h.size() * 4, cudaMemcpyHostToDevice, c->stream));
   int rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2);
   if (rc) return rc;
@@ -554,12 +570,11 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
   KL(c, k_transpose_key, nblk((size_t)K * 2 * Lk * I.N), 256, 0, d_tmp, d_key, K * 2, Lk, I.N);
   CKL();
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d_in));
-  CK(cudaFree(d_tmp));
   u32 *d_bal = nullptr;
   if (c->use_fused && c->tfree) {
     const size_t total = (size_t)K * 2 * Lk * I.N;
-    CK(cudaMalloc(&d_bal, total * 4));
+    CK(t_bal.alloc(total * 4));
+    d_bal = t_bal.u();
     KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_key, d_bal, K * 2, total);
     CKL();
     CK(cudaStreamSynchronize(c->stream));
@@ -581,12 +596,14 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
             else hi[(size_t)i * W + (w - ws)] = v;
           }
       }
-    u32 *d_in2 = nullptr, *d_tmp2 = nullptr, *d_t2 = nullptr;
+    DevTmp t_in2, t_tmp2, t_t2;
     const size_t total = (size_t)K * 4 * Ls * I.N;
-    CK(cudaMalloc(&d_in2, hs.size() * 4));
-    CK(cudaMalloc(&d_tmp2, total * 4));
-    CK(cudaMalloc(&d_t2, total * 4));
-    CK(cudaMalloc(&d_split, total * 4));
+    CK(t_in2.alloc(hs.size() * 4));
+    CK(t_tmp2.alloc(total * 4));
+    CK(t_t2.alloc(total * 4));
+    CK(t_split.alloc(total * 4));
+    u32 *d_in2 = t_in2.u(), *d_tmp2 = t_tmp2.u(), *d_t2 = t_t2.u();
+    d_split = t_split.u();
     CK(cudaMemcpyAsync(d_in2, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->stream));
     if ((rc = launch_fwd(c, d_in2, SRC_POLY, W, SC_KEYFORM, Ls, d_tmp2, (size_t)K * 4))) return rc;
     KL(c, k_transpose_key, nblk(total), 256, 0, d_tmp2, d_t2, K * 4, Ls, I.N);
@@ -594,11 +611,11 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
     KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_t2, d_split, K * 4, total);
     CKL();
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaFree(d_in2));
-    CK(cudaFree(d_tmp2));
-    CK(cudaFree(d_t2));
   }
-  fhesi_ksw *k = new fhesi_ksw{c, d_key, d_bal, d_split, parts};
+  fhesi_ksw *k = new fhesi_ksw{c, (u32 *)t_key.release(), (u32 *)t_bal.release(), (u32 *)t_split.release(), parts};
+  (void)d_key;
+  (void)d_bal;
+  (void)d_split;
   *out = k;
   return 0;
 }
@@ -617,19 +634,19 @@ int fhesi_key_create(fhesi_ctx *c, const uint32_t *h_polys, uint32_t parts, fhes
   CK(cudaSetDevice(c->device));
   const fhesi_info &I = c->info;
   const size_t polyw = (size_t)I.n * I.W;
-  u32 *d_in = nullptr, *d_tmp = nullptr, *d_key = nullptr;
-  CK(cudaMalloc(&d_in, parts * polyw * 4));
-  CK(cudaMalloc(&d_tmp, (size_t)parts * I.Le * I.N * 4));
-  CK(cudaMalloc(&d_key, (size_t)parts * I.Le * I.N * 4));
+  DevTmp t_in, t_tmp, t_key;
+  CK(t_in.alloc(parts * polyw * 4));
+  CK(t_tmp.alloc((size_t)parts * I.Le * I.N * 4));
+  CK(t_key.alloc((size_t)parts * I.Le * I.N * 4));
+  u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
   CK(cudaMemcpyAsync(d_in, h_polys, parts * polyw * 4, cudaMemcpyHostToDevice, c->stream));
   int rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, I.Le, d_tmp, parts);
   if (rc) return rc;
   KL(c, k_transpose_key, nblk((size_t)parts * I.Le * I.N), 256, 0, d_tmp, d_key, parts, I.Le, I.N);
   CKL();
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d_in));
-  CK(cudaFree(d_tmp));
-  *out = new fhesi_key{c, d_key, parts};
+  (void)d_key;
+  *out = new fhesi_key{c, (u32 *)t_key.release(), parts};
   return 0;
 }
 void fhesi_key_destroy(fhesi_key *k) {
@@ -695,14 +712,18 @@ int fhesi_ct_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uin
     if (e >= h) { e -= h; neg = 1; }
     tab[e] = (i << 1) | neg;
   }
-  u32 *d_tab = nullptr;
   size_t npolys = count * parts;
-  CK(cudaMalloc(&d_tab, h * 4));
-  CK(cudaMemcpyAsync(d_tab, tab.data(), h * 4, cudaMemcpyHostToDevice, c->stream));
+  u32 *&d_tab = c->automorph_tabs[k % I.m];  // one small table per Galois element, kept for reuse
+  if (!d_tab) {
+    void *pt = nullptr;
+    CK(cudaMalloc(&pt, h * 4));
+    c->tables.push_back(pt);
+    d_tab = (u32 *)pt;
+    CK(cudaMemcpyAsync(d_tab, tab.data(), h * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // tab is a stack-lifetime host buffer
+  }
   if (npolys) KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, out, npolys);
   CKL();
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d_tab));
   return 0;
 }
 
@@ -811,13 +832,13 @@ int fhesi_tprod_mul_scalar_dev(fhesi_ctx *c, uint32_t *io, int64_t l, uint32_t p
     if (r < 0) r += q;
     sc[i] = (u32)h_mulmod((u64)r, c->h_pc[i].r1, (u64)q);
   }
-  u32 *d_sc = nullptr;
-  CK(cudaMalloc(&d_sc, I.Lt * 4));
+  DevTmp t_sc;
+  CK(t_sc.alloc(I.Lt * 4));
+  u32 *d_sc = t_sc.u();
   CK(cudaMemcpyAsync(d_sc, sc.data(), I.Lt * 4, cudaMemcpyHostToDevice, c->stream));
   KL(c, k_tprod_mul_scalar, nblk(total), 256, 0, c->dc, io, d_sc, I.Lt, total);
   CKL();
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d_sc));
   return 0;
 }
 int fhesi_tprod_reduce_gathered_dev(fhesi_ctx *c, const uint32_t *g, uint32_t world, uint32_t parts,
