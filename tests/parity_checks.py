@@ -276,3 +276,35 @@ def check_mul_plain(sc: Scenario, count=2):
     got = da.download((count, 2, d.n, d.W))
     for i in range(count):
         assert_ct_equal(sc, got[i], A[i].copy().mul_plain(pt), f"ct *= plain [{i}]")
+
+
+def check_edge_cases(sc: Scenario, counts=(0, 1, 7)):
+    """Extreme operands and ragged batch sizes: every coefficient at -q/2 or q/2-1, the zero
+    ciphertext, unit polynomials; batch sizes 0, 1 and one that is not a multiple of the kernels'
+    group size."""
+    octx, n, logq = sc.octx, sc.octx.phim, sc.logq
+    lo, hi = -(1 << (logq - 1)), (1 << (logq - 1)) - 1
+    mk = lambda parts: O.Ciphertext(octx, parts)
+    specials = [
+        mk([[lo] * n, [lo] * n]), mk([[hi] * n, [hi] * n]), mk([[0] * n, [0] * n]),
+        mk([[1] + [0] * (n - 1), [0] * (n - 1) + [-1]]), mk([[hi if i % 2 else lo for i in range(n)], [lo] + [hi] * (n - 1)]),
+    ]
+    pairs = [(a, b) for a in specials for b in specials[:3]] + [(specials[3], specials[4])]
+    A, B = [p[0] for p in pairs], [p[1] for p in pairs]
+    out = sc.dev_mult_relin(A, B)
+    for i in range(len(pairs)):
+        assert_ct_equal(sc, out[i], O.mult_relin(sc.ks, A[i], B[i]), f"edge mult_relin[{i}]")
+    host = sc.dev_mult_relin(A[:5], B[:5], host=True)
+    assert np.array_equal(host, out[:5])
+    for cnt in counts:
+        if cnt == 0:
+            d = sc.dev
+            buf = d.alloc(16)
+            d.mult_relin_dev(sc.ksw, buf.ptr, buf.ptr, buf.ptr, 0)   # empty batch: a no-op, not an error
+            d.ct_add_dev(buf.ptr, buf.ptr, 2, 0)
+            d.sync()
+            continue
+        X, Y = sc.random_cts(cnt), sc.random_cts(cnt)
+        got = sc.dev_mult_relin(X, Y)
+        for i in (0, cnt - 1):
+            assert_ct_equal(sc, got[i], O.mult_relin(sc.ks, X[i], Y[i]), f"count={cnt} [{i}]")

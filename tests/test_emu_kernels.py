@@ -38,6 +38,10 @@ def test_emu_ref_rows_cfg1(sc1):
     P.check_ref_rows(sc1)
 
 
+def test_emu_edge_cases_cfg1(sc1):
+    P.check_edge_cases(sc1)
+
+
 def test_emu_golden_cfg1(emu_lib):
     P.check_golden("cfg1", emu_lib)
 

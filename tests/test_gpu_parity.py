@@ -61,6 +61,11 @@ def test_ref_rows(name, cuda_lib):
     P.check_ref_rows(scenario(name, cuda_lib))
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg5_128"])
+def test_edge_cases(name, cuda_lib):
+    P.check_edge_cases(scenario(name, cuda_lib), counts=(0, 1, 7, 13))
+
+
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4"])
 def test_golden_vectors(name, cuda_lib):
     P.check_golden(name, cuda_lib)
