@@ -65,6 +65,10 @@ struct fhesi_ctx {
   std::vector<u32> h_garner, h_Pfull, h_Phalf;  // host copies for the by-value CRT tables
   std::map<std::pair<int, u32>, std::vector<unsigned char>> crt_tables;
   std::map<u32, u32 *> automorph_tabs;  // Galois element -> device permutation table
+  // fhesi_malloc / fhesi_free pool
+  std::map<size_t, std::vector<void *>> pool_free;
+  std::map<void *, size_t> pool_size;
+  size_t pool_idle_bytes = 0, pool_cap_bytes = (size_t)8 << 30;
   u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
   u32 fused_chunk = 2048; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
@@ -358,6 +362,8 @@ void fhesi_ctx_destroy(fhesi_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (void *p : c->tables) cudaFree(p);
+  for (auto &kv : c->pool_free)
+    for (void *p : kv.second) cudaFree(p);
   if (c->scratch.ptr) cudaFree(c->scratch.ptr);
   if (c->stage.ptr) cudaFree(c->stage.ptr);
   if (c->work.ptr) cudaFree(c->work.ptr);
@@ -384,17 +390,44 @@ int fhesi_sync(fhesi_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
+// Device allocations made through the ABI are pooled per context: the host layer's value-semantics
+// Ciphertext allocates and frees a buffer per operator, and every operator is enqueued on the
+// context's one stream, so handing a freed block to the next fhesi_malloc is stream-ordered safe and
+// needs neither cudaFree nor a synchronisation.
 int fhesi_malloc(fhesi_ctx *c, size_t bytes, void **d) {
   if (!c || !d) return fail(FHESI_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
-  CK(cudaMalloc(d, bytes ? bytes : 16));
+  const size_t sz = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+  auto it = c->pool_free.find(sz);
+  if (it != c->pool_free.end() && !it->second.empty()) {
+    *d = it->second.back();
+    it->second.pop_back();
+    c->pool_idle_bytes -= sz;
+  } else {
+    CK(cudaMalloc(d, sz));
+  }
+  c->pool_size[*d] = sz;
   return 0;
 }
 int fhesi_free(fhesi_ctx *c, void *d) {
   if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  if (!d) return 0;
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaFree(d));
+  auto it = c->pool_size.find(d);
+  if (it == c->pool_size.end()) {  // not ours: release for real
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d));
+    return 0;
+  }
+  const size_t sz = it->second;
+  c->pool_size.erase(it);
+  if (c->pool_idle_bytes + sz > c->pool_cap_bytes) {
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d));
+  } else {
+    c->pool_free[sz].push_back(d);
+    c->pool_idle_bytes += sz;
+  }
   return 0;
 }
 int fhesi_h2d(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
