@@ -170,7 +170,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def result(self):
         sm = sorted(self.sm)
