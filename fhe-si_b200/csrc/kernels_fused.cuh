@@ -167,7 +167,9 @@ __device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A
   dif8<16>(x, twf + FTW_P2 + (tg & 15), p);
 #pragma unroll
   for (int j = 0; j < 8; ++j) bufB[A.a2b + 18 * j] = x[j];
-  fhesi_group_sync(g);
+  // exchange 2 stays inside a warp: warp w owns positions [256w, 256w+256) in both ownerships
+  // (pass 2: hi in {2w, 2w+1}; pass 3: u in [16w, 16w+16)), so a warp barrier is enough
+  __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufB[A.a3 + 2 * j];
   dif8<2>(x, twf + FTW_P3 + (tg & 1), p);
@@ -195,9 +197,10 @@ __device__ __forceinline__ void inv1024(u32 *x, const uint2 *twi, const XAddr &A
     x[j] = csub(v, p2);
   }
   dit8<2>(x, twi + FTW_P3 + (tg & 1), p);
+  __syncwarp();  // the warp's previous reads of its bufB region (last forward transform) are done
 #pragma unroll
   for (int j = 0; j < 8; ++j) bufB[A.a3 + 2 * j] = x[j];
-  fhesi_group_sync(g);
+  __syncwarp();  // intra-warp exchange (see fwd1024)
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufB[A.a2b + 18 * j];
   dit8<16>(x, twi + FTW_P2 + (tg & 15), p);
