@@ -349,7 +349,7 @@ struct FusedTensorArgs {
   u32 Lt, count, ops_per_group, to_tprod;
 };
 #define KG 6
-#define FUSED_SMEM_WORDS (2 * FTW_WORDS + KG * 2 * FPADN)
+#define FUSED_SMEM_WORDS (2 * FTW_WORDS + KG * 3 * FPADN)
 __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTensorArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
@@ -360,7 +360,10 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTen
   __syncthreads();
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
-  u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
+  // two alternating inter-warp exchange buffers (a warp may run one transform ahead of the
+  // others, since only the first exchange of a transform has a group barrier) + one intra-warp
+  u32 *bufA0 = sm + 2 * FTW_WORDS + g * 3 * FPADN, *bufA1 = bufA0 + FPADN, *bufB = bufA1 + FPADN;
+  u32 flip = 0;
   const XAddr A = make_xaddr(tg);
   for (u32 it = 0; it < a.ops_per_group; ++it) {
     const size_t op = ((size_t)blockIdx.y * a.ops_per_group + it) * KG + g;
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTen
         for (int j = 0; j < 4; ++j)
           xn[j] = (j * 128 + tg < c.n) ? __ldg(rin + (q + 1) * qstride + j * 128 + tg) : 0u;
       }
-      fwd1024(F[q], twf, A, bufA, bufB, g, tg, p);
+      fwd1024(F[q], twf, A, (flip++ & 1) ? bufA1 : bufA0, bufB, g, tg, p);
     }
     // tProd[k] = sum_{i+j=k} a_i * b_j   (Ciphertext.cpp:179-186)
 #pragma unroll
@@ -398,9 +401,9 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTen
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = csub(y[j], p);
       } else {
+        u32 *bufA = (flip++ & 1) ? bufA1 : bufA0;
         inv1024(y, twi, A, bufA, bufB, bufA, g, tg, p);
         phim_store_1024(bufA, a.res + ((op * 3 + k) * a.Lt + l) * (size_t)c.n, c.h, tg, p);
-        fhesi_group_sync(g);  // bufA (nat) is rewritten by the next transform
       }
     }
   }
@@ -420,7 +423,7 @@ struct FusedKsArgs {
 // the whole inner product of balanced residues fits one signed 64-bit accumulator and no
 // intermediate reduction (nor its 16 partial-sum registers) is needed.
 #define KSG 6
-#define KS_SMEM_WORDS (2 * FTW_WORDS + KSG * 2 * FPADN)
+#define KS_SMEM_WORDS (2 * FTW_WORDS + KSG * 3 * FPADN)
 template <bool TFREE>
 __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
   if (op >= a.count) return;  // whole group leaves together; only group barriers from here on
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p, half = p >> 1;
-  u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
+  u32 *bufA0 = sm + 2 * FTW_WORDS + g * 3 * FPADN, *bufA1 = bufA0 + FPADN, *bufB = bufA1 + FPADN;
   const XAddr A = make_xaddr(tg);
   u64 acc0[8], acc1[8];
   u32 t0[8], t1[8];
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
       for (int j = 0; j < 4; ++j)
         xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + (size_t)(k + 1) * c.n + j * 128 + tg) : 0u;
     }
-    fwd1024(x, twf, A, bufA, bufB, g, tg, p);
+    fwd1024(x, twf, A, (k & 1) ? bufA1 : bufA0, bufB, g, tg, p);
     const uint4 *kp = (const uint4 *)(key + (size_t)k * 2 * FN);
     const uint4 ka0 = __ldg(kp), ka1 = __ldg(kp + 1);
     const uint4 kb0 = __ldg(kp + FN / 4), kb1 = __ldg(kp + FN / 4 + 1);
@@ -493,11 +496,11 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
       t1[j] = s1 < 0 ? csub(p2 - r1, p2) : r1;
     }
   }
-  inv1024(t0, twi, A, bufA, bufB, bufA, g, tg, p);
-  phim_store_1024(bufA, a.res + ((op * 2 + 0) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
-  fhesi_group_sync(g);  // bufA (nat) is rewritten by the next inverse transform
-  inv1024(t1, twi, A, bufA, bufB, bufA, g, tg, p);
-  phim_store_1024(bufA, a.res + ((op * 2 + 1) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+  fhesi_group_sync(g);  // every warp is done with the forward transforms' buffers
+  inv1024(t0, twi, A, bufA0, bufB, bufA0, g, tg, p);
+  phim_store_1024(bufA0, a.res + ((op * 2 + 0) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+  inv1024(t1, twi, A, bufA1, bufB, bufA1, g, tg, p);
+  phim_store_1024(bufA1, a.res + ((op * 2 + 1) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
 }
 // ---------------------------------------------------------------------------------------
 // split-key key switch.  Every key polynomial K (mod q) is stored as two non-negative halves,
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
 // key: [Ls][K][4][N] balanced;  res: [count][4][Ls][n] in the order b_lo, b_hi, A_lo, A_hi.
 // ---------------------------------------------------------------------------------------
 #define KSS 4
-#define KSS_SMEM_WORDS (2 * FTW_WORDS + KSS * 2 * FPADN)
+#define KSS_SMEM_WORDS (2 * FTW_WORDS + KSS * 3 * FPADN)
 __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
   if (op >= a.count) return;
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p, half = p >> 1;
-  u32 *bufA = sm + 2 * FTW_WORDS + g * 2 * FPADN, *bufB = bufA + FPADN;
+  u32 *bufA0 = sm + 2 * FTW_WORDS + g * 3 * FPADN, *bufA1 = bufA0 + FPADN, *bufB = bufA1 + FPADN;
   const XAddr A = make_xaddr(tg);
   u64 acc[4][8];
 #pragma unroll
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
       for (int j = 0; j < 4; ++j)
         xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + (size_t)(k + 1) * c.n + j * 128 + tg) : 0u;
     }
-    fwd1024(x, twf, A, bufA, bufB, g, tg, p);
+    fwd1024(x, twf, A, (k & 1) ? bufA1 : bufA0, bufB, g, tg, p);
     int xb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) xb[j] = (int)x[j] - (x[j] > half ? (int)p : 0);
@@ -556,6 +559,7 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
       for (int j = 0; j < 8; ++j) acc[h][j] += (u64)((i64)xb[j] * (int)kv[j]);
     }
   }
+  fhesi_group_sync(g);  // every warp is done with the forward transforms' buffers
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
     u32 t[8];
@@ -565,9 +569,9 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
       const u32 r0 = csub(mont_red64((u64)(s0 < 0 ? -s0 : s0), p, pinv), p2);
       t[j] = s0 < 0 ? csub(p2 - r0, p2) : r0;
     }
+    u32 *bufA = (h & 1) ? bufA1 : bufA0;
     inv1024(t, twi, A, bufA, bufB, bufA, g, tg, p);
     phim_store_1024(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
-    fhesi_group_sync(g);  // bufA (nat) is rewritten by the next inverse transform
   }
 }
 
