@@ -411,7 +411,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=2048, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=8192, help="ciphertext pairs per GPU per step (SURVEY.md §8d: B in {1, 64, 1024, 8192})")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--logq", type=int, default=256, choices=[128, 256, 512],
                     help="BASELINE config 5 sweep; the headline metric is quoted at 256")

@@ -70,7 +70,7 @@ struct fhesi_ctx {
   std::map<void *, size_t> pool_size;
   size_t pool_idle_bytes = 0, pool_cap_bytes = (size_t)8 << 30;
   u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
-  u32 fused_chunk = 2048; // same for the fused path: large, so the grid is many waves deep
+  u32 fused_chunk = 8192; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
   bool tfree = false;  // every prime satisfies 3D (p/2)^2 < 2^63 (single-accumulator key switch)
   // launch accounting / per-kernel CUDA-event profiler (bench.py "roofline", "gpu_launches")
