@@ -81,7 +81,7 @@ struct fhesi_ctx {
   Arena stage;  // device staging for the *_host entry points
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the host pipeline
   std::vector<cudaEvent_t> pipe_events;
-  u32 pipe_chunk = 256;
+  u32 pipe_chunk = 0;  // 0 = choose from the batch size; FHESI_PIPE_CHUNK overrides
   Arena work;   // tprod / scaled-down intermediates of the generic mult_relin composition
 };
 static void prof_clear(fhesi_ctx *c);
@@ -1043,7 +1043,15 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
     CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   }
-  const size_t PC = c->pipe_chunk;
+  // pipeline chunk: ~10 chunks per call, a multiple of 12 (whole CTAs in both fused kernels), between
+  // 252 (below that the grids are too few waves deep) and 768 (above, fill/drain dominates) --
+  // measured on a B200 with PCIe gen5: 256 is best at 2048 pairs, 768 at 8192
+  size_t PC = c->pipe_chunk;
+  if (!PC) {
+    PC = ((count / 10 + 11) / 12) * 12;
+    if (PC < 252) PC = 252;
+    if (PC > 768) PC = 768;
+  }
   const size_t nchunks = (count + PC - 1) / PC;
   while (c->pipe_events.size() < 2 * nchunks) {
     cudaEvent_t e;
