@@ -87,54 +87,54 @@ static ZZX MulModPhim(const ZZX &a, const ZZX &b, const PAlgebra &zms) {
   if (!tiny(b) && tiny(a)) big = &b, sm = &a;
   ZZX r;
   if (tiny(*sm) && !big->rep.v.empty() && !sm->rep.v.empty()) {
-    size_t maxw = 1;
-    for (auto &c : big->rep.v) maxw = std::max(maxw, c.mag.size());
-    const size_t Wd = maxw + 2, nb = big->rep.v.size(), len = nb + sm->rep.v.size();
-    std::vector<uint32_t> src(nb * Wd), acc(len * Wd, 0);
-    for (size_t i = 0; i < nb; ++i) {  // two's complement, sign-extended to Wd words
+    // one operand has coefficients in {-1,0,1} (secret keys, encryption randomness): the product is
+    // a few hundred shifted signed adds.  Limbs are accumulated carry-save in int64 lanes (a sum of
+    // < 2^31 signed 32-bit limbs cannot overflow), so the inner loop is a plain vector add; carries
+    // are propagated once per output coefficient.
+    size_t Wd = 1;
+    for (auto &c : big->rep.v) Wd = std::max(Wd, c.mag.size());
+    const size_t nb = big->rep.v.size(), len = nb + sm->rep.v.size() - 1;
+    std::vector<int64_t> src(nb * Wd, 0), acc(len * Wd, 0);
+    for (size_t i = 0; i < nb; ++i) {
       const ZZ &c = big->rep.v[i];
-      uint32_t *w = &src[i * Wd];
-      for (size_t k = 0; k < Wd; ++k) w[k] = k < c.mag.size() ? c.mag[k] : 0u;
-      if (c.neg) {
-        uint64_t cy = 1;
-        for (size_t k = 0; k < Wd; ++k) {
-          cy += (uint32_t)~w[k];
-          w[k] = (uint32_t)cy;
-          cy >>= 32;
-        }
-      }
+      for (size_t k = 0; k < c.mag.size(); ++k) src[i * Wd + k] = c.neg ? -(int64_t)c.mag[k] : (int64_t)c.mag[k];
     }
+    const size_t span = nb * Wd;
     for (size_t j = 0; j < sm->rep.v.size(); ++j) {
       const ZZ &c = sm->rep.v[j];
       if (c.is_zero()) continue;
-      for (size_t i = 0; i < nb; ++i) {
-        const uint32_t *w = &src[i * Wd];
-        uint32_t *d = &acc[(i + j) * Wd];
-        uint64_t cy = c.neg ? 1 : 0;
-        for (size_t k = 0; k < Wd; ++k) {
-          cy += (uint64_t)d[k] + (c.neg ? (uint32_t)~w[k] : w[k]);
-          d[k] = (uint32_t)cy;
-          cy >>= 32;
-        }
-      }
+      int64_t *d = &acc[j * Wd];
+      const int64_t *w = src.data();
+      if (c.neg)
+        for (size_t t = 0; t < span; ++t) d[t] -= w[t];
+      else
+        for (size_t t = 0; t < span; ++t) d[t] += w[t];
     }
     r.rep.v.resize(len);
-    for (size_t i = 0; i < len; ++i) {
-      uint32_t *w = &acc[i * Wd];
-      ZZ c;
-      bool neg = w[Wd - 1] >> 31;
+    std::vector<uint32_t> limbs(Wd + 2);
+    for (size_t i = 0; i < len; ++i) {  // signed carry propagation -> two's complement -> sign + magnitude
+      const int64_t *d = &acc[i * Wd];
+      int64_t cy = 0;
+      for (size_t k = 0; k < Wd; ++k) {
+        int64_t v = d[k] + cy;
+        limbs[k] = (uint32_t)v;
+        cy = v >> 32;
+      }
+      limbs[Wd] = (uint32_t)cy;
+      limbs[Wd + 1] = (uint32_t)(cy >> 32);
+      const bool neg = cy < 0;
       if (neg) {
-        uint64_t cy = 1;
-        for (size_t k = 0; k < Wd; ++k) {
-          cy += (uint32_t)~w[k];
-          w[k] = (uint32_t)cy;
-          cy >>= 32;
+        uint64_t c2 = 1;
+        for (size_t k = 0; k < Wd + 2; ++k) {
+          c2 += (uint32_t)~limbs[k];
+          limbs[k] = (uint32_t)c2;
+          c2 >>= 32;
         }
       }
-      c.mag.assign(w, w + Wd);
+      ZZ &c = r.rep.v[i];
+      c.mag.assign(limbs.begin(), limbs.end());
       c.neg = neg;
       c.trim();
-      r.rep.v[i] = c;
     }
     r.normalize();
   } else {

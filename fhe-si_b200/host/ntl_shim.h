@@ -25,10 +25,101 @@ namespace NTL {
   std::abort();
 }
 
+// Limb storage for ZZ: up to 20 limbs (640 bits -- every coefficient, chain product and key value
+// of the five configurations) live inline, so ZZ temporaries do not touch the heap.
+class Limbs {
+  static constexpr uint32_t kInline = 20;
+  uint32_t n_ = 0, cap_ = kInline;
+  uint32_t *p_ = buf_;
+  uint32_t buf_[kInline];
+  void grow(size_t want) {
+    size_t cap = std::max<size_t>(want, 2 * (size_t)cap_);
+    uint32_t *q = (uint32_t *)std::malloc(cap * 4);
+    if (!q) std::abort();
+    std::memcpy(q, p_, (size_t)n_ * 4);
+    if (p_ != buf_) std::free(p_);
+    p_ = q;
+    cap_ = (uint32_t)cap;
+  }
+
+ public:
+  Limbs() {}
+  Limbs(size_t n, uint32_t v) { assign(n, v); }
+  Limbs(const Limbs &o) { assign(o.p_, o.p_ + o.n_); }
+  Limbs(Limbs &&o) noexcept { steal(o); }
+  ~Limbs() {
+    if (p_ != buf_) std::free(p_);
+  }
+  Limbs &operator=(const Limbs &o) {
+    if (this != &o) assign(o.p_, o.p_ + o.n_);
+    return *this;
+  }
+  Limbs &operator=(Limbs &&o) noexcept {
+    if (this != &o) {
+      if (p_ != buf_) std::free(p_);
+      p_ = buf_, cap_ = kInline, n_ = 0;
+      steal(o);
+    }
+    return *this;
+  }
+  void steal(Limbs &o) {
+    if (o.p_ == o.buf_) {
+      std::memcpy(buf_, o.buf_, (size_t)o.n_ * 4);
+      n_ = o.n_;
+    } else {
+      p_ = o.p_, cap_ = o.cap_, n_ = o.n_;
+      o.p_ = o.buf_, o.cap_ = kInline;
+    }
+    o.n_ = 0;
+  }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  uint32_t &operator[](size_t i) { return p_[i]; }
+  const uint32_t &operator[](size_t i) const { return p_[i]; }
+  uint32_t &back() { return p_[n_ - 1]; }
+  const uint32_t &back() const { return p_[n_ - 1]; }
+  uint32_t *data() { return p_; }
+  const uint32_t *data() const { return p_; }
+  uint32_t *begin() { return p_; }
+  uint32_t *end() { return p_ + n_; }
+  const uint32_t *begin() const { return p_; }
+  const uint32_t *end() const { return p_ + n_; }
+  void clear() { n_ = 0; }
+  void pop_back() { --n_; }
+  void push_back(uint32_t v) {
+    if (n_ == cap_) grow(n_ + 1);
+    p_[n_++] = v;
+  }
+  void resize(size_t n, uint32_t v = 0) {
+    if (n > cap_) grow(n);
+    for (size_t i = n_; i < n; ++i) p_[i] = v;
+    n_ = (uint32_t)n;
+  }
+  void assign(size_t n, uint32_t v) {
+    n_ = 0;
+    resize(n, v);
+  }
+  template <class It>
+  void assign(It a, It b) {
+    size_t n = (size_t)(b - a);
+    if (n > cap_) {
+      n_ = 0;
+      grow(n);
+    }
+    for (size_t i = 0; i < n; ++i) p_[i] = (uint32_t)a[i];
+    n_ = (uint32_t)n;
+  }
+  void swap(Limbs &o) {
+    Limbs t(std::move(o));
+    o = std::move(*this);
+    *this = std::move(t);
+  }
+};
+
 // ------------------------------------------------------------------------------- ZZ
 class ZZ {
  public:
-  std::vector<uint32_t> mag;  // little-endian, no leading zero limbs; empty = 0
+  Limbs mag;  // little-endian, no leading zero limbs; empty = 0
   bool neg = false;
 
   ZZ() {}
@@ -68,13 +159,13 @@ class ZZ {
   }
 
   // ---- magnitude helpers
-  static int cmp_mag(const std::vector<uint32_t> &a, const std::vector<uint32_t> &b) {
+  static int cmp_mag(const Limbs &a, const Limbs &b) {
     if (a.size() != b.size()) return a.size() < b.size() ? -1 : 1;
     for (size_t i = a.size(); i-- > 0;)
       if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
     return 0;
   }
-  static void add_mag(std::vector<uint32_t> &a, const std::vector<uint32_t> &b) {
+  static void add_mag(Limbs &a, const Limbs &b) {
     if (a.size() < b.size()) a.resize(b.size(), 0);
     uint64_t c = 0;
     for (size_t i = 0; i < a.size(); ++i) {
@@ -84,7 +175,7 @@ class ZZ {
     }
     if (c) a.push_back((uint32_t)c);
   }
-  static void sub_mag(std::vector<uint32_t> &a, const std::vector<uint32_t> &b) {  // a >= b
+  static void sub_mag(Limbs &a, const Limbs &b) {  // a >= b
     int64_t br = 0;
     for (size_t i = 0; i < a.size(); ++i) {
       int64_t t = (int64_t)a[i] - (i < b.size() ? b[i] : 0) - br;
@@ -104,7 +195,7 @@ class ZZ {
     } else if (cmp_mag(mag, o.mag) >= 0) {
       sub_mag(mag, o.mag);
     } else {
-      std::vector<uint32_t> t = o.mag;
+      Limbs t = o.mag;
       sub_mag(t, mag);
       mag.swap(t);
       neg = o.neg;
@@ -124,7 +215,7 @@ class ZZ {
       neg = false;
       return *this;
     }
-    std::vector<uint32_t> r(mag.size() + o.mag.size(), 0);
+    Limbs r(mag.size() + o.mag.size(), 0);
     for (size_t i = 0; i < mag.size(); ++i) {
       uint64_t c = 0;
       for (size_t j = 0; j < o.mag.size(); ++j) {
@@ -140,8 +231,8 @@ class ZZ {
     return *this;
   }
   // truncated magnitude division: q = |a| / |b|, r = |a| % |b|
-  static void divmod_mag(const std::vector<uint32_t> &a, const std::vector<uint32_t> &b,
-                         std::vector<uint32_t> &q, std::vector<uint32_t> &r) {
+  static void divmod_mag(const Limbs &a, const Limbs &b,
+                         Limbs &q, Limbs &r) {
     if (b.empty()) Error("ZZ: division by zero");
     q.assign(a.size(), 0);
     r.clear();
@@ -175,7 +266,7 @@ class ZZ {
   }
   // floor division and non-negative-for-positive-modulus remainder (NTL semantics)
   static void DivRem(ZZ &q, ZZ &r, const ZZ &a, const ZZ &b) {
-    std::vector<uint32_t> qm, rm;
+    Limbs qm, rm;
     divmod_mag(a.mag, b.mag, qm, rm);
     q.mag = qm;
     q.neg = (a.neg != b.neg) && !qm.empty();
@@ -202,7 +293,7 @@ class ZZ {
     if (k < 0) return *this >>= -k;
     if (mag.empty() || k == 0) return *this;
     size_t ws = k / 32, bs = k % 32;
-    std::vector<uint32_t> r(mag.size() + ws + 1, 0);
+    Limbs r(mag.size() + ws + 1, 0);
     for (size_t i = 0; i < mag.size(); ++i) {
       uint64_t v = (uint64_t)mag[i] << bs;
       r[i + ws] |= (uint32_t)v;
@@ -220,7 +311,7 @@ class ZZ {
       neg = false;
       return *this;
     }
-    std::vector<uint32_t> r(mag.size() - ws, 0);
+    Limbs r(mag.size() - ws, 0);
     for (size_t i = 0; i < r.size(); ++i) {
       uint64_t v = mag[i + ws];
       if (i + ws + 1 < mag.size()) v |= (uint64_t)mag[i + ws + 1] << 32;
@@ -403,7 +494,7 @@ inline long NextPowerOfTwo(long m) {
 inline std::ostream &operator<<(std::ostream &os, const ZZ &a) {
   if (a.is_zero()) return os << "0";
   std::string s;
-  std::vector<uint32_t> m = a.mag;
+  Limbs m = a.mag;
   while (!m.empty()) {
     uint64_t rem = 0;
     for (size_t i = m.size(); i-- > 0;) {
