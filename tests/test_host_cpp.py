@@ -74,20 +74,76 @@ def test_host_client_matches_oracle_cfg1_emu(emu_lib, tmp_path):
     check_against_golden(run_client(emu_lib, tmp_path, "cfg1"), "cfg1")
 
 
+def _write_data(path, d, n, seed=12345):
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from generate_random_data import generate
+    rows, labels = generate(d, n, seed)
+    with open(path, "w") as f:
+        f.write("%d %d\n" % (d, n))
+        for r, l in zip(rows, labels):
+            f.write(" ".join(str(v) for v in r) + " %d\n" % l)
+
+
+def _numbers(text):
+    """All integers of a driver's value section, in print order ('[]' is NTL's zero polynomial)."""
+    import re
+    return [int(t) if t != "[]" else 0 for t in re.findall(r"\[\]|-?\d+", re.sub(r"theta\[\d+\]", "theta", text))]
+
+
+def run_regression_client(exe, datafile, p, g, timeout=900):
+    """Test_Regression.cpp prints RegressPT's values, then the decrypted ones: they must agree."""
+    r = subprocess.run([exe, datafile, str(p), str(g)], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    out = r.stdout
+    want = _numbers(out[out.index("Expected values:"):out.index("Setup time")])
+    got = _numbers(out[out.index("Computed values:"):out.index("Decryption time")])
+    assert want and got == want, out[-1500:]
+    return out
+
+
+def run_statistics_client(exe, datafile, p, g, timeout=900):
+    r = subprocess.run([exe, datafile, str(p), str(g)], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    out = r.stdout
+    want = _numbers(out[out.index("Expected values:"):out.index("Setup time")].replace("N^2", "NN"))
+    got = _numbers(out[out.index("Computed values:"):out.index("Decryption time")].replace("N^2", "NN"))
+    assert want and got == want, out[-2500:]
+    return out
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
-def test_reference_clients_compile_unchanged(emu_lib, tmp_path):
-    client = tmp_path / "client"
-    client.mkdir()
-    for f in ("Test_AddMul.cpp", "Test_General.cpp", "Test_Regression.cpp", "Test_Statistics.cpp", "Regression.h",
-              "Statistics.h", "Matrix.h", "Matrix.cpp"):
-        shutil.copy(os.path.join(REF, f), client / f)  # scratch copy, never enters the repo
-    exes = {}
-    for t in ("Test_AddMul", "Test_General", "Test_Regression", "Test_Statistics"):
-        exes[t] = compile_client([str(client / (t + ".cpp"))], emu_lib, str(tmp_path / (t + "_x")))
+def test_reference_clients_run_unchanged_emu(emu_lib, tmp_path):
+    """Test_AddMul.cpp, Test_General.cpp, Test_Regression.cpp and Test_Statistics.cpp (+ Regression.h,
+    Statistics.h, Matrix.*) compile unchanged against our headers; each one's own check passes."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpp"))
+    from build_ref_clients import build_ref_clients
+    exes = build_ref_clients(emu_lib, str(tmp_path / "bin"))
     for seed in (1, 2):
         r = subprocess.run([exes["Test_AddMul"], "80", "23", "7", str(seed)], capture_output=True, text=True,
                            timeout=600)
         assert r.returncode == 0 and "Test SUCCEEDED" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    _write_data(tmp_path / "reg.dat", 2, 20)
+    run_regression_client(exes["Test_Regression"], str(tmp_path / "reg.dat"), 23, 7)
+    _write_data(tmp_path / "stat.dat", 3, 20)
+    run_statistics_client(exes["Test_Statistics"], str(tmp_path / "stat.dat"), 23, 7)
+
+
+@pytest.mark.gpu
+def test_reference_clients_run_unchanged_gpu(cuda_lib, tmp_path):
+    """The same four programs, prebuilt against libfhesi_b200.so by __graft_entry__.build() in the
+    build container (the reference tree does not exist on the GPU box)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpp"))
+    from build_ref_clients import prebuilt
+    exes = prebuilt()
+    if len(exes) < 4:
+        pytest.skip("tests/cpp/_ref_build not populated (reference tree was not mounted at build time)")
+    for args in (["80", "23", "7", "1"], ["256", "1019", "3", "2"]):
+        r = subprocess.run([exes["Test_AddMul"]] + args, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "Test SUCCEEDED" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    _write_data(tmp_path / "reg.dat", 3, 1500)      # 6 blocks of 256 at p = 1019
+    run_regression_client(exes["Test_Regression"], str(tmp_path / "reg.dat"), 1019, 3)
+    _write_data(tmp_path / "stat.dat", 3, 1500)
+    run_statistics_client(exes["Test_Statistics"], str(tmp_path / "stat.dat"), 1019, 3)
 
 
 @pytest.mark.gpu
