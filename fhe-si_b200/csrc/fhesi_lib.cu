@@ -437,6 +437,12 @@ int fhesi_h2d(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
+int fhesi_h2d_async(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
 int fhesi_d2h(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
   if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
   CK(cudaSetDevice(c->device));

@@ -77,6 +77,23 @@ static void RemPhim(ZZX &a, const PAlgebra &zms) {
 // a * b mod Phi_m.  Secret keys are ternary and sparse (Hamming weight 64), so the products key
 // generation needs are shift-and-add; they run on fixed-width two's-complement word arrays
 // (no allocation per coefficient), which keeps KeySwitchSI::Init at set-up-time cost.
+// Inner loops of the host-side samplers/packers, cloned for AVX2 (resolved at load time: the
+// library is built in one container and runs on another host).
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define FHESI_SIMD_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define FHESI_SIMD_CLONES
+#endif
+FHESI_SIMD_CLONES static void MacRow32(uint64_t *acc, const uint32_t *b, uint32_t c, long n) {
+  for (long k = 0; k < n; ++k) acc[k] += (uint64_t)b[k] * c;
+}
+FHESI_SIMD_CLONES static void AddRow64(int64_t *d, const int64_t *w, size_t n) {
+  for (size_t t = 0; t < n; ++t) d[t] += w[t];
+}
+FHESI_SIMD_CLONES static void SubRow64(int64_t *d, const int64_t *w, size_t n) {
+  for (size_t t = 0; t < n; ++t) d[t] -= w[t];
+}
+
 static ZZX MulModPhim(const ZZX &a, const ZZX &b, const PAlgebra &zms) {
   auto tiny = [](const ZZX &x) {
     for (auto &c : x.rep.v)
@@ -105,10 +122,8 @@ static ZZX MulModPhim(const ZZX &a, const ZZX &b, const PAlgebra &zms) {
       if (c.is_zero()) continue;
       int64_t *d = &acc[j * Wd];
       const int64_t *w = src.data();
-      if (c.neg)
-        for (size_t t = 0; t < span; ++t) d[t] -= w[t];
-      else
-        for (size_t t = 0; t < span; ++t) d[t] += w[t];
+      if (c.neg) SubRow64(d, w, span);
+      else AddRow64(d, w, span);
     }
     r.rep.v.resize(len);
     std::vector<uint32_t> limbs(Wd + 2);
@@ -213,21 +228,27 @@ void sampleSmall(ZZX &poly, long n) {  // NumbTh.cpp:361-375
   }
   poly.normalize();
 }
-void sampleGaussian(ZZX &poly, long n, double stdev) {  // NumbTh.cpp:377-404
+// Box-Muller as NumbTh.cpp:377-404 draws it: two uniforms per pair of outputs, rounded to nearest
+static void SampleGaussianInts(int32_t *out, long n, double stdev) {
   static double const Pi = 4.0 * atan(1.0);
   static long const bignum = 0xfffffff;
-  if (n <= 0) n = deg(poly) + 1;
-  if (n <= 0) return;
-  poly.rep.v.assign(n, ZZ());
   for (long i = 0; i < n; i += 2) {
     double r1 = (1 + RandomBnd(bignum)) / ((double)bignum + 1);
     double r2 = (1 + RandomBnd(bignum)) / ((double)bignum + 1);
     double theta = 2 * Pi * r1;
     double rr = sqrt(-2.0 * std::log(r2)) * stdev;
     assert(rr < 8 * stdev);
-    poly.rep.v[i] = ZZ((long)floor(rr * cos(theta) + 0.5));
-    if (i + 1 < n) poly.rep.v[i + 1] = ZZ((long)floor(rr * sin(theta) + 0.5));
+    out[i] = (int32_t)floor(rr * cos(theta) + 0.5);
+    if (i + 1 < n) out[i + 1] = (int32_t)floor(rr * sin(theta) + 0.5);
   }
+}
+void sampleGaussian(ZZX &poly, long n, double stdev) {  // NumbTh.cpp:377-404
+  if (n <= 0) n = deg(poly) + 1;
+  if (n <= 0) return;
+  std::vector<int32_t> g(n);
+  SampleGaussianInts(g.data(), n, stdev);
+  poly.rep.v.assign(n, ZZ());
+  for (long i = 0; i < n; ++i) poly.rep.v[i] = ZZ((long)g[i]);
   poly.normalize();
 }
 
@@ -290,21 +311,41 @@ void PlaintextSpace::Init(const ZZX &PhiX, const ZZ &pp) {
     long di = InvMod(d, P);
     for (long i = 0; i < n; ++i) b[i] = MulMod(b[i], di, P);
   }
+  basis32.clear();
+  if (P < (1L << 26)) {
+    basis32.resize((size_t)n * n);
+    for (long j = 0; j < n; ++j)
+      for (long i = 0; i < n; ++i) basis32[(size_t)j * n + i] = (uint32_t)basis[j][i];
+  }
 }
 void PlaintextSpace::EmbedInSlots(ZZ_pX &embedded, const vector<ZZ_pX> &msgs, bool onlyUsable) const {
   if (!totalSlots) Error("PlaintextSpace: slots need a prime p = 1 mod m and a generator of Z_m^*");
   const long P = to_long(p), n = totalSlots;
-  std::vector<unsigned __int128> acc(n, 0);
-  unsigned msgInd = 0;
-  for (unsigned i = 0; i < totalSlots && msgInd < msgs.size(); i++) {
-    if (onlyUsable && i >= usableSlots) break;
-    const ZZ_pX &mi = msgs[msgInd++];
-    long c = eval(mi, ZZ_p(roots[i])).v;  // a slot only sees the message modulo its factor X - r_i
-    if (!c) continue;
-    for (long k = 0; k < n; ++k) acc[k] += (unsigned __int128)basis[i][k] * c;
-  }
   embedded.rep.v.assign(n, ZZ_p());
-  for (long k = 0; k < n; ++k) embedded.rep.v[k].v = (long)(acc[k] % (unsigned long)P);
+  auto slotValue = [&](const ZZ_pX &mi, unsigned i) -> long {
+    // a slot only sees the message modulo its factor X - r_i
+    return deg(mi) <= 0 ? (deg(mi) < 0 ? 0 : mi.rep.v[0].v) : eval(mi, ZZ_p(roots[i])).v;
+  };
+  unsigned msgInd = 0;
+  if (P < (1L << 26)) {  // products < 2^52, at most 2^12 of them per sum: plain 64-bit lanes
+    std::vector<uint64_t> acc(n, 0);
+    for (unsigned i = 0; i < totalSlots && msgInd < msgs.size(); i++) {
+      if (onlyUsable && i >= usableSlots) break;
+      const uint32_t c = (uint32_t)slotValue(msgs[msgInd++], i);
+      if (!c) continue;
+      MacRow32(acc.data(), &basis32[(size_t)i * n], c, n);
+    }
+    for (long k = 0; k < n; ++k) embedded.rep.v[k].v = (long)(acc[k] % (uint64_t)P);
+  } else {
+    std::vector<unsigned __int128> acc(n, 0);
+    for (unsigned i = 0; i < totalSlots && msgInd < msgs.size(); i++) {
+      if (onlyUsable && i >= usableSlots) break;
+      long c = slotValue(msgs[msgInd++], i);
+      if (!c) continue;
+      for (long k = 0; k < n; ++k) acc[k] += (unsigned __int128)basis[i][k] * c;
+    }
+    for (long k = 0; k < n; ++k) embedded.rep.v[k].v = (long)(acc[k] % (unsigned long)P);
+  }
   embedded.normalize();
 }
 void PlaintextSpace::DecodeSlot(ZZ_pX &val, const ZZ_pX &msg, unsigned ind) const {
@@ -742,7 +783,6 @@ Ciphertext &Ciphertext::operator+=(const Ciphertext &o) {  // Ciphertext.cpp:123
     if (scaledUp) Check(fhesi_tprod_add_dev(d, buf->ptr, rhs->buf->ptr, rhs->nparts, 1), "fhesi_tprod_add_dev");
     else Check(fhesi_ct_add_dev(d, buf->ptr, rhs->buf->ptr, rhs->nparts, 1), "fhesi_ct_add_dev");
   }
-  Check(fhesi_sync(d), "fhesi_sync");  // tmp / rhs buffers may be released on return
   hostStale = true;
   return *this;
 }
@@ -759,9 +799,8 @@ Ciphertext &Ciphertext::operator+=(const ZZX &other) {  // Ciphertext.cpp:147-16
   }
   std::vector<uint32_t> w = PackPoly(sc, n, W);
   DevBuf t(d, w.size() * 4);
-  Check(fhesi_h2d(d, t.ptr, w.data(), w.size() * 4), "fhesi_h2d");
+  Check(fhesi_h2d_async(d, t.ptr, w.data(), w.size() * 4), "fhesi_h2d_async");
   Check(fhesi_ct_add_dev(d, buf->ptr, t.ptr, 1, 1), "fhesi_ct_add_dev");
-  Check(fhesi_sync(d), "fhesi_sync");
   hostStale = true;
   return *this;
 }
@@ -774,7 +813,6 @@ Ciphertext &Ciphertext::operator*=(const Ciphertext &o) {  // Ciphertext.cpp:167
   const unsigned po = nparts + rhs.nparts - 1;
   auto nb = make_shared<DevBuf>(d, fhesi_tprod_bytes(d, po));
   Check(fhesi_ct_tensor_dev(d, buf->ptr, nparts, rhs.buf->ptr, rhs.nparts, nb->ptr, 1, 0), "fhesi_ct_tensor_dev");
-  Check(fhesi_sync(d), "fhesi_sync");
   buf = nb;
   nparts = po;
   wordsPer = 0;
@@ -807,9 +845,8 @@ Ciphertext &Ciphertext::operator*=(const ZZX &other) {  // Ciphertext.cpp:246-25
   // NOTE: the reference multiplies by `other` as an integer polynomial; callers pass to_ZZX of a
   // ZZ_pX (coefficients in [0,p)), for which reducing mod p is the identity.
   DevBuf t(d, n * 4);
-  Check(fhesi_h2d(d, t.ptr, pt.data(), n * 4), "fhesi_h2d");
+  Check(fhesi_h2d_async(d, t.ptr, pt.data(), n * 4), "fhesi_h2d_async");
   Check(fhesi_ct_mul_plain_dev(d, buf->ptr, t.ptr, nparts, 1), "fhesi_ct_mul_plain_dev");
-  Check(fhesi_sync(d), "fhesi_sync");
   hostStale = true;
   return *this;
 }
@@ -831,7 +868,6 @@ void Ciphertext::ScaleDown() {  // Ciphertext.cpp:194-218
   fhesi_ctx *d = context->Dev();
   auto nb = make_shared<DevBuf>(d, fhesi_ct_bytes(d, nparts));
   Check(fhesi_scaledown_dev(d, buf->ptr, nparts, nb->ptr, 1), "fhesi_scaledown_dev");
-  Check(fhesi_sync(d), "fhesi_sync");
   buf = nb;
   wordsPer = context->Words();
   scaledUp = false;
@@ -904,26 +940,22 @@ void FHESIPubKey::Encrypt(Ciphertext &ctxt, const Plaintext &ptxt) const {  // F
   if (!devKey) devKey = UploadKey(context, publicKey);
   fhesi_ctx *d = context.Dev();
   const unsigned n = context.zMstar.phiM();
-  std::vector<uint8_t> r(n);
+  // one staging block: message | e0 | e1 | r, one stream-ordered copy, no synchronisation -- the
+  // next call's sampling overlaps this call's device work
+  std::vector<uint32_t> stage(3 * n + (n + 3) / 4, 0);
+  uint8_t *r = (uint8_t *)&stage[3 * n];
   for (unsigned i = 0; i < n; i++) r[i] = (uint8_t)RandomBnd(2L);        // :14-17
-  std::vector<int32_t> e(2 * n, 0);
-  for (unsigned i = 0; i < 2; ++i) {                                       // :24, one draw per part
-    ZZX g;
-    sampleGaussian(g, n, context.stdev);
-    for (long j = 0; j <= deg(g); ++j) e[i * n + j] = (int32_t)to_long(g.rep.v[j]);
-  }
-  std::vector<uint32_t> msg(n, 0);
-  for (long j = 0; j <= deg(ptxt.message) && j < (long)n; ++j) msg[j] = (uint32_t)ptxt.message.rep.v[j].v;
-  DevBuf dm(d, n * 4), dr(d, n), de(d, 2 * n * 4);
-  Check(fhesi_h2d(d, dm.ptr, msg.data(), n * 4), "fhesi_h2d");
-  Check(fhesi_h2d(d, dr.ptr, r.data(), n), "fhesi_h2d");
-  Check(fhesi_h2d(d, de.ptr, e.data(), 2 * n * 4), "fhesi_h2d");
+  for (unsigned i = 0; i < 2; ++i)                                         // :24, one draw per part
+    SampleGaussianInts((int32_t *)&stage[(1 + i) * n], n, context.stdev);
+  for (long j = 0; j <= deg(ptxt.message) && j < (long)n; ++j) stage[j] = (uint32_t)ptxt.message.rep.v[j].v;
+  auto ds = make_shared<DevBuf>(d, stage.size() * 4);
+  Check(fhesi_h2d_async(d, ds->ptr, stage.data(), stage.size() * 4), "fhesi_h2d_async");
+  const uint32_t *dw = (const uint32_t *)ds->ptr;
   ctxt.context = &context;
   ctxt.Clear();
   ctxt.Alloc(2, context.Words());
-  Check(fhesi_encrypt_dev(d, devKey.get(), dm.ptr, (const uint8_t *)dr.ptr, (const int32_t *)de.ptr, ctxt.buf->ptr, 1),
-        "fhesi_encrypt_dev");
-  Check(fhesi_sync(d), "fhesi_sync");
+  Check(fhesi_encrypt_dev(d, devKey.get(), dw, (const uint8_t *)(dw + 3 * n), (const int32_t *)(dw + n),
+                          ctxt.buf->ptr, 1), "fhesi_encrypt_dev");
   ctxt.hostStale = true;
 }
 void FHESIPubKey::Export(ofstream &out) const { ::Export(out, publicKey); }
@@ -1003,7 +1035,6 @@ void KeySwitchSI::ApplyKeySwitch(Ciphertext &ctxt) const {  // FHE-SI.cpp:241-26
   fhesi_ctx *d = context.Dev();
   auto nb = make_shared<DevBuf>(d, fhesi_ct_bytes(d, 2));
   Check(fhesi_keyswitch_dev(d, Dev(), ctxt.buf->ptr, nb->ptr, 1), "fhesi_keyswitch_dev");
-  Check(fhesi_sync(d), "fhesi_sync");
   ctxt.buf = nb;
   ctxt.nparts = 2;
   ctxt.hostStale = true;

@@ -90,6 +90,7 @@ class PlaintextSpace {
   unsigned m = 0, totalSlots = 0, usableSlots = 0;
   vector<long> roots;            // roots[j] = rho^(g^j) mod p
   vector<vector<long>> basis;    // basis[j] = CRT idempotent of slot j, phi(m) coefficients
+  vector<uint32_t> basis32;      // the same, flat, when p < 2^26 (vectorisable embedding)
   friend class FHEcontext;
 };
 

@@ -570,7 +570,15 @@ inline ZZ RandomBnd(const ZZ &n) {
     if (v < n) return v;
   }
 }
-inline long RandomBnd(long n) { return to_long(RandomBnd(ZZ(n))); }
+inline long RandomBnd(long n) {  // same draws as the ZZ version: one 64-bit word per attempt
+  if (n <= 1) return 0;
+  const int nbits = 64 - __builtin_clzl((unsigned long)(n - 1));
+  const uint64_t mask = nbits >= 64 ? ~0ull : (1ull << nbits) - 1;
+  for (;;) {
+    uint64_t v = GlobalRandomStream().next64() & mask;
+    if (v < (uint64_t)n) return (long)v;
+  }
+}
 inline void RandomBnd(ZZ &x, const ZZ &n) { x = RandomBnd(n); }
 
 // ------------------------------------------------------------------------------- vectors

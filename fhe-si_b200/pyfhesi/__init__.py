@@ -43,6 +43,7 @@ SYMBOLS = {
     "fhesi_malloc": (C.c_int, [_P, _SZ, C.POINTER(_P)]),
     "fhesi_free": (C.c_int, [_P, _P]),
     "fhesi_h2d": (C.c_int, [_P, _P, _P, _SZ]),
+    "fhesi_h2d_async": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_d2h": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_d2d": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_ct_mul_plain_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),

@@ -80,6 +80,11 @@ int fhesi_sync(fhesi_ctx *ctx);
 int fhesi_malloc(fhesi_ctx *ctx, size_t bytes, void **dptr);
 int fhesi_free(fhesi_ctx *ctx, void *dptr);
 int fhesi_h2d(fhesi_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+/* Stream-ordered copy without the trailing synchronisation.  For pageable `src_host` the source has
+ * been consumed when the call returns; a pinned source must stay untouched until fhesi_sync.  The
+ * host layer uses it so that a client's next operator (sampling, packing) overlaps the device
+ * work of the previous one. */
+int fhesi_h2d_async(fhesi_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int fhesi_d2h(fhesi_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 int fhesi_d2d(fhesi_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
 size_t fhesi_ct_bytes(const fhesi_ctx *ctx, uint32_t parts);    /* parts*n*W*4      */
