@@ -82,6 +82,13 @@ struct fhesi_ctx {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the host pipeline
   std::vector<cudaEvent_t> pipe_events;
   u32 pipe_chunk = 0;  // 0 = choose from the batch size; FHESI_PIPE_CHUNK overrides
+  u32 pipe_taper = 1;  // FHESI_PIPE_TAPER=0: equal chunks
+  int sm_count = 148;  // from the device at context creation
+  // second compute lane of the host pipeline: alternate chunks run on their own stream with their
+  // own scratch, so one chunk's first waves fill the SMs that the other chunk's last wave leaves idle
+  u32 pipe_lanes = 2;  // FHESI_PIPE_LANES=1: single compute stream
+  cudaStream_t lane_stream = nullptr;
+  Arena lane_scratch;
   Arena work;   // tprod / scaled-down intermediates of the generic mult_relin composition
 };
 static void prof_clear(fhesi_ctx *c);
@@ -335,12 +342,21 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   }
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.multiProcessorCount > 0) c->sm_count = prop.multiProcessorCount;
+  }
   const char *ev = getenv("FHESI_CHUNK");
   if (ev && atoi(ev) > 0) c->chunk = (u32)atoi(ev);
   ev = getenv("FHESI_FUSED_CHUNK");
   if (ev && atoi(ev) > 0) c->fused_chunk = (u32)atoi(ev);
   ev = getenv("FHESI_PIPE_CHUNK");
   if (ev && atoi(ev) > 0) c->pipe_chunk = (u32)atoi(ev);
+  ev = getenv("FHESI_PIPE_TAPER");
+  if (ev) c->pipe_taper = atoi(ev) > 0;
+  ev = getenv("FHESI_PIPE_LANES");
+  if (ev && atoi(ev) > 0) c->pipe_lanes = atoi(ev) > 1 ? 2 : 1;
   ev = getenv("FHESI_NO_SPLIT");
   if (ev && atoi(ev) > 0) c->info.Ls = 0, c->info.split_words = 0;
   ev = getenv("FHESI_NO_FUSED");
@@ -365,12 +381,14 @@ void fhesi_ctx_destroy(fhesi_ctx *c) {
   for (auto &kv : c->pool_free)
     for (void *p : kv.second) cudaFree(p);
   if (c->scratch.ptr) cudaFree(c->scratch.ptr);
+  if (c->lane_scratch.ptr) cudaFree(c->lane_scratch.ptr);
   if (c->stage.ptr) cudaFree(c->stage.ptr);
   if (c->work.ptr) cudaFree(c->work.ptr);
   prof_clear(c);
   for (auto e : c->pipe_events) cudaEventDestroy(e);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  if (c->lane_stream) cudaStreamDestroy(c->lane_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -572,7 +590,18 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
   ResidueArgs r{a, b, resid, I.Lt, cnt};
   KL(c, k_residues, nblk(cnt * 4 * I.n, 128), 128, (I.Lt * 2 * c->dc.CW + 2 * I.Lt) * 4, c->dc, r);
   CKL();
-  const u32 opg = cnt >= 4096 ? 4 : (cnt >= 1024 ? 2 : 1);  // ops per group: amortise the table fill
+  // ops per group: more of them amortise the CTA's twiddle-table fill (about 0.35 of one op's
+  // work), fewer keep the last wave full; pick the best product of the two
+  u32 opg = 1;
+  {
+    double best = 0;
+    for (u32 o = 1; o <= 4; ++o) {
+      const double ctas = (double)I.Lt * (double)((cnt + KG * o - 1) / (KG * o));
+      const double waves = ctas / c->sm_count;
+      const double eff = waves / std::ceil(waves) / (1.0 + 0.35 / o);
+      if (eff > best * 1.0001) best = eff, opg = o;
+    }
+  }
   FusedTensorArgs t{resid, out, I.Lt, (u32)cnt, opg, (u32)to_tprod};
   dim3 grid(I.Lt, (unsigned)((cnt + KG * opg - 1) / (KG * opg)));
   KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
@@ -1048,17 +1077,68 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
   if (!c->h2d_stream) {
     CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->lane_stream, cudaStreamNonBlocking));
   }
-  // pipeline chunk: ~10 chunks per call, a multiple of 12 (whole CTAs in both fused kernels), between
-  // 252 (below that the grids are too few waves deep) and 768 (above, fill/drain dominates) --
-  // measured on a B200 with PCIe gen5: 256 is best at 2048 pairs, 768 at 8192
+  // pipeline chunk: ~14 chunks per call, a multiple of 12 (whole CTAs in both fused kernels), between
+  // 252 (below that the grids are too few waves deep) and 576 (above, the compute stream's lag
+  // behind the upload -- one chunk -- costs more than the better kernel efficiency returns);
+  // measured on a B200 behind PCIe gen5 with two compute lanes, batch 8192: 384 -> 705 k ops/s,
+  // 576 -> 708 k, 768 -> 702 k, 1024 -> 669 k, 1536 -> 658 k
   size_t PC = c->pipe_chunk;
   if (!PC) {
-    PC = ((count / 10 + 11) / 12) * 12;
+    PC = ((count / 14 + 11) / 12) * 12;
     if (PC < 252) PC = 252;
-    if (PC > 768) PC = 768;
+    if (PC > 576) PC = 576;
   }
-  const size_t nchunks = (count + PC - 1) / PC;
+  // chunk schedule: full chunks in the middle, a quarter and a half chunk at either end when the
+  // batch is long enough -- the first upload and the last compute + download are the only parts
+  // of the call that do not overlap anything (FHESI_PIPE_TAPER=0 turns the taper off)
+  std::vector<size_t> sizes;
+  if (const char *sched = getenv("FHESI_PIPE_SCHED")) {
+    // explicit schedule for tuning runs: "192,384,*1536,384,192" -- head sizes, one repeated
+    // middle size (marked *), tail sizes; anything that does not fit the batch is dropped
+    std::vector<size_t> head, tail;
+    size_t mid = PC;
+    bool after = false;
+    for (const char *q = sched; *q;) {
+      const bool star = *q == '*';
+      if (star) ++q;
+      const size_t v = strtoul(q, (char **)&q, 10);
+      if (*q == ',') ++q;
+      if (!v) break;
+      if (star) mid = v, after = true;
+      else (after ? tail : head).push_back(v);
+    }
+    size_t rest = count, tsum = 0;
+    for (size_t v : tail) tsum += v;
+    for (size_t v : head)
+      if (rest > tsum + v) sizes.push_back(v), rest -= v;
+    if (rest <= tsum) tail.clear(), tsum = 0;
+    rest -= tsum;
+    while (rest) {
+      const size_t t = rest < mid ? rest : mid;
+      sizes.push_back(t);
+      rest -= t;
+    }
+    sizes.insert(sizes.end(), tail.begin(), tail.end());
+  } else {
+    size_t rest = count;
+    const size_t q = ((PC / 4 + 11) / 12) * 12, h = ((PC / 2 + 11) / 12) * 12;
+    const bool taper = c->pipe_taper && count >= 6 * PC;
+    std::vector<size_t> tail;
+    if (taper) {
+      sizes.push_back(q), sizes.push_back(h);
+      tail.push_back(h), tail.push_back(q);
+      rest -= 2 * (q + h);
+    }
+    while (rest) {
+      const size_t t = rest < PC ? rest : PC;
+      sizes.push_back(t);
+      rest -= t;
+    }
+    sizes.insert(sizes.end(), tail.begin(), tail.end());
+  }
+  const size_t nchunks = sizes.size();
   while (c->pipe_events.size() < 2 * nchunks) {
     cudaEvent_t e;
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1069,21 +1149,51 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
   // the copy stream must not overtake work already queued on the compute stream
   CK(cudaEventRecord(c->pipe_events[0], c->stream));
   CK(cudaStreamWaitEvent(c->h2d_stream, c->pipe_events[0], 0));
+  CK(cudaStreamWaitEvent(c->lane_stream, c->pipe_events[0], 0));
+  // FHESI_PIPE_TRACE=1: per-chunk timeline (upload done / compute done / download done, ms from the
+  // start of the call) on stderr -- a debugging aid, off by default
+  static const bool trace = getenv("FHESI_PIPE_TRACE") && atoi(getenv("FHESI_PIPE_TRACE")) > 0;
+  std::vector<cudaEvent_t> tev;
+  if (trace) {
+    tev.resize(3 * nchunks + 1);
+    for (auto &e : tev) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(tev[3 * nchunks], c->stream));
+  }
+  size_t off = 0;
   for (size_t ci = 0; ci < nchunks; ++ci) {
-    const size_t off = ci * PC, cnt = count - off < PC ? count - off : PC;
-    cudaEvent_t ev_in = c->pipe_events[2 * ci], ev_done = c->pipe_events[2 * ci + 1];
+    const size_t cnt = sizes[ci];
+    cudaEvent_t ev_in = trace ? tev[3 * ci] : c->pipe_events[2 * ci];
+    cudaEvent_t ev_done = trace ? tev[3 * ci + 1] : c->pipe_events[2 * ci + 1];
     CK(cudaMemcpyAsync(da + off * ctb, (const char *)h_a + off * ctb, cnt * ctb, cudaMemcpyHostToDevice, c->h2d_stream));
     CK(cudaMemcpyAsync(db + off * ctb, (const char *)h_b + off * ctb, cnt * ctb, cudaMemcpyHostToDevice, c->h2d_stream));
     CK(cudaEventRecord(ev_in, c->h2d_stream));
-    CK(cudaStreamWaitEvent(c->stream, ev_in, 0));
-    int rc = fhesi_mult_relin_dev(c, ksw, (const u32 *)(da + off * ctb), (const u32 *)(db + off * ctb),
-                                  (u32 *)(dout + off * ctb), cnt);
+    const bool lane1 = c->pipe_lanes > 1 && (ci & 1);
+    if (lane1) std::swap(c->stream, c->lane_stream), std::swap(c->scratch, c->lane_scratch);
+    int rc = cudaStreamWaitEvent(c->stream, ev_in, 0) == cudaSuccess ? 0 : fail(FHESI_ERR_CUDA, "cudaStreamWaitEvent");
+    if (!rc)
+      rc = fhesi_mult_relin_dev(c, ksw, (const u32 *)(da + off * ctb), (const u32 *)(db + off * ctb),
+                                (u32 *)(dout + off * ctb), cnt);
+    if (!rc && cudaEventRecord(ev_done, c->stream) != cudaSuccess) rc = fail(FHESI_ERR_CUDA, "cudaEventRecord");
+    if (lane1) std::swap(c->stream, c->lane_stream), std::swap(c->scratch, c->lane_scratch);
     if (rc) return rc;
-    CK(cudaEventRecord(ev_done, c->stream));
     CK(cudaStreamWaitEvent(c->d2h_stream, ev_done, 0));
     CK(cudaMemcpyAsync((char *)h_out + off * ctb, dout + off * ctb, cnt * ctb, cudaMemcpyDeviceToHost, c->d2h_stream));
+    if (trace) CK(cudaEventRecord(tev[3 * ci + 2], c->d2h_stream));
+    off += cnt;
+  }
+  if (trace) {
+    CK(cudaStreamSynchronize(c->d2h_stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->lane_stream));
+    for (size_t ci = 0; ci < nchunks; ++ci) {
+      float t[3];
+      for (int k = 0; k < 3; ++k) CK(cudaEventElapsedTime(&t[k], tev[3 * nchunks], tev[3 * ci + k]));
+      fprintf(stderr, "pipe chunk %2zu size %4zu  h2d %.3f  compute %.3f  d2h %.3f\n", ci, sizes[ci], t[0], t[1], t[2]);
+    }
+    for (auto &e : tev) cudaEventDestroy(e);
   }
   CK(cudaStreamSynchronize(c->d2h_stream));
+  CK(cudaStreamSynchronize(c->lane_stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
