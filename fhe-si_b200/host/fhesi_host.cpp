@@ -209,9 +209,9 @@ void sampleHWt(ZZX &poly, long Hwt, long n) {  // NumbTh.cpp:340-359
   if (Hwt > n) Hwt = n;
   long i = 0;
   while (i < Hwt) {
-    long u = RandomBnd(n);
+    long u = RandomLibc31() % n;  // :349 -- lrand48(), i.e. rand() (NumbTh.h:32-35)
     if (poly.rep.v[u].is_zero()) {
-      long b = 2 * to_long(RandomBits_ZZ(1)) - 1;
+      long b = (RandomLibc31() & 2) - 1;  // :351-352
       poly.rep.v[u] = ZZ(b);
       i++;
     }
@@ -223,7 +223,7 @@ void sampleSmall(ZZX &poly, long n) {  // NumbTh.cpp:361-375
   if (n <= 0) return;
   poly.rep.v.assign(n, ZZ());
   for (long i = 0; i < n; i++) {
-    long u = to_long(RandomBits_ZZ(2));
+    long u = RandomLibc31();  // :367
     if (u & 1) poly.rep.v[i] = ZZ((long)(u & 2) - 1);
   }
   poly.normalize();
@@ -375,7 +375,9 @@ FHEcontext::~FHEcontext() {
   if (dev) fhesi_ctx_destroy(dev);
   if (activeContext == this) activeContext = NULL;
 }
-static long RootOfUnity2m(long p, long m) {  // deterministic (CModulus.cpp:66-76 picks at random)
+// FindPrimRootT (NumbTh.cpp:84-118) as Cmod::privateInit calls it for e = 2m (CModulus.cpp:66-76):
+// random s from the global stream, root = s^(phi(q)/e), accepted when its order is exactly e
+static long FindPrimitiveRoot2m(long p, long m) {
   long e = 2 * m;
   std::vector<long> fs;
   for (long t = e, d = 2; t > 1; ++d)
@@ -383,20 +385,23 @@ static long RootOfUnity2m(long p, long m) {  // deterministic (CModulus.cpp:66-7
       fs.push_back(d);
       while (t % d == 0) t /= d;
     }
-  for (long x = 2;; ++x) {
-    long r = PowerMod(x, (p - 1) / e, p);
+  for (int it = 0; it < 1000; ++it) {
+    long s = RandomBnd(p);
+    long r = PowerMod(s, (p - 1) / e, p);
+    if (PowerMod(r, e, p) != 1) continue;
     bool ok = true;
     for (long f : fs)
       if (PowerMod(r, e / f, p) == 1) ok = false;
     if (ok) return r;
   }
+  Error("FindPrimitiveRoot(): gave up after 1000 trials");
 }
 void FHEcontext::AddPrime(long p, bool special, long root) {  // FHEContext.cpp:30-43
   long twoM = 2 * zMstar.M();
   assert(ProbPrime(p) && p % twoM == 1 && !inChain(p));
   CmodulusInfo mo;
   mo.q = p;
-  mo.root = root ? root : RootOfUnity2m(p, zMstar.M());
+  mo.root = root ? root : FindPrimitiveRoot2m(p, zMstar.M());
   long i = moduli.size();
   moduli.push_back(mo);
   if (special) specialPrimes.insert(i);
@@ -996,13 +1001,13 @@ void KeySwitchSI::InitS2(const FHESISecKey &s) {  // FHE-SI.cpp:211-227
   tKeys.assign(sKeys.size() * 2 - 1, sKeys[1]);
   tKeys[0] = sKeys[0];
   for (unsigned i = 2; i < tKeys.size(); i++) tKeys[i] *= tKeys[i - 1];
-  FHESISecKey tensoredKey(s.GetContext(), FHESISecKey::Empty());
+  FHESISecKey tensoredKey(s.GetContext());  // FHE-SI.cpp:222 samples a key it then overwrites: same draws
   tensoredKey.UpdateRepresentation(tKeys);
   Init(tensoredKey, s);
 }
 void KeySwitchSI::InitAutomorph(const FHESISecKey &s, unsigned k) {  // FHE-SI.cpp:229-239
   vector<DoubleCRT> sKeys = s.GetRepresentation();
-  FHESISecKey automorphedKey(s.GetContext(), FHESISecKey::Empty());
+  FHESISecKey automorphedKey(s.GetContext());  // :233, likewise
   for (unsigned i = 0; i < sKeys.size(); i++) sKeys[i].automorph(k);
   automorphedKey.UpdateRepresentation(sKeys);
   Init(automorphedKey, s);

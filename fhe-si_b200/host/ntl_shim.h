@@ -20,6 +20,8 @@
 
 namespace NTL {
 
+enum INIT_SIZE_TYPE { INIT_SIZE };
+
 [[noreturn]] inline void Error(const char *msg) {
   std::cerr << msg << std::endl;
   std::abort();
@@ -338,8 +340,10 @@ FHESI_ZZ_BINOP(+)
 FHESI_ZZ_BINOP(-)
 FHESI_ZZ_BINOP(*)
 FHESI_ZZ_BINOP(/)
-FHESI_ZZ_BINOP(%)
 #undef FHESI_ZZ_BINOP
+inline ZZ operator%(const ZZ &a, const ZZ &b) { ZZ r = a; r %= b; return r; }
+inline long to_long(const ZZ &a);
+inline long operator%(const ZZ &a, long b) { ZZ r = a; r %= ZZ(b); return to_long(r); }  // NTL: long
 inline ZZ operator<<(const ZZ &a, long k) { ZZ r = a; r <<= k; return r; }
 inline ZZ operator>>(const ZZ &a, long k) { ZZ r = a; r >>= k; return r; }
 #define FHESI_ZZ_CMP(op)                                                          \
@@ -374,6 +378,8 @@ inline unsigned long to_ulong(const ZZ &a) { return (unsigned long)to_long(a); }
 inline void conv(long &x, const ZZ &a) { x = to_long(a); }
 inline void conv(ZZ &x, long a) { x = ZZ(a); }
 inline void conv(ZZ &x, const ZZ &a) { x = a; }
+inline double to_double(double d) { return d; }
+inline double to_double(long d) { return (double)d; }
 inline double to_double(const ZZ &a) {
   double r = 0;
   for (size_t i = a.mag.size(); i-- > 0;) r = r * 4294967296.0 + a.mag[i];
@@ -580,6 +586,9 @@ inline long RandomBnd(long n) {  // same draws as the ZZ version: one 64-bit wor
   }
 }
 inline void RandomBnd(ZZ &x, const ZZ &n) { x = RandomBnd(n); }
+// libc rand() stand-in (the reference's sampleHWt draws from lrand48(), which NumbTh.h:32-35 maps
+// to rand()): 31 bits of the same stream
+inline long RandomLibc31() { return (long)(GlobalRandomStream().next64() >> 33); }
 
 // ------------------------------------------------------------------------------- vectors
 template <class T>
@@ -589,6 +598,7 @@ class Vec {
   Vec() {}
   long length() const { return (long)v.size(); }
   void SetLength(long n) { v.resize(n); }
+  void FixLength(long n) { v.resize(n); }
   void SetMaxLength(long n) { v.reserve(n); }
   void kill() { v.clear(); }
   T &operator[](long i) { return v[i]; }
@@ -757,6 +767,7 @@ class ZZ_pX {
  public:
   vec_ZZ_p rep;
   ZZ_pX() {}
+  ZZ_pX(INIT_SIZE_TYPE, long n) { rep.v.reserve(n); }
   static const ZZ_pX &zero() {
     static const ZZ_pX z;
     return z;
@@ -903,7 +914,35 @@ inline std::ostream &operator<<(std::ostream &os, const ZZ_pX &a) {
 }
 typedef Vec<ZZ_pX> vec_ZZ_pX;
 
-class xdouble {};
+// extended-exponent double: long double has range to spare for the parameter sizing it is used for
+class xdouble {
+ public:
+  long double v = 0;
+  xdouble() {}
+  xdouble(double d) : v(d) {}
+  xdouble(long double d, int) : v(d) {}
+};
+inline xdouble to_xdouble(const ZZ &a) {
+  long double r = 0;
+  for (size_t i = a.mag.size(); i-- > 0;) r = r * 4294967296.0L + a.mag[i];
+  return xdouble(a.neg ? -r : r, 0);
+}
+inline xdouble to_xdouble(double d) { return xdouble(d); }
+inline xdouble to_xdouble(long d) { return xdouble((long double)d, 0); }
+inline void conv(xdouble &x, const ZZ &a) { x = to_xdouble(a); }
+inline void conv(xdouble &x, double a) { x = xdouble(a); }
+inline double to_double(const xdouble &x) { return (double)x.v; }
+inline double log(const xdouble &x) { return (double)std::log(x.v); }
+inline xdouble operator*(const xdouble &a, const xdouble &b) { return xdouble(a.v * b.v, 0); }
+inline xdouble operator/(const xdouble &a, const xdouble &b) { return xdouble(a.v / b.v, 0); }
+inline xdouble operator+(const xdouble &a, const xdouble &b) { return xdouble(a.v + b.v, 0); }
+inline xdouble operator-(const xdouble &a, const xdouble &b) { return xdouble(a.v - b.v, 0); }
+inline xdouble &operator*=(xdouble &a, const xdouble &b) { a.v *= b.v; return a; }
+inline xdouble &operator/=(xdouble &a, const xdouble &b) { a.v /= b.v; return a; }
+inline xdouble &operator+=(xdouble &a, const xdouble &b) { a.v += b.v; return a; }
+inline bool operator<(const xdouble &a, const xdouble &b) { return a.v < b.v; }
+inline bool operator>(const xdouble &a, const xdouble &b) { return a.v > b.v; }
+inline std::ostream &operator<<(std::ostream &os, const xdouble &x) { return os << (double)x.v; }
 
 }  // namespace NTL
 

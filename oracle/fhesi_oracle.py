@@ -16,18 +16,23 @@ substitution on big integers) and asserts that every value the reference would h
 DoubleCRT form is below P/2 (P = product of the reference chain), i.e. that the reference
 itself would not have wrapped.
 
-Parity status: **parity unpinned** with respect to the NTL build.  The reference ships no
-golden vectors and no known-answer tests and cannot be compiled here
-(NTL/GMP headers absent).  The oracle is pinned instead by (i) the reference's own
-self-consistency identities from Test_AddMul.cpp:84-86 over many seeds, (ii) chain
-independence, (iii) an independent second implementation of the same arithmetic through
-the reference's *algorithm* (oracle/ref_restate.c: per-prime Bluestein transforms +
-incremental CRT), and (iv) serialization round trips.  See tests/test_oracle_*.py.
+Parity status: pinned against the reference's own sources, with NTL substituted.  The
+reference ships no golden vectors or known-answer tests and NTL/GMP are
+absent here, so oracle/build_ref.py compiles the reference's library sources -- unmodified,
+where they lie -- against oracle/ntl_compat (our stand-in for the NTL interface they use)
+into oracle/_ref.  tests/golden/ref_golden.json holds what that build writes for a seeded
+scenario at every BASELINE configuration, and tests/test_oracle.py requires this oracle to
+reproduce every byte (context, ciphertexts, add, tensor + ScaleDown, mult + relin, decrypt,
+square, scalar, automorphism, DoubleCRT key rows).  Not pinned: NTL's own big-integer code
+and both random streams (NTL's, libc rand()), which the stand-in replaces.  Also: (i) the
+reference's self-consistency identities from Test_AddMul.cpp:84-86 over many seeds,
+(ii) chain independence, (iii) an independent second implementation of the reference's
+*algorithm* (oracle/ref_restate.c), (iv) serialization round trips.
 
-Randomness: the reference draws from NTL's PRNG / lrand48 / libm Box-Muller, none of which
-is pinned.  Parity is functional: identical explicit inputs (keys, r, e,
-message) give identical outputs.  ``Rng`` below is a SplitMix64 counter stream that the
-oracle, the tests and the C++ host layer share.
+Randomness: the reference draws from NTL's PRNG / lrand48 (= rand(), NumbTh.h:32-35) / libm
+Box-Muller; the streams themselves are not pinned.  ``Rng`` below is a
+SplitMix64 counter stream that the oracle, the tests, the C++ host layer and oracle/_ref
+share, and every sampler follows the reference's order and number of draws.
 """
 from __future__ import annotations
 
@@ -66,6 +71,11 @@ class Rng:
         for i in range(words):
             v |= self.next64() << (64 * i)
         return v & ((1 << nbits) - 1)
+
+    def rand31(self) -> int:
+        """libc rand() stand-in: 31 bits of the same stream.  The reference's sampleHWt draws
+        from lrand48(), which NumbTh.h:32-35 maps to rand()."""
+        return self.next64() >> 33
 
     def random_bnd(self, n: int) -> int:
         """Uniform in [0, n) -- NTL RandomBnd semantics, our stream."""
@@ -166,6 +176,23 @@ def root_of_unity_2m(p: int, m: int) -> int:
         if all(pow(r, e // f, p) != 1 for f in fs):
             return r
         x += 1
+
+
+def find_primitive_root(rng: "Rng", q: int, e: int) -> int:
+    """FindPrimRootT, NumbTh.cpp:84-118, as Cmod::privateInit calls it for e = 2m
+    (CModulus.cpp:66-76): random s, root = s^(phi(q)/e), accepted when its order is exactly e.
+    The draws come from the caller's stream, as the reference takes them from NTL's."""
+    assert (q - 1) % e == 0
+    fs = factorize(e)
+    exp = (q - 1) // e
+    for _ in range(1000):
+        s = rng.random_bnd(q)                       # :103 random(s)
+        root = pow(s, exp, q)                       # :104
+        if pow(root, e, q) != 1:                    # :105-106 (s = 0)
+            continue
+        if all(pow(root, e // f, q) != 1 for f in fs):  # :108-113
+            return root
+    raise RuntimeError("FindPrimitiveRoot(): gave up after 1000 trials")
 
 
 def add_primes_by_size(m: int, total_size: float, start_bits: int = 60) -> List[int]:
@@ -328,13 +355,23 @@ class Context:
         self.roots: List[int] = []
         self.xi = 1
 
-    def setup_si(self, xi: int = 1, start_bits: int = 60, roots: Optional[List[int]] = None):
-        """SetUpSIContext, FHEContext.cpp:83-85."""
+    def setup_si(self, xi: int = 1, start_bits: int = 60, roots: Optional[List[int]] = None,
+                 rng: Optional["Rng"] = None):
+        """SetUpSIContext, FHEContext.cpp:83-85.  Each AddPrime constructs a Cmodulus, which
+        draws its 2m-th root of unity from the random stream (CModulus.cpp:66-76): pass ``rng``
+        to follow those draws (a client that has not called SetSeed yet is ``Rng(0)``); without
+        it the roots are the deterministic ones of root_of_unity_2m.  Roots only matter for
+        DoubleCRT rows and the exported context, never for coefficient-domain results."""
         total = (math.log(self.q) * 2 + math.log(self.p) + math.log(self.phim) * 2
                  + math.log(2) + math.log(xi))
         self.xi = xi
         self.primes = add_primes_by_size(self.m, total, start_bits)
-        self.roots = roots or [root_of_unity_2m(q, self.m) for q in self.primes]
+        if roots:
+            self.roots = list(roots)
+        elif rng is not None:
+            self.roots = [find_primitive_root(rng, q, 2 * self.m) for q in self.primes]
+        else:
+            self.roots = [root_of_unity_2m(q, self.m) for q in self.primes]
         return self
 
     def set_chain(self, primes: List[int], roots: List[int]):
@@ -436,9 +473,9 @@ def sample_hwt(rng: Rng, hwt: int, n: int) -> Poly:
     hwt = min(hwt, n)
     i = 0
     while i < hwt:
-        u = rng.random_bnd(n)
+        u = rng.rand31() % n           # NumbTh.cpp:349
         if a[u] == 0:
-            a[u] = 2 * rng.random_bits(1) - 1
+            a[u] = (rng.rand31() & 2) - 1  # :351-352
             i += 1
     return a
 
@@ -529,6 +566,7 @@ class KeySwitch:
         """InitS2, FHE-SI.cpp:211-227: src = (1, s, s^2), dst = s."""
         ctx = sk.ctx
         t = [sk.s[0], sk.s[1], ctx.ring.mul(sk.s[1], sk.s[1])]
+        SecKey.generate(ctx, rng)  # :222 constructs a fresh FHESISecKey before overwriting it: draws
         return KeySwitch.init(ctx, t, sk.s[1], rng)
 
     @staticmethod
@@ -536,6 +574,7 @@ class KeySwitch:
         """InitAutomorph, FHE-SI.cpp:229-239: src = (1, s(X^k)), dst = s."""
         ctx = sk.ctx
         src = [ctx.ring.automorph(x, k) for x in sk.s]
+        SecKey.generate(ctx, rng)  # :233, as in InitS2: a throw-away key is sampled first
         return KeySwitch.init(ctx, src, sk.s[1], rng)
 
 

@@ -1,0 +1,4 @@
+// NTL/vec_GF2.h -- forwarding header of the NTL stand-in used to compile the reference's own sources
+// (oracle/_ref).  Test infrastructure.
+#pragma once
+#include "../ntl_compat.h"

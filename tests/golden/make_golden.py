@@ -1,7 +1,9 @@
 """Generate the committed golden vectors from the oracle (run from the repo root:
-`python tests/golden/make_golden.py`).  The reference ships no known-answer vectors and
-cannot be built here, so these pin the ORACLE's output -- any later change
-to oracle/ or to the CUDA path must still reproduce them byte for byte.
+`python tests/golden/make_golden.py`).  The reference ships no known-answer vectors
+(SURVEY.md §4, §8c); these are the ORACLE's outputs, and tests/golden/ref_golden.json
+(make_ref_golden.py) holds the same scenario run through the reference's own sources
+(oracle/_ref) -- tests/test_oracle.py requires the two to agree byte for byte.  Any later
+change to oracle/ or to the CUDA path must still reproduce them.
 
 cfg1 (logQ=80, p=23, g=7): full inputs and outputs in the reference's Export byte format
 (Serialization.cpp:3-119), hex-encoded.  cfg2/cfg3/cfg4 (p=1019, g=3): inputs are derived from
@@ -19,7 +21,9 @@ SEED = 20240611
 
 
 def scenario(logq, p, g, seed=SEED, nct=2):
-    ctx = O.Context(p - 1, logq, p, g).setup_si()
+    # the client builds its context before it seeds the stream: the chain's roots of unity are
+    # drawn from a fresh stream (CModulus.cpp:66-76), everything else from the seeded one
+    ctx = O.Context(p - 1, logq, p, g).setup_si(rng=O.Rng(0))
     rng = O.Rng(seed)
     sk = O.SecKey.generate(ctx, rng)
     pk = O.PubKey.generate(sk, rng)

@@ -1,0 +1,57 @@
+"""Golden vectors made by the REFERENCE's own code: runs oracle/_ref/golden_client_ref (the
+reference's library sources compiled against the NTL stand-in, oracle/build_ref.py; the client is
+tests/cpp/host_client.cpp built against the reference's headers) on every configuration and
+records the bytes it writes -- context, two fresh ciphertexts, add, tensor + ScaleDown, mult +
+relinearise, its decryption, a second-level square, scalar multiple, automorphism, the public key
+as DoubleCRT rows -- in tests/golden/ref_golden.json (hex for cfg1, SHA-256 otherwise).
+
+Run in the build container (needs /root/reference):  python tests/golden/make_ref_golden.py
+The JSON is committed; tests compare the oracle, the host layer and the CUDA path against it."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from build_ref import build_ref  # noqa: E402
+
+SEED = 20240611
+CONFIGS = {  # name: (logQ, p, g) -- BASELINE.json configs 1-5 (g = 3 for p = 1019)
+    "cfg1": (80, 23, 7), "cfg2": (256, 1019, 3), "cfg3": (100, 1019, 3), "cfg4": (176, 1019, 3),
+    "cfg5_128": (128, 1019, 3), "cfg5_512": (512, 1019, 3),
+}
+FILES = ["context", "ct0", "ct1", "add", "tensor_scaledown", "mult_relin", "decrypt_mult_relin", "square_relin",
+         "mul_scalar_m7", "automorph_3", "pk", "mult_relin_roundtrip", "pk_roundtrip"]
+
+
+def run(exe, logq, p, g, seed=SEED):
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.check_call([exe, str(logq), str(p), str(g), str(seed), d], stdout=subprocess.DEVNULL)
+        return {f: open(os.path.join(d, f + ".bin"), "rb").read() for f in FILES}
+
+
+def main():
+    exes = build_ref()
+    if "golden_client_ref" not in exes:
+        raise SystemExit("oracle/_ref is not built and /root/reference is not mounted")
+    gold = {"seed": SEED, "generator": "oracle/_ref/golden_client_ref: reference sources + oracle/ntl_compat",
+            "configs": {}}
+    for name, (logq, p, g) in CONFIGS.items():
+        out = run(exes["golden_client_ref"], logq, p, g)
+        entry = {"params": {"logQ": logq, "p": p, "g": g},
+                 "sha256": {f: hashlib.sha256(b).hexdigest() for f, b in out.items()}}
+        if name == "cfg1":
+            entry["hex"] = {f: b.hex() for f, b in out.items()}
+        gold["configs"][name] = entry
+        print(name, "done", flush=True)
+    with open(os.path.join(HERE, "ref_golden.json"), "w") as f:
+        json.dump(gold, f, indent=1)
+    print("wrote", os.path.join(HERE, "ref_golden.json"))
+
+
+if __name__ == "__main__":
+    main()

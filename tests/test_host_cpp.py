@@ -2,7 +2,8 @@
 
 CPU CI links it against the kernel-logic emulator; the GPU run links the same sources against
 libfhesi_b200.so.  Checks: (1) our own client follows the golden draw order and every file it
-writes (context, ciphertexts, results, DoubleCRT key rows) equals the oracle's bytes;
+writes (context, ciphertexts, results, DoubleCRT key rows) equals, byte for byte, what the SAME
+client wrote when compiled against the reference's own sources (tests/golden/ref_golden.json);
 (2) when the reference tree is mounted (build container only), its client sources
 (Test_AddMul.cpp, Test_General.cpp, Test_Regression.cpp, Test_Statistics.cpp, Regression.h,
 Statistics.h, Matrix.*) compile UNCHANGED against our headers and Test_AddMul passes."""
@@ -23,6 +24,7 @@ sys.path.insert(0, os.path.join(ROOT, "fhe-si_b200", "host"))
 from build_host import build_host, compile_client  # noqa: E402
 
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+REF_GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_golden.json")))
 REF = "/root/reference"
 
 
@@ -47,27 +49,15 @@ def run_client(backend, tmp_path, name):
 
 
 def check_against_golden(out, name):
-    g = GOLD["configs"][name]
-    rd = lambda f: open(out / f, "rb").read()
-    keys = ["add", "tensor_scaledown", "mult_relin", "decrypt_mult_relin", "square_relin", "mul_scalar_m7",
-            "automorph_3"]
-    ctx, sk, pk, ks, msgs, rand, cts = _golden_scenario(name)
-    assert rd("context.bin") == O.export_context(ctx)
-    if "out" in g:
-        assert [rd("ct0.bin").hex(), rd("ct1.bin").hex()] == g["cts"]
-        for k in keys:
-            assert rd(k + ".bin").hex() == g["out"][k], k
-    else:
-        assert [hashlib.sha256(rd(f)).hexdigest() for f in ("ct0.bin", "ct1.bin")] == g["cts_sha256"]
-        for k in keys:
-            assert hashlib.sha256(rd(k + ".bin")).hexdigest() == g["out_sha256"][k], k
-    assert rd("mult_relin_roundtrip.bin") == rd("mult_relin.bin")
-    # public key as DoubleCRT rows on the reference chain: vector<DoubleCRT> = u32 size + each
-    want = (2).to_bytes(4, "little") + b"".join(O.export_dcrt(O.dcrt_rows(ctx, x)) for x in pk.pk) \
-        if name == "cfg1" else None
-    if want is not None:
-        assert rd("pk.bin") == want
-    assert rd("pk_roundtrip.bin") == rd("pk.bin")
+    """Every file the client writes against tests/golden/ref_golden.json -- the bytes the
+    reference's own sources wrote for the same seed (make_ref_golden.py)."""
+    ref = REF_GOLD["configs"][name]
+    rd = lambda f: open(out / (f + ".bin"), "rb").read()
+    for f, h in ref["sha256"].items():
+        blob = rd(f)
+        if "hex" in ref:
+            assert blob.hex() == ref["hex"][f], (name, f)
+        assert hashlib.sha256(blob).hexdigest() == h, (name, f)
 
 
 def test_host_client_matches_oracle_cfg1_emu(emu_lib, tmp_path):

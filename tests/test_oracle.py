@@ -194,3 +194,52 @@ def test_golden_digests(name):
     assert [hashlib.sha256(O.export_ciphertext(c)).hexdigest() for c in cts] == g["cts_sha256"]
     out = mg.outputs(ctx, sk, ks, cts)
     assert {k: hashlib.sha256(v).hexdigest() for k, v in out.items()} == g["out_sha256"]
+
+
+# ---- the reference's own code (oracle/_ref: reference sources + NTL stand-in) pins the oracle
+REF_GOLD = json.load(open(os.path.join(HERE, "golden", "ref_golden.json")))
+
+
+def _oracle_files(mg, logq, p, g):
+    """Everything tests/cpp/host_client.cpp writes, computed by the oracle."""
+    ctx, sk, pk, ks, msgs, rand, cts = mg.scenario(logq, p, g, REF_GOLD["seed"])
+    files = {"context": O.export_context(ctx), "ct0": O.export_ciphertext(cts[0]), "ct1": O.export_ciphertext(cts[1])}
+    files.update(mg.outputs(ctx, sk, ks, cts))
+    # vector<DoubleCRT>: u32 count, then each DoubleCRT's rows on the reference chain and roots
+    files["pk"] = (2).to_bytes(4, "little") + b"".join(O.export_dcrt(O.dcrt_rows(ctx, x)) for x in pk.pk)
+    files["mult_relin_roundtrip"] = files["mult_relin"]
+    files["pk_roundtrip"] = files["pk"]
+    return files
+
+
+@pytest.mark.parametrize("name", sorted(REF_GOLD["configs"]))
+def test_oracle_matches_reference_golden(name):
+    """Byte equality with what the reference's own DoubleCRT / Bluestein / Ciphertext / FHE-SI code
+    wrote for the same seed (tests/golden/make_ref_golden.py), file by file."""
+    mg, _ = _golden_scenario("cfg1")
+    ref = REF_GOLD["configs"][name]
+    P = ref["params"]
+    if name == "cfg5_512" and os.environ.get("FHESI_SKIP_SLOW"):
+        pytest.skip("slow")
+    files = _oracle_files(mg, P["logQ"], P["p"], P["g"])
+    assert set(files) == set(ref["sha256"])
+    for f, blob in files.items():
+        assert hashlib.sha256(blob).hexdigest() == ref["sha256"][f], (name, f)
+        if "hex" in ref:
+            assert blob.hex() == ref["hex"][f], (name, f)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(HERE, "..", "oracle", "_ref", "golden_client_ref")),
+                    reason="oracle/_ref not built (needs the reference tree at build time)")
+def test_reference_golden_is_reproducible(tmp_path):
+    """Re-run the reference build on cfg1 and cfg3: the committed JSON is what it writes."""
+    import subprocess
+    exe = os.path.join(HERE, "..", "oracle", "_ref", "golden_client_ref")
+    for name in ("cfg1", "cfg3"):
+        P = REF_GOLD["configs"][name]["params"]
+        d = tmp_path / name
+        d.mkdir()
+        subprocess.check_call([exe, str(P["logQ"]), str(P["p"]), str(P["g"]), str(REF_GOLD["seed"]), str(d)],
+                              stdout=subprocess.DEVNULL)
+        for f, h in REF_GOLD["configs"][name]["sha256"].items():
+            assert hashlib.sha256(open(d / (f + ".bin"), "rb").read()).hexdigest() == h, (name, f)
