@@ -105,6 +105,51 @@ int main(int argc, char **argv) {
     secretKey.Decrypt(d2, c2);
     if (!(d2.message == m[0])) return 3;
   }
+  // ---- second group (appended, so the draws above keep their positions)
+  // tensor-form accumulation (Matrix sums): a*b + b*b in DoubleCRT form, then one key switch
+  Ciphertext acc = a;
+  acc *= b;
+  {
+    Ciphertext bb = b;
+    bb *= b;
+    acc += bb;
+  }
+  Save(dir + "/tensor_accumulate.bin", acc);  // Export applies ScaleDown to a copy
+  {
+    Ciphertext ts = acc;
+    ts *= 5;  // scalar multiple in tensor form
+    Save(dir + "/tensor_mul_scalar.bin", ts);
+  }
+  keySwitch.ApplyKeySwitch(acc);
+  Save(dir + "/accumulate_relin.bin", acc);
+  // plaintext operands
+  {
+    Ciphertext x = a;
+    x *= m[1];
+    Save(dir + "/mul_plain.bin", x);
+    Ciphertext y = a;
+    y += m[1];
+    Save(dir + "/add_plain.bin", y);
+  }
+  // a 3-part and a 2-part ciphertext
+  {
+    Ciphertext t3 = a;
+    t3 *= b;
+    t3.ScaleDown();
+    t3 += a;
+    Save(dir + "/add_3part.bin", t3);
+  }
+  // rotation: automorphism by the generator, then the key switch back to s (Regression.h:166-178)
+  {
+    KeySwitchSI rotKey(secretKey, g);
+    Ciphertext x = a;
+    x >>= g;
+    rotKey.ApplyKeySwitch(x);
+    Save(dir + "/rotate_keyswitch.bin", x);
+    Plaintext dr;
+    secretKey.Decrypt(dr, x);
+    Save(dir + "/decrypt_rotate.bin", to_ZZX(dr.message));
+  }
   // the identities of Test_AddMul.cpp:84-86, for good measure
   Plaintext dsum;
   secretKey.Decrypt(dsum, sum);

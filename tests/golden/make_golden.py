@@ -35,6 +35,12 @@ def scenario(logq, p, g, seed=SEED, nct=2):
         e = [O.sample_gaussian(rng, ctx.phim, ctx.stdev) for _ in range(2)]
         rand.append((r, e))
     cts = [O.encrypt(pk, m, r, e) for m, (r, e) in zip(msgs, rand)]
+    # later draws of tests/cpp/host_client.cpp: one more encryption (its import check), then the
+    # rotation key of its second group
+    O.encrypt_rng(pk, msgs[0], rng)
+    ks.rot_g = O.KeySwitch.init_automorph(sk, g, rng)
+    ks.rot_k = g
+    ks.plain = msgs[1]
     return ctx, sk, pk, ks, msgs, rand, cts
 
 
@@ -51,6 +57,17 @@ def outputs(ctx, sk, ks, cts):
     out["square_relin"] = O.export_ciphertext(sq)
     out["mul_scalar_m7"] = O.export_ciphertext(a.copy().mul_scalar(-7))
     out["automorph_3"] = O.export_ciphertext(a.copy().automorph(3))
+    # second group
+    acc = a.copy().mul(b).add(b.copy().mul(b))
+    out["tensor_accumulate"] = O.export_ciphertext(acc)
+    out["tensor_mul_scalar"] = O.export_ciphertext(acc.copy().mul_scalar(5))
+    out["accumulate_relin"] = O.export_ciphertext(O.apply_key_switch(ks, acc.copy()))
+    out["mul_plain"] = O.export_ciphertext(a.copy().mul_plain(ks.plain))
+    out["add_plain"] = O.export_ciphertext(a.copy().add_plain(ks.plain))
+    out["add_3part"] = O.export_ciphertext(a.copy().mul(b).scale_down().add(a))
+    rot = O.apply_key_switch(ks.rot_g, a.copy().automorph(ks.rot_k))
+    out["rotate_keyswitch"] = O.export_ciphertext(rot)
+    out["decrypt_rotate"] = O.export_zzx(O.decrypt(sk, rot))
     return out
 
 

@@ -3,7 +3,8 @@ reference's library sources compiled against the NTL stand-in, oracle/build_ref.
 tests/cpp/host_client.cpp built against the reference's headers) on every configuration and
 records the bytes it writes -- context, two fresh ciphertexts, add, tensor + ScaleDown, mult +
 relinearise, its decryption, a second-level square, scalar multiple, automorphism, the public key
-as DoubleCRT rows -- in tests/golden/ref_golden.json (hex for cfg1, SHA-256 otherwise).
+as DoubleCRT rows, tensor-form accumulation and its key switch, tensor-form scalar multiple,
+plaintext multiply and add, a 3-part + 2-part sum, a rotation with its key switch -- in tests/golden/ref_golden.json (hex for cfg1, SHA-256 otherwise).
 
 Run in the build container (needs /root/reference):  python tests/golden/make_ref_golden.py
 The JSON is committed; tests compare the oracle, the host layer and the CUDA path against it."""
@@ -25,7 +26,9 @@ CONFIGS = {  # name: (logQ, p, g) -- BASELINE.json configs 1-5 (g = 3 for p = 10
     "cfg5_128": (128, 1019, 3), "cfg5_512": (512, 1019, 3),
 }
 FILES = ["context", "ct0", "ct1", "add", "tensor_scaledown", "mult_relin", "decrypt_mult_relin", "square_relin",
-         "mul_scalar_m7", "automorph_3", "pk", "mult_relin_roundtrip", "pk_roundtrip"]
+         "mul_scalar_m7", "automorph_3", "pk", "mult_relin_roundtrip", "pk_roundtrip", "tensor_accumulate",
+         "tensor_mul_scalar", "accumulate_relin", "mul_plain", "add_plain", "add_3part", "rotate_keyswitch",
+         "decrypt_rotate"]
 
 
 def run(exe, logq, p, g, seed=SEED):

@@ -39,7 +39,7 @@ def _golden_scenario(name):
 def run_client(backend, tmp_path, name):
     exe = compile_client([os.path.join(ROOT, "tests", "cpp", "host_client.cpp")], backend,
                          str(tmp_path / "host_client"))
-    P = GOLD["configs"][name]["params"]
+    P = REF_GOLD["configs"][name]["params"]
     out = tmp_path / name
     out.mkdir()
     r = subprocess.run([exe, str(P["logQ"]), str(P["p"]), str(P["g"]), str(GOLD["seed"]), str(out)],
@@ -137,6 +137,6 @@ def test_reference_clients_run_unchanged_gpu(cuda_lib, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+@pytest.mark.parametrize("name", sorted(REF_GOLD["configs"]))
 def test_host_client_matches_oracle_gpu(cuda_lib, tmp_path, name):
     check_against_golden(run_client(cuda_lib, tmp_path, name), name)
