@@ -213,6 +213,7 @@ def check_golden(name, lib_path, device=0):
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
     ctx, sk, pk, ks, msgs, rand, cts = mg.scenario(logq, p, P["g"], gold["seed"])
+    rot, rot_k, plain = ks.rot_g, ks.rot_k, ks.plain
     if "cts" in g:  # full vectors: take every input from the fixture, not from the RNG
         imp = lambda h: O.import_zzx(bytes.fromhex(h), 0, ctx.phim)[0]
         sk = O.SecKey(ctx, [imp(h) for h in g["sk"]])
@@ -258,6 +259,58 @@ def check_golden(name, lib_path, device=0):
     d.sync()
     got["mul_scalar_m7"] = O.export_ciphertext(unpack(dx.download((2, n, W))))
     got["automorph_3"] = O.export_ciphertext(unpack(dw.download((2, n, W + 1))))
+    # ---- second group: tensor-form accumulation a*b + b*b, scalar multiple in tensor form, key switch
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, 1)
+    dt2 = d.alloc(d.tprod_words(3) * 4)
+    d.ct_tensor_dev(db.ptr, 2, db.ptr, 2, dt2.ptr, 1)
+    d.tprod_add_dev(dt.ptr, dt2.ptr, 3, 1)
+    # the same sum through the batch-accumulating form: pairs (a, b), (b, b) summed into one tprod
+    dab = d.to_device(np.stack([pack(cts[0].parts), pack(cts[1].parts)]))
+    dbb = d.to_device(np.stack([pack(cts[1].parts), pack(cts[1].parts)]))
+    d.ct_tensor_dev(dab.ptr, 2, dbb.ptr, 2, dt2.ptr, 2, accumulate=True)
+    dc2 = d.alloc(d.ct_words(3) * 4)
+    d.scaledown_dev(dt2.ptr, 3, dc2.ptr, 1)
+    d.sync()
+    got["tensor_accumulate_batched"] = O.export_ciphertext(unpack(dc2.download((3, n, W))))
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.keyswitch_dev(ksw, dc.ptr, do.ptr, 1)
+    d.sync()
+    got["tensor_accumulate"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
+    got["accumulate_relin"] = O.export_ciphertext(unpack(do.download((2, n, W))))
+    d.tprod_mul_scalar_dev(dt.ptr, 5, 3, 1)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.sync()
+    got["tensor_mul_scalar"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
+    # plaintext operands: *= ZZX, and += ZZX as the host layer issues it (floor(c 2^logQ / p) added to part 0)
+    dx.upload(pack(cts[0].parts)[None])
+    dp = d.to_device(np.array(plain, dtype=np.uint32))
+    d.ct_mul_plain_dev(dx.ptr, dp.ptr, 2, 1)
+    d.sync()
+    got["mul_plain"] = O.export_ciphertext(unpack(dx.download((2, n, W))))
+    dx.upload(pack(cts[0].parts)[None])
+    scaled = O.reduce_poly([(c << logq) // p for c in plain], logq)
+    dsc = d.to_device(pack([scaled])[None])
+    d.ct_add_dev(dx.ptr, dsc.ptr, 1, 1)
+    d.sync()
+    got["add_plain"] = O.export_ciphertext(unpack(dx.download((2, n, W))))
+    # 3-part + 2-part: ScaleDown(a*b), then the first two parts += a
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, 1)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.ct_add_dev(dc.ptr, da.ptr, 2, 1)
+    d.sync()
+    got["add_3part"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
+    # rotation: signed permutation, reduction mod q, key switch with the (1, s(X^k)) -> s matrix
+    rksw = d.ksw_create(pack(rot.b), pack([O.reduce_poly(a, logq) for a in rot.A]), 2)
+    d.ct_automorph_dev(da.ptr, 2, rot_k, dw.ptr, 1)
+    dr = d.alloc(d.ct_words(2) * 4)
+    d.reduce_wide_dev(dw.ptr, W + 1, dr.ptr, 2, 1)
+    d.keyswitch_dev(rksw, dr.ptr, do.ptr, 1)
+    d.decrypt_dev(dsk, do.ptr, 2, dm.ptr, 1)
+    d.sync()
+    got["rotate_keyswitch"] = O.export_ciphertext(unpack(do.download((2, n, W))))
+    got["decrypt_rotate"] = O.export_zzx(dm.download((n,)).tolist())
+    d.lib.fhesi_ksw_destroy(rksw)
+    assert got.pop("tensor_accumulate_batched") == got["tensor_accumulate"]
     if "out" in g:
         assert {k: v.hex() for k, v in got.items()} == g["out"]
     else:
