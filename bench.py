@@ -84,10 +84,34 @@ def cpu_baseline_single_core(logq, p, g, budget_s=12.0):
     for _ in range(nf):
         port.mult_relin(a, b)
     faithful = nf / (time.perf_counter() - t)
-    return {"value": fixed, "unit": "ops/s", "cores": 1, "kind": "port",
-            "sample": f"{nops} mult+relin ops at logQ={logq} p={p} (oracle/ref_restate.c: m-point Bluestein "
-                      f"N=2^{(2 * (p - 1) - 1).bit_length()}, incremental bigint CRT), tables cached",
-            "faithful_table_bug_ops_per_s": faithful, "faithful_sample_ops": nf}
+    out = {"value": fixed, "unit": "ops/s", "cores": 1, "kind": "port",
+           "sample": f"{nops} mult+relin ops at logQ={logq} p={p} (oracle/ref_restate.c: m-point Bluestein "
+                     f"N=2^{(2 * (p - 1) - 1).bit_length()}, incremental bigint CRT), tables cached",
+           "faithful_table_bug_ops_per_s": faithful, "faithful_sample_ops": nf}
+    out.update(reference_sources_figure(logq, p, g))
+    return out
+
+
+def reference_sources_figure(logq, p, g, ops=3):
+    """The reference's OWN sources (oracle/_ref, built against the NTL stand-in by
+    oracle/build_ref.py) on the same op, when the prebuilt binary travelled with the snapshot.
+    Reported beside the port, not instead of it: the stand-in's big integers are slower than
+    NTL/GMP, so the port is the faster -- fairer -- CPU figure."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+    if not os.path.exists(exe):
+        return {}
+    try:
+        r = subprocess.run([exe, str(logq), str(p), str(g), str(ops), str(SEED)], capture_output=True, text=True,
+                           timeout=180)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"reference_sources_on_ntl_standin": {"ops_per_s": j["ops_per_s"], "ops": j["ops"], "cores": 1,
+                                                     "decrypt_ok": j["decrypt_ok"],
+                                                     "what": "oracle/_ref/ref_bench: the reference's DoubleCRT/"
+                                                             "Bluestein/key-switch code, NTL replaced by "
+                                                             "oracle/ntl_compat"}}
+    except Exception as e:  # a missing or broken side figure must not break the bench line
+        return {"reference_sources_on_ntl_standin": {"error": str(e)[:200]}}
 
 
 def run_reference(args, rank, world):
