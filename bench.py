@@ -202,6 +202,31 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned host buffer exists, so
+    the end-to-end path's staging memory is local to the GPU's PCIe root (8 ranks otherwise share
+    whichever node the launcher started them on).  Returns the node, or None when the topology is
+    not exposed; never fatal."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
@@ -211,6 +236,7 @@ def run_ours(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = None if os.environ.get("FHESI_NO_NUMA_BIND") else bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -385,7 +411,8 @@ def run_ours(args, rank, local_rank, world):
                        "l2": f"inputs {2 * B * ct_words * 4 / 2**20:.0f} MiB per step > 126 MB L2",
                        "chain": f"{dev.Lt} x 30-bit primes (tensor), {dev.Lk} (key switch"
                                 + (f", {dev.Ls} with split keys" if dev.Ls else "") + f"), N={dev.N}",
-                       "seed": SEED},
+                       "seed": SEED,
+                       "host_numa_node_rank0": numa_node},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_words * 4,
