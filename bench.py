@@ -238,6 +238,9 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     numa_node = None if os.environ.get("FHESI_NO_NUMA_BIND") else bind_to_gpu_numa_node(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO print banners there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("FHESI_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import build as fhesi_build
