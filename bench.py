@@ -431,10 +431,10 @@ def run_ours(args, rank, local_rank, world):
 
 
 # DRAM traffic per op of each hot kernel, from `ncu --set full` captures (dram__bytes_read.sum +
-# dram__bytes_write.sum over a 2046-op launch, profiles/r01_summary_v11.md); the driver-timed run
-# itself is never profiled.
-NCU_DRAM_BYTES_PER_OP = {"k_fused_keyswitch": 96.9e3, "k_fused_keyswitch_split": 104.4e3, "k_fused_tensor": 238.9e3,
-                         "k_residues": 184.2e3}
+# dram__bytes_write.sum over one 8192-op launch, profiles/r01_summary_v16.md; the unsplit kernel from
+# the 2046-op capture of r01_summary_v11.md); the driver-timed run itself is never profiled.
+NCU_DRAM_BYTES_PER_OP = {"k_fused_keyswitch": 96.9e3, "k_fused_keyswitch_split": 113.0e3, "k_fused_tensor": 251.5e3,
+                         "k_residues": 204.5e3}
 
 
 def kernel_work_per_op(dev):
