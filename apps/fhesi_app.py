@@ -136,16 +136,21 @@ def rotation_exponents(g, m, usable):
     return out
 
 
-def embed_batch(slots, values, device):
-    """values: int array [count][<= usable] -> uint32 message coefficients [count][n] on `device`
-    (EmbedInSlots for a whole batch: one matrix product with the CRT-idempotent basis; exact in
-    float64 since entries < p < 2^10 and row sums < 2^29)."""
+def embed_batch(env, slots, values):
+    """values: int array [count][<= usable] -> uint32 message coefficients [count][n] on the device:
+    PlaintextSpace::EmbedInSlots for a whole batch (fhesi_embed_slots_dev, exact integer arithmetic)."""
+    dev = env.dev
     cnt, width = values.shape
-    v = torch.zeros((max(cnt, 1), slots.total), dtype=torch.float64, device=device)
+    v = np.zeros((max(cnt, 1), slots.total), dtype=np.int32)
     if cnt:
-        v[:cnt, :width] = torch.from_numpy(np.ascontiguousarray(values % slots.p)).to(device=device, dtype=torch.float64)
-    basis = torch.from_numpy(slots.basis).to(device=device, dtype=torch.float64)
-    return torch.remainder(torch.round(v @ basis).to(torch.int64), slots.p).to(torch.int32).contiguous()
+        v[:cnt, :width] = values % slots.p
+    if not hasattr(slots, "d_basis") or slots.d_basis.device != torch.device(env.device):
+        slots.d_basis = torch.from_numpy(slots.basis.astype(np.int32)).to(env.device)
+    d_vals = torch.from_numpy(v).to(env.device)
+    d_msgs = torch.empty((max(cnt, 1), dev.n), dtype=torch.int32, device=env.device)
+    if cnt:
+        dev.embed_slots_dev(slots.d_basis, slots.total, d_vals, d_msgs, cnt)
+    return d_msgs
 
 
 def encrypt_batch(env, dpk, d_msgs, count, nrng):

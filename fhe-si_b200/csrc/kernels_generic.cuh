@@ -640,6 +640,26 @@ __global__ void __launch_bounds__(128) k_crt_split(DevCtx c, CrtSplitArgs a, con
   }
 }
 
+// PlaintextSpace::EmbedInSlots over a batch (PlaintextSpace.cpp:112-134; BatchData, Regression.h:43-66):
+// msg[c][j] = sum_k vals[c][k] * basis[k][j] mod p_pt, with basis[k] the CRT idempotent of slot k.
+// One thread per output coefficient; a block shares its row of slot values through shared memory.
+// Products are < p_pt^2 <= 2^52 (p_pt < 2^26), so a 64-bit sum of up to 2^12 of them cannot overflow.
+__global__ void __launch_bounds__(128) k_embed_slots(const u32 *basis, const u32 *vals, u32 *msg, u32 nslots, u32 n,
+                                                     u32 p_pt) {
+  FHESI_SMEM(sv);
+  const size_t row = blockIdx.y;
+  for (u32 k = threadIdx.x; k < nslots; k += blockDim.x) sv[k] = vals[row * nslots + k];
+  __syncthreads();
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  u64 acc = 0;
+  for (u32 k = 0; k < nslots; ++k) {
+    const u32 v = sv[k];
+    if (v) acc += (u64)v * basis[(size_t)k * n + j];
+  }
+  msg[row * n + j] = (u32)(acc % p_pt);
+}
+
 // ---------------------------------------------------------------------------------------
 // coefficient-domain multiword kernels (one thread per coefficient)
 // ---------------------------------------------------------------------------------------

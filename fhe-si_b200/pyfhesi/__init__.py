@@ -65,6 +65,7 @@ SYMBOLS = {
     "fhesi_keyswitch_dev": (C.c_int, [_P, _P, _P, _P, _SZ]),
     "fhesi_encrypt_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _SZ]),
     "fhesi_decrypt_dev": (C.c_int, [_P, _P, _P, _U32, _P, _SZ]),
+    "fhesi_embed_slots_dev": (C.c_int, [_P, _P, _U32, _P, _P, _SZ]),
     "fhesi_ct_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
     "fhesi_reduce_wide_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
     "fhesi_ref_rows_host": (C.c_int, [_P, _P, _U32, _P, _P, _U32, _P]),
@@ -255,6 +256,9 @@ class Context:
 
     def decrypt_dev(self, sk, inp, parts, msg, count):
         self._ck(self.lib.fhesi_decrypt_dev(self.h, sk, _ptr(inp), parts, _ptr(msg), count))
+
+    def embed_slots_dev(self, basis, nslots, vals, msg, count):
+        self._ck(self.lib.fhesi_embed_slots_dev(self.h, _ptr(basis), nslots, _ptr(vals), _ptr(msg), count))
 
     def ct_automorph_dev(self, inp, parts, k, out_wide, count):
         self._ck(self.lib.fhesi_ct_automorph_dev(self.h, _ptr(inp), parts, k, _ptr(out_wide), count))

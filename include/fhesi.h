@@ -164,6 +164,14 @@ int fhesi_encrypt_dev(fhesi_ctx *ctx, const fhesi_key *pk, const uint32_t *d_msg
 int fhesi_decrypt_dev(fhesi_ctx *ctx, const fhesi_key *sk, const uint32_t *d_in, uint32_t parts,
                       uint32_t *d_msg, size_t count);
 
+/* PlaintextSpace::EmbedInSlots (PlaintextSpace.cpp:112-134) for a batch of plaintexts, as BatchData
+ * issues it (Regression.h:43-66, Test_Statistics.cpp:35-63): msg[c] = sum_k vals[c][k] * basis[k] mod p.
+ * basis: DEVICE uint32 [nslots][n], row k = the CRT idempotent of slot k (values in [0,p)); vals:
+ * DEVICE uint32 [count][nslots] slot values in [0,p); msg: [count][n] coefficients in [0,p), the layout
+ * fhesi_encrypt_dev takes.  Needs p < 2^26 and nslots <= 4096. */
+int fhesi_embed_slots_dev(fhesi_ctx *ctx, const uint32_t *d_basis, uint32_t nslots, const uint32_t *d_vals,
+                          uint32_t *d_msg, size_t count);
+
 /* CiphertextPart::operator>>=(long k) (Ciphertext.cpp:54-59; DoubleCRT::automorph,
  * DoubleCRT.cpp:439-465): a(X) -> a(X^k) mod Phi_m.  The reference does NOT reduce the
  * result mod q; out is therefore [count][parts][n][W+1] words (one word of head-room). */

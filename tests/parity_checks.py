@@ -317,6 +317,42 @@ def check_golden(name, lib_path, device=0):
         assert {k: hashlib.sha256(v).hexdigest() for k, v in got.items()} == g["out_sha256"]
 
 
+def check_embed_slots(sc: Scenario, g, count=5):
+    """fhesi_embed_slots_dev = PlaintextSpace::EmbedInSlots for a batch (PlaintextSpace.cpp:112-134):
+    exact against integer arithmetic, and the defining property -- the embedded polynomial evaluates
+    to the k-th value at the k-th slot root (DecodeSlots, :136-146); ragged (short) value rows."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "apps"))
+    from fhesi_app import Slots
+    d, p, m = sc.dev, sc.p, sc.octx.m
+    n = d.n
+    phi = [int(c) for c in sc.octx.ring.PhimX]
+    sl = Slots(m, p, g, phi)
+    nslots = sl.total
+    vals = np.zeros((count, nslots), dtype=np.uint32)
+    for c in range(count):
+        width = nslots if c == 0 else (1 if c == 1 else sc.rng.random_bnd(nslots) + 1)
+        vals[c, :width] = [sc.rng.random_bnd(p) for _ in range(width)]
+    if count > 2:
+        vals[2] = 0                                   # the zero plaintext
+    dbasis = d.to_device(sl.basis.astype(np.uint32))
+    dvals = d.to_device(vals)
+    dmsg = d.alloc(count * n * 4)
+    d.embed_slots_dev(dbasis.ptr, nslots, dvals.ptr, dmsg.ptr, count)
+    d.sync()
+    got = dmsg.download((count, n))
+    B = [[int(x) for x in row] for row in sl.basis]
+    for c in range(count):
+        want = [sum(int(vals[c, k]) * B[k][j] for k in range(nslots)) % p for j in range(n)]
+        assert got[c].tolist() == want, f"embed_slots row {c}"
+        for k in range(nslots):                       # evaluate at the slot's root
+            acc = 0
+            for coef in reversed(want):
+                acc = (acc * sl.roots[k] + coef) % p
+            assert acc == int(vals[c, k]), f"slot {k} of row {c} does not decode"
+
+
 def check_mul_plain(sc: Scenario, count=2):
     """Ciphertext *= ZZX in coefficient form (Ciphertext.cpp:246-250)."""
     d = sc.dev
