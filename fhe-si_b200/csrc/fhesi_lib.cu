@@ -91,6 +91,18 @@ struct fhesi_ctx {
   Arena lane_scratch;
   Arena work;   // tprod / scaled-down intermediates of the generic mult_relin composition
 };
+// scratch for set-up paths (key upload): blocks come from the context's pool (fhesi_malloc /
+// fhesi_free), so repeated key creation costs no cudaMalloc / cudaFree and no implicit device sync
+struct PoolTmp {
+  fhesi_ctx *c;
+  void *p = nullptr;
+  explicit PoolTmp(fhesi_ctx *ctx) : c(ctx) {}
+  ~PoolTmp() {
+    if (p) fhesi_free(c, p);
+  }
+  int alloc(size_t bytes) { return fhesi_malloc(c, bytes, &p); }
+  u32 *u() const { return (u32 *)p; }
+};
 static void prof_clear(fhesi_ctx *c);
 static void prof_begin(fhesi_ctx *c, const char *name) {
   c->launches++;
@@ -626,18 +638,19 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
     memcpy(&h[((size_t)k * 2 + 0) * polyw], h_b + (size_t)k * polyw, polyw * 4);
     memcpy(&h[((size_t)k * 2 + 1) * polyw], h_A + (size_t)k * polyw, polyw * 4);
   }
-  DevTmp t_in, t_tmp, t_key, t_bal, t_split;
-  CK(t_in.alloc(h.size() * 4));
-  CK(t_tmp.alloc((size_t)K * 2 * Lk * I.N * 4));
+  DevTmp t_key, t_bal, t_split;  // the key's own buffers
+  PoolTmp t_in(c), t_tmp(c);     // scratch
+  int rc = t_in.alloc(h.size() * 4);
+  if (!rc) rc = t_tmp.alloc((size_t)K * 2 * Lk * I.N * 4);
+  if (rc) return rc;
   CK(t_key.alloc((size_t)K * 2 * Lk * I.N * 4));
   u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
   CK(cudaMemcpyAsync(d_in, h.data(), h.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  int rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2);
+  rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2);
   if (rc) return rc;
   // [K*2][Lk][N] -> [Lk][K*2][N]
   KL(c, k_transpose_key, nblk((size_t)K * 2 * Lk * I.N), 256, 0, d_tmp, d_key, K * 2, Lk, I.N);
   CKL();
-  CK(cudaStreamSynchronize(c->stream));
   u32 *d_bal = nullptr;
   if (c->use_fused && c->tfree) {
     const size_t total = (size_t)K * 2 * Lk * I.N;
@@ -645,13 +658,14 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
     d_bal = t_bal.u();
     KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_key, d_bal, K * 2, total);
     CKL();
-    CK(cudaStreamSynchronize(c->stream));
   }
   u32 *d_split = nullptr;
+  PoolTmp t_in2(c), t_tmp2(c), t_t2(c);
+  std::vector<u32> hs;  // outlives the asynchronous copy below
   if (c->use_fused && c->tfree && I.Ls) {
     // K mod q (non-negative) = lo + 2^(32 ws) hi, each half as a non-negative W-word polynomial
     const u32 ws = I.split_words, W = I.W, Ls = I.Ls, tb = I.logQ & 31;
-    std::vector<u32> hs((size_t)K * 4 * polyw, 0);
+    hs.assign((size_t)K * 4 * polyw, 0);
     for (u32 k = 0; k < K; ++k)
       for (u32 r = 0; r < 2; ++r) {
         const u32 *src = (r ? h_A : h_b) + (size_t)k * polyw;
@@ -664,11 +678,11 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
             else hi[(size_t)i * W + (w - ws)] = v;
           }
       }
-    DevTmp t_in2, t_tmp2, t_t2;
     const size_t total = (size_t)K * 4 * Ls * I.N;
-    CK(t_in2.alloc(hs.size() * 4));
-    CK(t_tmp2.alloc(total * 4));
-    CK(t_t2.alloc(total * 4));
+    rc = t_in2.alloc(hs.size() * 4);
+    if (!rc) rc = t_tmp2.alloc(total * 4);
+    if (!rc) rc = t_t2.alloc(total * 4);
+    if (rc) return rc;
     CK(t_split.alloc(total * 4));
     u32 *d_in2 = t_in2.u(), *d_tmp2 = t_tmp2.u(), *d_t2 = t_t2.u();
     d_split = t_split.u();
@@ -678,8 +692,8 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
     CKL();
     KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_t2, d_split, K * 4, total);
     CKL();
-    CK(cudaStreamSynchronize(c->stream));
   }
+  CK(cudaStreamSynchronize(c->stream));  // one synchronisation: the host staging vectors die here
   fhesi_ksw *k = new fhesi_ksw{c, (u32 *)t_key.release(), (u32 *)t_bal.release(), (u32 *)t_split.release(), parts};
   (void)d_key;
   (void)d_bal;
@@ -702,13 +716,15 @@ int fhesi_key_create(fhesi_ctx *c, const uint32_t *h_polys, uint32_t parts, fhes
   CK(cudaSetDevice(c->device));
   const fhesi_info &I = c->info;
   const size_t polyw = (size_t)I.n * I.W;
-  DevTmp t_in, t_tmp, t_key;
-  CK(t_in.alloc(parts * polyw * 4));
-  CK(t_tmp.alloc((size_t)parts * I.Le * I.N * 4));
+  DevTmp t_key;
+  PoolTmp t_in(c), t_tmp(c);
+  int rc = t_in.alloc(parts * polyw * 4);
+  if (!rc) rc = t_tmp.alloc((size_t)parts * I.Le * I.N * 4);
+  if (rc) return rc;
   CK(t_key.alloc((size_t)parts * I.Le * I.N * 4));
   u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
   CK(cudaMemcpyAsync(d_in, h_polys, parts * polyw * 4, cudaMemcpyHostToDevice, c->stream));
-  int rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, I.Le, d_tmp, parts);
+  rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, I.Le, d_tmp, parts);
   if (rc) return rc;
   KL(c, k_transpose_key, nblk((size_t)parts * I.Le * I.N), 256, 0, d_tmp, d_key, parts, I.Le, I.N);
   CKL();

@@ -17,7 +17,7 @@ def build_host(backend, out_dir=None, force=False):
         return out
     bdir, bname = os.path.dirname(backend), os.path.basename(backend)
     assert bname.startswith("lib") and bname.endswith(".so")
-    cmd = ["g++", "-std=c++17", "-O3", "-g", "-fPIC", "-shared", "-Wall", "-Wno-sign-compare",
+    cmd = ["g++", "-std=c++17", "-O3", "-g", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-sign-compare",
            "-I", HERE, "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "fhesi_host.cpp"),
            "-o", out, "-L", bdir, "-l" + bname[3:-3], "-Wl,-rpath," + bdir]
     subprocess.check_call(cmd)

@@ -3,6 +3,13 @@
 // CI, against the kernel-logic emulator build of the same sources, tests/emu).
 #include "fhesi_host.h"
 
+#include <sched.h>
+
+#include <atomic>
+#include <chrono>
+#include <memory>
+#include <thread>
+
 #include <map>
 
 FHEcontext *activeContext = NULL;
@@ -77,6 +84,30 @@ static void RemPhim(ZZX &a, const PAlgebra &zms) {
 // a * b mod Phi_m.  Secret keys are ternary and sparse (Hamming weight 64), so the products key
 // generation needs are shift-and-add; they run on fixed-width two's-complement word arrays
 // (no allocation per coefficient), which keeps KeySwitchSI::Init at set-up-time cost.
+// Run fn(0..total-1) over the host's cores (at most 16 workers); fn must not touch shared state.
+template <class F>
+static void ParallelFor(size_t total, F fn) {
+  static const unsigned cap = [] {
+    const char *e = getenv("FHESIH_THREADS");  // 1 = serial
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) hw = std::min<unsigned>(hw, std::max(1, CPU_COUNT(&set)));
+    return e && atoi(e) > 0 ? (unsigned)atoi(e) : std::min(hw, 16u);
+  }();
+  unsigned workers = std::min<unsigned>((unsigned)total, cap);
+  if (workers <= 1) {
+    for (size_t i = 0; i < total; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (unsigned w = 0; w < workers; ++w)
+    pool.emplace_back([&] {
+      for (size_t i; (i = next.fetch_add(1)) < total;) fn(i);
+    });
+  for (auto &th : pool) th.join();
+}
+
 // Inner loops of the host-side samplers/packers, cloned for AVX2 (resolved at load time: the
 // library is built in one container and runs on another host).
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
@@ -199,6 +230,43 @@ void ReduceCoefficients(ZZX &poly, unsigned logQ, bool positive) {
 void SampleRandom(ZZX &poly, const ZZ &modulus, unsigned d) {  // Util.cpp:49-56
   ZZ offset = modulus / 2;
   poly.rep.v.assign(d, ZZ());
+  const size_t k = modulus.bits() - 1;  // modulus == 2^k ?
+  bool pow2 = !modulus.is_zero() && k >= 2 && (modulus.mag.back() & (modulus.mag.back() - 1)) == 0;
+  for (size_t i = 0; pow2 && i + 1 < modulus.mag.size(); ++i) pow2 = modulus.mag[i] == 0;
+  if (pow2) {
+    // RandomBnd(2^k) is RandomBits(k): ceil(k/64) words of the stream, low k bits kept, never
+    // rejected.  v - 2^(k-1) is formed on the limbs directly: same draws, same values, no ZZ temporaries.
+    const size_t words64 = (k + 63) / 64, limbs = (k + 31) / 32, top = (k - 1) / 32;
+    const uint32_t topbit = 1u << ((k - 1) % 32);
+    uint32_t w[2 * 64];
+    if (words64 <= 64) {
+      for (unsigned i = 0; i < d; i++) {
+        for (size_t t = 0; t < words64; ++t) {
+          uint64_t x = GlobalRandomStream().next64();
+          w[2 * t] = (uint32_t)x, w[2 * t + 1] = (uint32_t)(x >> 32);
+        }
+        if (k % 32) w[limbs - 1] &= (1u << (k % 32)) - 1;
+        ZZ &c = poly.rep.v[i];
+        if (w[top] & topbit) {  // v >= q/2: v - q/2 clears the top bit
+          w[top] &= ~topbit;
+          c.mag.assign(w, w + limbs);
+          c.neg = false;
+        } else {  // -(q/2 - v)
+          uint64_t borrow = 0;
+          for (size_t t = 0; t < limbs; ++t) {
+            uint64_t sub = (uint64_t)w[t] + borrow, from = t == top ? topbit : 0u;
+            borrow = from < sub;
+            w[t] = (uint32_t)(from - sub);
+          }
+          c.mag.assign(w, w + limbs);
+          c.neg = true;
+        }
+        c.trim();
+      }
+      poly.normalize();
+      return;
+    }
+  }
   for (unsigned i = 0; i < d; i++) poly.rep.v[i] = RandomBnd(modulus) - offset;
   poly.normalize();
 }
@@ -972,27 +1040,37 @@ void KeySwitchSI::Init(const FHESISecKey &src, const FHESISecKey &dst) {  // FHE
   for (size_t i = 0; i < s.size(); i++) s[i].toPoly(sCoeff[i]);
   ZZX t;
   dst.GetRepresentation()[1].toPoly(t);
-  const size_t n = src.GetSize();
-  vector<DoubleCRT> A, b;
-  for (unsigned i = 0; i < n; i++) {
-    for (unsigned j = 0; j < context.ndigits; j++) {
-      ZZX poly;
-      SampleRandom(poly, context.modulusQ, context.zMstar.phiM());
-      ZZX bCoeff = MulModPhim(poly, t, context.zMstar);
-      ZZX err;
-      sampleGaussian(err, context.zMstar.phiM(), context.stdev);
-      bCoeff += err;
-      bCoeff += sCoeff[i];
-      for (long k = 0; k <= deg(sCoeff[i]); k++) sCoeff[i].rep[k] <<= (long)(8 * context.decompSize);
-      ReduceCoefficients(bCoeff, context.logQ);
-      poly *= -1;  // A = -poly, not reduced (FHE-SI.cpp:178-180)
-      A.push_back(DoubleCRT(poly, context));
-      b.push_back(DoubleCRT(bCoeff, context));
-    }
+  const size_t n = src.GetSize(), D = context.ndigits, total = n * D;
+  static const bool timing = getenv("FHESIH_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tt0 = now();
+  // 1. the random draws, in the reference's order (:176 SampleRandom, :188 sampleGaussian per entry)
+  vector<ZZX> polys(total), errs(total);
+  for (size_t ind = 0; ind < total; ++ind) {
+    SampleRandom(polys[ind], context.modulusQ, context.zMstar.phiM());
+    sampleGaussian(errs[ind], context.zMstar.phiM(), context.stdev);
   }
+  const double tt1 = now();
+  // 2. the arithmetic of each entry is independent of the others: b = poly * t + err + s_i * 2^(24 j)
+  // reduced mod q (:182-199), A = -poly unreduced (:178-180); spread over the host's cores
+  vector<DoubleCRT> A(total, DoubleCRT(context)), b(total, DoubleCRT(context));
+  auto entry = [&](size_t ind) {
+    const size_t i = ind / D, j = ind % D;
+    ZZX bCoeff = MulModPhim(polys[ind], t, context.zMstar);
+    bCoeff += errs[ind];
+    ZZX sh = sCoeff[i];
+    for (long k = 0; k <= deg(sh); k++) sh.rep[k] <<= (long)(8 * context.decompSize * j);
+    bCoeff += sh;
+    ReduceCoefficients(bCoeff, context.logQ);
+    polys[ind] *= -1;
+    A[ind] = DoubleCRT(polys[ind], context);
+    b[ind] = DoubleCRT(bCoeff, context);
+  };
+  ParallelFor(total, entry);
+  if (timing) fprintf(stderr, "KeySwitchSI::Init: draws %.4f  arithmetic %.4f s (%zu entries)\n", tt1 - tt0, now() - tt1, total);
   keySwitchMatrix.resize(2);
-  keySwitchMatrix[0] = b;
-  keySwitchMatrix[1] = A;
+  keySwitchMatrix[0] = std::move(b);
+  keySwitchMatrix[1] = std::move(A);
   devKsw.reset();
 }
 void KeySwitchSI::InitS2(const FHESISecKey &s) {  // FHE-SI.cpp:211-227
@@ -1140,6 +1218,9 @@ extern "C" int fhesih_keygen(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, 
                              uint64_t seed, uint32_t n_rot, const uint32_t *rot_k, uint32_t *sk_words,
                              uint32_t *pk_words, uint32_t *ks_b, uint32_t *ks_A, uint32_t *rot_b, uint32_t *rot_A) {
   FHEcontext *saved = activeContext;
+  const bool timing = getenv("FHESIH_TIMING") != nullptr;  // phase times on stderr, for tuning
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now(), t1, t2, t3, t4;
   {
     FHEcontext context(m, logQ, to_ZZ((unsigned long)p), g, decompSize);
     activeContext = &context;
@@ -1154,25 +1235,35 @@ extern "C" int fhesih_keygen(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, 
       std::vector<uint32_t> w = PackPoly(poly, n, W);
       memcpy(dst, w.data(), pw * 4);
     };
+    t1 = now();
     FHESISecKey sk(context);
     FHESIPubKey pk(sk);
     KeySwitchSI ks(sk);
+    t2 = now();
+    std::vector<std::pair<uint32_t *, const DoubleCRT *>> jobs;
     for (int i = 0; i < 2; ++i) {
-      put(sk_words + i * pw, sk.GetRepresentation()[i]);
-      put(pk_words + i * pw, pk.GetRepresentation()[i]);
+      jobs.emplace_back(sk_words + i * pw, &sk.GetRepresentation()[i]);
+      jobs.emplace_back(pk_words + i * pw, &pk.GetRepresentation()[i]);
     }
     for (unsigned k = 0; k < 3 * D; ++k) {
-      put(ks_b + k * pw, ks.GetRepresentation()[0][k]);
-      put(ks_A + k * pw, ks.GetRepresentation()[1][k]);
+      jobs.emplace_back(ks_b + k * pw, &ks.GetRepresentation()[0][k]);
+      jobs.emplace_back(ks_A + k * pw, &ks.GetRepresentation()[1][k]);
     }
+    std::vector<std::unique_ptr<KeySwitchSI>> rks;
     for (uint32_t r = 0; r < n_rot; ++r) {
-      KeySwitchSI rk(sk, rot_k[r]);
+      rks.emplace_back(new KeySwitchSI(sk, rot_k[r]));
       for (unsigned k = 0; k < 2 * D; ++k) {
-        put(rot_b + ((size_t)r * 2 * D + k) * pw, rk.GetRepresentation()[0][k]);
-        put(rot_A + ((size_t)r * 2 * D + k) * pw, rk.GetRepresentation()[1][k]);
+        jobs.emplace_back(rot_b + ((size_t)r * 2 * D + k) * pw, &rks.back()->GetRepresentation()[0][k]);
+        jobs.emplace_back(rot_A + ((size_t)r * 2 * D + k) * pw, &rks.back()->GetRepresentation()[1][k]);
       }
     }
+    t3 = now();
+    ParallelFor(jobs.size(), [&](size_t j) { put(jobs[j].first, *jobs[j].second); });
+    t4 = now();
   }
+  if (timing)
+    fprintf(stderr, "fhesih_keygen: context %.4f  sk+pk+s2 matrix %.4f  rotation matrices %.4f  pack %.4f  s\n", t1 - t0,
+            t2 - t1, t3 - t2, t4 - t3);
   activeContext = saved;
   return 0;
 }
