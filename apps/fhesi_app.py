@@ -153,13 +153,28 @@ def embed_batch(env, slots, values):
     return d_msgs
 
 
+def encryption_randomness(env, count, nrng):
+    """r (uniform bits) and e (rounded Gaussians, sigma = 3.2) for `count` encryptions
+    (FHE-SI.cpp:14-25).  On a GPU they are drawn on the device (torch's generator, seeded from
+    `nrng`): no host sampling, no upload.  Host tensors (emulator tests) use numpy."""
+    n = env.dev.n
+    if str(env.device).startswith("cuda"):
+        gen = torch.Generator(device=env.device)
+        gen.manual_seed(int(nrng.integers(0, 2**62)))
+        r_bits = torch.randint(0, 2, (count, n), dtype=torch.uint8, device=env.device, generator=gen)
+        e = torch.round(torch.randn((count, 2, n), device=env.device, generator=gen) * 3.2).to(torch.int32)
+        return r_bits, e
+    r_bits = torch.from_numpy(nrng.integers(0, 2, size=(count, n), dtype=np.uint8)).to(env.device)
+    e = torch.from_numpy(np.rint(nrng.normal(0.0, 3.2, size=(count, 2, n))).astype(np.int32)).to(env.device)
+    return r_bits, e
+
+
 def encrypt_batch(env, dpk, d_msgs, count, nrng):
     """FHESIPubKey::Encrypt over a batch with explicit randomness (FHE-SI.cpp:10-36)."""
-    dev, n = env.dev, env.dev.n
+    dev = env.dev
     cts = env.empty(max(count, 1) * dev.ct_words(2)).view(max(count, 1), -1)
     if count:
-        r_bits = torch.from_numpy(nrng.integers(0, 2, size=(count, n), dtype=np.uint8)).to(env.device)
-        e = torch.from_numpy(np.rint(nrng.normal(0.0, 3.2, size=(count, 2, n))).astype(np.int32)).to(env.device)
+        r_bits, e = encryption_randomness(env, count, nrng)
         dev.encrypt_dev(dpk, d_msgs, r_bits, e, cts, count)
     return cts
 

@@ -36,7 +36,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-from fhesi_app import Ct, Env, Slots, embed_batch  # noqa: E402
+from fhesi_app import Ct, Env, Slots, embed_batch, encrypt_batch  # noqa: E402
 
 
 def determinant(M, rows, cols, reduce):
@@ -163,12 +163,7 @@ def main():
     t_batch = time.perf_counter()
     nrng = np.random.default_rng(args.seed + 1000 + rank)
     cnt = nb * (d + 1)
-    r_bits = nrng.integers(0, 2, size=(max(cnt, 1), n), dtype=np.uint8)
-    e_gauss = np.rint(nrng.normal(0.0, 3.2, size=(max(cnt, 1), 2, n))).astype(np.int32)
-    cts = env.empty(max(cnt, 1) * dev.ct_words(2)).view(max(cnt, 1), -1)
-    to_dev = lambda a: torch.from_numpy(a).to(device)
-    if cnt:
-        dev.encrypt_dev(dpk, d_msgs, to_dev(r_bits), to_dev(e_gauss), cts, cnt)
+    cts = encrypt_batch(env, dpk, d_msgs, cnt, nrng)
     dev.sync()
     t_enc = time.perf_counter()
 
@@ -233,6 +228,7 @@ def main():
             reduce(acc)
             theta.append(acc)
     # masking noise in every slot but the first (Regression.h:180-189)
+    to_dev = lambda a: torch.from_numpy(a).to(device)
     for ct in theta + [det]:
         vals = [0] + [int(v) for v in nrng.integers(0, p, size=slots.total - 1)]
         v = np.zeros(slots.total, dtype=np.int64)
