@@ -131,6 +131,9 @@ def main():
         torch.cuda.set_stream(stream)
         dev.set_stream(stream.cuda_stream)
     env = Env(dev, device)
+    if not args.cpu_tensors:  # load torch's generator kernels now: process start-up, like the CUDA context
+        from fhesi_app import encryption_randomness
+        encryption_randomness(env, 1, np.random.default_rng(0))
     if world > 1:  # the communicator is process start-up, like the CUDA context: created before the clock
         warm = torch.zeros(8, dtype=torch.int32, device=device)
         dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
