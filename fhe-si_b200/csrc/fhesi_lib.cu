@@ -781,6 +781,86 @@ int fhesi_reduce_wide_dev(fhesi_ctx *c, const uint32_t *in, uint32_t Win, uint32
   CKL();
   return 0;
 }
+// device table of the signed index permutation of X -> X^k (one per Galois element, kept for reuse)
+static int automorph_table(fhesi_ctx *c, uint32_t k, u32 **out) {
+  const fhesi_info &I = c->info;
+  const u32 h = I.m / 2;
+  u32 *&d_tab = c->automorph_tabs[k % I.m];
+  if (!d_tab) {
+    std::vector<u32> tab(h, 0xFFFFFFFFu);
+    for (u32 i = 0; i < I.n; ++i) {
+      u32 e = (u32)(((u64)i * k) % I.m), neg = 0;
+      if (e >= h) { e -= h; neg = 1; }
+      tab[e] = (i << 1) | neg;
+    }
+    void *pt = nullptr;
+    CK(cudaMalloc(&pt, h * 4));
+    c->tables.push_back(pt);
+    d_tab = (u32 *)pt;
+    CK(cudaMemcpyAsync(d_tab, tab.data(), h * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // tab is a stack-lifetime host buffer
+  }
+  *out = d_tab;
+  return 0;
+}
+// ---- tensor-form branches of the plaintext / automorphism operators (Ciphertext.cpp:153-159,252-256,269-273)
+int fhesi_tprod_add_poly_dev(fhesi_ctx *c, uint32_t *tprod, uint32_t parts, const uint32_t *poly, uint32_t Win,
+                             size_t count) {
+  if (!c || !tprod || !poly || !parts) return fail(FHESI_ERR_INVALID, "null argument");
+  const fhesi_info &I = c->info;
+  if (!Win || Win > I.W + 1) return fail(FHESI_ERR_INVALID, "fhesi_tprod_add_poly_dev: 1 <= Win <= W + 1");
+  CK(cudaSetDevice(c->device));
+  if (!count) return 0;
+  const size_t per = (size_t)I.Lt * I.N;
+  PoolTmp img(c);
+  int rc = img.alloc(count * per * 4);
+  if (rc) return rc;
+  // DoubleCRT(poly) in the tprod convention (images carry 1/N)
+  if ((rc = launch_fwd(c, poly, SRC_POLY, Win, SC_NINV, I.Lt, img.u(), count))) return rc;
+  for (size_t b = 0; b < count; ++b) {  // tProd[0] += ...
+    KL(c, k_tprod_add, nblk(per), 256, 0, c->dc, tprod + b * parts * per, img.u() + b * per, I.Lt, per);
+    CKL();
+  }
+  return 0;
+}
+int fhesi_tprod_mul_poly_dev(fhesi_ctx *c, uint32_t *tprod, uint32_t parts, const uint32_t *poly, uint32_t Win,
+                             size_t count) {
+  if (!c || !tprod || !poly || !parts) return fail(FHESI_ERR_INVALID, "null argument");
+  const fhesi_info &I = c->info;
+  if (!Win || Win > I.W + 1) return fail(FHESI_ERR_INVALID, "fhesi_tprod_mul_poly_dev: 1 <= Win <= W + 1");
+  CK(cudaSetDevice(c->device));
+  const size_t per = (size_t)I.Lt * I.N, total = count * parts * per;
+  if (!total) return 0;
+  PoolTmp img(c);
+  int rc = img.alloc(per * 4);
+  if (rc) return rc;
+  if ((rc = launch_fwd(c, poly, SRC_POLY, Win, SC_MONT, I.Lt, img.u(), 1))) return rc;
+  KL(c, k_tprod_mul_img, nblk(total), 256, 0, c->dc, tprod, img.u(), I.Lt, total);
+  CKL();
+  return 0;
+}
+int fhesi_tprod_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uint32_t k, uint32_t *out,
+                              size_t count) {
+  if (!c || !in || !out || !parts) return fail(FHESI_ERR_INVALID, "null argument");
+  const fhesi_info &I = c->info;
+  u64 a = k % I.m, b = I.m;
+  while (b) { u64 t = a % b; a = b; b = t; }
+  if (a != 1) return fail(FHESI_ERR_INVALID, "DoubleCRT::automorph: k not in Zm*");
+  CK(cudaSetDevice(c->device));
+  const size_t npolys = count * parts;
+  if (!npolys) return 0;
+  u32 *d_tab = nullptr;
+  int rc = automorph_table(c, k, &d_tab);
+  if (rc) return rc;
+  PoolTmp r0(c), r1(c);
+  const size_t words = npolys * I.Lt * I.n;
+  if ((rc = r0.alloc(words * 4)) || (rc = r1.alloc(words * 4))) return rc;
+  // transform domain -> coefficient residues (Phi_m fold included) -> signed permutation -> back
+  if ((rc = launch_inv(c, in, I.Lt, r0.u(), npolys))) return rc;
+  KL(c, k_automorph_res, nblk(words), 256, 0, c->dc, r0.u(), d_tab, r1.u(), I.Lt, npolys);
+  CKL();
+  return launch_fwd(c, r1.u(), SRC_RES, 0, SC_NINV, I.Lt, out, npolys);
+}
 int fhesi_embed_slots_dev(fhesi_ctx *c, const uint32_t *basis, uint32_t nslots, const uint32_t *vals,
                           uint32_t *msg, size_t count) {
   if (!c || !basis || !vals || !msg) return fail(FHESI_ERR_INVALID, "null argument");
@@ -805,23 +885,10 @@ int fhesi_ct_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uin
   while (b) { u64 t = a % b; a = b; b = t; }
   if (a != 1) return fail(FHESI_ERR_INVALID, "DoubleCRT::automorph: k not in Zm*");
   CK(cudaSetDevice(c->device));
-  const u32 h = I.m / 2;
-  std::vector<u32> tab(h, 0xFFFFFFFFu);
-  for (u32 i = 0; i < I.n; ++i) {
-    u32 e = (u32)(((u64)i * k) % I.m), neg = 0;
-    if (e >= h) { e -= h; neg = 1; }
-    tab[e] = (i << 1) | neg;
-  }
   size_t npolys = count * parts;
-  u32 *&d_tab = c->automorph_tabs[k % I.m];  // one small table per Galois element, kept for reuse
-  if (!d_tab) {
-    void *pt = nullptr;
-    CK(cudaMalloc(&pt, h * 4));
-    c->tables.push_back(pt);
-    d_tab = (u32 *)pt;
-    CK(cudaMemcpyAsync(d_tab, tab.data(), h * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));  // tab is a stack-lifetime host buffer
-  }
+  u32 *d_tab = nullptr;
+  int rc = automorph_table(c, k, &d_tab);
+  if (rc) return rc;
   if (npolys) KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, out, npolys);
   CKL();
   return 0;

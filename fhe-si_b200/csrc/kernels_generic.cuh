@@ -117,8 +117,10 @@ __device__ __forceinline__ u32 digit_from_words(const u32 *__restrict__ w, u32 W
   return v & ((1u << valid) - 1u);
 }
 
-enum { SRC_POLY = 0, SRC_DIGIT = 1, SRC_U8 = 2, SRC_I32 = 3, SRC_U32 = 4 };
-enum { SC_NONE = 0, SC_TENSOR = 1, SC_KEYFORM = 2, SC_NINV = 3 };
+// SRC_RES: per-prime residues [npolys][L][n] (e.g. the output of k_inv)
+enum { SRC_POLY = 0, SRC_DIGIT = 1, SRC_U8 = 2, SRC_I32 = 3, SRC_U32 = 4, SRC_RES = 5 };
+// SC_MONT: to Montgomery form (x R), no 1/N
+enum { SC_NONE = 0, SC_TENSOR = 1, SC_KEYFORM = 2, SC_NINV = 3, SC_MONT = 4 };
 
 struct FwdArgs {
   const void *src;
@@ -139,6 +141,7 @@ __global__ void k_fwd(DevCtx c, FwdArgs a) {
   if (a.scale_mode == SC_TENSOR) sc = pc.tensor_c;
   else if (a.scale_mode == SC_KEYFORM) sc = pc.ninv_r2;
   else if (a.scale_mode == SC_NINV) sc = pc.ninv_r;
+  else if (a.scale_mode == SC_MONT) sc = pc.r2;
   for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) {
     u32 r = 0;
     if (i < c.n) {
@@ -159,6 +162,7 @@ __global__ void k_fwd(DevCtx c, FwdArgs a) {
           r = v < 0 ? p - ((u32)(-v)) % p : ((u32)v) % p;
           break;
         }
+        case SRC_RES: r = ((const u32 *)a.src)[((size_t)q * a.L + l) * c.n + i]; break;
         default: r = ((const u32 *)a.src)[(size_t)q * c.n + i] % p; break;
       }
       if (a.scale_mode != SC_NONE) r = mont_mul(r, sc, p, pinv);
@@ -308,6 +312,38 @@ __global__ void k_tprod_mul_scalar(DevCtx c, u32 *io, const u32 *scal, u32 L, si
   u32 l = (u32)((idx / c.N) % L);
   const PrimeConst pc = c.pc[l];
   io[idx] = csub(mont_mul(io[idx], scal[l], pc.p, pc.pinv), pc.p);
+}
+// io[b][part][l][e] *= img[l][e] (img in Montgomery form): DoubleCRT *= DoubleCRT with one shared
+// right-hand side, the tensor-form branch of Ciphertext::operator*=(const ZZX&) (Ciphertext.cpp:252-256)
+__global__ void k_tprod_mul_img(DevCtx c, u32 *io, const u32 *img, u32 L, size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t per = (size_t)L * c.N;
+  u32 l = (u32)((idx / c.N) % L);
+  const PrimeConst pc = c.pc[l];
+  io[idx] = csub(mont_mul(io[idx], img[idx % per], pc.p, pc.pinv), pc.p);
+}
+// DoubleCRT::automorph (DoubleCRT.cpp:439-465) on coefficient residues: in, out [npolys][L][n];
+// tab[e] = (source index << 1) | negate for the h = n + 1 positions of the permuted polynomial,
+// 0xFFFFFFFF where no source lands; the X^n position is folded with Phi_m: w_j = v_j - (-1)^j v_n
+__global__ void k_automorph_res(DevCtx c, const u32 *in, const u32 *tab, u32 *out, u32 L, size_t npolys) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npolys * L * c.n) return;
+  const u32 j = (u32)(idx % c.n);
+  const size_t row = idx / c.n;  // poly * L + l
+  const u32 p = c.pc[row % L].p;
+  const u32 *base = in + row * c.n;
+  const u32 tj = tab[j], tt = tab[c.n];
+  u32 a = 0, t = 0;
+  if (tj != 0xFFFFFFFFu) {
+    a = base[tj >> 1];
+    if ((tj & 1) && a) a = p - a;
+  }
+  if (tt != 0xFFFFFFFFu) {
+    t = base[tt >> 1];
+    if ((tt & 1) && t) t = p - t;
+  }
+  out[idx] = (j & 1) ? csub(a + t, p) : csub(a + p - t, p);
 }
 // io[e] += sum_b in[b][e] over a batch of tprods (the data-phase sums of Matrix.cpp:80-97,149-173)
 __global__ void k_tprod_batch_sum(DevCtx c, const u32 *in, u32 count, u32 L, size_t per, u32 *io) {

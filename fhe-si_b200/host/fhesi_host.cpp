@@ -860,10 +860,22 @@ Ciphertext &Ciphertext::operator+=(const Ciphertext &o) {  // Ciphertext.cpp:123
   return *this;
 }
 Ciphertext &Ciphertext::operator+=(const ZZX &other) {  // Ciphertext.cpp:147-161
-  if (scaledUp) Error("Ciphertext += ZZX on a tensor-form ciphertext is not supported: ScaleDown first");
-  EnsureReduced();
   fhesi_ctx *d = context->Dev();
   const unsigned n = context->zMstar.phiM(), W = context->Words();
+  if (scaledUp) {  // :157-159  tProd[0] += scaledConstant, nothing reduced
+    if (!buf) return *this;
+    ZZX sc = other;
+    for (long i = 0; i <= deg(sc); i++) {
+      sc.rep[i] <<= (long)context->logQ;
+      sc.rep[i] /= context->ModulusP();
+    }
+    std::vector<uint32_t> w = PackPoly(sc, n, W + 1);
+    DevBuf t(d, w.size() * 4);
+    Check(fhesi_h2d_async(d, t.ptr, w.data(), w.size() * 4), "fhesi_h2d_async");
+    Check(fhesi_tprod_add_poly_dev(d, buf->ptr, nparts, t.ptr, W + 1, 1), "fhesi_tprod_add_poly_dev");
+    return *this;
+  }
+  EnsureReduced();
   ZZX sc = other;
   for (long i = 0; i <= deg(sc); i++) {
     sc.rep[i] <<= (long)context->logQ;
@@ -907,11 +919,20 @@ Ciphertext &Ciphertext::operator*=(long l) {  // Ciphertext.cpp:233-244
   return *this;
 }
 Ciphertext &Ciphertext::operator*=(const ZZX &other) {  // Ciphertext.cpp:246-258
-  if (scaledUp) Error("Ciphertext *= ZZX on a tensor-form ciphertext is not supported: ScaleDown first");
   if (!buf) return *this;
-  EnsureReduced();
   fhesi_ctx *d = context->Dev();
   const unsigned n = context->zMstar.phiM();
+  if (scaledUp) {  // :252-256  tProd[i] *= DoubleCRT(other), `other` as an integer polynomial
+    const unsigned W = context->Words();
+    ZZX o = other;
+    RemPhim(o, context->zMstar);
+    std::vector<uint32_t> w = PackPoly(o, n, W + 1);
+    DevBuf t(d, w.size() * 4);
+    Check(fhesi_h2d_async(d, t.ptr, w.data(), w.size() * 4), "fhesi_h2d_async");
+    Check(fhesi_tprod_mul_poly_dev(d, buf->ptr, nparts, t.ptr, W + 1, 1), "fhesi_tprod_mul_poly_dev");
+    return *this;
+  }
+  EnsureReduced();
   std::vector<uint32_t> pt(n, 0);
   const ZZ &P = context->ModulusP();
   for (long i = 0; i <= deg(other) && i < (long)n; ++i) pt[i] = (uint32_t)to_long(other.rep.v[i] % P);
@@ -924,10 +945,15 @@ Ciphertext &Ciphertext::operator*=(const ZZX &other) {  // Ciphertext.cpp:246-25
   return *this;
 }
 Ciphertext &Ciphertext::operator>>=(long k) {  // Ciphertext.cpp:264-275
-  if (scaledUp) Error("Ciphertext >>= on a tensor-form ciphertext is not supported: ScaleDown first");
   if (!buf) return *this;
-  EnsureReduced();
   fhesi_ctx *d = context->Dev();
+  if (scaledUp) {  // :269-273  tProd[i] >>= k
+    auto nb = make_shared<DevBuf>(d, fhesi_tprod_bytes(d, nparts));
+    Check(fhesi_tprod_automorph_dev(d, buf->ptr, nparts, (uint32_t)k, nb->ptr, 1), "fhesi_tprod_automorph_dev");
+    buf = nb;
+    return *this;
+  }
+  EnsureReduced();
   const unsigned n = context->zMstar.phiM(), W = context->Words();
   auto nb = make_shared<DevBuf>(d, (size_t)nparts * n * (W + 1) * 4);
   Check(fhesi_ct_automorph_dev(d, buf->ptr, nparts, (uint32_t)k, nb->ptr, 1), "fhesi_ct_automorph_dev");

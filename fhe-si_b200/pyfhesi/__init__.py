@@ -65,6 +65,9 @@ SYMBOLS = {
     "fhesi_keyswitch_dev": (C.c_int, [_P, _P, _P, _P, _SZ]),
     "fhesi_encrypt_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _SZ]),
     "fhesi_decrypt_dev": (C.c_int, [_P, _P, _P, _U32, _P, _SZ]),
+    "fhesi_tprod_add_poly_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
+    "fhesi_tprod_mul_poly_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
+    "fhesi_tprod_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
     "fhesi_embed_slots_dev": (C.c_int, [_P, _P, _U32, _P, _P, _SZ]),
     "fhesi_ct_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
     "fhesi_reduce_wide_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
@@ -256,6 +259,15 @@ class Context:
 
     def decrypt_dev(self, sk, inp, parts, msg, count):
         self._ck(self.lib.fhesi_decrypt_dev(self.h, sk, _ptr(inp), parts, _ptr(msg), count))
+
+    def tprod_add_poly_dev(self, tprod, parts, poly, win, count):
+        self._ck(self.lib.fhesi_tprod_add_poly_dev(self.h, _ptr(tprod), parts, _ptr(poly), win, count))
+
+    def tprod_mul_poly_dev(self, tprod, parts, poly, win, count):
+        self._ck(self.lib.fhesi_tprod_mul_poly_dev(self.h, _ptr(tprod), parts, _ptr(poly), win, count))
+
+    def tprod_automorph_dev(self, inp, parts, k, out, count):
+        self._ck(self.lib.fhesi_tprod_automorph_dev(self.h, _ptr(inp), parts, k, _ptr(out), count))
 
     def embed_slots_dev(self, basis, nslots, vals, msg, count):
         self._ck(self.lib.fhesi_embed_slots_dev(self.h, _ptr(basis), nslots, _ptr(vals), _ptr(msg), count))

@@ -164,6 +164,24 @@ int fhesi_encrypt_dev(fhesi_ctx *ctx, const fhesi_key *pk, const uint32_t *d_msg
 int fhesi_decrypt_dev(fhesi_ctx *ctx, const fhesi_key *sk, const uint32_t *d_in, uint32_t parts,
                       uint32_t *d_msg, size_t count);
 
+/* Tensor-form (scaledUp) branches of the plaintext and automorphism operators.  tprod buffers are
+ * [count][parts][Lt][N] as fhesi_ct_tensor_dev writes them.  As in the reference, nothing here reduces
+ * modulo q, and results are only meaningful while the represented integers stay inside the prime
+ * chain's range (the reference wraps modulo ITS chain product beyond that).
+ *  - Ciphertext::operator+=(const ZZX&) (Ciphertext.cpp:153-159): tProd[0] += DoubleCRT(poly), poly =
+ *    the caller's floor(c * 2^logQ / p) polynomial, DEVICE [count][n][Win] two's-complement words,
+ *    Win <= W + 1 (use W + 1 with a zero top word for non-negative values of logQ bits).
+ *  - Ciphertext::operator*=(const ZZX&) (Ciphertext.cpp:252-256): every part of every tprod times
+ *    DoubleCRT(poly), ONE polynomial [n][Win] shared by the batch.
+ *  - Ciphertext::operator>>=(long k) (Ciphertext.cpp:269-273; DoubleCRT::automorph,
+ *    DoubleCRT.cpp:439-465): a(X) -> a(X^k) mod Phi_m on every part; out may not alias in. */
+int fhesi_tprod_add_poly_dev(fhesi_ctx *ctx, uint32_t *d_tprod, uint32_t parts, const uint32_t *d_poly,
+                             uint32_t Win, size_t count);
+int fhesi_tprod_mul_poly_dev(fhesi_ctx *ctx, uint32_t *d_tprod, uint32_t parts, const uint32_t *d_poly,
+                             uint32_t Win, size_t count);
+int fhesi_tprod_automorph_dev(fhesi_ctx *ctx, const uint32_t *d_in, uint32_t parts, uint32_t k,
+                              uint32_t *d_out, size_t count);
+
 /* PlaintextSpace::EmbedInSlots (PlaintextSpace.cpp:112-134) for a batch of plaintexts, as BatchData
  * issues it (Regression.h:43-66, Test_Statistics.cpp:35-63): msg[c] = sum_k vals[c][k] * basis[k] mod p.
  * basis: DEVICE uint32 [nslots][n], row k = the CRT idempotent of slot k (values in [0,p)); vals:

@@ -150,6 +150,26 @@ int main(int argc, char **argv) {
     secretKey.Decrypt(dr, x);
     Save(dir + "/decrypt_rotate.bin", to_ZZX(dr.message));
   }
+  // ---- third group: the tensor-form (scaledUp) branches of += ZZX, *= ZZX, >>= (Ciphertext.cpp:157-159,
+  // 252-256, 269-273).  The multiplier is small (1 + X): DoubleCRT arithmetic only represents the
+  // integers while they stay inside the chain's range.
+  {
+    Ciphertext t = a;
+    t *= b;
+    t += m[1];
+    Save(dir + "/tensor_add_plain.bin", t);
+    Ciphertext u = a;
+    u *= b;
+    u >>= g;
+    Save(dir + "/tensor_automorph.bin", u);
+    ZZX onePlusX;
+    SetCoeff(onePlusX, 0, 1);
+    SetCoeff(onePlusX, 1, 1);
+    Ciphertext v = a;
+    v *= b;
+    v *= onePlusX;
+    Save(dir + "/tensor_mul_plain.bin", v);
+  }
   // the identities of Test_AddMul.cpp:84-86, for good measure
   Plaintext dsum;
   secretKey.Decrypt(dsum, sum);

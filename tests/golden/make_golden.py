@@ -68,6 +68,10 @@ def outputs(ctx, sk, ks, cts):
     rot = O.apply_key_switch(ks.rot_g, a.copy().automorph(ks.rot_k))
     out["rotate_keyswitch"] = O.export_ciphertext(rot)
     out["decrypt_rotate"] = O.export_zzx(O.decrypt(sk, rot))
+    # third group: tensor-form branches of += ZZX, >>=, *= ZZX
+    out["tensor_add_plain"] = O.export_ciphertext(a.copy().mul(b).add_plain(ks.plain))
+    out["tensor_automorph"] = O.export_ciphertext(a.copy().mul(b).automorph(ks.rot_k))
+    out["tensor_mul_plain"] = O.export_ciphertext(a.copy().mul(b).mul_plain([1, 1] + [0] * (ctx.phim - 2)))
     return out
 
 

@@ -311,6 +311,24 @@ def check_golden(name, lib_path, device=0):
     got["decrypt_rotate"] = O.export_zzx(dm.download((n,)).tolist())
     d.lib.fhesi_ksw_destroy(rksw)
     assert got.pop("tensor_accumulate_batched") == got["tensor_accumulate"]
+    # ---- third group: tensor-form += ZZX, >>=, *= ZZX (Ciphertext.cpp:157-159, 269-273, 252-256)
+    pack1 = lambda poly: np.stack([O.pack_poly_words(poly, 32 * (W + 1))])  # W + 1 words per coefficient
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, 1)
+    dpl = d.to_device(pack1([(c << logq) // p for c in plain]))
+    d.tprod_add_poly_dev(dt.ptr, 3, dpl.ptr, W + 1, 1)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.sync()
+    got["tensor_add_plain"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
+    d.ct_tensor_dev(da.ptr, 2, db.ptr, 2, dt.ptr, 1)
+    d.tprod_automorph_dev(dt.ptr, 3, rot_k, dt2.ptr, 1)
+    d.scaledown_dev(dt2.ptr, 3, dc.ptr, 1)
+    d.sync()
+    got["tensor_automorph"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
+    dmul = d.to_device(pack1([1, 1] + [0] * (n - 2)))
+    d.tprod_mul_poly_dev(dt.ptr, 3, dmul.ptr, W + 1, 1)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.sync()
+    got["tensor_mul_plain"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
     if "out" in g:
         assert {k: v.hex() for k, v in got.items()} == g["out"]
     else:
