@@ -128,3 +128,36 @@ def test_full_batch_properties_cfg2(cuda_lib):
     b = O.Ciphertext(sc.octx, sc.unpack_ct(cts[count + 5]))
     from common import assert_ct_equal
     assert_ct_equal(sc, full[5], O.mult_relin(sc.ks, a, b), "big batch element 5")
+
+
+def test_host_pipeline_full_size_cfg2(cuda_lib):
+    """BASELINE.json's batch (8192 pairs per GPU) through fhesi_mult_relin_host -- two compute lanes,
+    tapered chunk schedule -- must equal the device-resident path element for element; ragged counts
+    exercise every shape of the schedule (no taper, taper with a short middle chunk, single chunk)."""
+    sc = scenario("cfg2", cuda_lib)
+    d = sc.dev
+    count, n, W = 8192, d.n, d.W
+    rng = np.random.default_rng(11)
+    msgs = rng.integers(0, sc.p, size=(2 * count, n), dtype=np.uint32)
+    rs = rng.integers(0, 2, size=(2 * count, n), dtype=np.uint8)
+    es = np.rint(rng.normal(0, 3.2, size=(2 * count, 2, n))).astype(np.int32)
+    dct = d.alloc(2 * count * d.ct_words(2) * 4)
+    dmsg, drs, des = d.to_device(msgs), d.to_device(rs), d.to_device(es)
+    d.encrypt_dev(sc.dpk, dmsg.ptr, drs.ptr, des.ptr, dct.ptr, 2 * count)
+    half = count * d.ct_words(2) * 4
+    dout = d.alloc(half)
+    d.mult_relin_dev(sc.ksw, dct.ptr, dct.ptr + half, dout.ptr, count)
+    dm = d.alloc(count * n * 4)
+    d.decrypt_dev(sc.dsk, dout.ptr, 2, dm.ptr, count)
+    d.sync()
+    want = dout.download((count, 2, n, W))
+    dec = dm.download((count, n))
+    cts = dct.download((2 * count, 2, n, W))
+    ha, hb = np.ascontiguousarray(cts[:count]), np.ascontiguousarray(cts[count:])
+    for cnt in (count, 3457, 600, 1):
+        got = d.mult_relin_host(sc.ksw, ha[:cnt], hb[:cnt])
+        assert np.array_equal(got, want[:cnt]), f"host pipeline differs at count {cnt}"
+    # the Test_AddMul.cpp:84-86 identity on a sample of the batch (plaintext product mod Phi_m, mod p)
+    ring = sc.octx.ring
+    for i in (0, 1, 4095, 4096, count - 1):
+        assert dec[i].tolist() == [c % sc.p for c in ring.mul(msgs[i].tolist(), msgs[count + i].tolist())]
