@@ -999,13 +999,14 @@ int fhesi_tprod_mul_scalar_dev(fhesi_ctx *c, uint32_t *io, int64_t l, uint32_t p
     if (r < 0) r += q;
     sc[i] = (u32)h_mulmod((u64)r, c->h_pc[i].r1, (u64)q);
   }
-  DevTmp t_sc;
-  CK(t_sc.alloc(I.Lt * 4));
+  PoolTmp t_sc(c);  // pooled, stream-ordered: no cudaMalloc / cudaFree / synchronisation per call
+  int rc = t_sc.alloc(I.Lt * 4);
+  if (rc) return rc;
   u32 *d_sc = t_sc.u();
+  // `sc` is pageable: the copy has consumed it when cudaMemcpyAsync returns
   CK(cudaMemcpyAsync(d_sc, sc.data(), I.Lt * 4, cudaMemcpyHostToDevice, c->stream));
   KL(c, k_tprod_mul_scalar, nblk(total), 256, 0, c->dc, io, d_sc, I.Lt, total);
   CKL();
-  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 int fhesi_tprod_reduce_gathered_dev(fhesi_ctx *c, const uint32_t *g, uint32_t world, uint32_t parts,
