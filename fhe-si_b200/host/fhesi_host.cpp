@@ -648,6 +648,31 @@ void DoubleCRT::toPoly(ZZX &p, bool positive) const {
   }
   p.normalize();
 }
+DoubleCRT &DoubleCRT::operator/=(const ZZ &num) {  // every row times num^-1 mod its prime == poly * num^-1 mod P
+  const ZZ P = context.productOfPrimes();
+  ZZ r = num % P;
+  poly *= InvMod(r, P);
+  wrap();
+  return *this;
+}
+void DoubleCRT::Exp(long e) {
+  vector<vector<long>> rows = getRows();
+  for (size_t i = 0; i < rows.size(); ++i) {
+    const long pi = context.ithPrime(i);
+    for (auto &v : rows[i]) v = PowerMod(v, e, pi);
+  }
+  setRows(rows);
+}
+void DoubleCRT::randomize(const ZZ *seed) {
+  if (seed != NULL) SetSeed(*seed);
+  const unsigned n = context.zMstar.phiM(), L = context.numPrimes();
+  vector<vector<long>> rows(L, vector<long>(n));
+  for (unsigned i = 0; i < L; ++i) {
+    const long pi = context.ithPrime(i);
+    for (unsigned j = 0; j < n; ++j) rows[i][j] = RandomBnd(pi);
+  }
+  setRows(rows);
+}
 void DoubleCRT::automorph(long k) {  // DoubleCRT.cpp:439-465 in coefficient form
   const PAlgebra &z = context.zMstar;
   if (!z.inZmStar(k)) Error("DoubleCRT::automorph: k not in Zm*");

@@ -226,6 +226,10 @@ class DoubleCRT {
   void toPoly(ZZX &p, bool positive = false) const;
   void automorph(long k);
   DoubleCRT &operator>>=(long k) { automorph(k); return *this; }
+  DoubleCRT &operator/=(const ZZ &num);                    // DoubleCRT.cpp:406-420
+  DoubleCRT &operator/=(long num) { return *this /= to_ZZ(num); }
+  void Exp(long e);                                        // :422-435, pointwise power of the rows
+  void randomize(const ZZ *seed = NULL);                   // :466-480, uniformly random rows
   const FHEcontext &getContext() const { return context; }
 
   // rows over the context's (reference) chain: DoubleCRT(const ZZX&), DoubleCRT.cpp:244-257

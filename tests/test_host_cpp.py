@@ -101,6 +101,12 @@ def run_statistics_client(exe, datafile, p, g, timeout=900):
     return out
 
 
+def test_host_doublecrt_row_ops_emu(emu_lib, tmp_path):
+    exe = compile_client([os.path.join(ROOT, "tests", "cpp", "dcrt_ops.cpp")], emu_lib, str(tmp_path / "dcrt_ops"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "dcrt ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 def test_reference_clients_run_unchanged_emu(emu_lib, tmp_path):
     """Test_AddMul.cpp, Test_General.cpp, Test_Regression.cpp and Test_Statistics.cpp (+ Regression.h,
