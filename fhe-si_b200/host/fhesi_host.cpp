@@ -648,6 +648,16 @@ void DoubleCRT::toPoly(ZZX &p, bool positive) const {
   }
   p.normalize();
 }
+IndexMap<vec_long> DoubleCRT::getMap() const {
+  IndexMap<vec_long> m;
+  vector<vector<long>> rows = getRows();
+  for (size_t i = 0; i < rows.size(); ++i) {
+    m.insert((long)i);
+    m[(long)i].v = rows[i];
+  }
+  return m;
+}
+IndexSet DoubleCRT::getIndexSet() const { return context.ctxtPrimes; }
 DoubleCRT &DoubleCRT::operator/=(const ZZ &num) {  // every row times num^-1 mod its prime == poly * num^-1 mod P
   const ZZ P = context.productOfPrimes();
   ZZ r = num % P;

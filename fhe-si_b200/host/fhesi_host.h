@@ -69,6 +69,28 @@ class IndexSet {
 };
 inline long card(const IndexSet &s) { return s.card(); }
 
+// The reference's IndexMap<T> (IndexMap.h): a map over a dynamic index set.  Index sets on the
+// Brakerski path are always the whole chain {0..L-1}, so a vector is enough.
+template <class T>
+class IndexMap {
+  std::vector<T> items;
+  IndexSet set;
+
+ public:
+  IndexMap() {}
+  const IndexSet &getIndexSet() const { return set; }
+  T &operator[](long j) { assert(set.contains(j)); return items[j]; }
+  const T &operator[](long j) const { assert(set.contains(j)); return items[j]; }
+  void insert(long j) {
+    set.insert(j);
+    if ((long)items.size() < set.card()) items.resize(set.card());
+  }
+  void insert(const IndexSet &s) {
+    for (long i = s.first(); i <= s.last(); i = s.next(i)) insert(i);
+  }
+  void clear() { items.clear(), set = IndexSet(); }
+};
+
 // ------------------------------------------------------------------------------- PlaintextSpace
 // Slot structure of Z_p[X]/Phi_m (PlaintextSpace.h, PlaintextSpace.cpp:22-134) for p = 1 mod m,
 // where Phi_m splits into linear factors: slot j <-> root rho^(g^j).
@@ -231,6 +253,9 @@ class DoubleCRT {
   void Exp(long e);                                        // :422-435, pointwise power of the rows
   void randomize(const ZZ *seed = NULL);                   // :466-480, uniformly random rows
   const FHEcontext &getContext() const { return context; }
+  // rows over the reference chain as the reference exposes them (DoubleCRT.h:296-297); computed on demand
+  IndexMap<vec_long> getMap() const;
+  IndexSet getIndexSet() const;
 
   // rows over the context's (reference) chain: DoubleCRT(const ZZX&), DoubleCRT.cpp:244-257
   vector<vector<long>> getRows() const;

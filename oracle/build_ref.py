@@ -8,6 +8,7 @@ Outputs (git-ignored, they travel to the GPU box with the snapshot):
                                   and objects: writes the byte files the golden vectors are made of
   oracle/_ref/Test_AddMul_ref     the reference's own test program
   oracle/_ref/ref_bench           oracle/ref_bench.cpp: times c *= b; ApplyKeySwitch(c)
+  oracle/_ref/api_probe_ref       tests/cpp/api_probe.cpp (every client-facing symbol of SURVEY.md §8b)
 
 What is and is not the reference here: DoubleCRT, Cmodulus/Bluestein, Ciphertext, FHE-SI (keys,
 Encrypt/Decrypt, key switching), Util, NumbTh samplers, PlaintextSpace, Serialization -- all the
@@ -32,6 +33,8 @@ PROGRAMS = {
     "golden_client_ref": os.path.join(ROOT, "tests", "cpp", "host_client.cpp"),
     "ref_bench": os.path.join(HERE, "ref_bench.cpp"),
     "Test_AddMul_ref": os.path.join(REF, "Test_AddMul.cpp"),
+    # tests/cpp/api_probe.cpp against the reference itself: proves the probe only uses real reference API
+    "api_probe_ref": os.path.join(ROOT, "tests", "cpp", "api_probe.cpp"),
 }
 
 

@@ -101,6 +101,30 @@ def run_statistics_client(exe, datafile, p, g, timeout=900):
     return out
 
 
+def _run_api_probe(backend, tmp_path):
+    exe = compile_client([os.path.join(ROOT, "tests", "cpp", "api_probe.cpp")], backend, str(tmp_path / "api_probe"))
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "api_probe ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_api_surface_probe_emu(emu_lib, tmp_path):
+    """Every client-facing symbol SURVEY.md §8b lists (constructors, operators, accessors, the
+    Export/Import overload set), used once, with self-checks; the same file is compiled against the
+    reference's own headers by oracle/build_ref.py (api_probe_ref), so it cannot drift from them."""
+    _run_api_probe(emu_lib, tmp_path)
+    ref_probe = os.path.join(ROOT, "oracle", "_ref", "api_probe_ref")
+    if os.path.exists(ref_probe):
+        d = tmp_path / "ref"
+        d.mkdir()
+        r = subprocess.run([ref_probe, str(d)], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "api_probe ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.gpu
+def test_api_surface_probe_gpu(cuda_lib, tmp_path):
+    _run_api_probe(cuda_lib, tmp_path)
+
+
 def test_host_doublecrt_row_ops_emu(emu_lib, tmp_path):
     exe = compile_client([os.path.join(ROOT, "tests", "cpp", "dcrt_ops.cpp")], emu_lib, str(tmp_path / "dcrt_ops"))
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
