@@ -142,6 +142,8 @@ def test_reference_clients_run_unchanged_emu(emu_lib, tmp_path):
         r = subprocess.run([exes["Test_AddMul"], "80", "23", "7", str(seed)], capture_output=True, text=True,
                            timeout=600)
         assert r.returncode == 0 and "Test SUCCEEDED" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    r = subprocess.run([exes["Test_General"]], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "All tests finished." in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
     _write_data(tmp_path / "reg.dat", 2, 20)
     run_regression_client(exes["Test_Regression"], str(tmp_path / "reg.dat"), 23, 7)
     _write_data(tmp_path / "stat.dat", 3, 20)
@@ -160,6 +162,8 @@ def test_reference_clients_run_unchanged_gpu(cuda_lib, tmp_path):
     for args in (["80", "23", "7", "1"], ["256", "1019", "3", "2"]):
         r = subprocess.run([exes["Test_AddMul"]] + args, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "Test SUCCEEDED" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    r = subprocess.run([exes["Test_General"]], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "All tests finished." in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
     _write_data(tmp_path / "reg.dat", 3, 1500)      # 6 blocks of 256 at p = 1019
     run_regression_client(exes["Test_Regression"], str(tmp_path / "reg.dat"), 1019, 3)
     _write_data(tmp_path / "stat.dat", 3, 1500)
