@@ -171,11 +171,21 @@ def encryption_randomness(env, count, nrng):
 
 def encrypt_batch(env, dpk, d_msgs, count, nrng):
     """FHESIPubKey::Encrypt over a batch with explicit randomness (FHE-SI.cpp:10-36)."""
+    import os
+    import sys
+    import time
     dev = env.dev
+    t0 = time.perf_counter()
     cts = env.empty(max(count, 1) * dev.ct_words(2)).view(max(count, 1), -1)
     if count:
         r_bits, e = encryption_randomness(env, count, nrng)
+        t1 = time.perf_counter()
         dev.encrypt_dev(dpk, d_msgs, r_bits, e, cts, count)
+        if os.environ.get("FHESI_APP_TIMING"):
+            t2 = time.perf_counter()
+            dev.sync()
+            print(f"encrypt_batch({count}): randomness {t1 - t0:.4f}  enqueue {t2 - t1:.4f}  device {time.perf_counter() - t2:.4f}",
+                  file=sys.stderr)
     return cts
 
 
