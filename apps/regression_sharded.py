@@ -20,6 +20,11 @@ against the plaintext computation mod p.
   python -m torch.distributed.run --nproc-per-node 8 ... apps/regression_sharded.py --dim 4 --points 100000
 """
 import argparse
+import os
+
+# load every kernel when the CUDA context is created (process start-up, before the drivers' clock)
+# instead of lazily at first launch, which would land in whichever phase uses a kernel first
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 import json
 import math
 import os

@@ -14,6 +14,11 @@ mod p.  One JSON line; phase names as in the reference driver.
   python apps/statistics_sharded.py --dim 4 --points 10000
 """
 import argparse
+import os
+
+# load every kernel when the CUDA context is created (process start-up, before the drivers' clock)
+# instead of lazily at first launch, which would land in whichever phase uses a kernel first
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 import json
 import math
 import os
