@@ -93,6 +93,7 @@ def main():
     # (Test_Statistics.cpp:112-173)
     t_start = time.perf_counter()
     keys = keygen(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
+    t_keygen = time.perf_counter()
     ksw = dev.ksw_create(keys["ks_b"], keys["ks_A"], 3)
     rot_ksw = [dev.ksw_create(keys["rot_b"][i], keys["rot_A"][i], 2) for i in range(len(rot_k))]
     dpk, dsk = dev.key_create(keys["pk"]), dev.key_create(keys["sk"])
@@ -189,6 +190,7 @@ def main():
             "metric": f"Test_Statistics N={N} d={d} wall time", "unit": "s", "higher_is_better": False,
             "value": t_dec - t_start, "n_gpus": world, "correct": bool(ok),
             "clock": "Test_Statistics.cpp:112-173 (key generation .. decryption)", "load_context_and_communicator_s": t_start - t_load0,
+            "setup_split_s": {"host_key_generation": t_keygen - t_start, "upload_and_transform": t_setup - t_keygen},
             "phases_s": {"setup": t_setup - t_start, "batch": t_batch - t_setup, "encryption": t_enc - t_batch,
                          "partial_sums_and_exchange": t_data - t_enc, "replicated_tail": t_comp - t_data,
                          "decryption": t_dec - t_comp},
