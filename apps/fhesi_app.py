@@ -97,14 +97,13 @@ class Ct:
         self.buf, self.parts = out, 2
         return self
 
-    def rotate_(self, k, ksw):  # tmp >>= k; autoKeySwitch.ApplyKeySwitch(tmp)
+    def rotate_(self, k, ksw):  # tmp >>= k; autoKeySwitch.ApplyKeySwitch(tmp), one fused call
         e, d = self.env, self.env.dev
-        wide = e.empty(self.parts * d.n * (d.W + 1))
-        d.ct_automorph_dev(self.buf, self.parts, k, wide, 1)
-        red = e.empty(d.ct_words(self.parts))
-        d.reduce_wide_dev(wide, d.W + 1, red, self.parts, 1)
-        self.buf = red
-        return self.keyswitch_(ksw)
+        assert self.parts == 2 and not self.scaled_up
+        out = e.empty(d.ct_words(2))
+        d.rotate_keyswitch_dev(ksw, self.buf, k, out, 1)
+        self.buf = out
+        return self
 
 
 class Env:

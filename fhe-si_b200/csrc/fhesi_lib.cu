@@ -1096,6 +1096,27 @@ static int fused_keyswitch(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, u3
   }
   return 0;
 }
+// tmp >>= k; ApplyKeySwitch(tmp) with the rotation folded into the digit extraction
+static int fused_rotate_keyswitch(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *in, const u32 *d_tab, u32 *out,
+                                  size_t count) {
+  const fhesi_info &I = c->info;
+  const u32 K = ksw->parts * I.D;
+  const size_t CH = c->fused_chunk;
+  const size_t rw = (size_t)(2 * I.Lk > 4 * I.Ls ? 2 * I.Lk : 4 * I.Ls);
+  size_t nd = al(CH * K * I.n), nr = al(CH * rw * I.n);
+  u32 *s = nullptr;
+  int rc = scratch(c, (nd + nr) * 4, &s);
+  if (rc) return rc;
+  u32 *sD = s, *sR = s + nd;
+  for (size_t off = 0; off < count; off += CH) {
+    size_t cnt = count - off < CH ? count - off : CH;
+    size_t npolys = cnt * ksw->parts;
+    KL(c, k_digits_automorph, nblk(npolys * I.n), 256, 0, c->dc, in + off * ksw->parts * I.n * I.W, d_tab, sD, npolys);
+    CKL();
+    if ((rc = fused_ks_from_digits(c, ksw, sD, sR, out + off * 2 * I.n * I.W, cnt))) return rc;
+  }
+  return 0;
+}
 static int fused_mult_relin(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *a, const u32 *b, u32 *out,
                             size_t count) {
   const fhesi_info &I = c->info;
@@ -1125,6 +1146,31 @@ int fhesi_keyswitch_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *in, 
   CK(cudaSetDevice(c->device));
   if (c->use_fused) return fused_keyswitch(c, ksw, in, out, count);
   return keyswitch_generic(c, ksw, in, out, count);
+}
+
+int fhesi_rotate_keyswitch_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *in, uint32_t k, uint32_t *out,
+                               size_t count) {
+  if (!c || !ksw || !in || !out) return fail(FHESI_ERR_INVALID, "null argument");
+  if (ksw->ctx != c) return fail(FHESI_ERR_INVALID, "key-switch matrix belongs to another context");
+  if (ksw->parts != 2) return fail(FHESI_ERR_INVALID, "rotation needs the (1, s(X^k)) -> s matrix (2 source parts)");
+  const fhesi_info &I = c->info;
+  u64 a = k % I.m, b = I.m;
+  while (b) { u64 t = a % b; a = b; b = t; }
+  if (a != 1) return fail(FHESI_ERR_INVALID, "DoubleCRT::automorph: k not in Zm*");
+  CK(cudaSetDevice(c->device));
+  if (!count) return 0;
+  u32 *d_tab = nullptr;
+  int rc = automorph_table(c, k, &d_tab);
+  if (rc) return rc;
+  if (c->use_fused) return fused_rotate_keyswitch(c, ksw, in, d_tab, out, count);
+  // generic kernels: the three steps separately
+  PoolTmp wide(c), red(c);
+  const size_t npolys = count * 2;
+  if ((rc = wide.alloc(npolys * I.n * (I.W + 1) * 4)) || (rc = red.alloc(npolys * I.n * I.W * 4))) return rc;
+  KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, wide.u(), npolys);
+  CKL();
+  if ((rc = fhesi_reduce_wide_dev(c, wide.u(), I.W + 1, red.u(), 2, count))) return rc;
+  return keyswitch_generic(c, ksw, red.u(), out, count);
 }
 
 int fhesi_mult_relin_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *a, const uint32_t *b,

@@ -595,6 +595,40 @@ __global__ void k_digits(DevCtx c, const u32 *in, u32 *out, size_t npolys) {
   for (u32 d = 0; d < c.D; ++d) out[(poly * c.D + d) * c.n + i] = digit_from_words(w, c.W, c.logQ, c.dbits, d);
 }
 
+// Rotation fused into the digit stage (SumBatchedData, Regression.h:166-178: tmp >>= k;
+// ApplyKeySwitch(tmp)): in coefficient form a(X) -> a(X^k) mod Phi_m is a signed index permutation
+// plus the X^n fold, so the digits of Reduce(a(X^k)) are produced directly from the ciphertext words --
+// no wide intermediate, no separate reduction, no transform.  in [npolys][n][W] -> out [npolys][D][n];
+// tab as in k_automorph.
+__global__ void k_digits_automorph(DevCtx c, const u32 *in, const u32 *tab, u32 *out, size_t npolys) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npolys * c.n) return;
+  const size_t poly = idx / c.n;
+  const u32 j = (u32)(idx % c.n), W = c.W;
+  const u32 *base = in + poly * c.n * W;
+  const u32 tj = tab[j], tt = tab[c.n];
+  const u32 neg_top = (j & 1) ? 0u : 1u;  // w_j = v_j - (-1)^j v_n
+  const bool ha = tj != 0xFFFFFFFFu, hb = tt != 0xFFFFFFFFu;
+  const u32 ca = (ha && (tj & 1)) ? 1u : 0u, cb = (hb && ((tt & 1) ^ neg_top)) ? 1u : 0u;
+  const u32 *sa = base + (size_t)(tj >> 1) * W, *sb = base + (size_t)(tt >> 1) * W;
+  u32 w[17];  // W <= 16 words of the sum; bits above logQ are dropped by the digit extraction
+  u32 ba = ca, bb = cb, c2 = 0;
+  for (u32 k = 0; k < W; ++k) {
+    u32 wa = 0, wb = 0;
+    if (ha) {
+      u64 t = (u64)(ca ? ~sa[k] : sa[k]) + ba;
+      wa = (u32)t, ba = (u32)(t >> 32);
+    }
+    if (hb) {
+      u64 t = (u64)(cb ? ~sb[k] : sb[k]) + bb;
+      wb = (u32)t, bb = (u32)(t >> 32);
+    }
+    u64 t = (u64)wa + wb + c2;
+    w[k] = (u32)t, c2 = (u32)(t >> 32);
+  }
+  for (u32 d = 0; d < c.D; ++d) out[(poly * c.D + d) * c.n + j] = digit_from_words(w, W, c.logQ, c.dbits, d);
+}
+
 static int fused_configure() {
   cudaError_t e = cudaFuncSetAttribute(k_fused_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(FUSED_SMEM_WORDS * 4));

@@ -65,6 +65,7 @@ SYMBOLS = {
     "fhesi_keyswitch_dev": (C.c_int, [_P, _P, _P, _P, _SZ]),
     "fhesi_encrypt_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _SZ]),
     "fhesi_decrypt_dev": (C.c_int, [_P, _P, _P, _U32, _P, _SZ]),
+    "fhesi_rotate_keyswitch_dev": (C.c_int, [_P, _P, _P, _U32, _P, _SZ]),
     "fhesi_tprod_add_poly_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
     "fhesi_tprod_mul_poly_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
     "fhesi_tprod_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
@@ -259,6 +260,9 @@ class Context:
 
     def decrypt_dev(self, sk, inp, parts, msg, count):
         self._ck(self.lib.fhesi_decrypt_dev(self.h, sk, _ptr(inp), parts, _ptr(msg), count))
+
+    def rotate_keyswitch_dev(self, ksw, inp, k, out, count):
+        self._ck(self.lib.fhesi_rotate_keyswitch_dev(self.h, ksw, _ptr(inp), k, _ptr(out), count))
 
     def tprod_add_poly_dev(self, tprod, parts, poly, win, count):
         self._ck(self.lib.fhesi_tprod_add_poly_dev(self.h, _ptr(tprod), parts, _ptr(poly), win, count))

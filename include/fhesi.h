@@ -164,6 +164,13 @@ int fhesi_encrypt_dev(fhesi_ctx *ctx, const fhesi_key *pk, const uint32_t *d_msg
 int fhesi_decrypt_dev(fhesi_ctx *ctx, const fhesi_key *sk, const uint32_t *d_in, uint32_t parts,
                       uint32_t *d_msg, size_t count);
 
+/* SumBatchedData's step `tmp >>= k; autoKeySwitch.ApplyKeySwitch(tmp)` (Regression.h:166-178,
+ * Statistics.h:146-158) in one call: in [count][2][n][W] reduced ciphertexts, ksw the (1, s(X^k)) -> s
+ * matrix (KeySwitchSI(sk, k)), out [count][2][n][W].  Same result as fhesi_ct_automorph_dev +
+ * fhesi_reduce_wide_dev + fhesi_keyswitch_dev; the rotation is folded into the digit extraction. */
+int fhesi_rotate_keyswitch_dev(fhesi_ctx *ctx, const fhesi_ksw *ksw, const uint32_t *d_in, uint32_t k,
+                               uint32_t *d_out, size_t count);
+
 /* Tensor-form (scaledUp) branches of the plaintext and automorphism operators.  tprod buffers are
  * [count][parts][Lt][N] as fhesi_ct_tensor_dev writes them.  As in the reference, nothing here reduces
  * modulo q, and results are only meaningful while the represented integers stay inside the prime

@@ -309,6 +309,14 @@ def check_golden(name, lib_path, device=0):
     d.sync()
     got["rotate_keyswitch"] = O.export_ciphertext(unpack(do.download((2, n, W))))
     got["decrypt_rotate"] = O.export_zzx(dm.download((n,)).tolist())
+    # the same through the fused entry point (rotation folded into the digit extraction), batch of 3
+    d3 = d.to_device(np.stack([pack(cts[0].parts)] * 3))
+    do3 = d.alloc(3 * d.ct_words(2) * 4)
+    d.rotate_keyswitch_dev(rksw, d3.ptr, rot_k, do3.ptr, 3)
+    d.sync()
+    fused = do3.download((3, 2, n, W))
+    for b in range(3):
+        assert O.export_ciphertext(unpack(fused[b])) == got["rotate_keyswitch"], "fhesi_rotate_keyswitch_dev"
     d.lib.fhesi_ksw_destroy(rksw)
     assert got.pop("tensor_accumulate_batched") == got["tensor_accumulate"]
     # ---- third group: tensor-form += ZZX, >>=, *= ZZX (Ciphertext.cpp:157-159, 269-273, 252-256)

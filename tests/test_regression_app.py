@@ -11,7 +11,15 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_app(extra, nproc, port, app="regression_sharded.py"):
+def free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def run_app(extra, nproc, port=None, app="regression_sharded.py"):
+    port = free_port()  # an unused rendezvous port: fixed numbers collide with lingering sockets
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "apps", app)] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)

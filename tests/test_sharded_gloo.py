@@ -61,8 +61,11 @@ def test_shard_bounds():
 @pytest.mark.parametrize("nblocks", [5, 1])
 def test_sharded_sum_world2_gloo(emu_lib, nblocks):
     world = 2
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:  # an unused rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, port + nblocks, emu_lib, nblocks, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, emu_lib, nblocks, results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}
