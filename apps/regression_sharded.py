@@ -136,6 +136,8 @@ def main():
         torch.cuda.set_stream(stream)
         dev.set_stream(stream.cuda_stream)
     env = Env(dev, device)
+    from pyfhesi.hostkeys import prepare as prepare_host_layer
+    prepare_host_layer(args.lib)  # build-if-stale + dlopen of the C++ host layer: start-up, not key generation
     if not args.cpu_tensors:  # load torch's generator kernels now: process start-up, like the CUDA context
         from fhesi_app import encryption_randomness
         encryption_randomness(env, 1, np.random.default_rng(0))

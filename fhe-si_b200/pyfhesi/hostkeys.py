@@ -13,11 +13,23 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 
 
+_LIBS = {}
+
+
 def _host_lib(backend_path: str) -> C.CDLL:
-    sys.path.insert(0, os.path.join(_PKG, "host"))
-    from build_host import build_host
-    C.CDLL(backend_path, mode=C.RTLD_GLOBAL)  # the host library resolves fhesi_* from the backend
-    return C.CDLL(build_host(backend_path))
+    if backend_path not in _LIBS:
+        sys.path.insert(0, os.path.join(_PKG, "host"))
+        from build_host import build_host
+        C.CDLL(backend_path, mode=C.RTLD_GLOBAL)  # the host library resolves fhesi_* from the backend
+        _LIBS[backend_path] = C.CDLL(build_host(backend_path))
+    return _LIBS[backend_path]
+
+
+def prepare(lib_path: str | None = None) -> None:
+    """Build (if stale) and load the host library now, so that a later keygen() call is key
+    generation only -- callers that time their set-up phase call this during start-up."""
+    from . import DEFAULT_LIB
+    _host_lib(lib_path or DEFAULT_LIB)
 
 
 def keygen(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
