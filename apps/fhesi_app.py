@@ -125,6 +125,25 @@ def sum_slots(ct, rot_k, rot_ksw):
     return ct
 
 
+def keyswitch_and_sum_slots_batch(env, tprods, count, ksw, rot_k, rot_ksw):
+    """ApplyKeySwitch + SumBatchedData for `count` tensor-form accumulators at once
+    (Regression.h:106-108,166-178): one scale-down, one key switch and log2(usableSlots)
+    rotate-and-add steps over the whole batch instead of one call per ciphertext.
+    tprods: [count][3 * Lt * N] words -> list of `count` 2-part Ct."""
+    dev = env.dev
+    cw = dev.ct_words(2)
+    c3 = env.empty(count * dev.ct_words(3))
+    dev.scaledown_dev(tprods, 3, c3, count)
+    cur = env.empty(count * cw)
+    dev.keyswitch_dev(ksw, c3, cur, count)
+    tmp = env.empty(count * cw)
+    for kk, rk in zip(rot_k, rot_ksw):
+        dev.rotate_keyswitch_dev(rk, cur, kk, tmp, count)
+        dev.ct_add_dev(cur, tmp, 2, count)
+    cur = cur.view(count, cw)
+    return [Ct(env, cur[i].clone(), 2) for i in range(count)]
+
+
 def rotation_exponents(g, m, usable):
     """k = g, g^2, g^4, ... (Regression.h:70-81)."""
     out, k, ns = [], g % m, usable

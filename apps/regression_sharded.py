@@ -41,7 +41,8 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-from fhesi_app import Ct, Env, Slots, embed_batch, encrypt_batch  # noqa: E402
+from fhesi_app import (Ct, Env, Slots, embed_batch, encrypt_batch,  # noqa: E402
+                       keyswitch_and_sum_slots_batch)
 
 
 def determinant(M, rows, cols, reduce):
@@ -201,13 +202,7 @@ def main():
     def reduce(ct):
         ct.keyswitch_(ksw)
 
-    def process(ct):  # ApplyKeySwitch + SumBatchedData (Regression.h:166-178)
-        ct.keyswitch_(ksw)
-        for kk, rk in zip(rot_k, rot_ksw):
-            tmp = ct.copy().rotate_(kk, rk)
-            ct.add_(tmp)
-        return ct
-    sums = [process(Ct(env, total[i].clone(), 3, True)) for i in range(len(pairs))]
+    sums = keyswitch_and_sum_slots_batch(env, total, len(pairs), ksw, rot_k, rot_ksw)
     xty = sums[:d]
     xtx = [[None] * d for _ in range(d)]
     it = iter(sums[d:])

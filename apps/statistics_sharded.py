@@ -32,6 +32,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 from fhesi_app import (Ct, Env, Slots, add_mask, decrypt_slot0, embed_batch, encrypt_batch,  # noqa: E402
+                       keyswitch_and_sum_slots_batch,
                        rotation_exponents, sum_slots)
 
 
@@ -156,10 +157,9 @@ def main():
         t.keyswitch_(ksw)
         mu[(i, j)] = t.neg_()
     cov = {}
+    summed = keyswitch_and_sum_slots_batch(env, quad, len(pairs), ksw, rot_k, rot_ksw)
     for idx, (i, j) in enumerate(pairs):
-        c = Ct(env, quad[idx].clone(), 3, True)
-        c.keyswitch_(ksw)
-        sum_slots(c, rot_k, rot_ksw)
+        c = summed[idx]
         c = c.mul(n_ct)
         c.keyswitch_(ksw)
         c.add_(mu[(i, j)])
