@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfhesi_b200.so")
 SOURCES = ["fhesi_lib.cu"]
@@ -28,16 +29,22 @@ def nvcc_path():
 
 
 def build(force=False, verbose=False):
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    from buildlock import build_lock, publish
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "fhesi.h")]
     if not force and not _stale(LIB, deps):
         return LIB
-    nvcc = nvcc_path()
-    if not os.path.exists(nvcc):
-        if os.path.exists(LIB):
-            return LIB  # GPU box without a toolchain: use the .so that travelled with the snapshot
-        raise RuntimeError("nvcc not found and no prebuilt libfhesi_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    with build_lock(LIB):  # one builder per tree; the other ranks wait, then find it fresh
+        if not force and not _stale(LIB, deps):
+            return LIB
+        nvcc = nvcc_path()
+        if not os.path.exists(nvcc):
+            if os.path.exists(LIB):
+                return LIB  # GPU box without a toolchain: use the .so that travelled with the snapshot
+            raise RuntimeError("nvcc not found and no prebuilt libfhesi_b200.so")
+        tmp = LIB + ".tmp.%d" % os.getpid()
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+        subprocess.check_call(cmd, cwd=CSRC)
+        publish(tmp, LIB)
     return LIB
 
 

@@ -15,12 +15,21 @@ def build_host(backend, out_dir=None, force=False):
     deps.append(os.path.join(ROOT, "include", "fhesi.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "fhe-si_b200"))
+    from buildlock import build_lock, publish
+    fresh = lambda: os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps)
     bdir, bname = os.path.dirname(backend), os.path.basename(backend)
     assert bname.startswith("lib") and bname.endswith(".so")
-    cmd = ["g++", "-std=c++17", "-O3", "-g", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-sign-compare",
-           "-I", HERE, "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "fhesi_host.cpp"),
-           "-o", out, "-L", bdir, "-l" + bname[3:-3], "-Wl,-rpath," + bdir]
-    subprocess.check_call(cmd)
+    with build_lock(out):  # several ranks may get here at once: one builds, the others find it fresh
+        if not force and fresh():
+            return out
+        tmp = out + ".tmp.%d" % os.getpid()
+        cmd = ["g++", "-std=c++17", "-O3", "-g", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-sign-compare",
+               "-I", HERE, "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "fhesi_host.cpp"),
+               "-o", tmp, "-L", bdir, "-l" + bname[3:-3], "-Wl,-rpath," + bdir]
+        subprocess.check_call(cmd)
+        publish(tmp, out)
     return out
 
 

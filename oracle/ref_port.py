@@ -18,9 +18,14 @@ LIB = os.path.join(HERE, "libref_restate.so")
 
 
 def build(force=False):
+    import fcntl
     src = os.path.join(HERE, "ref_restate.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(src) > os.path.getmtime(LIB):
-        subprocess.check_call(["make", "-C", HERE, "-s", "-B", "libref_restate.so"])
+    stale = lambda: not os.path.exists(LIB) or os.path.getmtime(src) > os.path.getmtime(LIB)
+    if force or stale():
+        with open(LIB + ".lock", "w") as lk:  # the all-core reference arm forks many workers
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if force or stale():
+                subprocess.check_call(["make", "-C", HERE, "-s", "-B", "libref_restate.so"])
     return LIB
 
 

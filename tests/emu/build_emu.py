@@ -15,11 +15,19 @@ def build_emu(force=False):
                                                                os.path.join(ROOT, "include", "fhesi.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-std=c++20", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-DFHESI_EMU=1",
-           "-include", os.path.join(HERE, "cuda_emu.h"), "-x", "c++", os.path.join(CSRC, "fhesi_lib.cu"),
-           "-o", OUT]
-    subprocess.check_call(cmd)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "fhe-si_b200"))
+    from buildlock import build_lock, publish
+    fresh = lambda: os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps)
+    with build_lock(OUT):  # torchrun ranks and xdist workers may build concurrently
+        if not force and fresh():
+            return OUT
+        tmp = OUT + ".tmp.%d" % os.getpid()
+        cmd = ["g++", "-std=c++20", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-DFHESI_EMU=1",
+               "-include", os.path.join(HERE, "cuda_emu.h"), "-x", "c++", os.path.join(CSRC, "fhesi_lib.cu"),
+               "-o", tmp]
+        subprocess.check_call(cmd)
+        publish(tmp, OUT)
     return OUT
 
 
