@@ -363,9 +363,17 @@ void PlaintextSpace::Init(const ZZX &PhiX, const ZZ &pp) {
   totalSlots = n;
   usableSlots = 1;
   for (unsigned t = totalSlots; t > 1; t >>= 1) usableSlots <<= 1;
-  // CRT idempotents: basis_j = Phi/(X - r_j) / Phi'(r_j)
-  std::vector<long> phi(n + 1);
-  for (long i = 0; i <= n; ++i) phi[i] = to_long(coeff(PhiX, i) % pp);
+  // the CRT idempotents are built on first use (EnsureBasis): key generation and pure ciphertext
+  // arithmetic never embed a plaintext
+  phiModP.assign(n + 1, 0);
+  for (long i = 0; i <= n; ++i) phiModP[i] = to_long(coeff(PhiX, i) % pp);
+  basis.clear();
+  basis32.clear();
+}
+void PlaintextSpace::EnsureBasis() const {  // basis_j = Phi/(X - r_j) / Phi'(r_j)
+  if (!basis.empty() || !totalSlots) return;
+  const long P = to_long(p), n = totalSlots;
+  const std::vector<long> &phi = phiModP;
   basis.assign(n, std::vector<long>(n));
   for (long j = 0; j < n; ++j) {
     std::vector<long> &b = basis[j];
@@ -379,7 +387,6 @@ void PlaintextSpace::Init(const ZZX &PhiX, const ZZ &pp) {
     long di = InvMod(d, P);
     for (long i = 0; i < n; ++i) b[i] = MulMod(b[i], di, P);
   }
-  basis32.clear();
   if (P < (1L << 26)) {
     basis32.resize((size_t)n * n);
     for (long j = 0; j < n; ++j)
@@ -388,6 +395,7 @@ void PlaintextSpace::Init(const ZZX &PhiX, const ZZ &pp) {
 }
 void PlaintextSpace::EmbedInSlots(ZZ_pX &embedded, const vector<ZZ_pX> &msgs, bool onlyUsable) const {
   if (!totalSlots) Error("PlaintextSpace: slots need a prime p = 1 mod m and a generator of Z_m^*");
+  EnsureBasis();
   const long P = to_long(p), n = totalSlots;
   embedded.rep.v.assign(n, ZZ_p());
   auto slotValue = [&](const ZZ_pX &mi, unsigned i) -> long {

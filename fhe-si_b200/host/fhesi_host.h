@@ -111,8 +111,10 @@ class PlaintextSpace {
  private:
   unsigned m = 0, totalSlots = 0, usableSlots = 0;
   vector<long> roots;            // roots[j] = rho^(g^j) mod p
-  vector<vector<long>> basis;    // basis[j] = CRT idempotent of slot j, phi(m) coefficients
-  vector<uint32_t> basis32;      // the same, flat, when p < 2^26 (vectorisable embedding)
+  void EnsureBasis() const;
+  vector<long> phiModP;                  // Phi_m mod p
+  mutable vector<vector<long>> basis;    // basis[j] = CRT idempotent of slot j, phi(m) coefficients (lazy)
+  mutable vector<uint32_t> basis32;      // the same, flat, when p < 2^26 (vectorisable embedding)
   friend class FHEcontext;
 };
 
