@@ -87,6 +87,13 @@ int main(int argc, char **argv) {
     std::ofstream out(dir + "/pk.bin", std::ios::binary);
     publicKey.Export(out);
   }
+  // the secret key and the s^2 -> s key-switch matrix in the same row format
+  {
+    std::ofstream out(dir + "/sk.bin", std::ios::binary);
+    secretKey.Export(out);
+    std::ofstream kout(dir + "/ksw.bin", std::ios::binary);
+    keySwitch.Export(kout);
+  }
   // round trip: import the ciphertext and the public key again, re-export, compare in Python
   {
     std::ifstream in(dir + "/mult_relin.bin", std::ios::binary);

@@ -209,6 +209,11 @@ def _oracle_files(mg, logq, p, g):
     files["pk"] = (2).to_bytes(4, "little") + b"".join(O.export_dcrt(O.dcrt_rows(ctx, x)) for x in pk.pk)
     files["mult_relin_roundtrip"] = files["mult_relin"]
     files["pk_roundtrip"] = files["pk"]
+    vec = lambda polys: len(polys).to_bytes(4, "little") + b"".join(O.export_dcrt(O.dcrt_rows(ctx, x)) for x in polys)
+    files["sk"] = vec(sk.s)
+    if ctx.phim <= 64:  # rows of the 6D key-switch polynomials by direct evaluation: small rings only
+        # KeySwitchSI::Export: vector<vector<DoubleCRT>> = {b, A}; A is stored unreduced (FHE-SI.cpp:178-180)
+        files["ksw"] = (2).to_bytes(4, "little") + vec(ks.b) + vec(ks.A)
     return files
 
 
@@ -222,7 +227,7 @@ def test_oracle_matches_reference_golden(name):
     if name == "cfg5_512" and os.environ.get("FHESI_SKIP_SLOW"):
         pytest.skip("slow")
     files = _oracle_files(mg, P["logQ"], P["p"], P["g"])
-    assert set(files) == set(ref["sha256"])
+    assert set(files) | {"ksw"} == set(ref["sha256"])
     for f, blob in files.items():
         assert hashlib.sha256(blob).hexdigest() == ref["sha256"][f], (name, f)
         if "hex" in ref:
