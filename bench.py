@@ -153,9 +153,12 @@ def run_reference(args, rank, world):
         "config": {"workload": workload_name(), "ops_per_step": ops_per_step,
                    "note": "one process per core, each set up (context, key matrix, cached tables) before "
                            "the timed steps; a step is ops only"},
-        "cpu_baseline": {"value": value, "unit": "ops/s", "cores": cores, "kind": "port",
-                         "sample": f"{ops_per_step} ops/step over {cores} processes, oracle/ref_restate.c "
-                                   "(the NTL build cannot be compiled in this image)"},
+        "cpu_baseline": dict({"value": value, "unit": "ops/s", "cores": cores, "kind": "port",
+                              "sample": f"{ops_per_step} ops/step over {cores} processes, oracle/ref_restate.c: the "
+                                        "reference's algorithm restated in C.  The reference's own sources also run "
+                                        "here (oracle/_ref, NTL replaced by a stand-in) but several times slower per "
+                                        "core than this port, so the port is the arm that is timed"},
+                             **reference_sources_figure(logq, p, g)),
         "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
