@@ -18,6 +18,34 @@ def check_mult_relin(sc: Scenario, count=2, host=False, random_inputs=False):
         assert_ct_equal(sc, out[i], want, f"mult_relin[{i}]")
 
 
+def check_rotate_keyswitch(sc: Scenario, g, count=2, compare_steps=True):
+    """One SumBatchedData step -- tmp >>= k; KeySwitchSI(sk, k).ApplyKeySwitch(tmp) (Regression.h:166-178)
+    -- through fhesi_rotate_keyswitch_dev (rotation folded into the digit extraction) against the
+    oracle, and against the three separate calls."""
+    d, logq = sc.dev, sc.logq
+    rot = O.KeySwitch.init_automorph(sc.sk, g, sc.rng)
+    pack = lambda polys: np.stack([O.pack_poly_words(a, logq) for a in polys])
+    rksw = d.ksw_create(pack(rot.b), pack([O.reduce_poly(a, logq) for a in rot.A]), 2)
+    _, cts = sc.fresh(count)
+    din = d.to_device(sc.pack_cts(cts))
+    dout = d.alloc(count * d.ct_words(2) * 4)
+    d.rotate_keyswitch_dev(rksw, din.ptr, g, dout.ptr, count)
+    if compare_steps:
+        dw = d.alloc(count * 2 * d.n * (d.W + 1) * 4)
+        dr, do2 = d.alloc(count * d.ct_words(2) * 4), d.alloc(count * d.ct_words(2) * 4)
+        d.ct_automorph_dev(din.ptr, 2, g, dw.ptr, count)
+        d.reduce_wide_dev(dw.ptr, d.W + 1, dr.ptr, 2, count)
+        d.keyswitch_dev(rksw, dr.ptr, do2.ptr, count)
+    d.sync()
+    got = dout.download((count, 2, d.n, d.W))
+    if compare_steps:
+        assert np.array_equal(got, do2.download((count, 2, d.n, d.W))), \
+            "fused rotation differs from automorph + reduce + key switch"
+    for i in range(count):
+        assert_ct_equal(sc, got[i], O.apply_key_switch(rot, cts[i].copy().automorph(g)), f"rotate_keyswitch[{i}]")
+    d.lib.fhesi_ksw_destroy(rksw)
+
+
 def check_pieces(sc: Scenario, count=2):
     """tensor -> (tprod add) -> ScaleDown -> key switch as separate calls, plus decrypt."""
     d = sc.dev

@@ -63,3 +63,4 @@ def test_emu_other_small_rings(emu_lib):
 def test_emu_mult_relin_cfg2(emu_lib):
     sc = Scenario(*CONFIGS["cfg2"], seed=2, lib_path=emu_lib)
     P.check_mult_relin(sc, count=1)
+    P.check_rotate_keyswitch(sc, CONFIGS["cfg2"][2], count=1, compare_steps=False)  # fused N=1024 digit kernel
