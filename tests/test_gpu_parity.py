@@ -71,6 +71,16 @@ def test_golden_vectors(name, cuda_lib):
     P.check_golden(name, cuda_lib)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg4", "cfg5_512"])
+def test_rotate_keyswitch(name, cuda_lib):
+    P.check_rotate_keyswitch(scenario(name, cuda_lib), CONFIGS[name][2], count=3)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_embed_slots(name, cuda_lib):
+    P.check_embed_slots(scenario(name, cuda_lib), CONFIGS[name][2], count=6)
+
+
 def test_generic_and_fused_paths_agree(cuda_lib, monkeypatch):
     """The fused N=1024 kernels and the generic kernels are two CUDA implementations of the
     same arithmetic; they must agree bit for bit (and both with the oracle, above)."""
