@@ -95,11 +95,23 @@ def main():
     # the reference's clock starts at `Statistics stats(context)` = key generation
     # (Test_Statistics.cpp:112-173)
     t_start = time.perf_counter()
-    keys = keygen(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
-    t_keygen = time.perf_counter()
-    ksw = dev.ksw_create(keys["ks_b"], keys["ks_A"], 3)
-    rot_ksw = [dev.ksw_create(keys["rot_b"][i], keys["rot_A"][i], 2) for i in range(len(rot_k))]
-    dpk, dsk = dev.key_create(keys["pk"]), dev.key_create(keys["sk"])
+    if os.environ.get("FHESI_HOST_KEYGEN"):  # key-switch arithmetic on the host (C++ layer), then upload
+        keys = keygen(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
+        t_keygen = time.perf_counter()
+        ksw = dev.ksw_create(keys["ks_b"], keys["ks_A"], 3)
+        rot_ksw = [dev.ksw_create(keys["rot_b"][i], keys["rot_A"][i], 2) for i in range(len(rot_k))]
+        dpk, dsk = dev.key_create(keys["pk"]), dev.key_create(keys["sk"])
+    else:  # draws on the host in the reference's order, b = A t + e + src 2^(24 j) on the device
+        from pyfhesi.hostkeys import keydraws
+        draws = keydraws(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
+        t_keygen = time.perf_counter()
+        ksw = dev.ksw_generate(draws["s2_src"], draws["sk"], draws["s2_A"], draws["s2_e"])
+        rot_ksw = [dev.ksw_generate(draws["rot_src"][i], draws["sk"], draws["rot_A"][i], draws["rot_e"][i])
+                   for i in range(len(rot_k))]
+        skw = np.zeros((2, dev.n, dev.W), np.uint32)
+        skw[0, 0, 0] = 1
+        skw[1] = (draws["sk"].astype(np.int64)[:, None] >> (32 * np.arange(dev.W))[None, :]).astype(np.uint32)
+        dpk, dsk = dev.key_create(draws["pk"]), dev.key_create(skw)
     dev.sync()
     t_setup = time.perf_counter()
 
@@ -192,7 +204,7 @@ def main():
             "metric": f"Test_Statistics N={N} d={d} wall time", "unit": "s", "higher_is_better": False,
             "value": t_dec - t_start, "n_gpus": world, "correct": bool(ok),
             "clock": "Test_Statistics.cpp:112-173 (key generation .. decryption)", "load_context_and_communicator_s": t_start - t_load0,
-            "setup_split_s": {"host_key_generation": t_keygen - t_start, "upload_and_transform": t_setup - t_keygen},
+            "setup_split_s": {"host_draws_or_keygen": t_keygen - t_start, "device_generation_or_upload": t_setup - t_keygen},
             "phases_s": {"setup": t_setup - t_start, "batch": t_batch - t_setup, "encryption": t_enc - t_batch,
                          "partial_sums_and_exchange": t_data - t_enc, "replicated_tail": t_comp - t_data,
                          "decryption": t_dec - t_comp},

@@ -624,81 +624,136 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
 // ---------------------------------------------------------------------------------------
 // keys
 // ---------------------------------------------------------------------------------------
+// Device half of the key upload: b, A as [K][n][W] coefficient words in HBM -> key-form images
+// (prime-major, balanced, split halves).  Enqueued on the context's stream; the caller synchronises.
+static int ksw_build_from_device(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, uint32_t parts, fhesi_ksw **out) {
+  const fhesi_info &I = c->info;
+  const u32 K = parts * I.D, Lk = I.Lk;
+  const size_t polyw = (size_t)I.n * I.W;
+  const bool split = c->use_fused && c->tfree && I.Ls;
+  DevTmp t_key, t_bal, t_split;  // the key's own buffers
+  PoolTmp t_in(c), t_tmp(c), t_in2(c), t_tmp2(c), t_t2(c);  // scratch
+  int rc = t_in.alloc((size_t)K * 2 * polyw * 4);
+  if (!rc) rc = t_tmp.alloc((size_t)K * 2 * Lk * I.N * 4);
+  if (!rc && split) rc = t_in2.alloc((size_t)K * 4 * polyw * 4);
+  if (rc) return rc;
+  CK(t_key.alloc((size_t)K * 2 * Lk * I.N * 4));
+  u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
+  // interleave to [K][2] so that one transform launch writes [K*2][Lk][N]; K mod q (non-negative)
+  // = lo + 2^(32 ws) hi, each half as a non-negative W-word polynomial
+  KL(c, k_key_stage, nblk((size_t)K * 2 * I.n), 256, 0, d_b, d_A, d_in, split ? t_in2.u() : (u32 *)nullptr, K, I.n,
+     I.W, I.split_words, I.logQ & 31);
+  CKL();
+  rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2);
+  if (rc) return rc;
+  // [K*2][Lk][N] -> [Lk][K*2][N]
+  KL(c, k_transpose_key, nblk((size_t)K * 2 * Lk * I.N), 256, 0, d_tmp, d_key, K * 2, Lk, I.N);
+  CKL();
+  if (c->use_fused && c->tfree) {
+    const size_t total = (size_t)K * 2 * Lk * I.N;
+    CK(t_bal.alloc(total * 4));
+    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_key, t_bal.u(), K * 2, total);
+    CKL();
+  }
+  if (split) {
+    const u32 Ls = I.Ls;
+    const size_t total = (size_t)K * 4 * Ls * I.N;
+    rc = t_tmp2.alloc(total * 4);
+    if (!rc) rc = t_t2.alloc(total * 4);
+    if (rc) return rc;
+    CK(t_split.alloc(total * 4));
+    if ((rc = launch_fwd(c, t_in2.u(), SRC_POLY, I.W, SC_KEYFORM, Ls, t_tmp2.u(), (size_t)K * 4))) return rc;
+    KL(c, k_transpose_key, nblk(total), 256, 0, t_tmp2.u(), t_t2.u(), K * 4, Ls, I.N);
+    CKL();
+    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, t_t2.u(), t_split.u(), K * 4, total);
+    CKL();
+  }
+  *out = new fhesi_ksw{c, (u32 *)t_key.release(), (u32 *)t_bal.release(), (u32 *)t_split.release(), parts};
+  return 0;
+}
 int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uint32_t parts,
                      fhesi_ksw **out) {
   if (!c || !h_b || !h_A || !out || parts < 1 || parts > 3)
     return fail(FHESI_ERR_INVALID, "fhesi_ksw_create: bad argument");
   CK(cudaSetDevice(c->device));
   const fhesi_info &I = c->info;
-  const u32 K = parts * I.D, Lk = I.Lk;
-  const size_t polyw = (size_t)I.n * I.W;
-  // interleave to [K][2] so that one transform launch writes [K*2][Lk][N]
-  std::vector<u32> h((size_t)K * 2 * polyw);
-  for (u32 k = 0; k < K; ++k) {
-    memcpy(&h[((size_t)k * 2 + 0) * polyw], h_b + (size_t)k * polyw, polyw * 4);
-    memcpy(&h[((size_t)k * 2 + 1) * polyw], h_A + (size_t)k * polyw, polyw * 4);
+  const size_t bytes = (size_t)parts * I.D * I.n * I.W * 4;
+  PoolTmp d_b(c), d_A(c);
+  int rc = d_b.alloc(bytes);
+  if (!rc) rc = d_A.alloc(bytes);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d_b.u(), h_b, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_A.u(), h_A, bytes, cudaMemcpyHostToDevice, c->stream));
+  rc = ksw_build_from_device(c, d_b.u(), d_A.u(), parts, out);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));  // h_b / h_A may be pinned: the caller gets them back consumed
+  return 0;
+}
+// KeySwitchSI::Init (FHE-SI.cpp:153-209) on the device, from the caller's draws (the reference's order
+// and number of draws stay with the caller): for entry (i, j), i < parts, j < D,
+//   b = A * t + e + src_i * 2^(dbits j)  reduced mod q  (:182-199),   A' = -A  (:178-180)
+// h_A: the SampleRandom polynomials [parts*D][n][W] (centred, two's complement), h_e: Gaussians
+// [parts*D][n], h_src: the source key polynomials [parts][n] (small integers: 1, s, s^2 or s(X^k)),
+// h_t: the target key [n].  Optionally returns b and Reduce(A') as [parts*D][n][W] host words.
+int fhesi_ksw_generate(fhesi_ctx *c, const int32_t *h_src, const int32_t *h_t, const uint32_t *h_A,
+                       const int32_t *h_e, uint32_t parts, fhesi_ksw **out, uint32_t *h_b_out,
+                       uint32_t *h_A_out) {
+  if (!c || !h_src || !h_t || !h_A || !h_e || !out || parts < 1 || parts > 3)
+    return fail(FHESI_ERR_INVALID, "fhesi_ksw_generate: bad argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const u32 K = parts * I.D, Le = I.Le, n = I.n;
+  const size_t polyw = (size_t)n * I.W, per = (size_t)Le * I.N;
+  PoolTmp d_A(c), d_An(c), d_b(c), d_e(c), d_src(c), d_t(c), d_pow(c), s0(c), s1(c), s2(c), s3(c), s4(c);
+  int rc = 0;
+  if ((rc = d_A.alloc(K * polyw * 4)) || (rc = d_An.alloc(K * polyw * 4)) || (rc = d_b.alloc(K * polyw * 4)) ||
+      (rc = d_e.alloc((size_t)K * n * 4)) || (rc = d_src.alloc((size_t)parts * n * 4)) || (rc = d_t.alloc(n * 4)) ||
+      (rc = d_pow.alloc((size_t)I.D * Le * 4)) || (rc = s0.alloc(per * 4)) || (rc = s1.alloc(per * 4)) ||
+      (rc = s2.alloc(K * per * 4)) || (rc = s3.alloc(K * per * 4)) || (rc = s4.alloc((size_t)K * Le * n * 4)))
+    return rc;
+  // 2^(dbits j) mod p_l in Montgomery form, [D][Le]
+  std::vector<u32> pw((size_t)I.D * Le);
+  for (u32 l = 0; l < Le; ++l) {
+    const u64 q = I.primes[l];
+    u64 v = c->h_pc[l].r1 % q, two = 1;
+    for (u32 t = 0; t < 8 * I.decompSize; ++t) two = two * 2 % q;
+    for (u32 j = 0; j < I.D; ++j) {
+      pw[(size_t)j * Le + l] = (u32)v;
+      v = h_mulmod(v, two, q);
+    }
   }
-  DevTmp t_key, t_bal, t_split;  // the key's own buffers
-  PoolTmp t_in(c), t_tmp(c);     // scratch
-  int rc = t_in.alloc(h.size() * 4);
-  if (!rc) rc = t_tmp.alloc((size_t)K * 2 * Lk * I.N * 4);
-  if (rc) return rc;
-  CK(t_key.alloc((size_t)K * 2 * Lk * I.N * 4));
-  u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
-  CK(cudaMemcpyAsync(d_in, h.data(), h.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2);
-  if (rc) return rc;
-  // [K*2][Lk][N] -> [Lk][K*2][N]
-  KL(c, k_transpose_key, nblk((size_t)K * 2 * Lk * I.N), 256, 0, d_tmp, d_key, K * 2, Lk, I.N);
+  CK(cudaMemcpyAsync(d_A.u(), h_A, K * polyw * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_e.u(), h_e, (size_t)K * n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_src.u(), h_src, (size_t)parts * n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_t.u(), h_t, n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_pow.u(), pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  // t in key form [Le][1][1][N]; images of every A; pointwise products; back with the addend
+  if ((rc = launch_fwd(c, d_t.u(), SRC_I32, 0, SC_KEYFORM, Le, s0.u(), 1))) return rc;
+  KL(c, k_transpose_key, nblk(per), 256, 0, s0.u(), s1.u(), 1, Le, I.N);
   CKL();
-  u32 *d_bal = nullptr;
-  if (c->use_fused && c->tfree) {
-    const size_t total = (size_t)K * 2 * Lk * I.N;
-    CK(t_bal.alloc(total * 4));
-    d_bal = t_bal.u();
-    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_key, d_bal, K * 2, total);
+  if ((rc = launch_fwd(c, d_A.u(), SRC_POLY, I.W, SC_NONE, Le, s2.u(), K))) return rc;
+  DotArgs d{s2.u(), s1.u(), 1, 1, Le, s3.u(), K};
+  KL(c, k_dot, nblk(per * K), 256, 0, c->dc, d);
+  CKL();
+  {
+    InvArgs a{s3.u(), Le, s4.u(), nullptr, nullptr};
+    a.add1 = (const int *)d_e.u();
+    a.sh_src = (const int *)d_src.u();
+    a.sh_pow = d_pow.u();
+    a.sh_D = I.D;
+    const DevCtx &dc = c->dc;
+    dim3 grid(K, Le), block(dc.N / 2 < 32 ? 32 : dc.N / 2);
+    KL(c, k_inv, grid, block, (dc.N + dc.h) * 4, dc, a);
     CKL();
   }
-  u32 *d_split = nullptr;
-  PoolTmp t_in2(c), t_tmp2(c), t_t2(c);
-  std::vector<u32> hs;  // outlives the asynchronous copy below
-  if (c->use_fused && c->tfree && I.Ls) {
-    // K mod q (non-negative) = lo + 2^(32 ws) hi, each half as a non-negative W-word polynomial
-    const u32 ws = I.split_words, W = I.W, Ls = I.Ls, tb = I.logQ & 31;
-    hs.assign((size_t)K * 4 * polyw, 0);
-    for (u32 k = 0; k < K; ++k)
-      for (u32 r = 0; r < 2; ++r) {
-        const u32 *src = (r ? h_A : h_b) + (size_t)k * polyw;
-        u32 *lo = &hs[((size_t)k * 4 + 2 * r) * polyw], *hi = lo + polyw;
-        for (u32 i = 0; i < I.n; ++i)
-          for (u32 w = 0; w < W; ++w) {
-            u32 v = src[(size_t)i * W + w];
-            if (w == W - 1 && tb) v &= (1u << tb) - 1;  // two's complement -> residue in [0, q)
-            if (w < ws) lo[(size_t)i * W + w] = v;
-            else hi[(size_t)i * W + (w - ws)] = v;
-          }
-      }
-    const size_t total = (size_t)K * 4 * Ls * I.N;
-    rc = t_in2.alloc(hs.size() * 4);
-    if (!rc) rc = t_tmp2.alloc(total * 4);
-    if (!rc) rc = t_t2.alloc(total * 4);
-    if (rc) return rc;
-    CK(t_split.alloc(total * 4));
-    u32 *d_in2 = t_in2.u(), *d_tmp2 = t_tmp2.u(), *d_t2 = t_t2.u();
-    d_split = t_split.u();
-    CK(cudaMemcpyAsync(d_in2, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = launch_fwd(c, d_in2, SRC_POLY, W, SC_KEYFORM, Ls, d_tmp2, (size_t)K * 4))) return rc;
-    KL(c, k_transpose_key, nblk(total), 256, 0, d_tmp2, d_t2, K * 4, Ls, I.N);
-    CKL();
-    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_t2, d_split, K * 4, total);
-    CKL();
-  }
-  CK(cudaStreamSynchronize(c->stream));  // one synchronisation: the host staging vectors die here
-  fhesi_ksw *k = new fhesi_ksw{c, (u32 *)t_key.release(), (u32 *)t_bal.release(), (u32 *)t_split.release(), parts};
-  (void)d_key;
-  (void)d_bal;
-  (void)d_split;
-  *out = k;
+  if ((rc = launch_crt(c, s4.u(), Le, CRT_REDUCE_Q, d_b.u(), I.W, K))) return rc;
+  // A' = Reduce(-A)
+  CK(cudaMemcpyAsync(d_An.u(), d_A.u(), K * polyw * 4, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = fhesi_ct_mul_scalar_dev(c, d_An.u(), -1, K, 1))) return rc;
+  if ((rc = ksw_build_from_device(c, d_b.u(), d_An.u(), parts, out))) return rc;
+  if (h_b_out) CK(cudaMemcpyAsync(h_b_out, d_b.u(), K * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (h_A_out) CK(cudaMemcpyAsync(h_A_out, d_An.u(), K * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 void fhesi_ksw_destroy(fhesi_ksw *k) {

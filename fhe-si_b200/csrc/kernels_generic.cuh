@@ -202,6 +202,12 @@ struct InvArgs {
   // Encrypt addend (FHE-SI.cpp:24-31): + p_pt*e[q][i] + (q even ? floor(q/p_pt)*msg[q/2][i] : 0)
   const int *e;
   const u32 *msg;
+  // key-generation addend (FHE-SI.cpp:187-196): + add1[q][i] + sh_src[q / sh_D][i] * 2^(dbits (q % sh_D));
+  // sh_pow[j][l] = 2^(dbits j) mod p_l in Montgomery form
+  const int *add1 = nullptr;
+  const int *sh_src = nullptr;
+  const u32 *sh_pow = nullptr;
+  u32 sh_D = 1;
 };
 
 // grid (npolys, L), block N/2.  dynamic smem: N + h words.
@@ -224,6 +230,17 @@ __global__ void k_inv(DevCtx c, InvArgs a) {
       u32 er = ev < 0 ? p - ((u32)(-ev)) % p : ((u32)ev) % p;
       v = csub(v + csub(mont_mul(er, pc.ptxt_r, p, pinv), p), p);
       if (msg) v = csub(v + csub(mont_mul(msg[i] % p, pc.scale_r, p, pinv), p), p);
+    }
+    if (a.add1) {
+      const int ev = a.add1[(size_t)q * c.n + i];
+      v = csub(v + (ev < 0 ? p - ((u32)(-ev)) % p : ((u32)ev) % p), p);
+    }
+    if (a.sh_src) {
+      const int sv = a.sh_src[(size_t)(q / a.sh_D) * c.n + i];
+      if (sv) {
+        const u32 sr = sv < 0 ? p - ((u32)(-sv)) % p : ((u32)sv) % p;
+        v = csub(v + csub(mont_mul(sr, a.sh_pow[(size_t)(q % a.sh_D) * a.L + l], p, pinv), p), p);
+      }
     }
     dst[i] = v;
   });
@@ -312,6 +329,30 @@ __global__ void k_tprod_mul_scalar(DevCtx c, u32 *io, const u32 *scal, u32 L, si
   u32 l = (u32)((idx / c.N) % L);
   const PrimeConst pc = c.pc[l];
   io[idx] = csub(mont_mul(io[idx], scal[l], pc.p, pc.pinv), pc.p);
+}
+// Key upload staging: interleave b and A to [K][2][n][W] (one transform launch then covers both) and,
+// when split is non-null, write the halves of (K mod q) >= 0 = lo + 2^(32 ws) hi as [K][4][n][W]
+// (b_lo, b_hi, A_lo, A_hi), each a non-negative W-word polynomial.  tb = logQ mod 32.
+__global__ void k_key_stage(const u32 *b, const u32 *A, u32 *inter, u32 *split, u32 K, u32 n, u32 W, u32 ws,
+                            u32 tb) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)K * 2 * n) return;
+  const u32 i = (u32)(idx % n), r = (u32)((idx / n) & 1), k = (u32)(idx / ((size_t)2 * n));
+  const u32 *src = (r ? A : b) + ((size_t)k * n + i) * W;
+  u32 *dst = inter + (((size_t)k * 2 + r) * n + i) * W;
+  u32 *lo = split ? split + (((size_t)k * 4 + 2 * r) * n + i) * W : nullptr;
+  u32 *hi = split ? lo + (size_t)n * W : nullptr;
+  for (u32 w = 0; w < W; ++w) {
+    u32 v = src[w];
+    dst[w] = v;
+    if (split) {
+      if (w == W - 1 && tb) v &= (1u << tb) - 1;  // two's complement -> residue in [0, q)
+      lo[w] = w < ws ? v : 0u;
+      if (w >= ws) hi[w - ws] = v;
+    }
+  }
+  if (split)
+    for (u32 w = W - ws; w < W; ++w) hi[w] = 0u;
 }
 // io[b][part][l][e] *= img[l][e] (img in Montgomery form): DoubleCRT *= DoubleCRT with one shared
 // right-hand side, the tensor-form branch of Ciphertext::operator*=(const ZZX&) (Ciphertext.cpp:252-256)

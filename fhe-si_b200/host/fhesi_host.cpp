@@ -1112,6 +1112,16 @@ void FHESIPubKey::Encrypt(Ciphertext &ctxt, const Plaintext &ptxt) const {  // F
 void FHESIPubKey::Export(ofstream &out) const { ::Export(out, publicKey); }
 void FHESIPubKey::Import(ifstream &in) { ::Import(in, publicKey); devKey.reset(); }
 
+// When set, KeySwitchSI::Init only performs its random draws (in the reference's order) and hands them
+// over instead of doing the arithmetic: fhesih_keydraws feeds them to fhesi_ksw_generate on the device.
+struct KeyDrawSink {
+  struct Matrix {
+    vector<ZZX> src, polys, errs;
+    ZZX t;
+  };
+  vector<Matrix> matrices;
+};
+static KeyDrawSink *g_drawSink = nullptr;
 void KeySwitchSI::Init(const FHESISecKey &src, const FHESISecKey &dst) {  // FHE-SI.cpp:153-209
   const vector<DoubleCRT> &s = src.GetRepresentation();
   vector<ZZX> sCoeff(s.size());
@@ -1127,6 +1137,12 @@ void KeySwitchSI::Init(const FHESISecKey &src, const FHESISecKey &dst) {  // FHE
   for (size_t ind = 0; ind < total; ++ind) {
     SampleRandom(polys[ind], context.modulusQ, context.zMstar.phiM());
     sampleGaussian(errs[ind], context.zMstar.phiM(), context.stdev);
+  }
+  if (g_drawSink) {
+    g_drawSink->matrices.push_back(KeyDrawSink::Matrix{sCoeff, polys, errs, t});
+    keySwitchMatrix.assign(2, vector<DoubleCRT>());
+    devKsw.reset();
+    return;
   }
   const double tt1 = now();
   // 2. the arithmetic of each entry is independent of the others: b = poly * t + err + s_i * 2^(24 j)
@@ -1347,6 +1363,67 @@ extern "C" int fhesih_keygen(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, 
   if (timing)
     fprintf(stderr, "fhesih_keygen: context %.4f  sk+pk+s2 matrix %.4f  rotation matrices %.4f  pack %.4f  s\n", t1 - t0,
             t2 - t1, t3 - t2, t4 - t3);
+  activeContext = saved;
+  return 0;
+}
+
+// The random draws of fhesih_keygen without the key-switch arithmetic: same objects, same order and
+// number of draws (secret key, public key, s^2 matrix incl. its throw-away key, one rotation matrix per
+// rot_k), with KeySwitchSI::Init diverted into a sink.  The caller passes the draws to
+// fhesi_ksw_generate, which does b = A t + e + src 2^(24 j) on the device.  sk: int32 [n] (the
+// polynomial s); pk_words: [2][n][W]; per matrix: src int32 [parts][n], A uint32 [parts*D][n][W],
+// e int32 [parts*D][n] (parts = 3 for s^2, 2 for rotations).
+extern "C" int fhesih_keydraws(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, uint32_t decompSize, uint64_t xi,
+                               uint64_t seed, uint32_t n_rot, const uint32_t *rot_k, int32_t *sk_out,
+                               uint32_t *pk_words, int32_t *s2_src, uint32_t *s2_A, int32_t *s2_e, int32_t *rot_src,
+                               uint32_t *rot_A, int32_t *rot_e) {
+  FHEcontext *saved = activeContext;
+  struct HostOnly {
+    bool was = g_eagerDevice;
+    HostOnly() { g_eagerDevice = false; }
+    ~HostOnly() { g_eagerDevice = was; }
+  } hostOnly;
+  KeyDrawSink sink;
+  {
+    FHEcontext context(m, logQ, to_ZZ((unsigned long)p), g, decompSize);
+    activeContext = &context;
+    context.SetUpSIContext((long)xi);
+    SetSeed(ZZ((unsigned long)seed));
+    const unsigned n = context.zMstar.phiM(), W = context.Words(), D = context.ndigits;
+    const size_t pw = (size_t)n * W;
+    FHESISecKey sk(context);
+    FHESIPubKey pk(sk);
+    g_drawSink = &sink;
+    KeySwitchSI ks(sk);
+    for (uint32_t r = 0; r < n_rot; ++r) KeySwitchSI rk(sk, rot_k[r]);
+    g_drawSink = nullptr;
+    auto small = [&](int32_t *dst, const ZZX &a) {
+      for (unsigned i = 0; i < n; ++i) dst[i] = i <= (unsigned)deg(a) ? (int32_t)to_long(a.rep.v[i]) : 0;
+    };
+    ZZX s;
+    sk.GetRepresentation()[1].toPoly(s);
+    small(sk_out, s);
+    for (int i = 0; i < 2; ++i) {
+      ZZX poly;
+      pk.GetRepresentation()[i].toPoly(poly);
+      ReduceCoefficients(poly, logQ);
+      std::vector<uint32_t> w = PackPoly(poly, n, W);
+      memcpy(pk_words + i * pw, w.data(), pw * 4);
+    }
+    for (size_t mi = 0; mi < sink.matrices.size(); ++mi) {
+      const KeyDrawSink::Matrix &M = sink.matrices[mi];
+      const size_t parts = M.src.size(), K = parts * D;
+      int32_t *src = mi == 0 ? s2_src : rot_src + (mi - 1) * parts * n;
+      uint32_t *A = mi == 0 ? s2_A : rot_A + (mi - 1) * K * pw;
+      int32_t *e = mi == 0 ? s2_e : rot_e + (mi - 1) * K * n;
+      for (size_t i = 0; i < parts; ++i) small(src + i * n, M.src[i]);
+      ParallelFor(K, [&](size_t k) {
+        std::vector<uint32_t> w = PackPoly(M.polys[k], n, W);
+        memcpy(A + k * pw, w.data(), pw * 4);
+        small(e + k * n, M.errs[k]);
+      });
+    }
+  }
   activeContext = saved;
   return 0;
 }

@@ -50,6 +50,7 @@ SYMBOLS = {
     "fhesi_ct_bytes": (_SZ, [_P, _U32]),
     "fhesi_tprod_bytes": (_SZ, [_P, _U32]),
     "fhesi_ksw_create": (C.c_int, [_P, _P, _P, _U32, C.POINTER(_P)]),
+    "fhesi_ksw_generate": (C.c_int, [_P, _P, _P, _P, _P, _U32, C.POINTER(_P), _P, _P]),
     "fhesi_ksw_destroy": (None, [_P]),
     "fhesi_key_create": (C.c_int, [_P, _P, _U32, C.POINTER(_P)]),
     "fhesi_key_destroy": (None, [_P]),
@@ -205,6 +206,23 @@ class Context:
         k = _P()
         self._ck(self.lib.fhesi_ksw_create(self.h, b.ctypes.data, A.ctypes.data, src_parts, C.byref(k)))
         return k.value
+
+    def ksw_generate(self, src: np.ndarray, t: np.ndarray, A: np.ndarray, e: np.ndarray, want_host=False):
+        """KeySwitchSI::Init on the device from explicit draws -> handle (and b, A' words if want_host)."""
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        t = np.ascontiguousarray(t, dtype=np.int32)
+        A = np.ascontiguousarray(A, dtype=np.uint32)
+        e = np.ascontiguousarray(e, dtype=np.int32)
+        parts = src.shape[0]
+        assert src.shape == (parts, self.n) and t.shape == (self.n,)
+        assert A.shape == (parts * self.D, self.n, self.W) and e.shape == (parts * self.D, self.n)
+        k = _P()
+        b_out = np.empty_like(A) if want_host else None
+        a_out = np.empty_like(A) if want_host else None
+        self._ck(self.lib.fhesi_ksw_generate(self.h, src.ctypes.data, t.ctypes.data, A.ctypes.data, e.ctypes.data,
+                                             parts, C.byref(k), b_out.ctypes.data if want_host else None,
+                                             a_out.ctypes.data if want_host else None))
+        return (k.value, b_out, a_out) if want_host else k.value
 
     def key_create(self, polys: np.ndarray) -> int:
         polys = np.ascontiguousarray(polys, dtype=np.uint32)

@@ -53,3 +53,43 @@ def keygen(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
     if rc:
         raise RuntimeError(f"fhesih_keygen failed ({rc})")
     return out
+
+
+def keydraws(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
+    """The random draws of keygen() (same stream, same order) without the key-switch arithmetic, for
+    Context.ksw_generate: dict(sk int32 [n], pk [2][n][W], s2_src [3][n], s2_A [3D][n][W], s2_e [3D][n],
+    rot_src [R][2][n], rot_A [R][2D][n][W], rot_e [R][2D][n])."""
+    from . import DEFAULT_LIB
+    lib = _host_lib(lib_path or DEFAULT_LIB)
+    i = ctx.info
+    n, W, D = ctx.n, ctx.W, ctx.D
+    rot = np.asarray(list(rot_k), dtype=np.uint32)
+    R = max(len(rot), 1)
+    out = {"sk": np.zeros(n, np.int32), "pk": np.zeros((2, n, W), np.uint32),
+           "s2_src": np.zeros((3, n), np.int32), "s2_A": np.zeros((3 * D, n, W), np.uint32),
+           "s2_e": np.zeros((3 * D, n), np.int32), "rot_src": np.zeros((R, 2, n), np.int32),
+           "rot_A": np.zeros((R, 2 * D, n, W), np.uint32), "rot_e": np.zeros((R, 2 * D, n), np.int32)}
+    fn = lib.fhesih_keydraws
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32] + \
+        [C.c_void_p] * 9
+    rc = fn(i.m, i.logQ, i.p, g, i.decompSize, i.xi, seed, len(rot), rot.ctypes.data if len(rot) else None,
+            out["sk"].ctypes.data, out["pk"].ctypes.data, out["s2_src"].ctypes.data, out["s2_A"].ctypes.data,
+            out["s2_e"].ctypes.data, out["rot_src"].ctypes.data, out["rot_A"].ctypes.data, out["rot_e"].ctypes.data)
+    if rc:
+        raise RuntimeError(f"fhesih_keydraws failed ({rc})")
+    return out
+
+
+def device_keys(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
+    """Keys for a device context with the key-switch matrices generated ON the device
+    (fhesi_ksw_generate) from host draws: -> (ksw, [rotation ksw ...], pk handle, sk handle).  Same keys
+    as keygen() + ksw_create for the same seed."""
+    d = keydraws(ctx, seed, g, rot_k, lib_path)
+    n, W = ctx.n, ctx.W
+    ksw = ctx.ksw_generate(d["s2_src"], d["sk"], d["s2_A"], d["s2_e"])
+    rot = [ctx.ksw_generate(d["rot_src"][r], d["sk"], d["rot_A"][r], d["rot_e"][r]) for r in range(len(list(rot_k)))]
+    skw = np.zeros((2, n, W), np.uint32)
+    skw[0, 0, 0] = 1                                             # sKeys[0] = 1
+    skw[1] = (d["sk"].astype(np.int64)[:, None] >> (32 * np.arange(W))[None, :]).astype(np.uint32)  # sign-extended
+    return ksw, rot, ctx.key_create(d["pk"]), ctx.key_create(skw)

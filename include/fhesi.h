@@ -99,6 +99,17 @@ size_t fhesi_tprod_bytes(const fhesi_ctx *ctx, uint32_t parts); /* parts*Lt*N*4 
  *   sKeys FHE-SI.cpp:86-91). */
 int fhesi_ksw_create(fhesi_ctx *ctx, const uint32_t *h_b, const uint32_t *h_A, uint32_t src_parts,
                      fhesi_ksw **out);
+/* KeySwitchSI::Init (FHE-SI.cpp:153-209) on the device from the caller's random draws (the order and
+ * number of draws are the caller's business).  For entry (i, j), i < parts, j < D:
+ *   b = A * t + e + src_i * 2^(8 decompSize j)  reduced mod q,   A' = Reduce(-A).
+ * h_src: HOST int32 [parts][n], the source key polynomials (1, s, s^2 or 1, s(X^k): small integers);
+ * h_t: int32 [n], the target key s; h_A: uint32 [parts*D][n][W], the SampleRandom polynomials (centred,
+ * two's complement); h_e: int32 [parts*D][n], the Gaussians.  The matrix is left on the device as a
+ * fhesi_ksw; h_b_out / h_A_out (nullable, [parts*D][n][W]) receive b and A' for callers that also
+ * need them on the host (Export). */
+int fhesi_ksw_generate(fhesi_ctx *ctx, const int32_t *h_src, const int32_t *h_t, const uint32_t *h_A,
+                       const int32_t *h_e, uint32_t parts, fhesi_ksw **out, uint32_t *h_b_out,
+                       uint32_t *h_A_out);
 void fhesi_ksw_destroy(fhesi_ksw *ksw);
 int fhesi_key_create(fhesi_ctx *ctx, const uint32_t *h_polys, uint32_t parts, fhesi_key **out);
 void fhesi_key_destroy(fhesi_key *key);

@@ -18,6 +18,43 @@ def check_mult_relin(sc: Scenario, count=2, host=False, random_inputs=False):
         assert_ct_equal(sc, out[i], want, f"mult_relin[{i}]")
 
 
+def check_ksw_generate(sc: Scenario, g):
+    """fhesi_ksw_generate = KeySwitchSI::Init on the device from explicit draws: b and A' against the
+    oracle's KeySwitch.init on the same draws (s^2 -> s matrix and a rotation matrix), and a mult+relin
+    through the generated matrix against the oracle's."""
+    import copy
+    d, octx, logq = sc.dev, sc.octx, sc.logq
+    n, D = octx.phim, octx.ndigits
+    pack = lambda polys: np.stack([O.pack_poly_words(a, logq) for a in polys])
+    s1 = sc.sk.s[1]
+    cases = {"s2": [sc.sk.s[0], s1, octx.ring.mul(s1, s1)], "rot": [octx.ring.automorph(x, g) for x in sc.sk.s]}
+    handles = {}
+    for name, src in cases.items():
+        rng = O.Rng(1234 + len(src))
+        rng2 = copy.deepcopy(rng)
+        A, E = [], []
+        for _ in range(len(src) * D):           # FHE-SI.cpp:176,188: SampleRandom then sampleGaussian per entry
+            A.append(O.sample_random(rng, octx.q, n))
+            E.append(O.sample_gaussian(rng, n, octx.stdev))
+        want = O.KeySwitch.init(octx, src, s1, rng2)
+        h, b_out, a_out = d.ksw_generate(np.array(src, dtype=np.int64), np.array(s1, dtype=np.int64), pack(A),
+                                         np.array(E, dtype=np.int64), want_host=True)
+        for k in range(len(src) * D):
+            assert O.unpack_poly_words(b_out[k]) == list(want.b[k]), f"{name}: b[{k}]"
+            assert O.unpack_poly_words(a_out[k]) == O.reduce_poly(want.A[k], logq), f"{name}: A[{k}]"
+        handles[name] = (h, want)
+    # the generated s^2 matrix relinearises like the oracle's
+    _, cts = sc.fresh(2)
+    da, db = d.to_device(sc.pack_cts(cts[:1])), d.to_device(sc.pack_cts(cts[1:]))
+    do = d.alloc(d.ct_words(2) * 4)
+    d.mult_relin_dev(handles["s2"][0], da.ptr, db.ptr, do.ptr, 1)
+    d.sync()
+    assert_ct_equal(sc, do.download((1, 2, d.n, d.W))[0], O.mult_relin(handles["s2"][1], cts[0], cts[1]),
+                    "mult_relin with a device-generated matrix")
+    for h, _ in handles.values():
+        d.lib.fhesi_ksw_destroy(h)
+
+
 def check_rotate_keyswitch(sc: Scenario, g, count=2, compare_steps=True):
     """One SumBatchedData step -- tmp >>= k; KeySwitchSI(sk, k).ApplyKeySwitch(tmp) (Regression.h:166-178)
     -- through fhesi_rotate_keyswitch_dev (rotation folded into the digit extraction) against the

@@ -38,6 +38,10 @@ def test_emu_ref_rows_cfg1(sc1):
     P.check_ref_rows(sc1)
 
 
+def test_emu_ksw_generate_cfg1(sc1):
+    P.check_ksw_generate(sc1, 7)
+
+
 def test_emu_embed_slots_cfg1(sc1):
     P.check_embed_slots(sc1, 7)
 
