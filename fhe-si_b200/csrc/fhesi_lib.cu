@@ -133,7 +133,8 @@ struct fhesi_ksw {
   fhesi_ctx *ctx;
   u32 *d_key;      // [Lk][parts*D][2][N] key form, residues in [0,p)
   u32 *d_key_bal;  // same, balanced residues (fused T-free path); NULL if unused
-  u32 *d_key_split;  // [Ls][parts*D][4][N] balanced key form of (b_lo, b_hi, A_lo, A_hi); NULL if unused
+  u32 *d_key_split;  // [Ls][parts*D][4][N] balanced key form of (b_lo, b_hi, A_lo, A_hi), then the
+                     // offset-correction table [Ls][4][N] (k_split_corr); NULL if unused
   u32 parts;
 };
 struct fhesi_key {
@@ -661,11 +662,13 @@ static int ksw_build_from_device(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, u
     rc = t_tmp2.alloc(total * 4);
     if (!rc) rc = t_t2.alloc(total * 4);
     if (rc) return rc;
-    CK(t_split.alloc(total * 4));
+    CK(t_split.alloc((total + (size_t)Ls * 4 * I.N) * 4));  // + the offset-correction table
     if ((rc = launch_fwd(c, t_in2.u(), SRC_POLY, I.W, SC_KEYFORM, Ls, t_tmp2.u(), (size_t)K * 4))) return rc;
     KL(c, k_transpose_key, nblk(total), 256, 0, t_tmp2.u(), t_t2.u(), K * 4, Ls, I.N);
     CKL();
     KL(c, k_balance_key, nblk(total), 256, 0, c->dc, t_t2.u(), t_split.u(), K * 4, total);
+    CKL();
+    KL(c, k_split_corr, nblk((size_t)Ls * 4 * I.N), 256, 0, c->dc, t_split.u(), t_split.u() + total, K, Ls);
     CKL();
   }
   *out = new fhesi_ksw{c, (u32 *)t_key.release(), (u32 *)t_bal.release(), (u32 *)t_split.release(), parts};

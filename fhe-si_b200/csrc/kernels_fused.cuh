@@ -140,7 +140,11 @@ __device__ __forceinline__ XAddr make_xaddr(u32 tg) {
 }
 
 // Forward transform of a polynomial whose upper half is zero.  In: x[0..3] = coefficients
-// j*128 + tg (< 2p; x[4..7] ignored).  Out: x[r] = value at storage index tg*8 + r, in [0,p).
+// j*128 + tg (< 2p; x[4..7] ignored).  Out: x[r] = value at storage index tg*8 + r, in [0,p);
+// with OFFS the output is the signed value v - (p >> 1), v in [0,p): a balanced residue of the
+// value minus the constant (p >> 1) -- one subtract instead of a compare/select/subtract, the
+// constant's contribution to an inner product is added back from a per-key table (k_split_corr).
+template <bool OFFS = false>
 __device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A, u32 *bufA, u32 *bufB,
                                         u32 g, u32 tg, u32 p) {
   const u32 p2 = 2 * p;
@@ -180,6 +184,7 @@ __device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A
     u32 o = __shfl_xor_sync(0xffffffffu, x[j], 1);
     u32 v = b0 ? o + p2 - x[j] : add_alu(x[j], o);
     x[j] = csub(csub(v, p2), p);
+    if (OFFS) x[j] = sub_alu(x[j], p >> 1);
   }
 }
 // Inverse transform.  In: x[r] = value at storage index tg*8 + r (< 2p).  Out: the natural
@@ -512,7 +517,9 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
 // key: [Ls][K][4][N] balanced;  res: [count][4][Ls][n] in the order b_lo, b_hi, A_lo, A_hi.
 // ---------------------------------------------------------------------------------------
 #define KSS 4
-#define KSS_SMEM_WORDS (2 * FTW_WORDS + KSS * 3 * FPADN)
+#define KSS_BUFA 2048u  // word distance of the two alternating exchange buffers (a power of two: XOR toggle)
+#define KSS_SMEM_WORDS (2 * FTW_WORDS + KSS * (2 * KSS_BUFA + FPADN))
+// key: [Ls][K][4][N] balanced, followed by the offset-correction table [Ls][4][N] (k_split_corr)
 __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
@@ -524,55 +531,74 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
   const size_t op = (size_t)blockIdx.y * KSS + g;
   if (op >= a.count) return;
   const PrimeConst pc = c.pc[l];
-  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p, half = p >> 1;
-  u32 *bufA0 = sm + 2 * FTW_WORDS + g * 3 * FPADN, *bufA1 = bufA0 + FPADN, *bufB = bufA1 + FPADN;
+  const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
+  u32 *bufA0 = sm + 2 * FTW_WORDS + g * (2 * KSS_BUFA + FPADN), *bufB = bufA0 + 2 * KSS_BUFA;
   const XAddr A = make_xaddr(tg);
   u64 acc[4][8];
 #pragma unroll
   for (int h = 0; h < 4; ++h)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[h][j] = 0;
-  const u32 *dig = a.digits + op * a.K * (size_t)c.n;
-  const u32 *key = a.key + (size_t)l * a.K * 4 * FN + tg * 8;
+  // digit rows are read unconditionally (a row is n <= 512 words; positions >= n fall into the next
+  // row or the scratch area that follows the digit buffer) and masked: N = 1024 means n > 256, so
+  // only the upper two of a thread's four coefficients can lie beyond n
+  const u32 m2 = (256 + tg < c.n) ? 0xFFFFFFFFu : 0u, m3 = (384 + tg < c.n) ? 0xFFFFFFFFu : 0u;
+  const u32 *dp = a.digits + op * a.K * (size_t)c.n + tg;
+  const uint4 *kp = (const uint4 *)(a.key + (size_t)l * a.K * 4 * FN + tg * 8);
   u32 xn[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + j * 128 + tg) : 0u;
+  xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256) & m2, xn[3] = __ldg(dp + 384) & m3;
+  u32 tgl = 0;
   for (u32 k = 0; k < a.K; ++k) {
     u32 x[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) x[j] = xn[j];
     if (k + 1 < a.K) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        xn[j] = (j * 128 + tg < c.n) ? __ldg(dig + (size_t)(k + 1) * c.n + j * 128 + tg) : 0u;
+      dp += c.n;
+      xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256) & m2, xn[3] = __ldg(dp + 384) & m3;
     }
-    fwd1024(x, twf, A, (k & 1) ? bufA1 : bufA0, bufB, g, tg, p);
-    int xb[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xb[j] = (int)x[j] - (x[j] > half ? (int)p : 0);
-    const uint4 *kp = (const uint4 *)(key + (size_t)k * 4 * FN);
+    fwd1024<true>(x, twf, A, bufA0 + tgl, bufB, g, tg, p);
+    tgl ^= KSS_BUFA;
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       const uint4 k0 = __ldg(kp + h * (FN / 4)), k1 = __ldg(kp + h * (FN / 4) + 1);
       const u32 kv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[h][j] += (u64)((i64)xb[j] * (int)kv[j]);
+      for (int j = 0; j < 8; ++j) acc[h][j] += (u64)((i64)(int)x[j] * (int)kv[j]);
     }
+    kp += FN;  // 4 * FN words
   }
   fhesi_group_sync(g);  // every warp is done with the forward transforms' buffers
+  const u32 *corr = a.key + (size_t)a.Lk * a.K * 4 * FN + (size_t)l * 4 * FN + tg * 8;
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
+    const uint4 c0 = __ldg((const uint4 *)(corr + h * FN)), c1 = __ldg((const uint4 *)(corr + h * FN) + 1);
+    const u32 cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
     u32 t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const i64 s0 = (i64)acc[h][j];
       const u32 r0 = csub(mont_red64((u64)(s0 < 0 ? -s0 : s0), p, pinv), p2);
-      t[j] = s0 < 0 ? csub(p2 - r0, p2) : r0;
+      t[j] = csub((s0 < 0 ? csub(p2 - r0, p2) : r0) + cv[j], p2);
     }
-    u32 *bufA = (h & 1) ? bufA1 : bufA0;
+    u32 *bufA = bufA0 + ((h & 1) ? KSS_BUFA : 0u);
     inv1024(t, twi, A, bufA, bufB, bufA, g, tg, p);
     phim_store_1024(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
   }
+}
+// Offset correction of the split key switch: the kernel accumulates (x - ch) * K with ch = p >> 1,
+// so sum_k x_k K_k = acc + ch * sum_k K_k; the second term depends on the key only.  One thread per
+// (prime, half, position): corr = ch * sum_k K_k * R^-1 mod p in [0,p) (the accumulator is Montgomery-
+// reduced before corr is added).  key: [Ls][K][4][N] balanced; corr: [Ls][4][N]
+__global__ void k_split_corr(DevCtx c, const u32 *key, u32 *corr, u32 K, u32 Ls) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Ls * 4 * c.N) return;
+  const u32 e = (u32)(idx % c.N), h = (u32)((idx / c.N) & 3), l = (u32)(idx / ((size_t)4 * c.N));
+  const PrimeConst pc = c.pc[l];
+  i64 s = 0;
+  for (u32 k = 0; k < K; ++k) s += (i64)(int)key[(((size_t)l * K + k) * 4 + h) * c.N + e];
+  i64 r = s % (i64)pc.p;
+  if (r < 0) r += pc.p;
+  corr[idx] = csub(mont_mul(pc.p >> 1, (u32)r, pc.p, pc.pinv), pc.p);
 }
 
 // key form [0,p) -> balanced (-p/2, p/2], same layout [L][P][N]

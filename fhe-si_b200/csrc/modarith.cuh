@@ -46,6 +46,14 @@ FHESI_HD u32 add_alu(u32 a, u32 b) {
   return a + b;
 #endif
 }
+// a - b (mod 2^32), likewise kept off the integer-multiply pipe (ptxas would emit IMAD.IADD)
+FHESI_HD u32 sub_alu(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+  return (u32)__viaddmax_s32((int)a, -(int)b, (int)0x80000000);
+#else
+  return a - b;
+#endif
+}
 // x in [0, 2*c) -> [0, c) by one conditional subtract (unsigned-min trick).
 FHESI_HD u32 csub(u32 x, u32 c) {
   u32 y = x - c;
