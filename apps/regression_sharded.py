@@ -82,6 +82,28 @@ def plaintext_regression(rows, labels, p):
     return theta, det(A) % p
 
 
+def load_shard_files(prefix):
+    """LoadData (Regression.h:14-41) over the files `generateRandomData.py name d N nFiles` writes
+    (README:82-84): prefix_0.dat, prefix_1.dat, ... (or prefix.dat alone).  -> list of int64 arrays
+    [rows_k][d + 1] (features then label), in file order."""
+    paths, k = [], 0
+    while os.path.exists(f"{prefix}_{k}.dat"):
+        paths.append(f"{prefix}_{k}.dat")
+        k += 1
+    if not paths and os.path.exists(prefix + ".dat"):
+        paths = [prefix + ".dat"]
+    if not paths:
+        raise SystemExit(f"no data files {prefix}_0.dat ... or {prefix}.dat")
+    out = []
+    for path in paths:
+        with open(path) as f:
+            d, n = (int(v) for v in f.readline().split())
+            a = np.loadtxt(f, dtype=np.int64, ndmin=2) if n else np.zeros((0, d + 1), np.int64)
+        assert a.shape == (n, d + 1), f"{path}: header says {n} x {d + 1}, file holds {a.shape}"
+        out.append(a)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dim", dest="d", type=int, default=4)
@@ -89,17 +111,31 @@ def main():
     ap.add_argument("--prime", dest="p", type=int, default=1019)
     ap.add_argument("--gen", dest="g", type=int, default=3)
     ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--data", default=None, help="read NAME_0.dat, NAME_1.dat, ... (scripts/generate_random_data.py "
+                    "NAME d N nFiles) instead of generating the data in-process; files are dealt to the ranks "
+                    "round-robin and each file is cut into its own blocks, as one reference process per file would")
     ap.add_argument("--lib", default=None, help="C-ABI library (default: the in-tree CUDA build)")
     ap.add_argument("--cpu-tensors", action="store_true", help="host tensors + gloo (emulator tests only)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    device = "cpu" if args.cpu_tensors else f"cuda:{local}"
     if not args.cpu_tensors:
         torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("gloo" if args.cpu_tensors else "nccl")
+    res = run(args, rank, world, local)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not res["correct"]:
+        raise SystemExit(f"rank {rank}: decrypted regression differs from the plaintext computation: "
+                         f"{res['theta_det']} vs {res['expected']}")
 
+
+def run(args, rank, world, local, quiet=False):
+    """One encrypted regression; the process group (world > 1) exists already.  -> the result dict
+    (rank 0 also prints it unless `quiet`)."""
+    device = "cpu" if args.cpu_tensors else f"cuda:{local}"
     import pyfhesi
     from generate_random_data import generate
     from pyfhesi.hostkeys import keygen
@@ -110,13 +146,24 @@ def main():
     p, g, d, N = args.p, args.g, args.d, args.n
     m = p - 1
     t_load0 = time.perf_counter()
-    rows, labels = generate(d, N, args.seed)            # every rank derives the same global data set
-    raw = np.empty((N, d + 1), dtype=np.int64)          # LoadData's Matrix<ZZ> rawData + labels
-    raw[:, :d] = np.asarray(rows, dtype=np.int64)
-    raw[:, d] = np.asarray(labels, dtype=np.int64)
     nslots = (p - 1) // 2 - 1
     block = 1 << (nslots.bit_length() - 1)              # Test_Regression.cpp:86-91
-    nblocks = (N + block - 1) // block
+    if getattr(args, "data", None):
+        files = load_shard_files(args.data)             # every rank reads the headers; LoadData is outside the clock
+        d = files[0].shape[1] - 1
+        N = sum(len(f) for f in files)
+        raw = np.concatenate(files)
+        # one reference process per file would cut each file into its own blocks (the last one ragged)
+        file_blocks = [(len(f) + block - 1) // block for f in files]
+        nblocks = sum(file_blocks)
+    else:
+        rows_, labels_ = generate(d, N, args.seed)      # every rank derives the same global data set
+        raw = np.empty((N, d + 1), dtype=np.int64)      # LoadData's Matrix<ZZ> rawData + labels
+        raw[:, :d] = np.asarray(rows_, dtype=np.int64)
+        raw[:, d] = np.asarray(labels_, dtype=np.int64)
+        files, file_blocks = [raw], [(N + block - 1) // block]
+        nblocks = file_blocks[0]
+    rows, labels = raw[:, :d].tolist(), raw[:, d].tolist()
     xi = max(nblocks, d)
     lgq = 4.5 * math.log(nslots) + max(1, d - 1) * (math.log(1280) + 2 * math.log(nslots) + math.log(xi))
     logq = int(math.ceil(lgq / math.log(2) + 24.7))     # Test_Regression.cpp:107-108
@@ -158,29 +205,36 @@ def main():
         ksw = dev.ksw_create(keys["ks_b"], keys["ks_A"], 3)
         rot_ksw = [dev.ksw_create(keys["rot_b"][i], keys["rot_A"][i], 2) for i in range(len(rot_k))]
         dpk, dsk = dev.key_create(keys["pk"]), dev.key_create(keys["sk"])
-    else:  # draws on the host in the reference's order, b = A t + e + src 2^(24 j) on the device
-        from pyfhesi.hostkeys import keydraws
-        draws = keydraws(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
+    else:  # draws on the host in the reference's stream order (flat arrays, no big-integer temporaries); every
+        # matrix and the public key in one pass of kernels on the device (fhesi_keygen_batch)
+        from pyfhesi.hostkeys import keydraws_flat, sk_words
+        draws = keydraws_flat(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
         t_keygen = time.perf_counter()
-        ksw = dev.ksw_generate(draws["s2_src"], draws["sk"], draws["s2_A"], draws["s2_e"])
-        rot_ksw = [dev.ksw_generate(draws["rot_src"][i], draws["sk"], draws["rot_A"][i], draws["rot_e"][i])
-                   for i in range(len(rot_k))]
-        skw = np.zeros((2, dev.n, dev.W), np.uint32)
-        skw[0, 0, 0] = 1
-        skw[1] = (draws["sk"].astype(np.int64)[:, None] >> (32 * np.arange(dev.W))[None, :]).astype(np.uint32)
-        dpk, dsk = dev.key_create(draws["pk"]), dev.key_create(skw)
+        ksws, dpk = dev.keygen_batch(draws["parts"], draws["src"], draws["sk"], draws["A"], draws["e"], with_pk=True)
+        ksw, rot_ksw = ksws[0], ksws[1:]
+        dsk = dev.key_create(sk_words(dev, draws["sk"]))
     dev.sync()
     t_setup = time.perf_counter()
 
     # ---- Batch + Encryption of this rank's blocks (BatchData, Regression.h:43-66; AddData :83-95)
-    lo, hi = shard_bounds(nblocks, rank, world)
-    nb = hi - lo
     n = dev.n
     # all of this rank's plaintexts at once: [nb][d+1][block] slot values -> PlaintextSpace::EmbedInSlots
     # on the device (fhesi_embed_slots_dev, exact integer arithmetic)
-    data = np.zeros((nblocks * block, d + 1), dtype=np.int64)
-    data[:N] = raw
-    mine = (data[lo * block:hi * block] % p).reshape(max(nb, 0), block, d + 1).transpose(0, 2, 1)
+    if len(files) >= world and len(files) > 1:          # whole files per rank, round-robin
+        parts = []
+        for k in range(rank, len(files), world):
+            padded = np.zeros((file_blocks[k] * block, d + 1), dtype=np.int64)
+            padded[:len(files[k])] = files[k]
+            parts.append(padded)
+        data = np.concatenate(parts) if parts else np.zeros((0, d + 1), np.int64)
+        nb = len(data) // block
+        mine = (data % p).reshape(nb, block, d + 1).transpose(0, 2, 1)
+    else:                                               # fewer files than ranks: split the global block list
+        lo, hi = shard_bounds(nblocks, rank, world)
+        nb = hi - lo
+        data = np.zeros((nblocks * block, d + 1), dtype=np.int64)
+        data[:N] = raw
+        mine = (data[lo * block:hi * block] % p).reshape(max(nb, 0), block, d + 1).transpose(0, 2, 1)
     d_msgs = embed_batch(env, slots, np.ascontiguousarray(mine).reshape(nb * (d + 1), block))
     dev.sync()
     t_batch = time.perf_counter()
@@ -200,14 +254,8 @@ def main():
         if nb:
             dev.ct_tensor_dev(col(i), 2, col(j), 2, partial[idx], nb, accumulate=True)
     dev.sync()
-    if world > 1:
-        gathered = torch.empty((world,) + tuple(partial.shape), dtype=torch.int32, device=device)
-        dist.all_gather([gathered[w] for w in range(world)], partial)
-        total = torch.empty_like(partial)
-        dev.tprod_reduce_gathered_dev(gathered, world, 3 * len(pairs), total)
-        dev.sync()
-    else:
-        total = partial
+    from pyfhesi.sharded import allgather_add
+    total = allgather_add(dev, partial, 3 * len(pairs))  # the one exchange step (world == 1: a no-op)
     t_data = time.perf_counter()
 
     # ---- serial tail, replicated (Regression.h:106-148)
@@ -270,29 +318,32 @@ def main():
 
     want_theta, want_det = plaintext_regression(rows, labels, p)
     ok = out[:-1] == want_theta and out[-1] == want_det
-    if rank == 0:
+    total_s = t_dec - t_start
+    if world > 1:  # wall time of the job = the slowest rank
+        tt = torch.tensor([total_s], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_s = float(tt.item())
+    res = {
+        "metric": f"Test_Regression N={N} d={d} wall time", "unit": "s", "higher_is_better": False,
+        "value": total_s, "n_gpus": world, "correct": bool(ok),
+        "clock": "Test_Regression.cpp:24-63 (key generation .. decryption), max over ranks",
+        "load_context_and_communicator_s": t_start - t_load0,
+        "setup_split_s": {"host_draws_or_keygen": t_keygen - t_start, "device_generation_or_upload": t_setup - t_keygen},
+        "phases_s": {"setup": t_setup - t_start, "batch": t_batch - t_setup, "encryption": t_enc - t_batch,
+                     "data_phase_and_exchange": t_data - t_enc, "serial_tail": t_reg - t_data,
+                     "decryption": t_dec - t_reg},
+        "config": {"p": p, "g": g, "logQ": logq, "xi": xi, "blocks": nblocks, "block_size": block,
+                   "chain": f"{dev.Lt}/{dev.Lk}", "blocks_per_rank": nb,
+                   "input": (f"{len(files)} shard files {os.path.basename(args.data)}_k.dat" if getattr(args, "data", None)
+                             else "generated in-process")},
+        "theta_det": out, "expected": want_theta + [want_det]}
+    if rank == 0 and not quiet:
         print(f"Setup time: {t_setup - t_start:.3f}\nBatch time: {t_batch - t_setup:.3f}\n"
               f"Encryption time: {t_enc - t_batch:.3f}\nRegression time: {t_reg - t_enc:.3f} "
               f"(data phase + exchange {t_data - t_enc:.3f})\nDecryption time: {t_dec - t_reg:.3f}\n"
               f"Total time: {t_dec - t_start:.3f}")
-        print(json.dumps({
-            "metric": f"Test_Regression N={N} d={d} wall time", "unit": "s", "higher_is_better": False,
-            "value": t_dec - t_start, "n_gpus": world, "correct": ok,
-            "clock": "Test_Regression.cpp:24-63 (key generation .. decryption)",
-            "load_context_and_communicator_s": t_start - t_load0,
-            "setup_split_s": {"host_draws_or_keygen": t_keygen - t_start, "device_generation_or_upload": t_setup - t_keygen},
-            "phases_s": {"setup": t_setup - t_start, "batch": t_batch - t_setup, "encryption": t_enc - t_batch,
-                         "data_phase_and_exchange": t_data - t_enc, "serial_tail": t_reg - t_data,
-                         "decryption": t_dec - t_reg},
-            "config": {"p": p, "g": g, "logQ": logq, "xi": xi, "blocks": nblocks, "block_size": block,
-                       "chain": f"{dev.Lt}/{dev.Lk}", "blocks_per_rank": nb},
-            "theta_det": out, "expected": want_theta + [want_det]}), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if not ok:
-        raise SystemExit(f"rank {rank}: decrypted regression differs from the plaintext computation: {out} "
-                         f"vs {want_theta + [want_det]}")
+        print(json.dumps(res), flush=True)
+    return res
 
 
 if __name__ == "__main__":

@@ -101,17 +101,14 @@ def main():
         ksw = dev.ksw_create(keys["ks_b"], keys["ks_A"], 3)
         rot_ksw = [dev.ksw_create(keys["rot_b"][i], keys["rot_A"][i], 2) for i in range(len(rot_k))]
         dpk, dsk = dev.key_create(keys["pk"]), dev.key_create(keys["sk"])
-    else:  # draws on the host in the reference's order, b = A t + e + src 2^(24 j) on the device
-        from pyfhesi.hostkeys import keydraws
-        draws = keydraws(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
+    else:  # draws on the host in the reference's stream order (flat arrays, no big-integer temporaries); every
+        # matrix and the public key in one pass of kernels on the device (fhesi_keygen_batch)
+        from pyfhesi.hostkeys import keydraws_flat, sk_words
+        draws = keydraws_flat(dev, args.seed, g, rot_k=rot_k, lib_path=args.lib)
         t_keygen = time.perf_counter()
-        ksw = dev.ksw_generate(draws["s2_src"], draws["sk"], draws["s2_A"], draws["s2_e"])
-        rot_ksw = [dev.ksw_generate(draws["rot_src"][i], draws["sk"], draws["rot_A"][i], draws["rot_e"][i])
-                   for i in range(len(rot_k))]
-        skw = np.zeros((2, dev.n, dev.W), np.uint32)
-        skw[0, 0, 0] = 1
-        skw[1] = (draws["sk"].astype(np.int64)[:, None] >> (32 * np.arange(dev.W))[None, :]).astype(np.uint32)
-        dpk, dsk = dev.key_create(draws["pk"]), dev.key_create(skw)
+        ksws, dpk = dev.keygen_batch(draws["parts"], draws["src"], draws["sk"], draws["A"], draws["e"], with_pk=True)
+        ksw, rot_ksw = ksws[0], ksws[1:]
+        dsk = dev.key_create(sk_words(dev, draws["sk"]))
     dev.sync()
     t_setup = time.perf_counter()
 

@@ -10,6 +10,12 @@ over one batch of B independent fresh ciphertext pairs per GPU at the cfg2 param
 
 Under torchrun (N>1) every rank drives its own GPU over its own disjoint batch (no data-path
 collective: the units are independent); time is the max over ranks.
+
+The same JSON line carries BASELINE.json's second metric under "regression": Test_Regression on
+d=4, N=100000 split into 8 files (config 4), wall time on the reference's clock
+(Test_Regression.cpp:24-63), through apps/regression_sharded.py on the same N GPUs -- the data
+blocks sharded over the ranks, one NCCL all-gather + modular add, replicated tail -- with the
+reference's own Regression.h (oracle/_ref/ref_regression, CPU) timed beside it.
 """
 import argparse
 import json
@@ -127,12 +133,12 @@ def run_reference(args, rank, world):
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
     logq, p, g = CFG["logQ"], CFG["p"], CFG["g"]
-    # size one step to ~4 s of wall time
+    # size one step to ~2 s of wall time
     port, a, b, _ = _cpu_setup(logq, p, g)
     t = time.perf_counter()
     port.mult_relin(a, b)
     one = time.perf_counter() - t
-    per_worker = max(1, int(4.0 / one))
+    per_worker = max(1, int(2.0 / one))
     ctxm = mp.get_context("fork")
     times = []
     with ctxm.Pool(cores, initializer=_cpu_worker_init, initargs=(logq, p, g, False)) as pool:
@@ -150,7 +156,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "ops/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": workload_name(), "ops_per_step": ops_per_step,
+        "config": bench_config(args.batch, args.gpus),
+        "sample": {"ops_per_step": ops_per_step,
                    "note": "one process per core, each set up (context, key matrix, cached tables) before "
                            "the timed steps; a step is ops only"},
         "cpu_baseline": dict({"value": value, "unit": "ops/s", "cores": cores, "kind": "port",
@@ -162,7 +169,24 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_regression:
+        ref = regression_reference(full_tail=True)
+        line["regression"] = dict({"metric": REG_METRIC, "value": ref.get("value"), "unit": "s",
+                                   "higher_is_better": False, "n_gpus": args.gpus,
+                                   "config": {"d": REG["d"], "N": REG["n"], "p": REG["p"], "g": REG["g"],
+                                              "logQ": REG["logQ"], "xi": REG["xi"], "blocks": 392}},
+                                  cpu_baseline=ref)
     print(json.dumps(line), flush=True)
+
+
+def bench_config(batch, world):
+    """The `config` object, identical in both arms (the reference arm times a bounded sample of the same
+    workload; what the sample was is in its cpu_baseline.sample)."""
+    n, W = (CFG["p"] - 1) // 2 - 1, (CFG["logQ"] + 31) // 32
+    return {"workload": workload_name(), "batch_per_gpu": batch, "global_batch": batch * world,
+            "parallelism": f"independent ciphertext shards x{world}, no data-path collective",
+            "l2": f"inputs {2 * batch * 2 * n * W * 4 / 2**20:.0f} MiB per step > 126 MB L2",
+            "seed": SEED}
 
 
 def workload_name():
@@ -240,6 +264,102 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 # ---------------------------------------------------------------------------------------
+# BASELINE.json metric 2: Test_Regression, d=4, N=100000 in 8 files, p=1019, g=3 (config 4)
+# ---------------------------------------------------------------------------------------
+REG = {"d": 4, "n": 100000, "p": 1019, "g": 3, "files": 8, "seed": 12345, "logQ": 176, "xi": 391}
+REG_METRIC = "Test_Regression N=1e5 wall time"
+
+
+def _regression_files(tmpdir):
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import generate_random_data
+    prefix = os.path.join(tmpdir, "reg4")
+    generate_random_data.main(["generate_random_data.py", prefix, str(REG["d"]), str(REG["n"]), str(REG["files"]),
+                               "--seed", str(REG["seed"])])
+    return prefix
+
+
+def run_regression_ours(args, rank, local_rank, world, lib_path, runs=3):
+    """apps/regression_sharded.py on the N GPUs of this job, reading the 8 shard files; the clock is the
+    reference driver's (key generation .. decryption, Test_Regression.cpp:24-63), max over ranks.  The first run
+    pays one-off costs (buffer pool growth, first use of every kernel at these sizes); all runs are reported,
+    `value` is the best."""
+    import tempfile
+    import types
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "apps"))
+    import regression_sharded
+    tmp = None
+    if rank == 0:
+        tmp = tempfile.mkdtemp(prefix="fhesi_reg_")
+        _regression_files(tmp)
+    if world > 1:
+        box = [tmp]
+        dist.broadcast_object_list(box, src=0)
+        tmp = box[0]
+    a = types.SimpleNamespace(d=REG["d"], n=REG["n"], p=REG["p"], g=REG["g"], seed=REG["seed"],
+                              data=os.path.join(tmp, "reg4"), lib=lib_path, cpu_tensors=False)
+    res = [regression_sharded.run(a, rank, world, local_rank, quiet=True) for _ in range(runs)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    best = min(res, key=lambda r: r["value"])
+    if not all(r["correct"] for r in res):
+        raise SystemExit("bench: the encrypted regression does not decrypt to RegressPT mod p: %r" % (res[0],))
+    return {"metric": REG_METRIC, "value": best["value"], "unit": "s", "higher_is_better": False, "n_gpus": world,
+            "runs_s": [r["value"] for r in res], "clock": best["clock"], "phases_s": best["phases_s"],
+            "setup_split_s": best["setup_split_s"], "config": dict(best["config"], d=REG["d"], N=REG["n"]),
+            "theta_det": best["theta_det"], "expected": best["expected"], "correct": True,
+            "scaling": "strong (the 392 data blocks are dealt to the ranks; keys and the 4x4 tail are replicated)"}
+
+
+def regression_reference(full_tail):
+    """The reference's own Regression.h / Matrix.cpp / FHE-SI code (oracle/_ref/ref_regression: its sources
+    compiled against the NTL stand-in, one thread -- the reference is single-threaded) at config 4's
+    parameters (logQ=176, xi=391).  The N-independent phases (set-up, and with full_tail the key-switch /
+    rotation / adjugate tail and decryption) run whole; the N-proportional ones (batch, encryption,
+    data-phase products) are timed on the first block of file 0 and scaled to the 392 blocks."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_regression")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_regression was not built (no reference tree at build time)"}
+    with tempfile.TemporaryDirectory(prefix="fhesi_regref_") as tmp:
+        prefix = _regression_files(tmp)
+        cmd = [exe, prefix + "_0.dat", str(REG["p"]), str(REG["g"]), str(REG["logQ"]), str(REG["xi"]), "1",
+               str(REG["seed"]), "0" if full_tail else "1"]
+        t = time.perf_counter()
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            return {"unavailable": "ref_regression failed: " + str(e)[:200]}
+        wall = time.perf_counter() - t
+    blocks = 392
+    per_block = j["batch_s"] + j["encryption_s"] + j["data_phase_s"]
+    out = {"kind": "reference", "cores": 1, "unit": "s",
+           "what": "oracle/_ref/ref_regression: the reference's Regression.h, Matrix.cpp, FHE-SI.cpp, DoubleCRT.cpp ... "
+                   "unmodified, NTL replaced by oracle/ntl_compat (slower than NTL/GMP; labelled, not corrected)",
+           "sample": "set-up whole%s; batch + encryption + data-phase products on 1 block of 256 points, x %d blocks"
+                     % (", tail and decryption whole" if full_tail else "", blocks),
+           "sample_wall_s": wall, "setup_s": j["setup_s"], "per_block_s": per_block,
+           "n_proportional_s_extrapolated": per_block * blocks}
+    if full_tail:
+        tail = j["regression_s"] - j["data_phase_s"]
+        out.update({"tail_s": tail, "decryption_s": j["decryption_s"], "decrypt_ok": j["correct"],
+                    "value": j["setup_s"] + per_block * blocks + tail + j["decryption_s"]})
+    else:
+        out.update({"tail_s": None, "value": j["setup_s"] + per_block * blocks,
+                    "note": "lower bound: the N-independent tail (~250 key switches, 160 rotations, the 4x4 adjugate) "
+                            "is not sampled in this bounded leg; `bench.py --impl reference` runs it whole"})
+    return out
+
+
+# ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
@@ -250,9 +370,10 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     numa_node = None if os.environ.get("FHESI_NO_NUMA_BIND") else bind_to_gpu_numa_node(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO print banners there
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("FHESI_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's own log (NCCL_DEBUG=INFO: communicator, rank count, transports) is left at the level the
+        # launcher asked for; it only moves off stdout -- which carries the one JSON line -- to stderr
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import build as fhesi_build
@@ -357,11 +478,63 @@ def run_ours(args, rank, local_rank, world):
     e2e_ms = max(e2e_ms, e2e_wall_ms) / e2e_steps  # host-blocking call: wall clock is the honest one
     assert np.array_equal(h_o.numpy().view(np.uint32).reshape(B, 2, n, W), h_out), "e2e result differs"
 
+    # ---- the host's share of the end-to-end figure, measured: the same bytes per step as the e2e call
+    # moves, copied concurrently in both directions on every rank at once (no kernels).  N ranks share one
+    # host; this is the ceiling the host path sets on e2e at this N.
+    cs1, cs2 = torch.cuda.Stream(), torch.cuda.Stream()
+    d_pa, d_po = torch.empty_like(d_ct), torch.empty_like(d_out)
+
+    def copy_step():
+        with torch.cuda.stream(cs1):
+            d_pa[:B].copy_(h_a, non_blocking=True)
+            d_pa[B:].copy_(h_b, non_blocking=True)
+        with torch.cuda.stream(cs2):
+            h_o.copy_(d_po, non_blocking=True)
+
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copy_step()
+    barrier()
+    pcie_ms = (time.perf_counter() - t0) * 1e3 / 3
+    del d_pa, d_po
+
+    # ---- the data-phase exchange on its own (N > 1): all-gather of every rank's 14 partial sums in tensor
+    # form + the modular-add kernel, timed on the device
+    exchange = None
+    if world > 1:
+        from pyfhesi.sharded import allgather_add
+        part = torch.randint(0, 1 << 29, (14, 3, dev.Lt, dev.N), dtype=torch.int32, device="cuda")
+        for _ in range(3):
+            allgather_add(dev, part, 3 * 14)
+        barrier()
+        ev0.record(stream)
+        reps = 20
+        for _ in range(reps):
+            allgather_add(dev, part, 3 * 14)
+        ev1.record(stream)
+        barrier()
+        ex_ms = ev0.elapsed_time(ev1) / reps
+        exchange = {"what": "ncclAllGather of 14 x 3 x Lt x N words per rank + k_tprod_reduce_world",
+                    "bytes_per_rank": part.numel() * 4, "bytes_received_per_rank": part.numel() * 4 * (world - 1),
+                    "us": ex_ms * 1e3}
+
+    # ---- BASELINE.json's second metric: Test_Regression d=4 N=100000 (config 4)
+    regression = None
+    if not args.no_regression:
+        regression = run_regression_ours(args, rank, local_rank, world, lib_path)
+
     ms_step = ms_total / args.steps
     if world > 1:
-        t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_step, e2e_ms, pcie_ms] + ([exchange["us"]] if exchange else []), dtype=torch.float64,
+                         device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms = t.tolist()
+        vals = t.tolist()
+        ms_step, e2e_ms, pcie_ms = vals[:3]
+        if exchange:
+            exchange["us"] = vals[3]
+            exchange["algbw_GBs"] = exchange["bytes_received_per_rank"] / (vals[3] * 1e-6) / 1e9
     value = world * B / (ms_step * 1e-3)
     e2e_value = world * B / (e2e_ms * 1e-3)
 
@@ -376,63 +549,92 @@ def run_ours(args, rank, local_rank, world):
         peak64 = dev.modmul_peak(64)
         pipes = {name: dev.pipe_peak(kind) for kind, name in
                  enumerate(["imad_lo32", "imad_wide64", "imad_hi32", "shoup_modmul32", "alu_csub", "dfma"])}
-        # roofline denominator: the faster of the two 32-bit modular-product formulations
-        peak32 = max(peak_mont32, pipes["shoup_modmul32"])
-        # dominant kernel by measured device time, with its algorithmic modmuls per launch
-        work_all = kernel_work_per_op(dev)
-        # kernels that actually ran (template instances report as name<...>)
+        # The integer-multiply (FMA-heavy) pipe executes three instruction classes at three different
+        # measured rates; a kernel's roofline is the pipe TIME its algorithmic instructions need.  Work is
+        # therefore counted per class and expressed in Shoup-modmul equivalents (one Shoup product =
+        # 2 IMAD + 1 IMAD.HI; one 64-bit multiply-accumulate = 1 IMAD.WIDE, about 0.66 of a Shoup product):
+        # achieved / peak is then the fraction of the pipe's time spent on algorithmic instructions, the
+        # quantity ncu reports as sm__inst_executed_pipe_fmaheavy (profiles/r02_summary.md).
+        cost = {"lo": 1.0 / pipes["imad_lo32"], "hi": 1.0 / pipes["imad_hi32"], "wide": 1.0 / pipes["imad_wide64"]}
+        shoup_cost = 2 * cost["lo"] + cost["hi"]
+        peak32 = 1.0 / shoup_cost  # Shoup products per second when nothing else shares the pipe
+        work_all = kernel_pipe_work_per_op(dev)
+        pipe_s = lambda w: w["lo"] * cost["lo"] + w["hi"] * cost["hi"] + w["wide"] * cost["wide"]
         work = {k: work_all[k.split("<")[0]] for k in prof if k.split("<")[0] in work_all}
         top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
         tname, (tcnt, tms) = top
         share = tms / max(sum(v[1] for v in prof.values()), 1e-9)
         ops_timed = B * args.steps
-        alg_per_launch = work.get(tname, 0) * ops_timed / max(tcnt, 1)
+        tw = work.get(tname, {"lo": 0, "hi": 0, "wide": 0, "modmul": 0, "mac": 0})
+        eq_per_launch = pipe_s(tw) / shoup_cost * ops_timed / max(tcnt, 1)
         avg_launch_s = tms * 1e-3 / max(tcnt, 1)
-        achieved = alg_per_launch / max(avg_launch_s, 1e-12)
+        achieved = eq_per_launch / max(avg_launch_s, 1e-12)
         canon = CANON_MODMUL[logq]
+        step_pipe_s = sum(pipe_s(w) for w in work.values())
+        traffic = kernel_compulsory_bytes_per_op(dev).get((tname or "").split("<")[0])
         roofline = {
-            "bound": "int32-modmul (integer pipe; SURVEY.md §8d -- HBM does not bind)",
+            "bound": "integer-multiply (FMA-heavy) pipe; SURVEY.md §8d -- HBM does not bind",
             "kernel": tname, "kernel_share_of_step": share,
-            "achieved": achieved / 1e9, "peak": peak32 / 1e9, "unit": "Gmodmul/s (32-bit Montgomery)",
+            "achieved": achieved / 1e9, "peak": peak32 / 1e9,
+            "unit": "G Shoup-modmul equivalents/s (32-bit; every multiply-pipe instruction class weighted by its "
+                    "measured cost: IMAD 1, IMAD.HI %.2f, IMAD.WIDE %.2f IMAD slots)" % (
+                        cost["hi"] / cost["lo"], cost["wide"] / cost["lo"]),
             "frac": achieved / peak32,
-            "traffic": (NCU_DRAM_BYTES_PER_OP.get((tname or "").split("<")[0]) or 0) * ops_timed / max(tcnt, 1) or None,
-            "traffic_unit": "bytes per launch (ncu dram read+write, per-op figure x ops in one launch)",
-            "peak_source": "measured in this run: max(fhesi_modmul_peak(32) Montgomery, fhesi_pipe_peak(3) Shoup), "
-                           "register-resident ILP-8 chains on all SMs",
+            "frac_is": "pipe-time fraction: algorithmic multiply-pipe instructions of the kernel x their measured "
+                       "per-class cost / the kernel's measured duration (comparable with ncu's fmaheavy pipe utilisation)",
+            "work_per_op": {"shoup_modmul": tw["modmul"], "mac64": tw["mac"], "imad": tw["lo"], "imad_hi": tw["hi"],
+                            "imad_wide": tw["wide"]},
+            "traffic": traffic * ops_timed / max(tcnt, 1) if traffic else None,
+            "traffic_unit": "bytes per launch: the kernel's compulsory HBM traffic (every input word read once, every "
+                            "output word written once; key tiles and tables stay in L2), confirmed against ncu "
+                            "dram__bytes_read.sum + dram__bytes_write.sum of the same launch in profiles/r02_summary.md",
+            "peak_source": "measured in this run (fhesi_pipe_peak: register-resident ILP-8 chains of one instruction "
+                           "class on all SMs)",
             "peak_montgomery32_Gmodmul_s": peak_mont32 / 1e9,
             "pipe_peaks_Gops_s": {k: v / 1e9 for k, v in pipes.items()},
-            "algorithmic_modmul_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+            "avg_launch_ms": avg_launch_s * 1e3,
             "whole_op": {
-                "executed_modmul32_per_op": sum(work.values()),
-                "frac_of_peak32": (value / world) * sum(work.values()) / peak32,
-                "canonical_modmul64_eq_per_op": canon,
-                "canonical_achieved_Gmodmul_s": (value / world) * canon / 1e9,
-                "peak64_Gmodmul_s": peak64 / 1e9,
-                "canonical_frac_of_peak64": (value / world) * canon / peak64,
-            },
+                "pipe_frac": (value / world) * step_pipe_s,
+                "shoup_modmul_eq_per_op": step_pipe_s / shoup_cost,
+                "work_reduction_vs_reference_formulation": {
+                    "canonical_modmul64_eq_per_op": canon,
+                    "note": "SURVEY.md §8d counts the reference's formulation (64-bit products, Bluestein at 2N, "
+                            "3D*L digit transforms); this build executes a cheaper one (30-bit limbs, zero-padded "
+                            "2^k transform, split keys), so that count is a work figure, not a roofline numerator",
+                    "peak64_Gmodmul_s": peak64 / 1e9}},
             "hbm": {"algorithmic_bytes_per_op": algorithmic_bytes_per_op(n, logq),
                     "achieved_GBs": (value / world) * algorithmic_bytes_per_op(n, logq) / 1e9,
                     "peak_GBs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                    "frac": (value / world) * algorithmic_bytes_per_op(n, logq) / 1e9 / hbm_peak},
-            "per_kernel_ms": {k: {"launches": v[0], "ms": v[1]} for k, v in sorted(prof.items())},
+                    "frac": (value / world) * algorithmic_bytes_per_op(n, logq) / 1e9 / hbm_peak,
+                    "compulsory_bytes_per_op_all_kernels": sum(kernel_compulsory_bytes_per_op(dev).get(k.split("<")[0], 0)
+                                                               for k in prof)},
+            "per_kernel_ms": {k: {"launches": v[0], "ms": v[1],
+                                  "pipe_frac": (pipe_s(work[k]) * ops_timed / (v[1] * 1e-3)) if k in work and v[1] > 0 else None}
+                              for k, v in sorted(prof.items())},
         }
         cpu = cpu_baseline_single_core(logq, p, g) if world == 1 and not args.no_cpu else None
+        if regression is not None and world == 1 and not args.no_cpu:
+            regression["cpu_baseline"] = regression_reference(full_tail=False)
         line = {
             "metric": METRIC, "value": value, "unit": "ops/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(), "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"independent ciphertext shards x{world}, no data-path collective",
-                       "l2": f"inputs {2 * B * ct_words * 4 / 2**20:.0f} MiB per step > 126 MB L2",
-                       "chain": f"{dev.Lt} x 30-bit primes (tensor), {dev.Lk} (key switch"
-                                + (f", {dev.Ls} with split keys" if dev.Ls else "") + f"), N={dev.N}",
-                       "seed": SEED,
-                       "host_numa_node_rank0": numa_node},
+            "config": bench_config(B, world),
+            "impl_details": {"chain": f"{dev.Lt} x 30-bit primes (tensor), {dev.Lk} (key switch"
+                                      + (f", {dev.Ls} with split keys" if dev.Ls else "") + f"), N={dev.N}",
+                             "host_numa_node_rank0": numa_node},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_words * 4,
                     "d2h_bytes_per_step": B * ct_words * 4, "ms_per_step": e2e_ms,
-                    "api": "fhesi_mult_relin_host (pinned host buffers)"},
+                    "api": "fhesi_mult_relin_host (pinned host buffers)",
+                    "host_copy_bound": {"ms_per_step": pcie_ms, "ops_s": world * B / (pcie_ms * 1e-3),
+                                        "GBs_all_ranks": world * 3 * B * ct_words * 4 / (pcie_ms * 1e-3) / 1e9,
+                                        "e2e_over_bound": e2e_value / (world * B / (pcie_ms * 1e-3)),
+                                        "what": "the step's H2D + D2H bytes copied with no kernels, both directions "
+                                                "at once, on all ranks concurrently (max over ranks)"}},
+            "exchange": exchange,
+            "regression": regression,
             "gpu_launches": launches,
             "clocks": sampler.result(),
         }
@@ -442,32 +644,52 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-# DRAM traffic per op of each hot kernel, from `ncu --set full` captures (dram__bytes_read.sum +
-# dram__bytes_write.sum over one 8192-op launch, profiles/r01_summary_v16.md; the unsplit kernel from
-# the 2046-op capture of r01_summary_v11.md); the driver-timed run itself is never profiled.
-NCU_DRAM_BYTES_PER_OP = {"k_fused_keyswitch": 96.9e3, "k_fused_keyswitch_split": 113.0e3, "k_fused_tensor": 251.5e3,
-                         "k_residues": 204.5e3}
-
-
-def kernel_work_per_op(dev):
-    """Algorithmic 32-bit modmuls per mult+relin op, by kernel (DESIGN.md "work accounting"):
-    butterflies (N/2 log2 N per transform) + pointwise products + Garner products."""
-    N, n, D = dev.N, dev.n, dev.D
-    Lt, Lk = dev.Lt, dev.Lk
-    bf = (N // 2) * int(math.log2(N))
+def kernel_pipe_work_per_op(dev):
+    """Integer-multiply-pipe instructions per mult+relin op, by kernel and instruction class, read off the
+    kernel sources (DESIGN.md "work accounting"):
+      Shoup product (butterfly twiddle, Garner step)   2 IMAD + 1 IMAD.HI
+      Montgomery product of two residues               1 IMAD + 2 IMAD.WIDE
+      64-bit multiply-accumulate                       1 IMAD.WIDE
+      Montgomery reduction of a 64-bit sum             1 IMAD + 1 IMAD.WIDE   (k_residues: 1 IMAD + 1 IMAD.HI)
+    A fused 1024-point transform is 36 Shoup products per thread x 128 threads (4608: the first forward stage
+    sees a zero upper half, the last stage's twiddle is 1)."""
+    N, n, D, W = dev.N, dev.n, dev.D, dev.W
+    Lt, Lk, Ls = dev.Lt, dev.Lk, dev.Ls
+    K = 3 * D
     garner = lambda L: L * (L - 1) // 2
+    horner = lambda L: L * (L + 1) // 2
+    tr = 4608 if N == 1024 else (N // 2) * int(math.log2(N))
+
+    def w(modmul=0, montmul=0, mac=0, red=0, red_hi=0):
+        return {"lo": 2 * modmul + montmul + red + red_hi, "hi": modmul + red_hi, "wide": 2 * montmul + mac + red,
+                "modmul": modmul + montmul, "mac": mac}
     return {
-        "k_fwd": (4 * Lt + 3 * D * Lk) * bf,
-        "k_inv": (3 * Lt + 2 * Lk) * bf,
-        "k_tensor_pw": 4 * Lt * N,
-        "k_dot": 2 * 3 * D * Lk * N,
-        "k_crt": 3 * n * garner(Lt) + (0 if dev.Ls else 2 * n * garner(Lk)),
-        # fused path (kernels_fused.cuh)
-        "k_residues": 4 * n * Lt * dev.W,
-        "k_fused_tensor": 7 * Lt * bf + 4 * Lt * N,
-        "k_fused_keyswitch": (3 * D + 2) * Lk * bf + 2 * 3 * D * Lk * N,
-        "k_fused_keyswitch_split": (3 * D + 4) * dev.Ls * bf + 4 * 3 * D * dev.Ls * N,
-        "k_crt_split": 2 * n * 2 * garner(dev.Ls),
+        "k_residues": w(mac=4 * n * Lt * W, red_hi=4 * n * Lt * ((W + 3) // 4)),
+        "k_fused_tensor": w(modmul=7 * Lt * tr, montmul=4 * Lt * N),
+        "k_crt": w(modmul=3 * n * garner(Lt), mac=3 * n * horner(Lt)),
+        "k_fused_keyswitch_split": w(modmul=(K + 4) * Ls * tr, mac=4 * K * Ls * N, red=4 * Ls * N),
+        "k_fused_keyswitch": w(modmul=(K + 2) * Lk * tr, mac=2 * K * Lk * N, red=2 * Lk * N),
+        "k_crt_split": w(modmul=4 * n * garner(Ls), mac=4 * n * horner(Ls)),
+        # generic path (one butterfly per thread per stage, Montgomery twiddles)
+        "k_fwd": w(montmul=(4 * Lt + K * Lk) * (N // 2) * int(math.log2(N))),
+        "k_inv": w(montmul=(3 * Lt + 2 * Lk) * (N // 2) * int(math.log2(N))),
+        "k_tensor_pw": w(montmul=4 * Lt * N),
+        "k_dot": w(mac=2 * K * Lk * N),
+    }
+
+
+def kernel_compulsory_bytes_per_op(dev):
+    """HBM bytes each hot kernel must move per op: inputs read once + outputs written once (tables and key
+    tiles are shared by the whole grid and stay in L2)."""
+    n, D, W, Lt, Ls, Lk = dev.n, dev.D, dev.W, dev.Lt, dev.Ls, dev.Lk
+    K = 3 * D
+    return {
+        "k_residues": 4 * n * W * 4 + 4 * Lt * n * 4,
+        "k_fused_tensor": 4 * Lt * n * 4 + 3 * Lt * n * 4,
+        "k_crt": 3 * Lt * n * 4 + K * n * 4,
+        "k_fused_keyswitch_split": K * n * 4 + 4 * Ls * n * 4,
+        "k_fused_keyswitch": K * n * 4 + 2 * Lk * n * 4,
+        "k_crt_split": 4 * Ls * n * 4 + 2 * n * W * 4,
     }
 
 
@@ -478,7 +700,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="ciphertext pairs per GPU per step (SURVEY.md §8d: B in {1, 64, 1024, 8192})")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-regression", action="store_true", help="skip the Test_Regression leg (BASELINE metric 2)")
     ap.add_argument("--logq", type=int, default=256, choices=[128, 256, 512],
                     help="BASELINE config 5 sweep; the headline metric is quoted at 256")
     args = ap.parse_args()

@@ -102,6 +102,11 @@ struct PoolTmp {
   }
   int alloc(size_t bytes) { return fhesi_malloc(c, bytes, &p); }
   u32 *u() const { return (u32 *)p; }
+  void *release() {
+    void *r = p;
+    p = nullptr;
+    return r;
+  }
 };
 static void prof_clear(fhesi_ctx *c);
 static void prof_begin(fhesi_ctx *c, const char *name) {
@@ -632,13 +637,15 @@ static int ksw_build_from_device(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, u
   const u32 K = parts * I.D, Lk = I.Lk;
   const size_t polyw = (size_t)I.n * I.W;
   const bool split = c->use_fused && c->tfree && I.Ls;
-  DevTmp t_key, t_bal, t_split;  // the key's own buffers
+  // the key's own buffers come from the context's pool as well: a client that regenerates its keys (one
+  // regression per request) re-uses the blocks of the previous set instead of paying cudaMalloc / cudaFree
+  PoolTmp t_key(c), t_bal(c), t_split(c);
   PoolTmp t_in(c), t_tmp(c), t_in2(c), t_tmp2(c), t_t2(c);  // scratch
   int rc = t_in.alloc((size_t)K * 2 * polyw * 4);
   if (!rc) rc = t_tmp.alloc((size_t)K * 2 * Lk * I.N * 4);
   if (!rc && split) rc = t_in2.alloc((size_t)K * 4 * polyw * 4);
   if (rc) return rc;
-  CK(t_key.alloc((size_t)K * 2 * Lk * I.N * 4));
+  if ((rc = t_key.alloc((size_t)K * 2 * Lk * I.N * 4))) return rc;
   u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
   // interleave to [K][2] so that one transform launch writes [K*2][Lk][N]; K mod q (non-negative)
   // = lo + 2^(32 ws) hi, each half as a non-negative W-word polynomial
@@ -652,7 +659,7 @@ static int ksw_build_from_device(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, u
   CKL();
   if (c->use_fused && c->tfree) {
     const size_t total = (size_t)K * 2 * Lk * I.N;
-    CK(t_bal.alloc(total * 4));
+    if ((rc = t_bal.alloc(total * 4))) return rc;
     KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_key, t_bal.u(), K * 2, total);
     CKL();
   }
@@ -662,7 +669,7 @@ static int ksw_build_from_device(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, u
     rc = t_tmp2.alloc(total * 4);
     if (!rc) rc = t_t2.alloc(total * 4);
     if (rc) return rc;
-    CK(t_split.alloc((total + (size_t)Ls * 4 * I.N) * 4));  // + the offset-correction table
+    if ((rc = t_split.alloc((total + (size_t)Ls * 4 * I.N) * 4))) return rc;  // + the offset-correction table
     if ((rc = launch_fwd(c, t_in2.u(), SRC_POLY, I.W, SC_KEYFORM, Ls, t_tmp2.u(), (size_t)K * 4))) return rc;
     KL(c, k_transpose_key, nblk(total), 256, 0, t_tmp2.u(), t_t2.u(), K * 4, Ls, I.N);
     CKL();
@@ -692,27 +699,23 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
   CK(cudaStreamSynchronize(c->stream));  // h_b / h_A may be pinned: the caller gets them back consumed
   return 0;
 }
-// KeySwitchSI::Init (FHE-SI.cpp:153-209) on the device, from the caller's draws (the reference's order
-// and number of draws stay with the caller): for entry (i, j), i < parts, j < D,
-//   b = A * t + e + src_i * 2^(dbits j)  reduced mod q  (:182-199),   A' = -A  (:178-180)
-// h_A: the SampleRandom polynomials [parts*D][n][W] (centred, two's complement), h_e: Gaussians
-// [parts*D][n], h_src: the source key polynomials [parts][n] (small integers: 1, s, s^2 or s(X^k)),
-// h_t: the target key [n].  Optionally returns b and Reduce(A') as [parts*D][n][W] host words.
-int fhesi_ksw_generate(fhesi_ctx *c, const int32_t *h_src, const int32_t *h_t, const uint32_t *h_A,
-                       const int32_t *h_e, uint32_t parts, fhesi_ksw **out, uint32_t *h_b_out,
-                       uint32_t *h_A_out) {
-  if (!c || !h_src || !h_t || !h_A || !h_e || !out || parts < 1 || parts > 3)
-    return fail(FHESI_ERR_INVALID, "fhesi_ksw_generate: bad argument");
-  CK(cudaSetDevice(c->device));
+// KeySwitchSI::Init (FHE-SI.cpp:153-209) and FHESIPubKey::Init (FHE-SI.cpp:42-62) on the device, from the
+// caller's draws (the reference's order and number of draws stay with the caller).  Every
+// entry q of every matrix has the same shape,
+//   b_q = A_q * t + e_q + src_{q / D} * 2^(dbits (q % D))  reduced mod q  (:182-199),   A'_q = -A_q  (:178-180),
+// and the public key is one more entry with no source term (c0 = e + s * c1, c1' = -c1, :44-58) -- so all
+// matrices of a set-up (s^2 -> s and the log2(slots) rotation keys: 9 at p = 1019) and the public key go
+// through ONE pass of kernels over the concatenated entries: one upload, one transform launch, one CRT.
+// d_A [Kt][n][W], d_e [Kt][n], d_src [rows][n] (rows >= ceil(Kt / D)), d_t [n]  ->  d_b, d_An [Kt][n][W].
+static int keygen_entries(fhesi_ctx *c, u32 Kt, const u32 *d_A, const int *d_e, const int *d_src, const int *d_t,
+                          u32 *d_b, u32 *d_An) {
   const fhesi_info &I = c->info;
-  const u32 K = parts * I.D, Le = I.Le, n = I.n;
+  const u32 Le = I.Le, n = I.n;
   const size_t polyw = (size_t)n * I.W, per = (size_t)Le * I.N;
-  PoolTmp d_A(c), d_An(c), d_b(c), d_e(c), d_src(c), d_t(c), d_pow(c), s0(c), s1(c), s2(c), s3(c), s4(c);
+  PoolTmp d_pow(c), s0(c), s1(c), s2(c), s3(c), s4(c);
   int rc = 0;
-  if ((rc = d_A.alloc(K * polyw * 4)) || (rc = d_An.alloc(K * polyw * 4)) || (rc = d_b.alloc(K * polyw * 4)) ||
-      (rc = d_e.alloc((size_t)K * n * 4)) || (rc = d_src.alloc((size_t)parts * n * 4)) || (rc = d_t.alloc(n * 4)) ||
-      (rc = d_pow.alloc((size_t)I.D * Le * 4)) || (rc = s0.alloc(per * 4)) || (rc = s1.alloc(per * 4)) ||
-      (rc = s2.alloc(K * per * 4)) || (rc = s3.alloc(K * per * 4)) || (rc = s4.alloc((size_t)K * Le * n * 4)))
+  if ((rc = d_pow.alloc((size_t)I.D * Le * 4)) || (rc = s0.alloc(per * 4)) || (rc = s1.alloc(per * 4)) ||
+      (rc = s2.alloc(Kt * per * 4)) || (rc = s3.alloc(Kt * per * 4)) || (rc = s4.alloc((size_t)Kt * Le * n * 4)))
     return rc;
   // 2^(dbits j) mod p_l in Montgomery form, [D][Le]
   std::vector<u32> pw((size_t)I.D * Le);
@@ -725,70 +728,124 @@ int fhesi_ksw_generate(fhesi_ctx *c, const int32_t *h_src, const int32_t *h_t, c
       v = h_mulmod(v, two, q);
     }
   }
-  CK(cudaMemcpyAsync(d_A.u(), h_A, K * polyw * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_e.u(), h_e, (size_t)K * n * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_src.u(), h_src, (size_t)parts * n * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_t.u(), h_t, n * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_pow.u(), pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_pow.u(), pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, c->stream));  // pageable: consumed on return
   // t in key form [Le][1][1][N]; images of every A; pointwise products; back with the addend
-  if ((rc = launch_fwd(c, d_t.u(), SRC_I32, 0, SC_KEYFORM, Le, s0.u(), 1))) return rc;
+  if ((rc = launch_fwd(c, d_t, SRC_I32, 0, SC_KEYFORM, Le, s0.u(), 1))) return rc;
   KL(c, k_transpose_key, nblk(per), 256, 0, s0.u(), s1.u(), 1, Le, I.N);
   CKL();
-  if ((rc = launch_fwd(c, d_A.u(), SRC_POLY, I.W, SC_NONE, Le, s2.u(), K))) return rc;
-  DotArgs d{s2.u(), s1.u(), 1, 1, Le, s3.u(), K};
-  KL(c, k_dot, nblk(per * K), 256, 0, c->dc, d);
+  if ((rc = launch_fwd(c, d_A, SRC_POLY, I.W, SC_NONE, Le, s2.u(), Kt))) return rc;
+  DotArgs d{s2.u(), s1.u(), 1, 1, Le, s3.u(), Kt};
+  KL(c, k_dot, nblk(per * Kt), 256, 0, c->dc, d);
   CKL();
   {
     InvArgs a{s3.u(), Le, s4.u(), nullptr, nullptr};
-    a.add1 = (const int *)d_e.u();
-    a.sh_src = (const int *)d_src.u();
+    a.add1 = d_e;
+    a.sh_src = d_src;
     a.sh_pow = d_pow.u();
     a.sh_D = I.D;
     const DevCtx &dc = c->dc;
-    dim3 grid(K, Le), block(dc.N / 2 < 32 ? 32 : dc.N / 2);
+    dim3 grid(Kt, Le), block(dc.N / 2 < 32 ? 32 : dc.N / 2);
     KL(c, k_inv, grid, block, (dc.N + dc.h) * 4, dc, a);
     CKL();
   }
-  if ((rc = launch_crt(c, s4.u(), Le, CRT_REDUCE_Q, d_b.u(), I.W, K))) return rc;
+  if ((rc = launch_crt(c, s4.u(), Le, CRT_REDUCE_Q, d_b, I.W, Kt))) return rc;
   // A' = Reduce(-A)
-  CK(cudaMemcpyAsync(d_An.u(), d_A.u(), K * polyw * 4, cudaMemcpyDeviceToDevice, c->stream));
-  if ((rc = fhesi_ct_mul_scalar_dev(c, d_An.u(), -1, K, 1))) return rc;
-  if ((rc = ksw_build_from_device(c, d_b.u(), d_An.u(), parts, out))) return rc;
-  if (h_b_out) CK(cudaMemcpyAsync(h_b_out, d_b.u(), K * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (h_A_out) CK(cudaMemcpyAsync(h_A_out, d_An.u(), K * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpyAsync(d_An, d_A, Kt * polyw * 4, cudaMemcpyDeviceToDevice, c->stream));
+  return fhesi_ct_mul_scalar_dev(c, d_An, -1, Kt, 1);
+}
+static int key_build_from_device(fhesi_ctx *c, const u32 *d_polys, uint32_t parts, fhesi_key **out);
+
+int fhesi_keygen_batch(fhesi_ctx *c, uint32_t M, const uint32_t *parts, const int32_t *h_src, const int32_t *h_t,
+                       const uint32_t *h_A, const int32_t *h_e, fhesi_ksw **out, uint32_t *h_b_out, uint32_t *h_A_out,
+                       fhesi_key **pk_out, uint32_t *h_pk_out) {
+  if (!c || !h_t || !h_A || !h_e || (M && (!parts || !h_src || !out)) || (!M && !pk_out))
+    return fail(FHESI_ERR_INVALID, "fhesi_keygen_batch: bad argument");
+  CK(cudaSetDevice(c->device));
+  const fhesi_info &I = c->info;
+  const u32 n = I.n;
+  u32 rows = 0;
+  for (u32 m = 0; m < M; ++m) {
+    if (parts[m] < 1 || parts[m] > 3) return fail(FHESI_ERR_INVALID, "fhesi_keygen_batch: parts must be 1..3");
+    rows += parts[m];
+  }
+  const u32 Km = rows * I.D, Kt = Km + (pk_out ? 1 : 0);  // the public key is the last entry, with a zero source row
+  const size_t polyw = (size_t)n * I.W;
+  PoolTmp d_A(c), d_An(c), d_b(c), d_e(c), d_src(c), d_t(c);
+  int rc = 0;
+  if ((rc = d_A.alloc(Kt * polyw * 4)) || (rc = d_An.alloc(Kt * polyw * 4)) || (rc = d_b.alloc(Kt * polyw * 4)) ||
+      (rc = d_e.alloc((size_t)Kt * n * 4)) || (rc = d_src.alloc((size_t)(rows + 1) * n * 4)) || (rc = d_t.alloc(n * 4)))
+    return rc;
+  CK(cudaMemcpyAsync(d_A.u(), h_A, Kt * polyw * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_e.u(), h_e, (size_t)Kt * n * 4, cudaMemcpyHostToDevice, c->stream));
+  if (rows) CK(cudaMemcpyAsync(d_src.u(), h_src, (size_t)rows * n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(d_src.u() + (size_t)rows * n, 0, n * 4, c->stream));
+  CK(cudaMemcpyAsync(d_t.u(), h_t, n * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = keygen_entries(c, Kt, d_A.u(), (const int *)d_e.u(), (const int *)d_src.u(), (const int *)d_t.u(),
+                           d_b.u(), d_An.u())))
+    return rc;
+  size_t off = 0;
+  for (u32 m = 0; m < M; ++m) {
+    out[m] = nullptr;
+    if ((rc = ksw_build_from_device(c, d_b.u() + off * polyw, d_An.u() + off * polyw, parts[m], &out[m]))) {
+      for (u32 k = 0; k < m; ++k) fhesi_ksw_destroy(out[k]), out[k] = nullptr;
+      return rc;
+    }
+    off += (size_t)parts[m] * I.D;
+  }
+  PoolTmp d_pk(c);
+  if (pk_out) {  // publicKey = (c0, c1') (FHE-SI.cpp:59-61)
+    if ((rc = d_pk.alloc(2 * polyw * 4))) return rc;
+    CK(cudaMemcpyAsync(d_pk.u(), d_b.u() + (size_t)Km * polyw, polyw * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_pk.u() + polyw, d_An.u() + (size_t)Km * polyw, polyw * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = key_build_from_device(c, d_pk.u(), 2, pk_out))) return rc;
+    if (h_pk_out) CK(cudaMemcpyAsync(h_pk_out, d_pk.u(), 2 * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (h_b_out && Km) CK(cudaMemcpyAsync(h_b_out, d_b.u(), Km * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (h_A_out && Km) CK(cudaMemcpyAsync(h_A_out, d_An.u(), Km * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // the caller's host buffers are consumed / filled on return
   return 0;
+}
+int fhesi_ksw_generate(fhesi_ctx *c, const int32_t *h_src, const int32_t *h_t, const uint32_t *h_A,
+                       const int32_t *h_e, uint32_t parts, fhesi_ksw **out, uint32_t *h_b_out,
+                       uint32_t *h_A_out) {
+  if (!c || !h_src || !h_t || !h_A || !h_e || !out || parts < 1 || parts > 3)
+    return fail(FHESI_ERR_INVALID, "fhesi_ksw_generate: bad argument");
+  return fhesi_keygen_batch(c, 1, &parts, h_src, h_t, h_A, h_e, out, h_b_out, h_A_out, nullptr, nullptr);
 }
 void fhesi_ksw_destroy(fhesi_ksw *k) {
   if (!k) return;
   cudaSetDevice(k->ctx->device);
-  cudaStreamSynchronize(k->ctx->stream);
-  cudaFree(k->d_key);
-  if (k->d_key_bal) cudaFree(k->d_key_bal);
-  if (k->d_key_split) cudaFree(k->d_key_split);
+  cudaStreamSynchronize(k->ctx->stream);  // (the host pipeline's lane streams are drained by its own call)
+  fhesi_free(k->ctx, k->d_key);
+  if (k->d_key_bal) fhesi_free(k->ctx, k->d_key_bal);
+  if (k->d_key_split) fhesi_free(k->ctx, k->d_key_split);
   delete k;
+}
+static int key_build_from_device(fhesi_ctx *c, const u32 *d_polys, uint32_t parts, fhesi_key **out) {
+  const fhesi_info &I = c->info;
+  DevTmp t_key;
+  PoolTmp t_tmp(c);
+  int rc = t_tmp.alloc((size_t)parts * I.Le * I.N * 4);
+  if (rc) return rc;
+  CK(t_key.alloc((size_t)parts * I.Le * I.N * 4));
+  rc = launch_fwd(c, d_polys, SRC_POLY, I.W, SC_KEYFORM, I.Le, t_tmp.u(), parts);
+  if (rc) return rc;
+  KL(c, k_transpose_key, nblk((size_t)parts * I.Le * I.N), 256, 0, t_tmp.u(), t_key.u(), parts, I.Le, I.N);
+  CKL();
+  *out = new fhesi_key{c, (u32 *)t_key.release(), parts};
+  return 0;
 }
 int fhesi_key_create(fhesi_ctx *c, const uint32_t *h_polys, uint32_t parts, fhesi_key **out) {
   if (!c || !h_polys || !out || parts < 1 || parts > 3)
     return fail(FHESI_ERR_INVALID, "fhesi_key_create: bad argument");
   CK(cudaSetDevice(c->device));
-  const fhesi_info &I = c->info;
-  const size_t polyw = (size_t)I.n * I.W;
-  DevTmp t_key;
-  PoolTmp t_in(c), t_tmp(c);
+  const size_t polyw = (size_t)c->info.n * c->info.W;
+  PoolTmp t_in(c);
   int rc = t_in.alloc(parts * polyw * 4);
-  if (!rc) rc = t_tmp.alloc((size_t)parts * I.Le * I.N * 4);
   if (rc) return rc;
-  CK(t_key.alloc((size_t)parts * I.Le * I.N * 4));
-  u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
-  CK(cudaMemcpyAsync(d_in, h_polys, parts * polyw * 4, cudaMemcpyHostToDevice, c->stream));
-  rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, I.Le, d_tmp, parts);
-  if (rc) return rc;
-  KL(c, k_transpose_key, nblk((size_t)parts * I.Le * I.N), 256, 0, d_tmp, d_key, parts, I.Le, I.N);
-  CKL();
+  CK(cudaMemcpyAsync(t_in.u(), h_polys, parts * polyw * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = key_build_from_device(c, t_in.u(), parts, out))) return rc;
   CK(cudaStreamSynchronize(c->stream));
-  (void)d_key;
-  *out = new fhesi_key{c, (u32 *)t_key.release(), parts};
   return 0;
 }
 void fhesi_key_destroy(fhesi_key *k) {

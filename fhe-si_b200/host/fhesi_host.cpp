@@ -296,19 +296,33 @@ void sampleSmall(ZZX &poly, long n) {  // NumbTh.cpp:361-375
   }
   poly.normalize();
 }
-// Box-Muller as NumbTh.cpp:377-404 draws it: two uniforms per pair of outputs, rounded to nearest
-static void SampleGaussianInts(int32_t *out, long n, double stdev) {
+// Box-Muller as NumbTh.cpp:377-404 draws it: two uniforms per pair of outputs, rounded to nearest.  Split in
+// two so that a caller with many polynomials can take the draws from the (sequential) stream first and do
+// the floating-point part on all cores afterwards: raw holds 2 * ceil(n / 2) uniforms in draw order.
+static void SampleGaussianRaw(uint32_t *raw, long n) {
+  static long const bignum = 0xfffffff;
+  for (long i = 0; i < n; i += 2) {
+    raw[i] = (uint32_t)RandomBnd(bignum);
+    raw[i + 1] = (uint32_t)RandomBnd(bignum);
+  }
+}
+static void GaussianFromRaw(int32_t *out, const uint32_t *raw, long n, double stdev) {
   static double const Pi = 4.0 * atan(1.0);
   static long const bignum = 0xfffffff;
   for (long i = 0; i < n; i += 2) {
-    double r1 = (1 + RandomBnd(bignum)) / ((double)bignum + 1);
-    double r2 = (1 + RandomBnd(bignum)) / ((double)bignum + 1);
+    double r1 = (1 + (long)raw[i]) / ((double)bignum + 1);
+    double r2 = (1 + (long)raw[i + 1]) / ((double)bignum + 1);
     double theta = 2 * Pi * r1;
     double rr = sqrt(-2.0 * std::log(r2)) * stdev;
     assert(rr < 8 * stdev);
     out[i] = (int32_t)floor(rr * cos(theta) + 0.5);
     if (i + 1 < n) out[i + 1] = (int32_t)floor(rr * sin(theta) + 0.5);
   }
+}
+static void SampleGaussianInts(int32_t *out, long n, double stdev) {
+  std::vector<uint32_t> raw((size_t)n + 1);
+  SampleGaussianRaw(raw.data(), n);
+  GaussianFromRaw(out, raw.data(), n, stdev);
 }
 void sampleGaussian(ZZX &poly, long n, double stdev) {  // NumbTh.cpp:377-404
   if (n <= 0) n = deg(poly) + 1;
@@ -1072,23 +1086,70 @@ void FHESISecKey::Decrypt(Plaintext &ptxt, const Ciphertext &ct) const {  // FHE
 void FHESISecKey::Export(ofstream &out) const { ::Export(out, sKeys); }
 void FHESISecKey::Import(ifstream &in) { ::Import(in, sKeys); devKey.reset(); }
 
+// When set, KeySwitchSI::Init only performs its random draws (in the reference's order) and hands them
+// over instead of doing the arithmetic: fhesih_keydraws feeds them to fhesi_ksw_generate on the device.
+struct KeyDrawSink {
+  struct Matrix {
+    vector<ZZX> src, polys, errs;
+    ZZX t;
+  };
+  vector<Matrix> matrices;
+};
+static KeyDrawSink *g_drawSink = nullptr;
+static void SampleRandomWords(uint32_t *dst, unsigned n, unsigned W, unsigned k);
+// every coefficient fits an int32 (s, s^2, s(X^k): yes; an arbitrary imported key: maybe not)
+static bool SmallPoly(std::vector<int32_t> &dst, const ZZX &a, unsigned n) {
+  dst.assign(n, 0);
+  if (deg(a) >= (long)n) return false;
+  for (long i = 0; i <= deg(a); ++i) {
+    const ZZ &c = a.rep.v[i];
+    if (c.mag.size() > 1 || (c.mag.size() == 1 && c.mag[0] > 0x7fffffffu)) return false;
+    dst[i] = (int32_t)to_long(c);
+  }
+  return true;
+}
 void FHESIPubKey::Init(const FHESISecKey &secKey) {  // FHE-SI.cpp:42-62
+  const unsigned n = context.zMstar.phiM(), W = context.Words();
+  ZZX s;
+  secKey.GetRepresentation()[1].toPoly(s);
+  std::vector<int32_t> sv;
+  publicKey.clear();
+  hostWords.clear();
+  devKey.reset();
+  if (g_eagerDevice && !g_drawSink && SmallPoly(sv, s, n)) {
+    // on the device: c0 = e + s * c1 reduced, c1' = Reduce(-c1) -- one key-generation entry with no source
+    // term.  Draw order as the reference: the Gaussian first, then the uniform polynomial (:44-47).
+    std::vector<int32_t> e(n);
+    std::vector<uint32_t> c1((size_t)n * W);
+    SampleGaussianInts(e.data(), n, context.stdev);
+    SampleRandomWords(c1.data(), n, W, context.logQ);
+    hostWords.resize((size_t)2 * n * W);
+    fhesi_key *k = nullptr;
+    Check(fhesi_keygen_batch(context.Dev(), 0, nullptr, nullptr, sv.data(), c1.data(), e.data(), nullptr, nullptr, nullptr,
+                             &k, hostWords.data()),
+          "fhesi_keygen_batch (public key)");
+    devKey = shared_ptr<fhesi_key>(k, [](fhesi_key *p) { fhesi_key_destroy(p); });
+    return;
+  }
   ZZX c0, c1;
   sampleGaussian(c0, context.zMstar.phiM(), context.stdev);
   SampleRandom(c1, context.modulusQ, context.zMstar.phiM());
-  ZZX s;
-  secKey.GetRepresentation()[1].toPoly(s);
   c0 += MulModPhim(s, c1, context.zMstar);
   c1 *= -1;
   ReduceCoefficients(c0, context.logQ);
   ReduceCoefficients(c1, context.logQ);
-  publicKey.clear();
   publicKey.push_back(DoubleCRT(c0, context));
   publicKey.push_back(DoubleCRT(c1, context));
-  devKey.reset();
+}
+void FHESIPubKey::Materialize() const {
+  if (hostWords.empty()) return;
+  const unsigned n = context.zMstar.phiM(), W = context.Words();
+  publicKey.clear();
+  for (int i = 0; i < 2; ++i) publicKey.push_back(DoubleCRT(UnpackPoly(hostWords.data() + (size_t)i * n * W, n, W), context));
+  hostWords.clear();
 }
 void FHESIPubKey::Encrypt(Ciphertext &ctxt, const Plaintext &ptxt) const {  // FHE-SI.cpp:10-36
-  if (!devKey) devKey = UploadKey(context, publicKey);
+  if (!devKey) devKey = UploadKey(context, GetRepresentation());
   fhesi_ctx *d = context.Dev();
   const unsigned n = context.zMstar.phiM();
   // one staging block: message | e0 | e1 | r, one stream-ordered copy, no synchronisation -- the
@@ -1109,19 +1170,9 @@ void FHESIPubKey::Encrypt(Ciphertext &ctxt, const Plaintext &ptxt) const {  // F
                           ctxt.buf->ptr, 1), "fhesi_encrypt_dev");
   ctxt.hostStale = true;
 }
-void FHESIPubKey::Export(ofstream &out) const { ::Export(out, publicKey); }
-void FHESIPubKey::Import(ifstream &in) { ::Import(in, publicKey); devKey.reset(); }
+void FHESIPubKey::Export(ofstream &out) const { ::Export(out, GetRepresentation()); }
+void FHESIPubKey::Import(ifstream &in) { hostWords.clear(); ::Import(in, publicKey); devKey.reset(); }
 
-// When set, KeySwitchSI::Init only performs its random draws (in the reference's order) and hands them
-// over instead of doing the arithmetic: fhesih_keydraws feeds them to fhesi_ksw_generate on the device.
-struct KeyDrawSink {
-  struct Matrix {
-    vector<ZZX> src, polys, errs;
-    ZZX t;
-  };
-  vector<Matrix> matrices;
-};
-static KeyDrawSink *g_drawSink = nullptr;
 void KeySwitchSI::Init(const FHESISecKey &src, const FHESISecKey &dst) {  // FHE-SI.cpp:153-209
   const vector<DoubleCRT> &s = src.GetRepresentation();
   vector<ZZX> sCoeff(s.size());
@@ -1132,6 +1183,10 @@ void KeySwitchSI::Init(const FHESISecKey &src, const FHESISecKey &dst) {  // FHE
   static const bool timing = getenv("FHESIH_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double tt0 = now();
+  keySwitchMatrix.clear();
+  hostB.clear(), drawA.clear();
+  entries = total;
+  if (g_eagerDevice && !g_drawSink && InitOnDevice(sCoeff, t)) return;
   // 1. the random draws, in the reference's order (:176 SampleRandom, :188 sampleGaussian per entry)
   vector<ZZX> polys(total), errs(total);
   for (size_t ind = 0; ind < total; ++ind) {
@@ -1167,6 +1222,50 @@ void KeySwitchSI::Init(const FHESISecKey &src, const FHESISecKey &dst) {  // FHE
   keySwitchMatrix[1] = std::move(A);
   devKsw.reset();
 }
+// The same matrix generated on the device: this class makes the draws (same stream positions and values as
+// the loop above, flat arrays), fhesi_keygen_batch does b = A t + e + s_i 2^(24 j) and the key images.
+bool KeySwitchSI::InitOnDevice(const vector<ZZX> &sCoeff, const ZZX &t) {
+  const unsigned n = context.zMstar.phiM(), W = context.Words(), D = context.ndigits;
+  const size_t parts = sCoeff.size(), K = parts * D;
+  if (parts < 1 || parts > 3) return false;
+  std::vector<int32_t> src(parts * n), tv, one;
+  if (!SmallPoly(tv, t, n)) return false;
+  for (size_t i = 0; i < parts; ++i) {
+    if (!SmallPoly(one, sCoeff[i], n)) return false;
+    memcpy(&src[i * n], one.data(), n * 4);
+  }
+  drawA.resize(K * n * W);
+  hostB.resize(K * n * W);
+  std::vector<int32_t> e(K * n);
+  for (size_t k = 0; k < K; ++k) {  // :176 SampleRandom, :188 sampleGaussian per entry
+    SampleRandomWords(&drawA[k * n * W], n, W, context.logQ);
+    SampleGaussianInts(&e[k * n], n, context.stdev);
+  }
+  fhesi_ksw *k = nullptr;
+  const uint32_t p32 = (uint32_t)parts;
+  Check(fhesi_keygen_batch(context.Dev(), 1, &p32, src.data(), tv.data(), drawA.data(), e.data(), &k, hostB.data(), nullptr,
+                           nullptr, nullptr),
+        "fhesi_keygen_batch");
+  devKsw = shared_ptr<fhesi_ksw>(k, [](fhesi_ksw *p) { fhesi_ksw_destroy(p); });
+  return true;
+}
+// The reference's image of the matrix, when somebody asks: row 0 = b (reduced, as :198), row 1 = A' = -A
+// (NOT reduced: -(-q/2) stays +q/2, :178-180), both as DoubleCRT over the reference chain.
+void KeySwitchSI::Materialize() const {
+  if (hostB.empty()) return;
+  const unsigned n = context.zMstar.phiM(), W = context.Words();
+  vector<DoubleCRT> A(entries, DoubleCRT(context)), b(entries, DoubleCRT(context));
+  ParallelFor(entries, [&](size_t k) {
+    ZZX a = UnpackPoly(drawA.data() + k * n * W, n, W);
+    a *= -1;
+    A[k] = DoubleCRT(a, context);
+    b[k] = DoubleCRT(UnpackPoly(hostB.data() + k * n * W, n, W), context);
+  });
+  keySwitchMatrix.resize(2);
+  keySwitchMatrix[0] = std::move(b);
+  keySwitchMatrix[1] = std::move(A);
+  hostB.clear(), drawA.clear();
+}
 void KeySwitchSI::InitS2(const FHESISecKey &s) {  // FHE-SI.cpp:211-227
   vector<DoubleCRT> sKeys = s.GetRepresentation();
   vector<DoubleCRT> tKeys;
@@ -1186,6 +1285,7 @@ void KeySwitchSI::InitAutomorph(const FHESISecKey &s, unsigned k) {  // FHE-SI.c
 }
 const fhesi_ksw *KeySwitchSI::Dev() const {
   if (!devKsw) {
+    Materialize();
     const unsigned n = context.zMstar.phiM(), W = context.Words();
     std::vector<uint32_t> wb, wA;
     for (int r = 0; r < 2; ++r) {
@@ -1207,7 +1307,7 @@ const fhesi_ksw *KeySwitchSI::Dev() const {
 void KeySwitchSI::ApplyKeySwitch(Ciphertext &ctxt) const {  // FHE-SI.cpp:241-260
   ctxt.ScaleDown();
   ctxt.EnsureReduced();
-  if (keySwitchMatrix.size() != 2 || ctxt.size() * context.ndigits != keySwitchMatrix[0].size())
+  if (!entries || ctxt.size() * context.ndigits != entries)
     Error("ApplyKeySwitch: ciphertext size does not match the key-switch matrix");
   fhesi_ctx *d = context.Dev();
   auto nb = make_shared<DevBuf>(d, fhesi_ct_bytes(d, 2));
@@ -1216,8 +1316,13 @@ void KeySwitchSI::ApplyKeySwitch(Ciphertext &ctxt) const {  // FHE-SI.cpp:241-26
   ctxt.nparts = 2;
   ctxt.hostStale = true;
 }
-void KeySwitchSI::Export(ofstream &out) const { ::Export(out, keySwitchMatrix); }
-void KeySwitchSI::Import(ifstream &in) { ::Import(in, keySwitchMatrix); devKsw.reset(); }
+void KeySwitchSI::Export(ofstream &out) const { ::Export(out, GetRepresentation()); }
+void KeySwitchSI::Import(ifstream &in) {
+  hostB.clear(), drawA.clear();
+  ::Import(in, keySwitchMatrix);
+  entries = keySwitchMatrix.empty() ? 0 : keySwitchMatrix[0].size();
+  devKsw.reset();
+}
 
 // ------------------------------------------------------------------------------- Serialization
 void Export(ofstream &out, const ZZ &val) {  // Serialization.cpp:3-13
@@ -1367,6 +1472,137 @@ extern "C" int fhesih_keygen(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, 
   return 0;
 }
 
+// ---- flat draws: the same stream positions and values as SampleRandom / sampleGaussian, written straight
+// into the arrays the device consumes (no ZZ / ZZX temporaries).
+// SampleRandom(poly, 2^k, n) (Util.cpp:49-56): per coefficient RandomBits(k) - 2^(k-1), as W-word two's
+// complement: subtracting 2^(k-1) mod 2^k flips bit k-1, and the flipped bit is the sign.
+static void SampleRandomWords(uint32_t *dst, unsigned n, unsigned W, unsigned k) {
+  const size_t words64 = (k + 63) / 64, limbs = (k + 31) / 32, top = (k - 1) / 32;
+  const uint32_t topbit = 1u << ((k - 1) % 32);
+  if (limbs != W) Error("SampleRandomWords: word count does not match logQ");
+  std::vector<uint32_t> w(2 * words64);
+  for (unsigned i = 0; i < n; ++i) {
+    for (size_t t = 0; t < words64; ++t) {
+      const uint64_t x = GlobalRandomStream().next64();
+      w[2 * t] = (uint32_t)x, w[2 * t + 1] = (uint32_t)(x >> 32);
+    }
+    if (k % 32) w[limbs - 1] &= (1u << (k % 32)) - 1;
+    w[top] ^= topbit;
+    if (w[top] & topbit) w[top] |= ~(topbit | (topbit - 1));  // sign-extend inside the top word
+    memcpy(dst + (size_t)i * W, w.data(), W * 4);
+  }
+}
+// One KeySwitchSI::Init worth of draws (FHE-SI.cpp:174-189: per entry SampleRandom, then sampleGaussian)
+// raw: [K][n + 1] uniforms of the Gaussians, turned into e by GaussianFromRaw afterwards
+static void DrawMatrixFlat(uint32_t *A, uint32_t *raw, size_t K, unsigned n, unsigned W, unsigned logQ) {
+  for (size_t k = 0; k < K; ++k) {
+    SampleRandomWords(A + k * (size_t)n * W, n, W, logQ);
+    SampleGaussianRaw(raw + k * ((size_t)n + 1), n);
+  }
+}
+// sampleHWt (NumbTh.cpp:340-359) on a plain array: the same draws, the same polynomial
+static void SampleHWtSmall(int32_t *out, long Hwt, long n) {
+  std::fill(out, out + n, 0);
+  if (Hwt > n) Hwt = n;
+  for (long i = 0; i < Hwt;) {
+    const long u = RandomLibc31() % n;
+    if (out[u] == 0) {
+      out[u] = (int32_t)((RandomLibc31() & 2) - 1);
+      i++;
+    }
+  }
+}
+// a * b mod Phi_m and a(X^k) mod Phi_m for small-coefficient polynomials when m = 2h, h odd:
+// X^h = -1 and Phi_m = sum_{i<h} (-X)^i, so the X^(h-1) term folds as w_j = v_j - (-1)^j v_(h-1)
+static void FoldTopSmall(std::vector<int64_t> &v, int32_t *out, unsigned n) {
+  const int64_t top = v[n];
+  for (unsigned j = 0; j < n; ++j) out[j] = (int32_t)((j & 1) ? v[j] + top : v[j] - top);
+}
+static void MulSmallPhim(const int32_t *a, const int32_t *b, int32_t *out, unsigned n) {
+  const unsigned h = n + 1;
+  std::vector<int64_t> v(h, 0);
+  for (unsigned i = 0; i < n; ++i) {
+    if (!a[i]) continue;
+    for (unsigned j = 0; j < n; ++j) {
+      if (!b[j]) continue;
+      const unsigned e = i + j;
+      if (e >= h) v[e - h] -= (int64_t)a[i] * b[j];
+      else v[e] += (int64_t)a[i] * b[j];
+    }
+  }
+  FoldTopSmall(v, out, n);
+}
+static void AutomorphSmallPhim(const int32_t *a, int32_t *out, unsigned n, unsigned m, unsigned k) {
+  const unsigned h = n + 1;
+  std::vector<int64_t> v(h, 0);
+  for (unsigned i = 0; i < n; ++i) {
+    if (!a[i]) continue;
+    unsigned e = (unsigned)(((uint64_t)i * k) % m);
+    if (e >= h) v[e - h] -= a[i];
+    else v[e] += a[i];
+  }
+  FoldTopSmall(v, out, n);
+}
+// The whole set-up's draws in the layout fhesi_keygen_batch consumes: secret key; public key (its Gaussian,
+// then its uniform polynomial: FHE-SI.cpp:44-47) stored as the LAST entry; the s^2 -> s matrix (3 source rows
+// 1, s, s^2) preceded by the throw-away key FHE-SI.cpp:222 samples; one rotation matrix per rot_k (2 source
+// rows 1, s(X^k)), each likewise preceded by its throw-away key (:233).  Same seed => the same keys as the
+// C++ classes (fhesih_keygen) generate.  sk_out int32 [n]; src int32 [3 + 2 n_rot][n];
+// A uint32 [(3 + 2 n_rot) D + 1][n][W]; e int32 [(3 + 2 n_rot) D + 1][n].
+extern "C" int fhesih_keydraws_flat(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, uint32_t decompSize, uint64_t xi,
+                                    uint64_t seed, uint32_t n_rot, const uint32_t *rot_k, int32_t *sk_out, int32_t *src,
+                                    uint32_t *A, int32_t *e) {
+  FHEcontext *saved = activeContext;
+  struct HostOnly {
+    bool was = g_eagerDevice;
+    HostOnly() { g_eagerDevice = false; }
+    ~HostOnly() { g_eagerDevice = was; }
+  } hostOnly;
+  {
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const bool timing = getenv("FHESIH_TIMING") != nullptr;
+    const double T0 = now();
+    FHEcontext context(m, logQ, to_ZZ((unsigned long)p), g, decompSize);
+    activeContext = &context;
+    context.SetUpSIContext((long)xi);
+    const double T1 = now();
+    SetSeed(ZZ((unsigned long)seed));
+    const unsigned n = context.zMstar.phiM(), W = context.Words(), D = context.ndigits;
+    const size_t pw = (size_t)n * W, Km = (size_t)(3 + 2 * n_rot) * D;
+    std::vector<uint32_t> raw((Km + 1) * ((size_t)n + 1));
+    const bool twoh = m % 2 == 0 && (m / 2) % 2 == 1 && n + 1 == m / 2;  // m = 2h, h an odd prime (every device context)
+    if (!twoh) Error("fhesih_keydraws_flat: m must be 2 * (odd prime)");
+    std::vector<int32_t> tmp(n);
+    SampleHWtSmall(sk_out, 64, n);                            // FHESISecKey::Init
+    SampleGaussianRaw(raw.data() + Km * ((size_t)n + 1), n);  // FHESIPubKey::Init: c0's Gaussian ...
+    SampleRandomWords(A + Km * pw, n, W, logQ);               // ... then c1
+    {                                                         // KeySwitchSI(sk): InitS2
+      SampleHWtSmall(tmp.data(), 64, n);                      // the throw-away key of FHE-SI.cpp:222
+      std::fill(src, src + n, 0);
+      src[0] = 1;
+      memcpy(src + n, sk_out, n * 4);
+      MulSmallPhim(sk_out, sk_out, src + 2 * (size_t)n, n);
+      DrawMatrixFlat(A, raw.data(), 3 * (size_t)D, n, W, logQ);
+    }
+    for (uint32_t r = 0; r < n_rot; ++r) {                    // KeySwitchSI(sk, k): InitAutomorph
+      SampleHWtSmall(tmp.data(), 64, n);                      // :233
+      int32_t *rs = src + (3 + 2 * (size_t)r) * n;
+      std::fill(rs, rs + n, 0);
+      rs[0] = 1;                                              // 1(X^k) = 1
+      AutomorphSmallPhim(sk_out, rs + n, n, m, rot_k[r]);
+      const size_t off = (3 + 2 * (size_t)r) * D;
+      DrawMatrixFlat(A + off * pw, raw.data() + off * ((size_t)n + 1), 2 * (size_t)D, n, W, logQ);
+    }
+    const double T2 = now();
+    // the floating-point half of every Gaussian polynomial, on all cores
+    const double stdev = context.stdev;
+    ParallelFor(Km + 1, [&](size_t k) { GaussianFromRaw(e + k * n, raw.data() + k * ((size_t)n + 1), n, stdev); });
+    if (timing) fprintf(stderr, "keydraws_flat: context %.4f  draws %.4f  gaussian math %.4f\n", T1 - T0, T2 - T1, now() - T2);
+  }
+  activeContext = saved;
+  return 0;
+}
+
 // The random draws of fhesih_keygen without the key-switch arithmetic: same objects, same order and
 // number of draws (secret key, public key, s^2 matrix incl. its throw-away key, one rotation matrix per
 // rot_k), with KeySwitchSI::Init diverted into a sink.  The caller passes the draws to
@@ -1385,20 +1621,27 @@ extern "C" int fhesih_keydraws(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g
   } hostOnly;
   KeyDrawSink sink;
   {
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const bool timing = getenv("FHESIH_TIMING") != nullptr;
+    const double T0 = now();
     FHEcontext context(m, logQ, to_ZZ((unsigned long)p), g, decompSize);
     activeContext = &context;
+    const double T1 = now();
     context.SetUpSIContext((long)xi);
+    const double T2 = now();
     SetSeed(ZZ((unsigned long)seed));
     const unsigned n = context.zMstar.phiM(), W = context.Words(), D = context.ndigits;
     const size_t pw = (size_t)n * W;
     FHESISecKey sk(context);
     FHESIPubKey pk(sk);
+    const double T3 = now();
     g_drawSink = &sink;
     KeySwitchSI ks(sk);
     for (uint32_t r = 0; r < n_rot; ++r) KeySwitchSI rk(sk, rot_k[r]);
     g_drawSink = nullptr;
+    if (timing) fprintf(stderr, "keydraws: context %.4f setup %.4f sk+pk %.4f matrices %.4f\n", T1 - T0, T2 - T1, T3 - T2, now() - T3);
     auto small = [&](int32_t *dst, const ZZX &a) {
-      for (unsigned i = 0; i < n; ++i) dst[i] = i <= (unsigned)deg(a) ? (int32_t)to_long(a.rep.v[i]) : 0;
+      for (long i = 0; i < (long)n; ++i) dst[i] = i <= deg(a) ? (int32_t)to_long(a.rep.v[i]) : 0;
     };
     ZZX s;
     sk.GetRepresentation()[1].toPoly(s);

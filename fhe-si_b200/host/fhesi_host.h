@@ -463,8 +463,12 @@ class FHESISecKey {
 class FHESIPubKey {
   friend class Ciphertext;
   const FHEcontext &context;
-  vector<DoubleCRT> publicKey;
+  // Generated on the device (Init); the host image is made from the downloaded words only when a
+  // caller asks for it (GetRepresentation, Export, operator<<)
+  mutable vector<DoubleCRT> publicKey;
+  mutable std::vector<uint32_t> hostWords;  // [2][n][W], pending materialisation when non-empty
   mutable shared_ptr<fhesi_key> devKey;
+  void Materialize() const;
 
  public:
   FHESIPubKey(const FHEcontext &context) : context(context) {}
@@ -473,11 +477,12 @@ class FHESIPubKey {
   void Encrypt(Ciphertext &ctxt, const Plaintext &ptxt) const;
   void Init(const FHESISecKey &secKey);
   const FHEcontext &GetContext() const { return context; }
-  const vector<DoubleCRT> &GetRepresentation() const { return publicKey; }
-  void UpdateRepresentation(const vector<DoubleCRT> &rep) { publicKey = rep; devKey.reset(); }
+  const vector<DoubleCRT> &GetRepresentation() const { Materialize(); return publicKey; }
+  void UpdateRepresentation(const vector<DoubleCRT> &rep) { publicKey = rep; hostWords.clear(); devKey.reset(); }
   void Export(ofstream &out) const;
   void Import(ifstream &in);
   friend ostream &operator<<(ostream &os, const FHESIPubKey &k) {
+    k.Materialize();
     return os << k.publicKey[0] << ", " << k.publicKey[1];
   }
 };
@@ -496,23 +501,32 @@ class KeySwitchSI {
   KeySwitchSI(const FHESISecKey &s, const FHEcontext &context, unsigned k) : context(context) {
     InitAutomorph(s, k);
   }
-  KeySwitchSI(const KeySwitchSI &o) : context(o.context), keySwitchMatrix(o.keySwitchMatrix), devKsw(o.devKsw) {}
+  KeySwitchSI(const KeySwitchSI &o)
+      : context(o.context), keySwitchMatrix(o.keySwitchMatrix), hostB(o.hostB), drawA(o.drawA), entries(o.entries),
+        devKsw(o.devKsw) {}
 
   void Init(const FHESISecKey &src, const FHESISecKey &dst);
   void InitS2(const FHESISecKey &s);
   void InitAutomorph(const FHESISecKey &s, unsigned k);
   void ApplyKeySwitch(Ciphertext &ctxt) const;
-  const vector<vector<DoubleCRT>> &GetRepresentation() const { return keySwitchMatrix; }
-  void UpdateRepresentation(const vector<vector<DoubleCRT>> &rep) { keySwitchMatrix = rep; devKsw.reset(); }
+  const vector<vector<DoubleCRT>> &GetRepresentation() const { Materialize(); return keySwitchMatrix; }
+  void UpdateRepresentation(const vector<vector<DoubleCRT>> &rep) {
+    keySwitchMatrix = rep;
+    hostB.clear(), drawA.clear();
+    entries = rep.empty() ? 0 : rep[0].size();
+    devKsw.reset();
+  }
   void Export(ofstream &out) const;
   void Import(ifstream &in);
   KeySwitchSI &operator=(const KeySwitchSI &other) {
     if (&context != &other.context) Error("KeySwitchSI assignment: context mismatch");
     keySwitchMatrix = other.keySwitchMatrix;
+    hostB = other.hostB, drawA = other.drawA, entries = other.entries;
     devKsw = other.devKsw;
     return *this;
   }
   friend ostream &operator<<(ostream &os, const KeySwitchSI &k) {
+    k.Materialize();
     PrintVector(k.keySwitchMatrix, os);
     return os;
   }
@@ -521,8 +535,15 @@ class KeySwitchSI {
 
  private:
   const FHEcontext &context;
-  vector<vector<DoubleCRT>> keySwitchMatrix;
+  // Init generates the matrix on the device (fhesi_keygen_batch) from this class's draws; b comes back as
+  // words, A' = -A is known from the draws.  The vector<DoubleCRT> image the reference exposes is built from
+  // them only on demand (GetRepresentation, Export, operator<<) -- ApplyKeySwitch never needs it.
+  mutable vector<vector<DoubleCRT>> keySwitchMatrix;
+  mutable std::vector<uint32_t> hostB, drawA;  // [entries][n][W] each, pending materialisation when non-empty
+  size_t entries = 0;                           // source parts * ndigits
   mutable shared_ptr<fhesi_ksw> devKsw;
+  void Materialize() const;
+  bool InitOnDevice(const vector<ZZX> &sCoeff, const ZZX &t);
 };
 
 // ------------------------------------------------------------------------------- Serialization.h

@@ -51,6 +51,7 @@ SYMBOLS = {
     "fhesi_tprod_bytes": (_SZ, [_P, _U32]),
     "fhesi_ksw_create": (C.c_int, [_P, _P, _P, _U32, C.POINTER(_P)]),
     "fhesi_ksw_generate": (C.c_int, [_P, _P, _P, _P, _P, _U32, C.POINTER(_P), _P, _P]),
+    "fhesi_keygen_batch": (C.c_int, [_P, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fhesi_ksw_destroy": (None, [_P]),
     "fhesi_key_create": (C.c_int, [_P, _P, _U32, C.POINTER(_P)]),
     "fhesi_key_destroy": (None, [_P]),
@@ -223,6 +224,34 @@ class Context:
                                              parts, C.byref(k), b_out.ctypes.data if want_host else None,
                                              a_out.ctypes.data if want_host else None))
         return (k.value, b_out, a_out) if want_host else k.value
+
+    def keygen_batch(self, parts, src, t, A, e, with_pk=True, want_host=False):
+        """All key-switch matrices of a set-up and (with_pk) the public key in one pass of kernels
+        (fhesi_keygen_batch).  parts: list of source-part counts, one per matrix; src int32 [sum parts][n];
+        t int32 [n]; A uint32 [sum parts*D (+1)][n][W]; e int32 [sum parts*D (+1)][n] -- the public key's
+        c1 / e last.  -> (list of ksw handles, pk handle or None[, b, A', pk words])."""
+        parts = np.ascontiguousarray(parts, dtype=np.uint32)
+        src = np.ascontiguousarray(src, dtype=np.int32).reshape(-1, self.n)
+        t = np.ascontiguousarray(t, dtype=np.int32)
+        A = np.ascontiguousarray(A, dtype=np.uint32)
+        e = np.ascontiguousarray(e, dtype=np.int32)
+        M, rows = len(parts), int(parts.sum())
+        Kt = rows * self.D + (1 if with_pk else 0)
+        assert src.shape[0] == rows and t.shape == (self.n,)
+        assert A.shape == (Kt, self.n, self.W) and e.shape == (Kt, self.n), (A.shape, e.shape, Kt)
+        outs = (_P * max(M, 1))()
+        pk = _P()
+        b_out = np.empty((rows * self.D, self.n, self.W), np.uint32) if want_host else None
+        a_out = np.empty_like(b_out) if want_host else None
+        pk_out = np.empty((2, self.n, self.W), np.uint32) if (want_host and with_pk) else None
+        self._ck(self.lib.fhesi_keygen_batch(
+            self.h, M, parts.ctypes.data if M else None, src.ctypes.data if rows else None, t.ctypes.data,
+            A.ctypes.data, e.ctypes.data, C.cast(outs, _P) if M else None, _ptr(b_out), _ptr(a_out),
+            C.cast(C.pointer(pk), _P) if with_pk else None, _ptr(pk_out)))
+        ksws = [outs[i] for i in range(M)]
+        if want_host:
+            return ksws, (pk.value if with_pk else None), b_out, a_out, pk_out
+        return ksws, (pk.value if with_pk else None)
 
     def key_create(self, polys: np.ndarray) -> int:
         polys = np.ascontiguousarray(polys, dtype=np.uint32)

@@ -81,15 +81,43 @@ def keydraws(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
     return out
 
 
-def device_keys(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
-    """Keys for a device context with the key-switch matrices generated ON the device
-    (fhesi_ksw_generate) from host draws: -> (ksw, [rotation ksw ...], pk handle, sk handle).  Same keys
-    as keygen() + ksw_create for the same seed."""
-    d = keydraws(ctx, seed, g, rot_k, lib_path)
-    n, W = ctx.n, ctx.W
-    ksw = ctx.ksw_generate(d["s2_src"], d["sk"], d["s2_A"], d["s2_e"])
-    rot = [ctx.ksw_generate(d["rot_src"][r], d["sk"], d["rot_A"][r], d["rot_e"][r]) for r in range(len(list(rot_k)))]
-    skw = np.zeros((2, n, W), np.uint32)
+def keydraws_flat(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
+    """The draws of keygen() (same stream, same order) written straight into the arrays
+    Context.keygen_batch consumes: dict(parts [M], sk int32 [n], src int32 [3 + 2R][n],
+    A uint32 [(3 + 2R) D + 1][n][W], e int32 [(3 + 2R) D + 1][n]); the public key's c1 / e are the last entry."""
+    from . import DEFAULT_LIB
+    lib = _host_lib(lib_path or DEFAULT_LIB)
+    i = ctx.info
+    n, W, D = ctx.n, ctx.W, ctx.D
+    rot = np.asarray(list(rot_k), dtype=np.uint32)
+    R = len(rot)
+    Kt = (3 + 2 * R) * D + 1
+    out = {"parts": np.array([3] + [2] * R, np.uint32), "sk": np.empty(n, np.int32),
+           "src": np.empty((3 + 2 * R, n), np.int32), "A": np.empty((Kt, n, W), np.uint32),
+           "e": np.empty((Kt, n), np.int32)}
+    fn = lib.fhesih_keydraws_flat
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32] + \
+        [C.c_void_p] * 5
+    rc = fn(i.m, i.logQ, i.p, g, i.decompSize, i.xi, seed, R, rot.ctypes.data if R else None,
+            out["sk"].ctypes.data, out["src"].ctypes.data, out["A"].ctypes.data, out["e"].ctypes.data)
+    if rc:
+        raise RuntimeError(f"fhesih_keydraws_flat failed ({rc})")
+    return out
+
+
+def sk_words(ctx, sk: np.ndarray) -> np.ndarray:
+    """The secret key (1, s) in `poly` format for Context.key_create."""
+    skw = np.zeros((2, ctx.n, ctx.W), np.uint32)
     skw[0, 0, 0] = 1                                             # sKeys[0] = 1
-    skw[1] = (d["sk"].astype(np.int64)[:, None] >> (32 * np.arange(W))[None, :]).astype(np.uint32)  # sign-extended
-    return ksw, rot, ctx.key_create(d["pk"]), ctx.key_create(skw)
+    skw[1] = (sk.astype(np.int64)[:, None] >> (32 * np.arange(ctx.W))[None, :]).astype(np.uint32)  # sign-extended
+    return skw
+
+
+def device_keys(ctx, seed: int, g: int, rot_k=(), lib_path: str | None = None):
+    """Keys for a device context generated ON the device in one pass (fhesi_keygen_batch) from host
+    draws: -> (ksw, [rotation ksw ...], pk handle, sk handle).  Same keys as keygen() + ksw_create /
+    key_create for the same seed."""
+    d = keydraws_flat(ctx, seed, g, rot_k, lib_path)
+    ksws, pk = ctx.keygen_batch(d["parts"], d["src"], d["sk"], d["A"], d["e"], with_pk=True)
+    return ksws[0], ksws[1:], pk, ctx.key_create(sk_words(ctx, d["sk"]))

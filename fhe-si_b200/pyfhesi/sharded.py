@@ -39,9 +39,29 @@ def sharded_tensor_sum(ctx, a: torch.Tensor, b: torch.Tensor, parts_a: int = 2, 
     ctx.sync()
     if world == 1:
         return local
-    gathered = torch.empty((world, po, ctx.Lt, ctx.N), dtype=torch.int32, device=a.device)
-    dist.all_gather([gathered[w] for w in range(world)], local, group=group)  # NCCL / gloo
+    return allgather_add(ctx, local, po, group)
+
+
+def allgather_add(ctx, local: torch.Tensor, parts: int, group=None) -> torch.Tensor:
+    """The exchange step on its own: all-gather every rank's `local` partial sums (tprod form, any
+    leading shape, `parts` * count polynomials of Lt x N words in all) and add them mod p_i.
+
+    Stream discipline: the caller's kernels ran on the context's stream, the collective runs on
+    torch's current stream, the combine kernel on the context's stream again -- which may all be
+    different streams (a Context owns a non-blocking stream unless set_stream() was called).  Both
+    hand-overs are made explicit here: ctx.sync() before the collective, and a synchronise of torch's
+    current stream after it, so the combine never reads `gathered` early."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    ctx.sync()
+    gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)  # one ncclAllGather
+        torch.cuda.current_stream(local.device).synchronize()
+    else:
+        dist.all_gather([gathered[w] for w in range(world)], local, group=group)  # gloo (CPU tests)
     out = torch.empty_like(local)
-    ctx.tprod_reduce_gathered_dev(gathered, world, po, out)
+    ctx.tprod_reduce_gathered_dev(gathered, world, parts, out)
     ctx.sync()
     return out

@@ -110,6 +110,17 @@ int fhesi_ksw_create(fhesi_ctx *ctx, const uint32_t *h_b, const uint32_t *h_A, u
 int fhesi_ksw_generate(fhesi_ctx *ctx, const int32_t *h_src, const int32_t *h_t, const uint32_t *h_A,
                        const int32_t *h_e, uint32_t parts, fhesi_ksw **out, uint32_t *h_b_out,
                        uint32_t *h_A_out);
+/* The whole set-up of a client in one pass of kernels (Regression.h:68-81: `secretKey, publicKey(secretKey),
+ * keySwitch(secretKey)` and one KeySwitchSI(secretKey, k) per rotation): M key-switch matrices, matrix m with
+ * parts[m] source polynomials, and -- when pk_out is non-NULL -- FHESIPubKey::Init (FHE-SI.cpp:42-62), which is
+ * one more entry of the same shape with no source term: c0 = e + s * c1 reduced, c1' = Reduce(-c1).
+ * Draws are concatenated in matrix order: h_src int32 [sum parts][n]; h_A uint32 [sum parts*D (+1)][n][W]; h_e
+ * int32 [sum parts*D (+1)][n]; the public key's c1 and e are the LAST entry of h_A / h_e.  h_t: the secret key s.
+ * out[M] receives the matrices; h_b_out / h_A_out (nullable, [sum parts*D][n][W]) b and A'; h_pk_out (nullable,
+ * [2][n][W]) the public key polynomials.  M = 0 with pk_out generates only the public key. */
+int fhesi_keygen_batch(fhesi_ctx *ctx, uint32_t M, const uint32_t *parts, const int32_t *h_src, const int32_t *h_t,
+                       const uint32_t *h_A, const int32_t *h_e, fhesi_ksw **out, uint32_t *h_b_out,
+                       uint32_t *h_A_out, fhesi_key **pk_out, uint32_t *h_pk_out);
 void fhesi_ksw_destroy(fhesi_ksw *ksw);
 int fhesi_key_create(fhesi_ctx *ctx, const uint32_t *h_polys, uint32_t parts, fhesi_key **out);
 void fhesi_key_destroy(fhesi_key *key);

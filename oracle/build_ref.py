@@ -8,6 +8,9 @@ Outputs (git-ignored, they travel to the GPU box with the snapshot):
                                   and objects: writes the byte files the golden vectors are made of
   oracle/_ref/Test_AddMul_ref     the reference's own test program
   oracle/_ref/ref_bench           oracle/ref_bench.cpp: times c *= b; ApplyKeySwitch(c)
+  oracle/_ref/Test_Regression_ref the reference's own Test_Regression.cpp
+  oracle/_ref/ref_regression      oracle/ref_regression.cpp: Regression.h's phases with explicit (logQ, xi) and a
+                                  block limit -- the CPU baseline of the regression wall-time metric
   oracle/_ref/api_probe_ref       tests/cpp/api_probe.cpp (every client-facing symbol of SURVEY.md §8b)
 
 What is and is not the reference here: DoubleCRT, Cmodulus/Bluestein, Ciphertext, FHE-SI (keys,
@@ -33,6 +36,9 @@ PROGRAMS = {
     "golden_client_ref": os.path.join(ROOT, "tests", "cpp", "host_client.cpp"),
     "ref_bench": os.path.join(HERE, "ref_bench.cpp"),
     "Test_AddMul_ref": os.path.join(REF, "Test_AddMul.cpp"),
+    # the reference's own regression driver, unchanged, and our parameterised driver over its Regression.h
+    "Test_Regression_ref": os.path.join(REF, "Test_Regression.cpp"),
+    "ref_regression": os.path.join(HERE, "ref_regression.cpp"),
     # tests/cpp/api_probe.cpp against the reference itself: proves the probe only uses real reference API
     "api_probe_ref": os.path.join(ROOT, "tests", "cpp", "api_probe.cpp"),
 }

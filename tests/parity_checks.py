@@ -488,3 +488,37 @@ def check_edge_cases(sc: Scenario, counts=(0, 1, 7)):
         got = sc.dev_mult_relin(X, Y)
         for i in (0, cnt - 1):
             assert_ct_equal(sc, got[i], O.mult_relin(sc.ks, X[i], Y[i]), f"count={cnt} [{i}]")
+
+
+def check_keygen_batch(lib, cfg, xi, rot, seed=5):
+    """keydraws_flat + Context.keygen_batch (one pass of kernels for every matrix and the public key) give
+    byte for byte what the C++ classes compute on the host (keygen(): FHESIPubKey::Init, KeySwitchSI::Init)."""
+    import numpy as np
+    import pyfhesi
+    from pyfhesi.hostkeys import keydraws, keydraws_flat, keygen
+    logq, p, g = cfg
+    dev = pyfhesi.Context(p - 1, logq, p, 3, xi, 0, lib_path=lib)
+    k = keygen(dev, seed, g, rot_k=rot, lib_path=lib)
+    f = keydraws_flat(dev, seed, g, rot_k=rot, lib_path=lib)
+    d = keydraws(dev, seed, g, rot_k=rot, lib_path=lib)
+    D = dev.D
+    # the flat draws are the ZZX draws
+    assert np.array_equal(f["sk"], d["sk"]) and np.array_equal(f["src"][:3], d["s2_src"])
+    assert np.array_equal(f["A"][:3 * D], d["s2_A"]) and np.array_equal(f["e"][:3 * D], d["s2_e"])
+    for r in range(len(rot)):
+        o = (3 + 2 * r) * D
+        assert np.array_equal(f["src"][3 + 2 * r:5 + 2 * r], d["rot_src"][r])
+        assert np.array_equal(f["A"][o:o + 2 * D], d["rot_A"][r]) and np.array_equal(f["e"][o:o + 2 * D], d["rot_e"][r])
+    ksws, pk, b, a, pkw = dev.keygen_batch(f["parts"], f["src"], f["sk"], f["A"], f["e"], with_pk=True, want_host=True)
+    assert len(ksws) == 1 + len(rot) and pk
+    assert np.array_equal(pkw, k["pk"]), "public key generated on the device differs from FHESIPubKey::Init"
+    assert np.array_equal(b[:3 * D], k["ks_b"]) and np.array_equal(a[:3 * D], k["ks_A"])
+    for r in range(len(rot)):
+        o = (3 + 2 * r) * D
+        assert np.array_equal(b[o:o + 2 * D], k["rot_b"][r]) and np.array_equal(a[o:o + 2 * D], k["rot_A"][r])
+    # public key alone
+    _, pk2, _, _, pkw2 = dev.keygen_batch([], np.zeros((0, dev.n), np.int32), f["sk"], f["A"][-1:], f["e"][-1:],
+                                          with_pk=True, want_host=True)
+    assert pk2 and np.array_equal(pkw2, k["pk"])
+
+

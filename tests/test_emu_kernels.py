@@ -42,6 +42,10 @@ def test_emu_ksw_generate_cfg1(sc1):
     P.check_ksw_generate(sc1, 7)
 
 
+def test_emu_keygen_batch_cfg1(emu_lib):
+    P.check_keygen_batch(emu_lib, CONFIGS["cfg1"], 4, [7, 5])
+
+
 def test_emu_embed_slots_cfg1(sc1):
     P.check_embed_slots(sc1, 7)
 

@@ -35,6 +35,22 @@ def test_sharded_regression_world2_emu(emu_lib):
     assert out["theta_det"] == out["expected"]
 
 
+def test_sharded_regression_from_shard_files_world2_emu(emu_lib, tmp_path):
+    """README:82-84: the data split into files by the generator; each rank takes whole files and cuts
+    each into its own blocks (3 files of 17, 17, 16 points, blocks of 8 -> 3 + 3 + 2 blocks, the last of each file ragged or full;
+    the same 50 points as one set make 7 blocks)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from generate_random_data import main
+    assert main(["x", str(tmp_path / "reg"), "2", "50", "3", "--seed", "5"]) == 0
+    out = run_app(["--data", str(tmp_path / "reg"), "--prime", "23", "--gen", "7", "--lib", emu_lib, "--cpu-tensors"], 2)
+    assert out["correct"] and out["n_gpus"] == 2 and out["config"]["blocks"] == 8, out
+    assert out["theta_det"] == out["expected"] and "3 shard files" in out["config"]["input"]
+    # the same data as one in-process set: same answer (the sums do not depend on the blocking)
+    one = run_app(["--dim", "2", "--points", "50", "--seed", "5", "--prime", "23", "--gen", "7", "--lib", emu_lib,
+                   "--cpu-tensors"], 1)
+    assert one["theta_det"] == out["theta_det"] and one["config"]["blocks"] == 7
+
+
 def test_sharded_statistics_world2_emu(emu_lib):
     """BASELINE config 3 at toy size: encrypted mean / covariance over 2 gloo ranks."""
     out = run_app(["--dim", "2", "--points", "20", "--prime", "23", "--gen", "7", "--lib", emu_lib, "--cpu-tensors"],
@@ -66,3 +82,18 @@ def test_statistics_cfg3_gpu(cuda_lib):
 def test_regression_cfg_small_gpu(cuda_lib):
     out = run_app(["--dim", "3", "--points", "2000"], 1, 29700 + os.getpid() % 200)
     assert out["correct"], out
+
+
+@pytest.mark.gpu
+def test_regression_cfg4_full_size_gpu(cuda_lib, tmp_path):
+    """BASELINE config 4 at full size: d=4, N=100000 (seed 12345) split into 8 files, p=1019, g=3; parameters
+    from the global N (logQ=176).  theta*det and det are the values the reference's RegressPT gives mod 1019
+    (also what oracle/_ref's own Regression.h decrypts on a prefix of the data, tests/golden)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from generate_random_data import main
+    assert main(["x", str(tmp_path / "reg4"), "4", "100000", "8"]) == 0
+    out = run_app(["--data", str(tmp_path / "reg4")], 1)
+    assert out["correct"] and out["config"]["logQ"] == 176 and out["config"]["blocks"] == 392, out
+    assert out["theta_det"] == [15, 282, 867, 160, 436], out
+    gen = run_app(["--dim", "4", "--points", "100000"], 1)
+    assert gen["theta_det"] == [15, 282, 867, 160, 436] and gen["config"]["blocks"] == 391, gen

@@ -29,3 +29,9 @@ def test_device_keys_equal_host_keys(cuda_lib):
     for r in range(2):
         h, b, a = dev.ksw_generate(d["rot_src"][r], d["sk"], d["rot_A"][r], d["rot_e"][r], want_host=True)
         assert np.array_equal(b, k["rot_b"][r]) and np.array_equal(a, k["rot_A"][r])
+
+
+@pytest.mark.gpu
+def test_keygen_batch_equals_host_keys_gpu(cuda_lib):
+    P.check_keygen_batch(cuda_lib, CONFIGS["cfg4"], 391, [3, 9, 81])
+    P.check_keygen_batch(cuda_lib, CONFIGS["cfg2"], 1, [3])
