@@ -560,7 +560,8 @@ def run_ours(args, rank, local_rank, world):
         peak32 = 1.0 / shoup_cost  # Shoup products per second when nothing else shares the pipe
         work_all = kernel_pipe_work_per_op(dev)
         pipe_s = lambda w: w["lo"] * cost["lo"] + w["hi"] * cost["hi"] + w["wide"] * cost["wide"]
-        work = {k: work_all[k.split("<")[0]] for k in prof if k.split("<")[0] in work_all}
+        base = lambda k: {"k_residues_t": "k_residues"}.get(k.split("<")[0], k.split("<")[0])  # template instances
+        work = {k: work_all[base(k)] for k in prof if base(k) in work_all}
         top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
         tname, (tcnt, tms) = top
         share = tms / max(sum(v[1] for v in prof.values()), 1e-9)
@@ -571,7 +572,7 @@ def run_ours(args, rank, local_rank, world):
         achieved = eq_per_launch / max(avg_launch_s, 1e-12)
         canon = CANON_MODMUL[logq]
         step_pipe_s = sum(pipe_s(w) for w in work.values())
-        traffic = kernel_compulsory_bytes_per_op(dev).get((tname or "").split("<")[0])
+        traffic = kernel_compulsory_bytes_per_op(dev).get(base(tname or ""))
         roofline = {
             "bound": "integer-multiply (FMA-heavy) pipe; SURVEY.md §8d -- HBM does not bind",
             "kernel": tname, "kernel_share_of_step": share,
@@ -606,7 +607,7 @@ def run_ours(args, rank, local_rank, world):
                     "achieved_GBs": (value / world) * algorithmic_bytes_per_op(n, logq) / 1e9,
                     "peak_GBs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "frac": (value / world) * algorithmic_bytes_per_op(n, logq) / 1e9 / hbm_peak,
-                    "compulsory_bytes_per_op_all_kernels": sum(kernel_compulsory_bytes_per_op(dev).get(k.split("<")[0], 0)
+                    "compulsory_bytes_per_op_all_kernels": sum(kernel_compulsory_bytes_per_op(dev).get(base(k), 0)
                                                                for k in prof)},
             "per_kernel_ms": {k: {"launches": v[0], "ms": v[1],
                                   "pipe_frac": (pipe_s(work[k]) * ops_timed / (v[1] * 1e-3)) if k in work and v[1] > 0 else None}

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -260,6 +261,7 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   std::vector<PrimeConst> pc(L);
   std::vector<u32> twf((size_t)L * N), twi((size_t)L * N), cw((size_t)L * CW), gar((size_t)L * L, 0);
   std::vector<uint2> twsf((size_t)L * N), twsi((size_t)L * N);
+  std::vector<double2> twdf((size_t)L * N);
   std::vector<u32> cwr((size_t)L * 2 * CW);
   // floor(2^logQ / p_pt) mod q needs 2^logQ mod p_pt
   const u64 rem_q = h_powmod(2, logQ, p_pt);
@@ -271,6 +273,9 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
     u32 inv = 1;  // Newton: inv = q^-1 mod 2^32
     for (int it = 0; it < 5; ++it) inv *= 2 - (u32)q * inv;
     P.pinv = (u32)(0 - inv);
+    P.negp = 0u - (u32)q;
+    P.hic = 0x43300000u;
+    P.zop = 0u;
     const u64 R = (1ull << 32) % q, R2 = h_mulmod(R, R, q);
     const u64 ninv = h_invmod(N % q, q);
     P.r1 = (u32)R; P.r2 = (u32)R2;
@@ -293,6 +298,10 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
         twi[(size_t)l * N + hh + j] = (u32)b;
         const u64 ap = h_mulmod(a, h_invmod(R, q), q), bp = h_mulmod(b, h_invmod(R, q), q);  // plain
         twsf[(size_t)l * N + hh + j] = make_uint2((u32)ap, (u32)((ap << 32) / q));
+        {
+          const u64 kq = (u64)(((unsigned __int128)ap << 50) / q);  // < 2^50
+          twdf[(size_t)l * N + hh + j] = make_double2(std::ldexp((double)kq, -50), 4503599627370496.0 - 4.0 * (double)kq);
+        }
         twsi[(size_t)l * N + hh + j] = make_uint2((u32)bp, (u32)((bp << 32) / q));
         a = h_mulmod(a, step, q);
         b = h_mulmod(b, istep, q);
@@ -305,6 +314,10 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
       t = h_mulmod(t, R, q);
     }
     twsf[(size_t)l * N] = twsi[(size_t)l * N] = make_uint2(1u, (u32)((1ull << 32) / q));
+    {
+      const u64 kq = (u64)(((unsigned __int128)1 << 50) / q);
+      twdf[(size_t)l * N] = make_double2(std::ldexp((double)kq, -50), 4503599627370496.0 - 4.0 * (double)kq);
+    }
     for (u32 v = 0; v < 2; ++v) {
       const u64 sv = v ? h_mulmod(h_mulmod(p_pt % q, ninv, q), R, q) : 1;
       u64 c2 = h_mulmod(R, sv, q);  // 2^(32k) * R * s_v
@@ -354,7 +367,7 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
       (rc = upload(c, twi, &dc.tw_inv)) || (rc = upload(c, cw, &dc.cword)) ||
       (rc = upload(c, gar, &dc.garner)) || (rc = upload(c, Pf, &dc.Pfull)) ||
       (rc = upload(c, Ph, &dc.Phalf)) || (rc = upload(c, twsf, &dc.tws_fwd)) ||
-      (rc = upload(c, twsi, &dc.tws_inv)) || (rc = upload(c, cwr, &dc.cwr))) {
+      (rc = upload(c, twsi, &dc.tws_inv)) || (rc = upload(c, cwr, &dc.cwr)) || (rc = upload(c, twdf, &dc.twd_fwd))) {
     fhesi_ctx_destroy(c);
     return rc;
   }
@@ -398,6 +411,9 @@ void fhesi_ctx_destroy(fhesi_ctx *c) {
   for (void *p : c->tables) cudaFree(p);
   for (auto &kv : c->pool_free)
     for (void *p : kv.second) cudaFree(p);
+  // blocks still handed out (a caller's buffers, key images whose handle was never destroyed) die with
+  // the context they were allocated from
+  for (auto &kv : c->pool_size) cudaFree(kv.first);
   if (c->scratch.ptr) cudaFree(c->scratch.ptr);
   if (c->lane_scratch.ptr) cudaFree(c->lane_scratch.ptr);
   if (c->stage.ptr) cudaFree(c->stage.ptr);
@@ -577,7 +593,8 @@ static void launch_crt_split_t(fhesi_ctx *c, const CrtSplitArgs &a) {
 static int launch_crt_split(fhesi_ctx *c, const u32 *res, u32 L, u32 *out, size_t npolys) {
   if (!npolys) return 0;
   CrtSplitArgs a{res, L, c->info.split_words, out, npolys * c->dc.n};
-  if (L <= 8) launch_crt_split_t<8>(c, a);
+  if (L <= 6) launch_crt_split_t<6>(c, a);  // exact sizes for the common chains: no dead words in the Horner rows
+  else if (L <= 8) launch_crt_split_t<8>(c, a);
   else if (L <= 12) launch_crt_split_t<12>(c, a);
   else if (L <= 20) launch_crt_split_t<20>(c, a);
   else return fail(FHESI_ERR_UNSUPPORTED, "split CRT: too many primes");
@@ -591,7 +608,9 @@ static int launch_crt(fhesi_ctx *c, const u32 *res, u32 L, u32 mode, u32 *out, u
   // DECRYPT multiplies by p_pt before the shift: two words of head-room
   u32 need = L + (mode == CRT_DECRYPT ? 2 : 0);
   if (need <= 8) launch_crt_t<8>(c, a);
-  else if (need <= 12) launch_crt_t<12>(c, a);
+  else if (need <= 10) launch_crt_t<10>(c, a);
+  else if (need <= 13) launch_crt_t<13>(c, a);
+  else if (need <= 18) launch_crt_t<18>(c, a);
   else if (need <= 20) launch_crt_t<20>(c, a);
   else if (need <= 28) launch_crt_t<28>(c, a);
   else if (need <= 36) launch_crt_t<36>(c, a);
@@ -606,7 +625,15 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
                                int to_tprod) {
   const fhesi_info &I = c->info;
   ResidueArgs r{a, b, resid, I.Lt, cnt};
-  KL(c, k_residues, nblk(cnt * 4 * I.n, 128), 128, (I.Lt * 2 * c->dc.CW + 2 * I.Lt) * 4, c->dc, r);
+  const unsigned rg = nblk(cnt * 4 * I.n, 128);
+  const size_t rsm = [&](u32 row) { return (size_t)(I.Lt * 2 * row + 2 * I.Lt) * 4; }((I.W + 1 + 3) & ~3u);
+  switch (I.W) {  // word count as a compile-time constant for the common moduli (logQ = 128, 176, 256, 512)
+    case 4: KL(c, k_residues_t<4>, rg, 128, rsm, c->dc, r); break;
+    case 6: KL(c, k_residues_t<6>, rg, 128, rsm, c->dc, r); break;
+    case 8: KL(c, k_residues_t<8>, rg, 128, rsm, c->dc, r); break;
+    case 16: KL(c, k_residues_t<16>, rg, 128, rsm, c->dc, r); break;
+    default: KL(c, k_residues, rg, 128, (I.Lt * 2 * c->dc.CW + 2 * I.Lt) * 4, c->dc, r);
+  }
   CKL();
   // ops per group: more of them amortise the CTA's twiddle-table fill (about 0.35 of one op's
   // work), fewer keep the last wave full; pick the best product of the two
@@ -770,6 +797,9 @@ int fhesi_keygen_batch(fhesi_ctx *c, uint32_t M, const uint32_t *parts, const in
   }
   const u32 Km = rows * I.D, Kt = Km + (pk_out ? 1 : 0);  // the public key is the last entry, with a zero source row
   const size_t polyw = (size_t)n * I.W;
+  static const bool timing = getenv("FHESI_TIMING") && atoi(getenv("FHESI_TIMING")) > 0;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  const double T0 = now();
   PoolTmp d_A(c), d_An(c), d_b(c), d_e(c), d_src(c), d_t(c);
   int rc = 0;
   if ((rc = d_A.alloc(Kt * polyw * 4)) || (rc = d_An.alloc(Kt * polyw * 4)) || (rc = d_b.alloc(Kt * polyw * 4)) ||
@@ -780,9 +810,13 @@ int fhesi_keygen_batch(fhesi_ctx *c, uint32_t M, const uint32_t *parts, const in
   if (rows) CK(cudaMemcpyAsync(d_src.u(), h_src, (size_t)rows * n * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(d_src.u() + (size_t)rows * n, 0, n * 4, c->stream));
   CK(cudaMemcpyAsync(d_t.u(), h_t, n * 4, cudaMemcpyHostToDevice, c->stream));
+  if (timing) cudaStreamSynchronize(c->stream);
+  const double T1 = now();
   if ((rc = keygen_entries(c, Kt, d_A.u(), (const int *)d_e.u(), (const int *)d_src.u(), (const int *)d_t.u(),
                            d_b.u(), d_An.u())))
     return rc;
+  if (timing) cudaStreamSynchronize(c->stream);
+  const double T2 = now();
   size_t off = 0;
   for (u32 m = 0; m < M; ++m) {
     out[m] = nullptr;
@@ -803,6 +837,9 @@ int fhesi_keygen_batch(fhesi_ctx *c, uint32_t M, const uint32_t *parts, const in
   if (h_b_out && Km) CK(cudaMemcpyAsync(h_b_out, d_b.u(), Km * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
   if (h_A_out && Km) CK(cudaMemcpyAsync(h_A_out, d_An.u(), Km * polyw * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));  // the caller's host buffers are consumed / filled on return
+  if (timing)
+    fprintf(stderr, "fhesi_keygen_batch: alloc+upload %.4f  entries %.4f  key images + download %.4f s (%u entries)\n",
+            T1 - T0, T2 - T1, now() - T2, Kt);
   return 0;
 }
 int fhesi_ksw_generate(fhesi_ctx *c, const int32_t *h_src, const int32_t *h_t, const uint32_t *h_A,

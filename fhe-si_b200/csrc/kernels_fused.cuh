@@ -53,6 +53,11 @@ __device__ __forceinline__ u32 mulw(u32 x, uint2 w, u32 p) { return x * w.x - __
 #define FTW_P3 (7u * 128u + 7u * 16u) // entry offset of the pass-3 block
 #define FTW_ENTRIES (7u * 128u + 7u * 16u + 7u * 2u)
 #define FTW_WORDS (FTW_ENTRIES * 2u + 4u)  // uint2 entries, padded to a 16-byte multiple
+// FP64-quotient companions (mulw_dfma) for the pass-2 and pass-3 twiddles only: 7 * 16 + 7 * 2 entries of
+// (c, K).  Pass 1's twiddles differ per thread -- 16 more bytes per lane per butterfly would make shared-
+// memory bandwidth the limiter -- so pass 1 keeps the all-integer product.
+#define FTD_ENTRIES (7u * 16u + 7u * 2u)
+#define FTD_WORDS (FTD_ENTRIES * 4u)
 // tws layout: pass 1: [s][tg] (s < 7, 128 per row); pass 2: [s][lo] (16 per row); pass 3: [s][b0]
 __device__ __forceinline__ void fill_tw_table(uint2 *tws, const uint2 *__restrict__ table) {
   for (u32 e = threadIdx.x; e < FTW_ENTRIES; e += blockDim.x) {
@@ -71,6 +76,21 @@ __device__ __forceinline__ void fill_tw_table(uint2 *tws, const uint2 *__restric
   }
 }
 
+// twd[e - FTW_P2] for the pass-2 / pass-3 entries e of fill_tw_table, same source index
+__device__ __forceinline__ void fill_twd_table(double2 *twd, const double2 *__restrict__ table) {
+  for (u32 e = FTW_P2 + threadIdx.x; e < FTW_ENTRIES; e += blockDim.x) {
+    u32 idx;
+    if (e < FTW_P3) {
+      const u32 s = (e - FTW_P2) >> 4, lo = (e - FTW_P2) & 15;
+      idx = s < 4 ? 64 + s * 16 + lo : (s < 6 ? 32 + (s - 4) * 16 + lo : 16 + lo);
+    } else {
+      const u32 s = (e - FTW_P3) >> 1, b0 = (e - FTW_P3) & 1;
+      idx = s < 4 ? 8 + s * 2 + b0 : (s < 6 ? 4 + (s - 4) * 2 + b0 : 2 + b0);
+    }
+    twd[e - FTW_P2] = table[idx];
+  }
+}
+
 #define GSW(X, Y, W)                          \
   do {                                        \
     u32 s_ = add_alu((X), (Y)), d_ = (X) + p2 - (Y);  \
@@ -85,6 +105,34 @@ __device__ __forceinline__ void fill_tw_table(uint2 *tws, const uint2 *__restric
     (Y) = csub(d_, p2);                       \
   } while (0)
 
+#define GSWD(X, Y, W, C)                      \
+  do {                                        \
+    u32 s_ = add_alu((X), (Y)), d_ = (X) + p2 - (Y);  \
+    (X) = csub(s_, p2);                       \
+    (Y) = mulw_dfma(d_, (W).x, (C).x, (C).y, p, negp, hic, zop);  \
+  } while (0)
+// dif8 with the twiddle products' quotients on the FP64 pipe; td[] is indexed like tw[]
+template <int ST>
+__device__ __forceinline__ void dif8d(u32 *x, const uint2 *tw, const double2 *td, u32 p, u32 negp, u32 hic, u32 zop) {
+  const u32 p2 = 2 * p;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint2 w = tw[j * ST];
+    const double2 c = td[j * ST];
+    GSWD(x[j], x[j + 4], w, c);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint2 w = tw[(4 + j) * ST];
+    const double2 c = td[(4 + j) * ST];
+    GSWD(x[j], x[j + 2], w, c);
+    GSWD(x[j + 4], x[j + 6], w, c);
+  }
+  const uint2 w = tw[6 * ST];
+  const double2 c = td[6 * ST];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) GSWD(x[j], x[j + 1], w, c);
+}
 // three DIF stages on the 8 registers, twiddles tw[0..3], tw[4..5], tw[6] (stride 128 apart)
 template <int ST>
 __device__ __forceinline__ void dif8(u32 *x, const uint2 *tw, u32 p) {
@@ -144,9 +192,10 @@ __device__ __forceinline__ XAddr make_xaddr(u32 tg) {
 // with OFFS the output is the signed value v - (p >> 1), v in [0,p): a balanced residue of the
 // value minus the constant (p >> 1) -- one subtract instead of a compare/select/subtract, the
 // constant's contribution to an inner product is added back from a per-key table (k_split_corr).
-template <bool OFFS = false>
+// With DF (twd non-null at compile time) passes 2 and 3 take their quotients from the FP64 pipe.
+template <bool OFFS = false, bool DF = false>
 __device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A, u32 *bufA, u32 *bufB,
-                                        u32 g, u32 tg, u32 p) {
+                                        u32 g, u32 tg, u32 p, const double2 *twd = nullptr, u32 negp = 0, u32 hic = 0, u32 zop = 0) {
   const u32 p2 = 2 * p;
   const uint2 *tw = twf + tg;
   // pass 1; its first stage sees (X, 0): X stays, the partner becomes X * w
@@ -168,7 +217,8 @@ __device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A
   fhesi_group_sync(g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufA[A.a2a + 16 * j];
-  dif8<16>(x, twf + FTW_P2 + (tg & 15), p);
+  if (DF) dif8d<16>(x, twf + FTW_P2 + (tg & 15), twd + (tg & 15), p, negp, hic, zop);
+  else dif8<16>(x, twf + FTW_P2 + (tg & 15), p);
 #pragma unroll
   for (int j = 0; j < 8; ++j) bufB[A.a2b + 18 * j] = x[j];
   // exchange 2 stays inside a warp: warp w owns positions [256w, 256w+256) in both ownerships
@@ -176,7 +226,8 @@ __device__ __forceinline__ void fwd1024(u32 *x, const uint2 *twf, const XAddr &A
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = bufB[A.a3 + 2 * j];
-  dif8<2>(x, twf + FTW_P3 + (tg & 1), p);
+  if (DF) dif8d<2>(x, twf + FTW_P3 + (tg & 1), twd + (FTW_P3 - FTW_P2) + (tg & 1), p, negp, hic, zop);
+  else dif8<2>(x, twf + FTW_P3 + (tg & 1), p);
   // last stage (position bit 0) across lane pairs, twiddle 1
   const u32 b0 = tg & 1;
 #pragma unroll
@@ -340,6 +391,81 @@ __global__ void __launch_bounds__(128) k_residues(DevCtx c, ResidueArgs a) {
     }
     if (neg) r = csub(r + cw[W], p2);
     dst[(size_t)l * c.n] = csub(r, p);
+  }
+}
+
+// The same with the word count W a compile-time constant (the runtime-W kernel above spends most of its
+// instructions on `k < W` tests and selects): all word loops unrolled, the per-prime constants read as two or
+// three 128-bit shared-memory loads from a table padded to 4-word rows.  TW = 4, 6, 8, 16 cover logQ = 128,
+// 176, 256, 512; anything else takes the generic kernel.
+template <int TW>
+__global__ void __launch_bounds__(128) k_residues_t(DevCtx c, ResidueArgs a) {
+  constexpr int ROW = (TW + 1 + 3) & ~3;  // cw[0..TW] padded
+  FHESI_SMEM(sm);  // [Lt][2][ROW] constants, then (p, -p^-1) per prime
+  const u32 tabw = a.Lt * 2 * ROW;
+  for (u32 e = threadIdx.x; e < tabw; e += blockDim.x) {
+    const u32 k = e % ROW, lv = e / ROW;
+    sm[e] = k <= (u32)TW ? __ldg(c.cwr + (size_t)lv * c.CW + k) : 0u;
+  }
+  for (u32 e = threadIdx.x; e < a.Lt; e += blockDim.x) {
+    sm[tabw + 2 * e] = c.pc[e].p;
+    sm[tabw + 2 * e + 1] = 0u - c.pc[e].pinv;
+  }
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.count * 4 * c.n) return;
+  const u32 i = (u32)(idx % c.n);
+  const size_t pq = idx / c.n;  // op * 4 + q
+  const u32 q = (u32)(pq & 3);
+  const size_t op = pq >> 2;
+  const u32 *src = (q < 2 ? a.a : a.b) + ((op * 2 + (q & 1)) * c.n + i) * (size_t)TW;
+  u32 w[TW];
+  if (TW % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < TW; k += 4) {
+      const uint4 v = *(const uint4 *)(src + k);
+      w[k] = v.x, w[k + 1] = v.y, w[k + 2] = v.z, w[k + 3] = v.w;
+    }
+  } else if (TW % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < TW; k += 2) {
+      const uint2 v = *(const uint2 *)(src + k);
+      w[k] = v.x, w[k + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < TW; ++k) w[k] = src[k];
+  }
+  const bool neg = (w[TW - 1] >> 31) != 0;
+  const u32 *cwb = sm + (q < 2 ? ROW : 0);  // a-parts take the scaled constants (v = 1)
+  u32 *dst = a.out + pq * a.Lt * (size_t)c.n + i;
+  const u32 n = c.n;
+#pragma unroll 2
+  for (u32 l = 0; l < a.Lt; ++l) {
+    const uint2 pp = *(const uint2 *)(sm + tabw + 2 * l);
+    const u32 p = pp.x, p2 = 2 * p, ipinv = pp.y;
+    u32 cw[ROW];
+#pragma unroll
+    for (int k = 0; k < ROW; k += 4) {
+      const uint4 v = *(const uint4 *)(cwb + l * 2 * ROW + k);
+      cw[k] = v.x, cw[k + 1] = v.y, cw[k + 2] = v.z, cw[k + 3] = v.w;
+    }
+    u32 r = 0;
+#pragma unroll
+    for (int k0 = 0; k0 < TW; k0 += 4) {
+      u64 t = (u64)w[k0] * cw[k0];
+#pragma unroll
+      for (int k = k0 + 1; k < k0 + 4 && k < TW; ++k) t += (u64)w[k] * cw[k];
+      // t < 4 * 2^32 * p.  t - m*p == 0 mod 2^32 with m = t_lo * p^-1; quotient t_hi - hi(m p) in (-p, 4p)
+      const u32 m = (u32)t * ipinv;
+      const u32 th = (u32)(t >> 32), hm = __umulhi(m, p);
+      u32 qv = th - hm;
+      if (th < hm) qv += p;  // [0, 4p)
+      r = k0 == 0 ? csub(qv, p2) : csub(r + csub(qv, p2), p2);
+    }
+    if (neg) r = csub(r + cw[TW], p2);
+    *dst = csub(r, p);
+    dst += n;
   }
 }
 
@@ -517,22 +643,28 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
 // key: [Ls][K][4][N] balanced;  res: [count][4][Ls][n] in the order b_lo, b_hi, A_lo, A_hi.
 // ---------------------------------------------------------------------------------------
 #define KSS 4
+#ifndef KSS_DFMA
+#define KSS_DFMA false
+#endif
 #define KSS_BUFA 2048u  // word distance of the two alternating exchange buffers (a power of two: XOR toggle)
-#define KSS_SMEM_WORDS (2 * FTW_WORDS + KSS * (2 * KSS_BUFA + FPADN))
+#define KSS_SMEM_WORDS (2 * FTW_WORDS + FTD_WORDS + KSS * (2 * KSS_BUFA + FPADN))
 // key: [Ls][K][4][N] balanced, followed by the offset-correction table [Ls][4][N] (k_split_corr)
 __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
   const u32 l = blockIdx.x;
+  double2 *twd = (double2 *)(sm + 2 * FTW_WORDS);
   fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
   fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
+  fill_twd_table(twd, c.twd_fwd + (size_t)l * FN);
   __syncthreads();
   const size_t op = (size_t)blockIdx.y * KSS + g;
   if (op >= a.count) return;
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
-  u32 *bufA0 = sm + 2 * FTW_WORDS + g * (2 * KSS_BUFA + FPADN), *bufB = bufA0 + 2 * KSS_BUFA;
+  const u32 negp = pc.negp, hic = pc.hic, zop = pc.zop;  // loaded, hence opaque: see mulw_dfma
+  u32 *bufA0 = sm + 2 * FTW_WORDS + FTD_WORDS + g * (2 * KSS_BUFA + FPADN), *bufB = bufA0 + 2 * KSS_BUFA;
   const XAddr A = make_xaddr(tg);
   u64 acc[4][8];
 #pragma unroll
@@ -556,7 +688,7 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
       dp += c.n;
       xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256) & m2, xn[3] = __ldg(dp + 384) & m3;
     }
-    fwd1024<true>(x, twf, A, bufA0 + tgl, bufB, g, tg, p);
+    fwd1024<true, KSS_DFMA>(x, twf, A, bufA0 + tgl, bufB, g, tg, p, twd, negp, hic, zop);
     tgl ^= KSS_BUFA;
 #pragma unroll
     for (int h = 0; h < 4; ++h) {

@@ -24,7 +24,10 @@ struct PrimeConst {
   u32 tensor_c;     // p_pt * N^-1 * R^2 : mont(x, .) = x * p_pt / N * R
   u32 ptxt_r;       // p_pt * R
   u32 scale_r;      // floor(q / p_pt) * R
-  u32 pad[7];
+  // operands of mulw_dfma that must reach the kernel as loaded values (neither nvcc nor ptxas can fold
+  // what comes from memory): -p mod 2^32, the high word of the double 2^52, and zero
+  u32 negp, hic, zop;
+  u32 pad[4];
 };
 
 struct DevCtx {
@@ -38,6 +41,8 @@ struct DevCtx {
   const u32 *Pfull, *Phalf;               // [Lmax+1][Lmax]  words of prod_{i<l} p_i and its half
   // Shoup tables for the fused kernels: (w, floor(w * 2^32 / p)), plain (non-Montgomery) w
   const uint2 *tws_fwd, *tws_inv;         // [Lmax][N] same index h + j as tw_fwd / tw_inv
+  // FP64-quotient companions of tws_fwd (mulw_dfma): (c, K) per twiddle, [Lmax][N]
+  const double2 *twd_fwd;
   // multiword -> residue constants: cwr[l][v][k] = 2^(32k) * R * s_v mod p for k < W, and
   // cwr[l][v][W] = p - (2^(32W) * s_v mod p); s_0 = 1 (plain result after Montgomery
   // reduction), s_1 = p_pt / N * R (Montgomery form of the tensor's left operand)

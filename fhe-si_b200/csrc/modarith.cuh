@@ -8,7 +8,9 @@
 // Lazy ranges: with p < 2^30, mont_mul(a, b) < 2p whenever a*b < 2^32 * p, in particular
 // for a < 4p, b < p and for a, b < 2p.  Values in [0, 4p) always fit a uint32_t.
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #ifndef FHESI_EMU  // tests/emu/cuda_emu.h (CPU kernel-logic tests) pre-defines these
 #include <cuda_runtime.h>
 #define FHESI_LAUNCH(kern, grid, block, smem, stream, ...) \
@@ -60,6 +62,32 @@ FHESI_HD u32 csub(u32 x, u32 c) {
   return y < x ? y : x;
 }
 FHESI_HD u32 full_reduce(u32 x, u32 p) { return csub(csub(x, 2 * p), p); }  // [0,4p) -> [0,p)
+
+// Shoup-style product by a fixed w with the quotient estimated on the FP64 pipe instead of by IMAD.HI
+// (which costs two slots of the integer-multiply pipe that bounds these kernels; the FP64 pipe is idle).
+//   c = k 2^-50 with k = floor(w 2^50 / p)  (a double with at most 50 significant bits),  K = 2^52 - 4k.
+// The register pair (x, 0x43300000) IS the double 2^52 + x, so fma(2^52 + x, c, K) = x c + 2^52 exactly
+// before its single rounding: the low word of the result is q = round(x c), |q - x w / p| < 1/2 + 2^-18.
+// Then x w + p - q p lies in (p/2 - p 2^-18, 3p/2 + p 2^-18): inside [0, 2p), the contract of mulw().
+// Valid for every 32-bit x; checked exhaustively on the B200 (scripts/micro/shoup_dfma.cu).
+// hic, zop: registers holding 0x43300000 and 0 that the compiler cannot see through.  The pair's high
+// word is produced per use by one ALU-pipe instruction, hic | (x & zop): ptxas materialises a known or
+// loop-invariant value into the pair with IMAD.MOV -- on the very pipe this function is meant to relieve.
+FHESI_HD u32 mulw_dfma(u32 x, u32 w, double c, double K, u32 p, u32 negp, u32 hic, u32 zop) {
+#if defined(__CUDA_ARCH__)
+  const double Q = __fma_rn(__hiloint2double((int)(hic | (x & zop)), (int)x), c, K);  // zop == 0: one LOP3 per use
+  const u32 q = (u32)__double2loint(Q);
+#else
+  const u64 xb = 0x4330000000000000ull | x;
+  double xd;
+  memcpy(&xd, &xb, 8);
+  const double Q = fma(xd, c, K);
+  u64 qb;
+  memcpy(&qb, &Q, 8);
+  const u32 q = (u32)qb;
+#endif
+  return q * negp + (x * w + p);
+}
 
 // ---- host-side helpers (setup time) -------------------------------------------------
 static inline u64 h_mulmod(u64 a, u64 b, u64 m) { return (u64)((unsigned __int128)a * b % m); }

@@ -136,6 +136,10 @@ struct uint2 {
   unsigned x, y;
 };
 inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+struct double2 {
+  double x, y;
+};
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
 // named barrier over the 128-thread group `g` of the block (bar.sync g+1, 128 on the GPU)
