@@ -497,35 +497,44 @@ void FHEcontext::AddPrime(long p, bool special, long root) {  // FHEContext.cpp:
   if (special) specialPrimes.insert(i);
   else ctxtPrimes.insert(i);
 }
-double AddPrimesBySize(FHEcontext &context, double totalSize, bool special) {  // FHEContext.cpp:88-115
-  if (!context.zMstar.M() || context.zMstar.M() > (1 << 20)) Error("AddModuli1: m undefined or larger than 2^20");
-  long p = (1UL << NTL_SP_NBITS) - 1;
-  long twoM = 2 * context.zMstar.M();
-  p -= (p % twoM);
-  p += twoM + 1;
-  bool lastPrime = false;
-  double sizeLeft = totalSize;
-  while (sizeLeft > 0.0) {
-    if (sizeLeft < std::log((double)p) && !lastPrime) {
-      lastPrime = true;
-      p = ceil(exp(sizeLeft));
-      p -= (p % twoM) - 1;
-      twoM = -twoM;
+// The chain rule of FHEContext.cpp:88-115, stated as two searches over the values = 1 (mod 2m): word-size
+// primes downwards from just above 2^NTL_SP_NBITS - 1 while a whole one still fits into the size that is
+// left, then one closing prime searched UPWARDS from exp(what is left) -- so the chain covers totalSize
+// without overshooting by more than one stride.  (tests: test_chain_matches_survey pins the result.)
+double AddPrimesBySize(FHEcontext &context, double totalSize, bool special) {
+  const long m = context.zMstar.M();
+  if (m <= 0 || m > (1L << 20)) Error("AddModuli1: m undefined or larger than 2^20");
+  const long stride = 2 * m;
+  const auto nextPrime = [](long from, long step) {
+    do from += step;
+    while (!ProbPrime(from));
+    return from;
+  };
+  long cand = (((1L << NTL_SP_NBITS) - 1) / stride + 1) * stride + 1;
+  double remaining = totalSize;
+  bool closing = false;
+  while (remaining > 0.0) {
+    if (!closing && remaining < std::log((double)cand)) {
+      closing = true;
+      const long target = (long)ceil(exp(remaining));
+      cand = target - target % stride + 1;
     }
-    do { p -= twoM; } while (!ProbPrime(p));
-    if (!context.inChain(p)) {
-      context.AddPrime(p, special);
-      sizeLeft -= std::log((double)p);
-    }
+    cand = nextPrime(cand, closing ? stride : -stride);
+    if (context.inChain(cand)) continue;
+    context.AddPrime(cand, special);
+    remaining -= std::log((double)cand);
   }
-  return totalSize - sizeLeft;
+  return totalSize - remaining;
+}
+// Natural log of the size SetUpSIContext(1) asks of the chain (FHEContext.cpp:83-85)
+static double SIChainBaseSize(const FHEcontext &c) {
+  return NTL::log(c.modulusQ) * 2 + NTL::log(c.ModulusP()) + std::log((double)c.zMstar.phiM()) * 2 + std::log(2.0);
 }
 // Host-only users of the class surface (fhesih_keygen) switch this off: they never touch a device.
 static bool g_eagerDevice = true;
 void FHEcontext::SetUpSIContext(long xi) {  // FHEContext.cpp:83-85
   xiHint = xi < 1 ? 1 : xi;
-  AddPrimesBySize(*this, NTL::log(modulusQ) * 2 + NTL::log(ModulusP()) + std::log((double)zMstar.phiM()) * 2 +
-                             std::log(2.0) + std::log((double)xiHint), false);
+  AddPrimesBySize(*this, SIChainBaseSize(*this) + std::log((double)xiHint), false);
   // The reference builds every Cmodulus (roots, Bluestein tables) here; the device counterpart --
   // CUDA context, twiddle / CRT tables, kernel images -- is created here too, not at the first
   // operator, so that a client's own timers see operators and not start-up.
@@ -535,6 +544,11 @@ void FHEcontext::SetUpSIContext(long xi) {  // FHEContext.cpp:83-85
   }
 }
 fhesi_ctx *FHEcontext::Dev() const {
+  if (dev && devXi != xiHint) {
+    // the head-room changed after the device image was made (SetUpSIContext / ImportSIContext called again):
+    // objects of the old image would silently keep the old tensor chain
+    Error("FHEcontext: xi changed after the device context was created");
+  }
   if (!dev) {
     Check(fhesi_ctx_create(zMstar.M(), logQ, (uint64_t)to_long(ModulusP()), decompSize, (uint64_t)xiHint, device, &dev),
           "fhesi_ctx_create");
@@ -569,11 +583,19 @@ void FHEcontext::ImportSIContext(ifstream &in) {  // FHEContext.cpp:62-81
   uint32_t size;
   Import(in, size);
   long q, root;
+  double chain = 0;
   for (unsigned i = 0; i < size; i++) {
     Import(in, q);
     Import(in, root);
+    if (!in.good() || q < 3) Error("ImportSIContext: truncated or corrupt context file");
     AddPrime(q, false, root);
+    chain += std::log((double)q);
   }
+  // The file does not store xi; the chain it stores does: SetUpSIContext(xi) sized it to cover
+  // base + log(xi).  The device's own tensor chain gets the same head-room for sums of tensor products
+  // (Matrix sums in Regression.h / Statistics.h), instead of the default xi = 1.
+  const double room = chain - SIChainBaseSize(*this);
+  xiHint = room > 0 ? std::max(1L, (long)std::floor(std::exp(std::min(room, 40.0)))) : 1;
 }
 ostream &operator<<(ostream &os, const FHEcontext &context) {
   os << "logQ: " << context.logQ << endl << "p: " << context.ModulusP() << endl
@@ -808,7 +830,7 @@ DevBuf::~DevBuf() {
 Ciphertext::Ciphertext(const FHESIPubKey &pk) : context(&pk.GetContext()) {}
 Ciphertext::Ciphertext(const Ciphertext &o)
     : context(o.context), nparts(o.nparts), wordsPer(o.wordsPer), scaledUp(o.scaledUp), hostStale(o.hostStale),
-      parts(o.parts) {
+      hostDirty(o.hostDirty), parts(o.parts) {
   if (o.buf) {
     buf = make_shared<DevBuf>(o.buf->ctx, o.buf->bytes);
     Check(fhesi_d2d(buf->ctx, buf->ptr, o.buf->ptr, buf->bytes), "fhesi_d2d");
@@ -818,6 +840,7 @@ Ciphertext &Ciphertext::operator=(const Ciphertext &o) {
   if (this == &o) return *this;
   context = o.context;
   nparts = o.nparts, wordsPer = o.wordsPer, scaledUp = o.scaledUp, hostStale = o.hostStale;
+  hostDirty = o.hostDirty;
   parts = o.parts;
   buf.reset();
   if (o.buf) {
@@ -843,7 +866,7 @@ void Ciphertext::Initialize(unsigned n, const FHEcontext &c) {
 }
 void Ciphertext::Clear() {
   buf.reset();
-  nparts = 0, wordsPer = 0, scaledUp = false, hostStale = false;
+  nparts = 0, wordsPer = 0, scaledUp = false, hostStale = false, hostDirty = false;
   parts.clear();
 }
 void Ciphertext::SyncHost() const {
@@ -873,8 +896,14 @@ void Ciphertext::UploadHost() {  // after Import / a write through operator[]
   if (!w.empty()) Check(fhesi_h2d(buf->ctx, buf->ptr, w.data(), w.size() * 4), "fhesi_h2d");
   scaledUp = false;
   hostStale = false;
+  hostDirty = false;
+}
+// A write through the non-const operator[] reaches the device here, before any operator reads the buffer.
+void Ciphertext::Flush() const {
+  if (hostDirty) const_cast<Ciphertext *>(this)->UploadHost();
 }
 void Ciphertext::EnsureReduced() {
+  Flush();
   if (scaledUp || !buf || wordsPer == context->Words()) return;
   const unsigned W = context->Words();
   auto nb = make_shared<DevBuf>(buf->ctx, (size_t)nparts * context->zMstar.phiM() * W * 4);
@@ -889,9 +918,12 @@ CiphertextPart Ciphertext::GetPart(unsigned ind) const {
 }
 CiphertextPart &Ciphertext::operator[](unsigned ind) {
   SyncHost();
+  if (!scaledUp) hostDirty = true;  // the caller holds a writable reference into the mirror
   return parts[ind];
 }
 Ciphertext &Ciphertext::operator+=(const Ciphertext &o) {  // Ciphertext.cpp:123-145
+  Flush();
+  o.Flush();
   assert(scaledUp == o.scaledUp);
   if (!o.buf || o.nparts == 0) return *this;
   if (!buf || nparts == 0) return *this = o;
@@ -926,6 +958,7 @@ Ciphertext &Ciphertext::operator+=(const Ciphertext &o) {  // Ciphertext.cpp:123
   return *this;
 }
 Ciphertext &Ciphertext::operator+=(const ZZX &other) {  // Ciphertext.cpp:147-161
+  Flush();
   fhesi_ctx *d = context->Dev();
   const unsigned n = context->zMstar.phiM(), W = context->Words();
   if (scaledUp) {  // :157-159  tProd[0] += scaledConstant, nothing reduced
@@ -957,6 +990,8 @@ Ciphertext &Ciphertext::operator+=(const ZZX &other) {  // Ciphertext.cpp:147-16
 }
 Ciphertext &Ciphertext::operator*=(const Ciphertext &o) {  // Ciphertext.cpp:167-192
   if (scaledUp || o.scaledUp) Error("Ciphertext *= : operands must not be in tensor form (Ciphertext.cpp:169-176)");
+  Flush();
+  o.Flush();
   fhesi_ctx *d = context->Dev();
   Ciphertext rhs(o);  // also covers self-multiplication
   EnsureReduced();
@@ -973,6 +1008,7 @@ Ciphertext &Ciphertext::operator*=(const Ciphertext &o) {  // Ciphertext.cpp:167
   return *this;
 }
 Ciphertext &Ciphertext::operator*=(long l) {  // Ciphertext.cpp:233-244
+  Flush();
   if (!buf) return *this;
   fhesi_ctx *d = context->Dev();
   if (!scaledUp) {
@@ -985,6 +1021,7 @@ Ciphertext &Ciphertext::operator*=(long l) {  // Ciphertext.cpp:233-244
   return *this;
 }
 Ciphertext &Ciphertext::operator*=(const ZZX &other) {  // Ciphertext.cpp:246-258
+  Flush();
   if (!buf) return *this;
   fhesi_ctx *d = context->Dev();
   const unsigned n = context->zMstar.phiM();
@@ -1011,6 +1048,7 @@ Ciphertext &Ciphertext::operator*=(const ZZX &other) {  // Ciphertext.cpp:246-25
   return *this;
 }
 Ciphertext &Ciphertext::operator>>=(long k) {  // Ciphertext.cpp:264-275
+  Flush();
   if (!buf) return *this;
   fhesi_ctx *d = context->Dev();
   if (scaledUp) {  // :269-273  tProd[i] >>= k
@@ -1266,22 +1304,29 @@ void KeySwitchSI::Materialize() const {
   keySwitchMatrix[1] = std::move(A);
   hostB.clear(), drawA.clear();
 }
-void KeySwitchSI::InitS2(const FHESISecKey &s) {  // FHE-SI.cpp:211-227
-  vector<DoubleCRT> sKeys = s.GetRepresentation();
-  vector<DoubleCRT> tKeys;
-  tKeys.assign(sKeys.size() * 2 - 1, sKeys[1]);
-  tKeys[0] = sKeys[0];
-  for (unsigned i = 2; i < tKeys.size(); i++) tKeys[i] *= tKeys[i - 1];
-  FHESISecKey tensoredKey(s.GetContext());  // FHE-SI.cpp:222 samples a key it then overwrites: same draws
-  tensoredKey.UpdateRepresentation(tKeys);
-  Init(tensoredKey, s);
+// s^2 -> s (FHE-SI.cpp:211-227).  A tensor product of two k-part ciphertexts is linear in the 2k-1
+// monomials 1, s, ..., s^(2k-2); they are the source key, s is the target.
+void KeySwitchSI::InitS2(const FHESISecKey &s) {
+  const vector<DoubleCRT> &base = s.GetRepresentation();  // (1, s)
+  vector<DoubleCRT> powers;
+  powers.reserve(2 * base.size() - 1);
+  powers.push_back(base[0]);
+  while (powers.size() < 2 * base.size() - 1) {
+    DoubleCRT next = base[1];
+    if (powers.size() > 1) next *= powers.back();
+    powers.push_back(next);
+  }
+  FHESISecKey source(s.GetContext());  // the reference constructs -- hence samples -- a key here (:222): same draws
+  source.UpdateRepresentation(powers);
+  Init(source, s);
 }
-void KeySwitchSI::InitAutomorph(const FHESISecKey &s, unsigned k) {  // FHE-SI.cpp:229-239
-  vector<DoubleCRT> sKeys = s.GetRepresentation();
-  FHESISecKey automorphedKey(s.GetContext());  // :233, likewise
-  for (unsigned i = 0; i < sKeys.size(); i++) sKeys[i].automorph(k);
-  automorphedKey.UpdateRepresentation(sKeys);
-  Init(automorphedKey, s);
+// s(X^k) -> s (FHE-SI.cpp:229-239): the key under which a ciphertext decrypts after `>>= k`
+void KeySwitchSI::InitAutomorph(const FHESISecKey &s, unsigned k) {
+  vector<DoubleCRT> rotated = s.GetRepresentation();
+  FHESISecKey source(s.GetContext());  // sampled, then overwritten, as at :233
+  for (DoubleCRT &part : rotated) part.automorph(k);
+  source.UpdateRepresentation(rotated);
+  Init(source, s);
 }
 const fhesi_ksw *KeySwitchSI::Dev() const {
   if (!devKsw) {
@@ -1334,13 +1379,23 @@ void Export(ofstream &out, const ZZ &val) {  // Serialization.cpp:3-13
   BytesFromZZ(data.data(), val, nBytes);
   out.write((char *)data.data(), nBytes);
 }
+// Files come from another party: lengths are bounded before anything is allocated, and a short read is an
+// error, not a silently truncated value.  No integer of this scheme is wider than the chain product
+// (a few thousand bits); 1 MiB per integer, 2^24 coefficients / rows per vector are far above any real file.
+static const size_t kMaxImportBytes = (size_t)1 << 20, kMaxImportItems = (size_t)1 << 24;
+static void ImportCheck(ifstream &in, const char *what) {
+  if (!in.good()) Error((std::string("Import: truncated or unreadable ") + what).c_str());
+}
 void Import(ifstream &in, ZZ &val) {
-  uint32_t nBytes;
+  uint32_t nBytes = 0;
   in.read((char *)&nBytes, sizeof(uint32_t));
-  bool neg;
+  bool neg = false;
   in.read((char *)&neg, sizeof(bool));
-  std::vector<unsigned char> data(nBytes + 1);
+  ImportCheck(in, "integer header");
+  if ((size_t)nBytes > kMaxImportBytes) Error("Import: integer length out of range");
+  std::vector<unsigned char> data((size_t)nBytes + 1);
   in.read((char *)data.data(), nBytes);
+  ImportCheck(in, "integer");
   ZZFromBytes(val, data.data(), nBytes);
   if (neg) val *= -1;
 }
@@ -1351,10 +1406,12 @@ void Export(ofstream &out, const ZZX &poly) {  // Serialization.cpp:29-36
 }
 void Import(ifstream &in, ZZX &poly) {
   poly = ZZX::zero();
-  int32_t degree;
+  int32_t degree = -1;
   in.read((char *)&degree, sizeof(int32_t));
+  ImportCheck(in, "polynomial header");
   if (degree == -1) return;
-  poly.rep.v.resize(degree + 1);
+  if (degree < -1 || (size_t)degree >= kMaxImportItems) Error("Import: polynomial degree out of range");
+  poly.rep.v.resize((size_t)degree + 1);
   for (int i = 0; i <= degree; i++) Import(in, poly.rep.v[i]);
   poly.normalize();
 }
@@ -1364,10 +1421,13 @@ void Export(ofstream &out, const vec_long &vec) {  // Serialization.cpp:83-89
   for (long i = 0; i < vec.length(); i++) Export(out, vec[i]);
 }
 void Import(ifstream &in, vec_long &vec) {
-  uint32_t size;
+  uint32_t size = 0;
   Import(in, size);
+  ImportCheck(in, "vector header");
+  if ((size_t)size > kMaxImportItems) Error("Import: vector length out of range");
   vec.SetLength(size);
   for (uint32_t i = 0; i < size; i++) Import(in, vec[i]);
+  ImportCheck(in, "vector");
 }
 void Export(ofstream &out, const DoubleCRT &poly) {  // Serialization.cpp:56-65
   vector<vector<long>> rows = poly.getRows();

@@ -386,6 +386,10 @@ class Ciphertext {
   unsigned wordsPer = 0;   // W, or W+1 right after >>= (not reduced mod q, Ciphertext.cpp:54-59)
   bool scaledUp = false;
   mutable bool hostStale = false;
+  // set by the non-const operator[]: the caller may have written through the reference (the reference's
+  // `ctxt[i].poly = ...`, FHE-SI.cpp:29), so the host mirror is the truth until the next operator flushes it
+  mutable bool hostDirty = false;
+  void Flush() const;
 
   void Alloc(unsigned parts, unsigned words);
   void EnsureReduced();     // Reduce a wide (W+1 words) image to W words
@@ -427,7 +431,7 @@ class Ciphertext {
   friend ostream &operator<<(ostream &os, const Ciphertext &ctxt);
 
   // raw access for batch-aware callers
-  const uint32_t *DevWords() const { return buf ? buf->ptr : nullptr; }
+  const uint32_t *DevWords() const { Flush(); return buf ? buf->ptr : nullptr; }
 };
 
 // ------------------------------------------------------------------------------- keys

@@ -12,6 +12,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -531,27 +532,110 @@ inline std::istream &operator>>(std::istream &is, ZZ &a) {
   return is;
 }
 
-// -------------------------------------------------------------------- PRNG (SplitMix64)
-// Same stream as oracle/fhesi_oracle.py::Rng, so a seed gives the same keys and ciphertexts
-// in the C++ layer and in the oracle (NTL's own stream is not pinned).
+// -------------------------------------------------------------------- PRNG
+// NTL's stream is a cryptographic PRG and is not pinned by the reference.  Here:
+//  * ChaCha20 (the RFC 8439 block function; 256-bit key, 64-bit block counter) is the generator.  Unseeded,
+//    its key comes from the operating system (getrandom / /dev/urandom); SetSeed(seed) derives the key from
+//    EVERY byte of the seed, so equal seeds give equal streams and the key space is the seed's.
+//  * SplitMix64 is the documented deterministic TEST stream: the one oracle/fhesi_oracle.py::Rng draws from and
+//    the golden vectors were made with.  It has 64 bits of state and is NOT for keys that protect anything; it
+//    is selected only explicitly, by the environment variable FHESI_TEST_RNG=splitmix64 (read once per thread;
+//    tests/conftest.py and the golden generators set it) or by UseTestRandomStream(true).
+// The stream is per thread (as in NTL's thread-safe build): no shared mutable state, no locking.
 struct RandomStream {
-  uint64_t state = 0;
+  bool test = false;
+  uint64_t state = 0;                    // SplitMix64
+  uint32_t key[8] = {0}, block[16] = {0};  // ChaCha20
+  uint64_t counter = 0;
+  unsigned have = 0;                     // unread 64-bit words left in `block`
+
+  static uint32_t rotl(uint32_t v, int c) { return (v << c) | (v >> (32 - c)); }
+  static void quarter(uint32_t *x, int a, int b, int c, int d) {
+    x[a] += x[b], x[d] = rotl(x[d] ^ x[a], 16);
+    x[c] += x[d], x[b] = rotl(x[b] ^ x[c], 12);
+    x[a] += x[b], x[d] = rotl(x[d] ^ x[a], 8);
+    x[c] += x[d], x[b] = rotl(x[b] ^ x[c], 7);
+  }
+  static void chacha_block(uint32_t out[16], const uint32_t k[8], uint64_t ctr, uint32_t n0, uint32_t n1) {
+    const uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, k[0], k[1], k[2], k[3],
+                             k[4], k[5], k[6], k[7], (uint32_t)ctr, (uint32_t)(ctr >> 32), n0, n1};
+    uint32_t x[16];
+    for (int i = 0; i < 16; ++i) x[i] = in[i];
+    for (int r = 0; r < 10; ++r) {
+      quarter(x, 0, 4, 8, 12), quarter(x, 1, 5, 9, 13), quarter(x, 2, 6, 10, 14), quarter(x, 3, 7, 11, 15);
+      quarter(x, 0, 5, 10, 15), quarter(x, 1, 6, 11, 12), quarter(x, 2, 7, 8, 13), quarter(x, 3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
+  }
+  void rekey(const uint32_t k[8]) {
+    for (int i = 0; i < 8; ++i) key[i] = k[i];
+    counter = 0, have = 0;
+  }
+  // key <- absorb(words): 8 words at a time are XORed into the key, which is then replaced by a block of
+  // its own keystream (domain-separated from the output stream by the nonce)
+  void seed_words(const uint32_t *w, size_t n, uint32_t sign) {
+    uint32_t k[8] = {0x66686573u, 0x692d7369u, (uint32_t)n, sign, 0, 0, 0, 0}, out[16];
+    for (size_t i = 0; i < n || i == 0; i += 8) {
+      for (size_t j = 0; j < 8 && i + j < n; ++j) k[j] ^= w[i + j];
+      chacha_block(out, k, i, 0x73656564u, 0x6b657921u);
+      for (int j = 0; j < 8; ++j) k[j] = out[j];
+    }
+    rekey(k);
+  }
+  void seed_from_os() {
+    uint32_t k[8];
+    size_t got = 0;
+#if defined(__linux__)
+    FILE *f = fopen("/dev/urandom", "rb");
+    if (f) {
+      got = fread(k, 1, sizeof k, f);
+      fclose(f);
+    }
+#endif
+    if (got != sizeof k) Error("RandomStream: the operating system gave no entropy");
+    rekey(k);
+  }
+  RandomStream() {
+    const char *e = getenv("FHESI_TEST_RNG");
+    if (e && std::string(e) == "splitmix64") test = true;
+    else seed_from_os();
+  }
   uint64_t next64() {
-    state += 0x9E3779B97F4A7C15ull;
-    uint64_t z = state;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+    if (test) {
+      state += 0x9E3779B97F4A7C15ull;
+      uint64_t z = state;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      return z ^ (z >> 31);
+    }
+    if (!have) {
+      chacha_block(block, key, counter++, 0, 0);
+      have = 8;
+    }
+    const unsigned i = 8 - have--;
+    return (uint64_t)block[2 * i] | ((uint64_t)block[2 * i + 1] << 32);
   }
 };
 inline RandomStream &GlobalRandomStream() {
-  static RandomStream s;
+  static thread_local RandomStream s;
   return s;
 }
+// Test infrastructure switch (see above); returns the previous setting.
+inline bool UseTestRandomStream(bool on) {
+  RandomStream &s = GlobalRandomStream();
+  const bool was = s.test;
+  s.test = on;
+  return was;
+}
 inline void SetSeed(const ZZ &seed) {
-  uint64_t v = 0;
-  for (size_t i = 0; i < seed.mag.size() && i < 2; ++i) v |= (uint64_t)seed.mag[i] << (32 * i);
-  GlobalRandomStream().state = v;
+  RandomStream &s = GlobalRandomStream();
+  if (s.test) {  // the oracle's stream: state = the seed's low 64 bits
+    uint64_t v = 0;
+    for (size_t i = 0; i < seed.mag.size() && i < 2; ++i) v |= (uint64_t)seed.mag[i] << (32 * i);
+    s.state = v;
+    return;
+  }
+  s.seed_words(seed.mag.data(), seed.mag.size(), seed.neg ? 1u : 0u);
 }
 inline ZZ RandomBits_ZZ(long nbits) {
   ZZ r;

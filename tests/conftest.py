@@ -9,6 +9,12 @@ for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fhe-si_b200"), os.pa
         sys.path.insert(0, p)
 
 
+# The golden vectors and the oracle draw from the documented deterministic TEST stream (SplitMix64); the host
+# layer's production generator is ChaCha20 keyed from the OS or from the full seed (ntl_shim.h).  Every test
+# process and every client program the tests start inherits this.
+os.environ.setdefault("FHESI_TEST_RNG", "splitmix64")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

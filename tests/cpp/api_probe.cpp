@@ -133,6 +133,17 @@ int main(int argc, char **argv) {
   Plaintext got(context);
   secretKey.Decrypt(got, cm);
   REQUIRE(got == prod);
+  // a write through the non-const operator[] is a write to the ciphertext (FHE-SI.cpp:29 does exactly this)
+  Ciphertext cw = a;
+  cw[0].poly = b[0].poly;
+  cw[1].poly = b[1].poly;
+  secretKey.Decrypt(got, cw);
+  REQUIRE(got == p1);
+  cw += a;  // ... and the next operator sees it
+  secretKey.Decrypt(got, cw);
+  Plaintext p01 = p0;
+  p01 += p1;
+  REQUIRE(got == p01);
   Ciphertext cr = a;
   cr >>= 7;
   keys[0].ApplyKeySwitch(cr);

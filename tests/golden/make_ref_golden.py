@@ -33,7 +33,9 @@ FILES = ["context", "ct0", "ct1", "add", "tensor_scaledown", "mult_relin", "decr
 
 def run(exe, logq, p, g, seed=SEED):
     with tempfile.TemporaryDirectory() as d:
-        subprocess.check_call([exe, str(logq), str(p), str(g), str(seed), d], stdout=subprocess.DEVNULL)
+        # the golden files are made with the deterministic TEST stream (SplitMix64, shared with the oracle)
+        subprocess.check_call([exe, str(logq), str(p), str(g), str(seed), d], stdout=subprocess.DEVNULL,
+                              env=dict(os.environ, FHESI_TEST_RNG="splitmix64"))
         return {f: open(os.path.join(d, f + ".bin"), "rb").read() for f in FILES}
 
 

@@ -131,6 +131,53 @@ def test_host_doublecrt_row_ops_emu(emu_lib, tmp_path):
     assert r.returncode == 0 and "dcrt ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_random_stream_is_keyed_emu(emu_lib, tmp_path):
+    """Production stream (no FHESI_TEST_RNG): unseeded processes differ (key from the OS), a seed is
+    reproducible and EVERY limb of it matters; the test stream is SplitMix64 = the oracle's Rng."""
+    exe = compile_client([os.path.join(ROOT, "tests", "cpp", "rng_probe.cpp")], emu_lib, str(tmp_path / "rng_probe"))
+    prod = {k: v for k, v in os.environ.items() if k != "FHESI_TEST_RNG"}
+    run = lambda args, env: subprocess.run([exe] + args, capture_output=True, text=True, timeout=60, env=env).stdout.split()
+    a, b = run([], prod), run([], prod)
+    assert len(a) == 4 and a != b, "unseeded production streams must differ between processes"
+    s1, s2 = run(["12345"], prod), run(["12345"], prod)
+    assert s1 == s2 and s1 != a
+    big = 12345 + (1 << 64) * 7 + (1 << 200)
+    assert run([str(big)], prod) != s1, "the seed's high limbs must reach the key"
+    assert run([str(-12345)], prod) != s1
+    test_env = dict(prod, FHESI_TEST_RNG="splitmix64")
+    want = O.Rng(12345)
+    assert [int(v) for v in run(["12345"], test_env)] == [want.next64() for _ in range(4)]
+
+
+def test_import_rejects_hostile_files_emu(emu_lib, tmp_path):
+    """Serialization Import: lengths are bounded before allocation and short reads are errors."""
+    import struct
+    exe = compile_client([os.path.join(ROOT, "tests", "cpp", "import_probe.cpp")], emu_lib, str(tmp_path / "import_probe"))
+
+    def run(blob):
+        f = tmp_path / "in.bin"
+        f.write_bytes(blob)
+        return subprocess.run([exe, str(f)], capture_output=True, text=True, timeout=60)
+    zz = lambda v: struct.pack("<IB", (v.bit_length() + 7) // 8, 0) + v.to_bytes((v.bit_length() + 7) // 8, "little")
+    ok = run(struct.pack("<i", 1) + zz(5) + zz(7))
+    assert ok.returncode == 0 and "degree 1" in ok.stdout, ok.stdout + ok.stderr
+    for bad in (struct.pack("<i", 1) + struct.pack("<IB", 0xFFFFFFFF, 0) + b"\x01" * 8,   # wrapping length
+                struct.pack("<i", 1) + struct.pack("<IB", 64, 0) + b"\x01" * 8,           # short read
+                struct.pack("<i", 0x7FFFFFFF),                                             # absurd degree
+                struct.pack("<i", -5),                                                     # negative degree
+                b"\x01"):                                                                  # truncated header
+        r = run(bad)
+        assert r.returncode != 0 and "Import" in (r.stdout + r.stderr), (bad[:12], r.returncode, r.stdout, r.stderr)
+
+
+def test_imported_context_keeps_tensor_headroom_emu(emu_lib, tmp_path):
+    """ExportSIContext -> ImportSIContext: the imported context sizes the device's tensor chain for the xi the
+    exported chain was built for (the file does not store xi); xi summed products decrypt correctly."""
+    exe = compile_client([os.path.join(ROOT, "tests", "cpp", "ctx_roundtrip.cpp")], emu_lib, str(tmp_path / "ctx_rt"))
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ctx roundtrip ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 def test_reference_clients_run_unchanged_emu(emu_lib, tmp_path):
     """Test_AddMul.cpp, Test_General.cpp, Test_Regression.cpp and Test_Statistics.cpp (+ Regression.h,
