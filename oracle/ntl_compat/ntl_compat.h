@@ -343,7 +343,12 @@ inline void EDF(vec_ZZ_pX &factors, const ZZ_pX &f, long d) {
     for (;;) {
       // splitting polynomials come from a private stream, so that factoring Phi_m in the
       // FHEcontext constructor leaves the shared stream where the client seeded it
-      static RandomStream local{0x5DEECE66Dull};
+      static RandomStream local = [] {  // a fixed private SplitMix64 stream: factoring is deterministic
+        RandomStream r;
+        r.test = true;
+        r.state = 0x5DEECE66Dull;
+        return r;
+      }();
       ZZ_pX r;
       r.rep.v.resize(deg(g));
       for (auto &c : r.rep.v) c = ZZ_p((long)(local.next64() % (uint64_t)ZZ_p::mod()));
