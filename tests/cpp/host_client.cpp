@@ -177,6 +177,24 @@ int main(int argc, char **argv) {
     v *= onePlusX;
     Save(dir + "/tensor_mul_plain.bin", v);
   }
+  // ---- fourth group (no draws).  (1) A product whose left operand is the UNREDUCED output of >>=
+  // (Ciphertext.cpp:54-59 leaves a(X^k) mod Phi_m as it falls, coefficients in (-q, q)): the reference carries
+  // the extra multiple of q into the tensor product; this repository reduces first (DESIGN.md "known
+  // deviations") -- the file pins exactly where the two differ.  (2) PlaintextSpace::EmbedInSlots of a fixed
+  // slot vector (PlaintextSpace.cpp:112-134); which root is slot 0 depends on the factoring order of Phi_m
+  // mod p, so implementations agree up to a cyclic shift of the slots.
+  {
+    Ciphertext x = a;
+    x >>= g;
+    x *= b;
+    Save(dir + "/unreduced_rot_mul.bin", x);
+    const unsigned total = context.GetPlaintextSpace().GetTotalSlots();
+    std::vector<ZZ_pX> slots(total);
+    for (unsigned i = 0; i < total; ++i) slots[i] = to_ZZ_pX(to_ZZ_p((long)((i * 7 + 3) % p)));
+    Plaintext e(context);
+    e.EmbedInSlots(slots, false);
+    Save(dir + "/embed_slots.bin", to_ZZX(e.message));
+  }
   // the identities of Test_AddMul.cpp:84-86, for good measure
   Plaintext dsum;
   secretKey.Decrypt(dsum, sum);

@@ -72,6 +72,9 @@ def outputs(ctx, sk, ks, cts):
     out["tensor_add_plain"] = O.export_ciphertext(a.copy().mul(b).add_plain(ks.plain))
     out["tensor_automorph"] = O.export_ciphertext(a.copy().mul(b).automorph(ks.rot_k))
     out["tensor_mul_plain"] = O.export_ciphertext(a.copy().mul(b).mul_plain([1, 1] + [0] * (ctx.phim - 2)))
+    # fourth group: a product whose left operand is the unreduced output of >>= (the reference's semantics:
+    # the extra multiple of q is carried into the tensor product)
+    out["unreduced_rot_mul"] = O.export_ciphertext(a.copy().automorph(ks.rot_k).mul(b))
     return out
 
 

@@ -28,7 +28,8 @@ CONFIGS = {  # name: (logQ, p, g) -- BASELINE.json configs 1-5 (g = 3 for p = 10
 FILES = ["context", "ct0", "ct1", "add", "tensor_scaledown", "mult_relin", "decrypt_mult_relin", "square_relin",
          "mul_scalar_m7", "automorph_3", "pk", "mult_relin_roundtrip", "pk_roundtrip", "tensor_accumulate",
          "tensor_mul_scalar", "accumulate_relin", "mul_plain", "add_plain", "add_3part", "rotate_keyswitch",
-         "decrypt_rotate", "tensor_add_plain", "tensor_automorph", "tensor_mul_plain", "sk", "ksw"]
+         "decrypt_rotate", "tensor_add_plain", "tensor_automorph", "tensor_mul_plain", "sk", "ksw",
+         "unreduced_rot_mul", "embed_slots"]
 
 
 def run(exe, logq, p, g, seed=SEED):

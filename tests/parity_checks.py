@@ -18,6 +18,34 @@ def check_mult_relin(sc: Scenario, count=2, host=False, random_inputs=False):
         assert_ct_equal(sc, out[i], want, f"mult_relin[{i}]")
 
 
+def check_mult_relin_wide(logq, p, g, lib_path, pairs=64, seeds=(101, 202, 303), device=0, oracle_pairs=2):
+    """Breadth: `pairs` fresh ciphertext pairs x len(seeds) independent key sets, every output word compared.
+    The checker for all pairs is oracle/ref_restate.c -- the reference's ALGORITHM restated in C (m-point
+    Bluestein per 60-bit chain prime, incremental big-integer CRT), itself pinned to the exact-integer oracle by
+    tests/test_oracle.py; the first `oracle_pairs` of every seed are also checked against the Python oracle
+    directly.  Half of the pairs are fresh encryptions, half uniformly random reduced parts (full range)."""
+    import ref_port
+    for seed in seeds:
+        sc = Scenario(logq, p, g, seed=seed, lib_path=lib_path, device=device)
+        port = ref_port.RefPort(sc.octx)
+        port.set_key_switch(sc.ks)
+        nf = pairs // 2
+        _, cts = sc.fresh(2 * nf)
+        A = cts[:nf] + sc.random_cts(pairs - nf)
+        B = cts[nf:] + sc.random_cts(pairs - nf)
+        out = sc.dev_mult_relin(A, B)
+        pa, pb = sc.pack_cts(A), sc.pack_cts(B)
+        for i in range(pairs):
+            want = port.mult_relin(pa[i], pb[i])
+            if not np.array_equal(out[i], want):
+                bad = np.argwhere(out[i] != want)
+                raise AssertionError(f"seed {seed} pair {i}: {len(bad)} words differ from the reference algorithm, "
+                                     f"first at (part, coeff, word) = {bad[0].tolist()}")
+        for i in list(range(oracle_pairs)) + [pairs - 1]:
+            assert_ct_equal(sc, out[i], O.mult_relin(sc.ks, A[i], B[i]), f"seed {seed} mult_relin[{i}] vs oracle")
+        sc.dev.close()
+
+
 def check_ksw_generate(sc: Scenario, g):
     """fhesi_ksw_generate = KeySwitchSI::Init on the device from explicit draws: b and A' against the
     oracle's KeySwitch.init on the same draws (s^2 -> s matrix and a rotation matrix), and a mult+relin
@@ -402,6 +430,32 @@ def check_golden(name, lib_path, device=0):
     d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
     d.sync()
     got["tensor_mul_plain"] = O.export_ciphertext(unpack(dc.download((3, n, W))))
+    # ---- fourth group: the documented deviation, pinned.  x = a; x >>= k; x *= b.  The reference multiplies the
+    # UNREDUCED a(X^k) (coefficients in (-q, q)); the C ABI's tensor product takes W-word operands, so a caller
+    # reduces first (fhesi_reduce_wide_dev) -- what the host layer's Ciphertext *= does.  The two results differ
+    # exactly by the carried multiple of q: with a(X^k) = r + q K (r reduced), the reference's tensor is
+    # p (r + q K) * b, ours p r * b, and ScaleDown turns the difference into Reduce(p K * b) per part.
+    d.ct_automorph_dev(da.ptr, 2, rot_k, dw.ptr, 1)
+    d.reduce_wide_dev(dw.ptr, W + 1, dr.ptr, 2, 1)
+    d.ct_tensor_dev(dr.ptr, 2, db.ptr, 2, dt.ptr, 1)
+    d.scaledown_dev(dt.ptr, 3, dc.ptr, 1)
+    d.sync()
+    ours = unpack(dc.download((3, n, W)))
+    wide = cts[0].copy().automorph(rot_k)                                  # the reference's operand
+    red = O.Ciphertext(ctx, [O.reduce_poly(x, logq) for x in wide.parts])  # ours
+    assert O.export_ciphertext(ours) == O.export_ciphertext(red.copy().mul(cts[1])), "reduce-first product"
+    K = [[(w - r) >> logq for w, r in zip(wp, rp)] for wp, rp in zip(wide.parts, red.parts)]
+    assert all(set(k) <= {-1, 0, 1} for k in K)
+    ref_ct = wide.copy().mul(cts[1]).scale_down()
+    corr = [[0] * ctx.phim for _ in range(3)]
+    for i in range(2):
+        for j in range(2):
+            pr = ctx.ring.mul([p * c for c in K[i]], cts[1].parts[j])
+            corr[i + j] = [x + y for x, y in zip(corr[i + j], pr)]
+    want = [O.reduce_poly([x + y for x, y in zip(op, cp)], logq) for op, cp in zip(ours.parts, corr)]
+    assert [list(x) for x in ref_ct.parts] == want, "reference = ours + Reduce(p K * b)"
+    got["unreduced_rot_mul"] = O.export_ciphertext(ref_ct) if any(any(k) for k in K) else O.export_ciphertext(ours)
+    assert any(any(k) for k in K) == (O.export_ciphertext(ref_ct) != O.export_ciphertext(ours))
     if "out" in g:
         assert {k: v.hex() for k, v in got.items()} == g["out"]
     else:
@@ -442,6 +496,30 @@ def check_embed_slots(sc: Scenario, g, count=5):
             for coef in reversed(want):
                 acc = (acc * sl.roots[k] + coef) % p
             assert acc == int(vals[c, k]), f"slot {k} of row {c} does not decode"
+    # Against the REFERENCE's own PlaintextSpace::EmbedInSlots (oracle/_ref via tests/golden/ref_golden.json:
+    # slot k holds (7k + 3) mod p).  Which root is slot 0 follows from the factoring order of Phi_m mod p, which
+    # the reference does not pin, so the two agree up to a cyclic shift of the slot vector: the reference's
+    # polynomial must be the kernel's embedding of ONE of the n rotations -- all n computed in one launch.
+    import hashlib
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.json")))
+    for cfg in ref["configs"].values():
+        P = cfg["params"]
+        if (P["logQ"], P["p"], P["g"]) != (sc.logq, p, g) or "embed_slots" not in cfg["sha256"]:
+            continue
+        base = [(7 * k + 3) % p for k in range(nslots)]
+        rot = np.array([base[k:] + base[:k] for k in range(nslots)], dtype=np.uint32)
+        drot = d.to_device(rot)
+        dout = d.alloc(nslots * n * 4)
+        d.embed_slots_dev(dbasis.ptr, nslots, drot.ptr, dout.ptr, nslots)
+        d.sync()
+        polys = dout.download((nslots, n))
+        digests = {hashlib.sha256(O.export_zzx(row.tolist())).hexdigest() for row in polys}
+        assert cfg["sha256"]["embed_slots"] in digests, "reference EmbedInSlots is not a slot rotation of the kernel's"
+        break
+    else:
+        raise AssertionError("no reference golden for this parameter set")
 
 
 def check_mul_plain(sc: Scenario, count=2):

@@ -30,6 +30,12 @@ def test_mult_relin(name, cuda_lib):
     P.check_mult_relin(sc, count=2 if name == "cfg5_512" else 3)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5_128", "cfg5_512"])
+def test_mult_relin_wide(name, cuda_lib):
+    """64 pairs x 3 key sets per parameter set (24 x 3 at logQ = 512, where the CPU checker is slowest)."""
+    P.check_mult_relin_wide(*CONFIGS[name], cuda_lib, pairs=24 if name == "cfg5_512" else 64)
+
+
 def test_mult_relin_host_and_random_cfg2(cuda_lib):
     sc = scenario("cfg2", cuda_lib)
     P.check_mult_relin(sc, count=2, host=True)
@@ -45,7 +51,7 @@ def test_pieces(name, cuda_lib):
     P.check_gathered_reduce(sc)
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5_128", "cfg5_512"])
 def test_encrypt_decrypt(name, cuda_lib):
     P.check_encrypt_decrypt(scenario(name, cuda_lib), count=3)
 

@@ -54,10 +54,39 @@ def check_against_golden(out, name):
     ref = REF_GOLD["configs"][name]
     rd = lambda f: open(out / (f + ".bin"), "rb").read()
     for f, h in ref["sha256"].items():
+        if f in ("unreduced_rot_mul", "embed_slots"):
+            continue  # not byte-comparable by design: see below
         blob = rd(f)
         if "hex" in ref:
             assert blob.hex() == ref["hex"][f], (name, f)
         assert hashlib.sha256(blob).hexdigest() == h, (name, f)
+    P = ref["params"]
+    # (1) the documented deviation: `x >>= k; x *= b` reduces x first here, the reference carries the extra
+    # multiple of q.  Ours must be the oracle's reduce-first product (parity_checks.check_golden pins the exact
+    # difference: reference = ours + Reduce(p K * b)).
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ctx, sk, pk, ks, msgs, rand, cts = mg.scenario(P["logQ"], P["p"], P["g"], REF_GOLD["seed"])
+    wide = cts[0].copy().automorph(ks.rot_k)
+    red = O.Ciphertext(ctx, [O.reduce_poly(x, P["logQ"]) for x in wide.parts])
+    assert rd("unreduced_rot_mul") == O.export_ciphertext(red.copy().mul(cts[1])), (name, "reduce-first product")
+    if any(w != r for wp, rp in zip(wide.parts, red.parts) for w, r in zip(wp, rp)):
+        assert hashlib.sha256(rd("unreduced_rot_mul")).hexdigest() != ref["sha256"]["unreduced_rot_mul"]
+    # (2) EmbedInSlots: which root of Phi_m is slot 0 follows from the factoring order of Phi_m mod p (NTL's
+    # randomized SFCanZass; unpinned), so implementations agree up to a cyclic shift of the slot vector.  The
+    # reference's polynomial must be OUR embedding of some rotation of the same values.
+    sys.path.insert(0, os.path.join(ROOT, "apps"))
+    from fhesi_app import Slots
+    m, p = P["p"] - 1, P["p"]
+    slots = Slots(m, p, P["g"], [(-1) ** i for i in range(m // 2)])
+    vals = [(i * 7 + 3) % p for i in range(slots.total)]
+    pad = lambda c: list(c) + [0] * (ctx.phim - len(c))
+    ours = pad(O.import_zzx(rd("embed_slots"), 0, ctx.phim)[0])
+    assert ours == [int(c) for c in slots.embed(vals)], (name, "host EmbedInSlots vs the integer definition")
+    cand = {hashlib.sha256(O.export_zzx([int(c) for c in slots.embed(vals[k:] + vals[:k])])).hexdigest()
+            for k in range(slots.total)}
+    assert ref["sha256"]["embed_slots"] in cand, (name, "reference EmbedInSlots is not a slot rotation of ours")
 
 
 def test_host_client_matches_oracle_cfg1_emu(emu_lib, tmp_path):
@@ -147,6 +176,52 @@ def test_random_stream_is_keyed_emu(emu_lib, tmp_path):
     test_env = dict(prod, FHESI_TEST_RNG="splitmix64")
     want = O.Rng(12345)
     assert [int(v) for v in run(["12345"], test_env)] == [want.next64() for _ in range(4)]
+
+
+def test_zz_matches_python_integers(emu_lib, tmp_path):
+    """The big-integer type under the host layer AND under the reference build (oracle/ntl_compat shares
+    ntl_shim.h) against an independent implementation -- Python integers -- on random and edge operands, with
+    NTL's semantics (floor division, magnitude shifts, little-endian byte conversion)."""
+    import random
+    exe = compile_client([os.path.join(ROOT, "tests", "cpp", "zz_probe.cpp")], emu_lib, str(tmp_path / "zz_probe"))
+    rnd = random.Random(7)
+    M61 = (1 << 61) - 1
+
+    def operand(bits):
+        v = rnd.getrandbits(bits) if bits else 0
+        return -v if rnd.random() < 0.4 else v
+    edges = [0, 1, -1, 2**32 - 1, 2**32, -(2**32), 2**64 - 1, 2**64, 2**255, -(2**255), 2**256 - 1, 2**541 + 12345]
+    cases, want = [], []
+
+    def add(op, a, b, r):
+        cases.append(f"{op} {a} {b}")
+        want.append(str(r))
+    pool = edges + [operand(b) for b in (7, 31, 32, 33, 63, 64, 65, 128, 255, 256, 257, 512, 541, 1100) for _ in range(6)]
+    for a in pool:
+        for b in rnd.sample(pool, 8):
+            add("add", a, b, a + b), add("sub", a, b, a - b), add("mul", a, b, a * b)
+            add("cmp", a, b, (a > b) - (a < b))
+            if b != 0:
+                add("div", a, b, a // b), add("mod", a, b, a % b if b > 0 else -((-a) % (-b)))
+        for k in (0, 1, 31, 32, 33, 64, 100, 257):
+            add("shl", a, k, a << k)
+            add("shr", a, k, (abs(a) >> k) * (1 if a >= 0 else -1))  # magnitude shift, sign kept
+        add("nbits", a, 0, abs(a).bit_length()), add("nbytes", a, 0, (abs(a).bit_length() + 7) // 8)
+        for nb in (0, 1, 8, 33, 200):
+            add("bytes", a, nb, abs(a) % (1 << (8 * nb)))     # BytesFromZZ takes the magnitude, low n bytes
+        e = rnd.getrandbits(40)
+        add("powmod", a, e, pow(a % M61, e, M61))
+        add("modl", a, 1019, a % 1019)
+        mod = rnd.choice([1019, 2027, M61, 1152921504606820681])
+        if a % mod:
+            add("invmod", a, mod, pow(a % mod, -1, mod))
+    r = subprocess.run([exe], input="\n".join(cases) + "\n", capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = r.stdout.split()
+    assert len(got) == len(want)
+    bad = [(c, g, w) for c, g, w in zip(cases, got, want) if g != w]
+    assert not bad, bad[:5]
+    assert len(cases) > 5000
 
 
 def test_import_rejects_hostile_files_emu(emu_lib, tmp_path):
