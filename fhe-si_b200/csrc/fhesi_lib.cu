@@ -371,6 +371,18 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
     fhesi_ctx_destroy(c);
     return rc;
   }
+  if (N == FN) {  // the fused kernels' per-thread twiddle layout, laid out once
+    std::vector<uint2> lf((size_t)L * FTW_ENTRIES), li((size_t)L * FTW_ENTRIES);
+    for (u32 l = 0; l < L; ++l)
+      for (u32 e = 0; e < FTW_ENTRIES; ++e) {
+        lf[(size_t)l * FTW_ENTRIES + e] = twsf[(size_t)l * N + ftw_source_index(e)];
+        li[(size_t)l * FTW_ENTRIES + e] = twsi[(size_t)l * N + ftw_source_index(e)];
+      }
+    if ((rc = upload(c, lf, &dc.ftw_fwd)) || (rc = upload(c, li, &dc.ftw_inv))) {
+      fhesi_ctx_destroy(c);
+      return rc;
+    }
+  }
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   {
@@ -635,15 +647,15 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
     default: KL(c, k_residues, rg, 128, (I.Lt * 2 * c->dc.CW + 2 * I.Lt) * 4, c->dc, r);
   }
   CKL();
-  // ops per group: more of them amortise the CTA's twiddle-table fill (about 0.35 of one op's
-  // work), fewer keep the last wave full; pick the best product of the two
+  // ops per group: more of them amortise the CTA's twiddle-table fill (a straight 16 KB copy, about
+  // 0.04 of one op's work), fewer keep the last wave full; pick the best product of the two
   u32 opg = 1;
   {
     double best = 0;
     for (u32 o = 1; o <= 4; ++o) {
       const double ctas = (double)I.Lt * (double)((cnt + KG * o - 1) / (KG * o));
       const double waves = ctas / c->sm_count;
-      const double eff = waves / std::ceil(waves) / (1.0 + 0.35 / o);
+      const double eff = waves / std::ceil(waves) / (1.0 + 0.04 / o);
       if (eff > best * 1.0001) best = eff, opg = o;
     }
   }

@@ -59,36 +59,28 @@ __device__ __forceinline__ u32 mulw(u32 x, uint2 w, u32 p) { return x * w.x - __
 #define FTD_ENTRIES (7u * 16u + 7u * 2u)
 #define FTD_WORDS (FTD_ENTRIES * 4u)
 // tws layout: pass 1: [s][tg] (s < 7, 128 per row); pass 2: [s][lo] (16 per row); pass 3: [s][b0]
-__device__ __forceinline__ void fill_tw_table(uint2 *tws, const uint2 *__restrict__ table) {
-  for (u32 e = threadIdx.x; e < FTW_ENTRIES; e += blockDim.x) {
-    u32 idx;
-    if (e < FTW_P2) {
-      const u32 s = e >> 7, t = e & 127;
-      idx = s < 4 ? 512 + s * 128 + t : (s < 6 ? 256 + (s - 4) * 128 + t : 128 + t);
-    } else if (e < FTW_P3) {
-      const u32 s = (e - FTW_P2) >> 4, lo = (e - FTW_P2) & 15;
-      idx = s < 4 ? 64 + s * 16 + lo : (s < 6 ? 32 + (s - 4) * 16 + lo : 16 + lo);
-    } else {
-      const u32 s = (e - FTW_P3) >> 1, b0 = (e - FTW_P3) & 1;
-      idx = s < 4 ? 8 + s * 2 + b0 : (s < 6 ? 4 + (s - 4) * 2 + b0 : 2 + b0);
-    }
-    tws[e] = __ldg(table + idx);
+// index into the [N] Shoup table of entry e of the per-thread layout above
+__host__ __device__ __forceinline__ u32 ftw_source_index(u32 e) {
+  if (e < FTW_P2) {
+    const u32 s = e >> 7, t = e & 127;
+    return s < 4 ? 512 + s * 128 + t : (s < 6 ? 256 + (s - 4) * 128 + t : 128 + t);
   }
+  if (e < FTW_P3) {
+    const u32 s = (e - FTW_P2) >> 4, lo = (e - FTW_P2) & 15;
+    return s < 4 ? 64 + s * 16 + lo : (s < 6 ? 32 + (s - 4) * 16 + lo : 16 + lo);
+  }
+  const u32 s = (e - FTW_P3) >> 1, b0 = (e - FTW_P3) & 1;
+  return s < 4 ? 8 + s * 2 + b0 : (s < 6 ? 4 + (s - 4) * 2 + b0 : 2 + b0);
 }
-
+// The per-prime tables are stored in HBM already in this layout (DevCtx::ftw_fwd / ftw_inv, built once at
+// context creation), so a CTA's fill is a straight coalesced copy -- the index arithmetic above used to cost
+// a CTA of the tensor kernel a third of one ciphertext pair's work.
+__device__ __forceinline__ void fill_tw_table(uint2 *tws, const uint2 *__restrict__ laid_out) {
+  for (u32 e = threadIdx.x; e < FTW_ENTRIES; e += blockDim.x) tws[e] = __ldg(laid_out + e);
+}
 // twd[e - FTW_P2] for the pass-2 / pass-3 entries e of fill_tw_table, same source index
 __device__ __forceinline__ void fill_twd_table(double2 *twd, const double2 *__restrict__ table) {
-  for (u32 e = FTW_P2 + threadIdx.x; e < FTW_ENTRIES; e += blockDim.x) {
-    u32 idx;
-    if (e < FTW_P3) {
-      const u32 s = (e - FTW_P2) >> 4, lo = (e - FTW_P2) & 15;
-      idx = s < 4 ? 64 + s * 16 + lo : (s < 6 ? 32 + (s - 4) * 16 + lo : 16 + lo);
-    } else {
-      const u32 s = (e - FTW_P3) >> 1, b0 = (e - FTW_P3) & 1;
-      idx = s < 4 ? 8 + s * 2 + b0 : (s < 6 ? 4 + (s - 4) * 2 + b0 : 2 + b0);
-    }
-    twd[e - FTW_P2] = table[idx];
-  }
+  for (u32 e = FTW_P2 + threadIdx.x; e < FTW_ENTRIES; e += blockDim.x) twd[e - FTW_P2] = table[ftw_source_index(e)];
 }
 
 #define GSW(X, Y, W)                          \
@@ -486,8 +478,8 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTen
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
   const u32 l = blockIdx.x;
-  fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
-  fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
+  fill_tw_table(twf, c.ftw_fwd + (size_t)l * FTW_ENTRIES);
+  fill_tw_table(twi, c.ftw_inv + (size_t)l * FTW_ENTRIES);
   __syncthreads();
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
@@ -561,8 +553,8 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
   const u32 l = blockIdx.x;
-  fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
-  fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
+  fill_tw_table(twf, c.ftw_fwd + (size_t)l * FTW_ENTRIES);
+  fill_tw_table(twi, c.ftw_inv + (size_t)l * FTW_ENTRIES);
   __syncthreads();
   const size_t op = (size_t)blockIdx.y * KSG + g;
   if (op >= a.count) return;  // whole group leaves together; only group barriers from here on
@@ -655,8 +647,8 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
   const u32 l = blockIdx.x;
   double2 *twd = (double2 *)(sm + 2 * FTW_WORDS);
-  fill_tw_table(twf, c.tws_fwd + (size_t)l * FN);
-  fill_tw_table(twi, c.tws_inv + (size_t)l * FN);
+  fill_tw_table(twf, c.ftw_fwd + (size_t)l * FTW_ENTRIES);
+  fill_tw_table(twi, c.ftw_inv + (size_t)l * FTW_ENTRIES);
   fill_twd_table(twd, c.twd_fwd + (size_t)l * FN);
   __syncthreads();
   const size_t op = (size_t)blockIdx.y * KSS + g;

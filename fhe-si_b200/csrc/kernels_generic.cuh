@@ -43,6 +43,9 @@ struct DevCtx {
   const uint2 *tws_fwd, *tws_inv;         // [Lmax][N] same index h + j as tw_fwd / tw_inv
   // FP64-quotient companions of tws_fwd (mulw_dfma): (c, K) per twiddle, [Lmax][N]
   const double2 *twd_fwd;
+  // tws_fwd / tws_inv re-laid-out per thread for the fused N = 1024 kernels (kernels_fused.cuh, FTW layout):
+  // [Lmax][FTW_ENTRIES]; NULL when N != 1024
+  const uint2 *ftw_fwd, *ftw_inv;
   // multiword -> residue constants: cwr[l][v][k] = 2^(32k) * R * s_v mod p for k < W, and
   // cwr[l][v][W] = p - (2^(32W) * s_v mod p); s_0 = 1 (plain result after Montgomery
   // reduction), s_1 = p_pt / N * R (Montgomery form of the tensor's left operand)
