@@ -135,6 +135,12 @@ static void prof_end(fhesi_ctx *c) {
     FHESI_LAUNCH(kern, grid, block, smem, (c)->stream, __VA_ARGS__);       \
     prof_end((c));                                                         \
   } while (0)
+// One device allocation shared by the key images made in one call (a whole set-up's matrices come out of
+// fhesi_keygen_batch together): cudaMalloc costs ~0.1 ms a piece, three per matrix used to dominate key set-up
+struct KeyBlock {
+  void *ptr;
+  int refs;
+};
 struct fhesi_ksw {
   fhesi_ctx *ctx;
   u32 *d_key;      // [Lk][parts*D][2][N] key form, residues in [0,p)
@@ -142,6 +148,7 @@ struct fhesi_ksw {
   u32 *d_key_split;  // [Ls][parts*D][4][N] balanced key form of (b_lo, b_hi, A_lo, A_hi), then the
                      // offset-correction table [Ls][4][N] (k_split_corr); NULL if unused
   u32 parts;
+  KeyBlock *blk;
 };
 struct fhesi_key {
   fhesi_ctx *ctx;
@@ -671,53 +678,87 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
 // ---------------------------------------------------------------------------------------
 // Device half of the key upload: b, A as [K][n][W] coefficient words in HBM -> key-form images
 // (prime-major, balanced, split halves).  Enqueued on the context's stream; the caller synchronises.
-static int ksw_build_from_device(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, uint32_t parts, fhesi_ksw **out) {
+// words of scratch and of key images one matrix needs (ksw_build_from_device)
+static void ksw_sizes(const fhesi_ctx *c, uint32_t parts, size_t *scratch_words, size_t *key_words) {
+  const fhesi_info &I = c->info;
+  const size_t K = (size_t)parts * I.D, polyw = (size_t)I.n * I.W, full = K * 2 * I.Lk * I.N;
+  const bool bal = c->use_fused && c->tfree, split = bal && I.Ls;
+  const size_t sp = split ? K * 4 * I.Ls * I.N : 0;
+  *scratch_words = al(K * 2 * polyw) + al(full) + (split ? al(K * 4 * polyw) + 2 * al(sp) : 0);
+  *key_words = al(full) + (bal ? al(full) : 0) + (split ? al(sp + (size_t)I.Ls * 4 * I.N) : 0);
+}
+// b, A [K][n][W] on the device -> key-form images in `keymem` (ksw_sizes words), using `scr` as scratch.
+// Enqueued on the context's stream; the caller synchronises.  blk: the allocation keymem lives in.
+static int ksw_build_from_device(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, uint32_t parts, u32 *scr, u32 *keymem,
+                                 KeyBlock *blk, fhesi_ksw **out) {
   const fhesi_info &I = c->info;
   const u32 K = parts * I.D, Lk = I.Lk;
-  const size_t polyw = (size_t)I.n * I.W;
-  const bool split = c->use_fused && c->tfree && I.Ls;
-  // the key's own buffers come from the context's pool as well: a client that regenerates its keys (one
-  // regression per request) re-uses the blocks of the previous set instead of paying cudaMalloc / cudaFree
-  PoolTmp t_key(c), t_bal(c), t_split(c);
-  PoolTmp t_in(c), t_tmp(c), t_in2(c), t_tmp2(c), t_t2(c);  // scratch
-  int rc = t_in.alloc((size_t)K * 2 * polyw * 4);
-  if (!rc) rc = t_tmp.alloc((size_t)K * 2 * Lk * I.N * 4);
-  if (!rc && split) rc = t_in2.alloc((size_t)K * 4 * polyw * 4);
-  if (rc) return rc;
-  if ((rc = t_key.alloc((size_t)K * 2 * Lk * I.N * 4))) return rc;
-  u32 *d_in = t_in.u(), *d_tmp = t_tmp.u(), *d_key = t_key.u();
+  const size_t polyw = (size_t)I.n * I.W, full = (size_t)K * 2 * Lk * I.N;
+  const bool bal = c->use_fused && c->tfree, split = bal && I.Ls;
+  u32 *d_in = scr, *d_tmp = d_in + al((size_t)K * 2 * polyw), *d_in2 = d_tmp + al(full);
+  u32 *d_key = keymem, *d_bal = bal ? d_key + al(full) : nullptr, *d_split = split ? d_bal + al(full) : nullptr;
+  int rc = 0;
   // interleave to [K][2] so that one transform launch writes [K*2][Lk][N]; K mod q (non-negative)
   // = lo + 2^(32 ws) hi, each half as a non-negative W-word polynomial
-  KL(c, k_key_stage, nblk((size_t)K * 2 * I.n), 256, 0, d_b, d_A, d_in, split ? t_in2.u() : (u32 *)nullptr, K, I.n,
-     I.W, I.split_words, I.logQ & 31);
+  KL(c, k_key_stage, nblk((size_t)K * 2 * I.n), 256, 0, d_b, d_A, d_in, split ? d_in2 : (u32 *)nullptr, K, I.n, I.W,
+     I.split_words, I.logQ & 31);
   CKL();
-  rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2);
-  if (rc) return rc;
+  if ((rc = launch_fwd(c, d_in, SRC_POLY, I.W, SC_KEYFORM, Lk, d_tmp, (size_t)K * 2))) return rc;
   // [K*2][Lk][N] -> [Lk][K*2][N]
-  KL(c, k_transpose_key, nblk((size_t)K * 2 * Lk * I.N), 256, 0, d_tmp, d_key, K * 2, Lk, I.N);
+  KL(c, k_transpose_key, nblk(full), 256, 0, d_tmp, d_key, K * 2, Lk, I.N);
   CKL();
-  if (c->use_fused && c->tfree) {
-    const size_t total = (size_t)K * 2 * Lk * I.N;
-    if ((rc = t_bal.alloc(total * 4))) return rc;
-    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_key, t_bal.u(), K * 2, total);
+  if (bal) {
+    KL(c, k_balance_key, nblk(full), 256, 0, c->dc, d_key, d_bal, K * 2, full);
     CKL();
   }
   if (split) {
     const u32 Ls = I.Ls;
     const size_t total = (size_t)K * 4 * Ls * I.N;
-    rc = t_tmp2.alloc(total * 4);
-    if (!rc) rc = t_t2.alloc(total * 4);
-    if (rc) return rc;
-    if ((rc = t_split.alloc((total + (size_t)Ls * 4 * I.N) * 4))) return rc;  // + the offset-correction table
-    if ((rc = launch_fwd(c, t_in2.u(), SRC_POLY, I.W, SC_KEYFORM, Ls, t_tmp2.u(), (size_t)K * 4))) return rc;
-    KL(c, k_transpose_key, nblk(total), 256, 0, t_tmp2.u(), t_t2.u(), K * 4, Ls, I.N);
+    u32 *d_tmp2 = d_in2 + al((size_t)K * 4 * polyw), *d_t2 = d_tmp2 + al(total);
+    if ((rc = launch_fwd(c, d_in2, SRC_POLY, I.W, SC_KEYFORM, Ls, d_tmp2, (size_t)K * 4))) return rc;
+    KL(c, k_transpose_key, nblk(total), 256, 0, d_tmp2, d_t2, K * 4, Ls, I.N);
     CKL();
-    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, t_t2.u(), t_split.u(), K * 4, total);
+    KL(c, k_balance_key, nblk(total), 256, 0, c->dc, d_t2, d_split, K * 4, total);
     CKL();
-    KL(c, k_split_corr, nblk((size_t)Ls * 4 * I.N), 256, 0, c->dc, t_split.u(), t_split.u() + total, K, Ls);
+    KL(c, k_split_corr, nblk((size_t)Ls * 4 * I.N), 256, 0, c->dc, d_split, d_split + total, K, Ls);  // + correction table
     CKL();
   }
-  *out = new fhesi_ksw{c, (u32 *)t_key.release(), (u32 *)t_bal.release(), (u32 *)t_split.release(), parts};
+  blk->refs++;
+  *out = new fhesi_ksw{c, d_key, d_bal, d_split, parts, blk};
+  return 0;
+}
+// M matrices from consecutive entries of d_b / d_A: one scratch block, one key block for all of them
+static int ksw_build_many(fhesi_ctx *c, const u32 *d_b, const u32 *d_A, uint32_t M, const uint32_t *parts,
+                          fhesi_ksw **out) {
+  const size_t polyw = (size_t)c->info.n * c->info.W;
+  size_t scr_max = 0, key_total = 0;
+  for (u32 m = 0; m < M; ++m) {
+    size_t sw, kw;
+    ksw_sizes(c, parts[m], &sw, &kw);
+    scr_max = std::max(scr_max, sw);
+    key_total += kw;
+  }
+  PoolTmp scr(c), keys(c);
+  int rc = scr.alloc(scr_max * 4);
+  if (!rc) rc = keys.alloc(key_total * 4);
+  if (rc) return rc;
+  KeyBlock *blk = new KeyBlock{keys.u(), 0};
+  size_t off = 0, koff = 0;
+  for (u32 m = 0; m < M; ++m) {
+    out[m] = nullptr;
+    size_t sw, kw;
+    ksw_sizes(c, parts[m], &sw, &kw);
+    // stream order makes the shared scratch safe: matrix m+1's kernels run after matrix m's
+    if ((rc = ksw_build_from_device(c, d_b + off * polyw, d_A + off * polyw, parts[m], scr.u(), keys.u() + koff, blk,
+                                    &out[m]))) {
+      for (u32 k = 0; k < m; ++k) delete out[k], out[k] = nullptr;
+      delete blk;
+      return rc;  // `keys` is still owned by the PoolTmp and goes back to the pool
+    }
+    off += (size_t)parts[m] * c->info.D;
+    koff += kw;
+  }
+  keys.release();  // now owned by blk
   return 0;
 }
 int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uint32_t parts,
@@ -733,7 +774,7 @@ int fhesi_ksw_create(fhesi_ctx *c, const uint32_t *h_b, const uint32_t *h_A, uin
   if (rc) return rc;
   CK(cudaMemcpyAsync(d_b.u(), h_b, bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d_A.u(), h_A, bytes, cudaMemcpyHostToDevice, c->stream));
-  rc = ksw_build_from_device(c, d_b.u(), d_A.u(), parts, out);
+  rc = ksw_build_many(c, d_b.u(), d_A.u(), 1, &parts, out);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));  // h_b / h_A may be pinned: the caller gets them back consumed
   return 0;
@@ -829,15 +870,7 @@ int fhesi_keygen_batch(fhesi_ctx *c, uint32_t M, const uint32_t *parts, const in
     return rc;
   if (timing) cudaStreamSynchronize(c->stream);
   const double T2 = now();
-  size_t off = 0;
-  for (u32 m = 0; m < M; ++m) {
-    out[m] = nullptr;
-    if ((rc = ksw_build_from_device(c, d_b.u() + off * polyw, d_An.u() + off * polyw, parts[m], &out[m]))) {
-      for (u32 k = 0; k < m; ++k) fhesi_ksw_destroy(out[k]), out[k] = nullptr;
-      return rc;
-    }
-    off += (size_t)parts[m] * I.D;
-  }
+  if (M && (rc = ksw_build_many(c, d_b.u(), d_An.u(), M, parts, out))) return rc;
   PoolTmp d_pk(c);
   if (pk_out) {  // publicKey = (c0, c1') (FHE-SI.cpp:59-61)
     if ((rc = d_pk.alloc(2 * polyw * 4))) return rc;
@@ -865,9 +898,10 @@ void fhesi_ksw_destroy(fhesi_ksw *k) {
   if (!k) return;
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);  // (the host pipeline's lane streams are drained by its own call)
-  fhesi_free(k->ctx, k->d_key);
-  if (k->d_key_bal) fhesi_free(k->ctx, k->d_key_bal);
-  if (k->d_key_split) fhesi_free(k->ctx, k->d_key_split);
+  if (--k->blk->refs == 0) {
+    fhesi_free(k->ctx, k->blk->ptr);
+    delete k->blk;
+  }
   delete k;
 }
 static int key_build_from_device(fhesi_ctx *c, const u32 *d_polys, uint32_t parts, fhesi_key **out) {

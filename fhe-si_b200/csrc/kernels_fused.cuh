@@ -669,16 +669,16 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
   const u32 m2 = (256 + tg < c.n) ? 0xFFFFFFFFu : 0u, m3 = (384 + tg < c.n) ? 0xFFFFFFFFu : 0u;
   const u32 *dp = a.digits + op * a.K * (size_t)c.n + tg;
   const uint4 *kp = (const uint4 *)(a.key + (size_t)l * a.K * 4 * FN + tg * 8);
-  u32 xn[4];
-  xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256) & m2, xn[3] = __ldg(dp + 384) & m3;
+  u32 xn[4];  // raw words, prefetched one transform ahead; the masks are applied when they are consumed (an
+              // AND right behind the load would wait for it)
+  xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256), xn[3] = __ldg(dp + 384);
   u32 tgl = 0;
   for (u32 k = 0; k < a.K; ++k) {
     u32 x[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = xn[j];
+    x[0] = xn[0], x[1] = xn[1], x[2] = xn[2] & m2, x[3] = xn[3] & m3;
     if (k + 1 < a.K) {
       dp += c.n;
-      xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256) & m2, xn[3] = __ldg(dp + 384) & m3;
+      xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256), xn[3] = __ldg(dp + 384);
     }
     fwd1024<true, KSS_DFMA>(x, twf, A, bufA0 + tgl, bufB, g, tg, p, twd, negp, hic, zop);
     tgl ^= KSS_BUFA;
