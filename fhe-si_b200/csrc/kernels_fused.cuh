@@ -669,16 +669,37 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
   const u32 m2 = (256 + tg < c.n) ? 0xFFFFFFFFu : 0u, m3 = (384 + tg < c.n) ? 0xFFFFFFFFu : 0u;
   const u32 *dp = a.digits + op * a.K * (size_t)c.n + tg;
   const uint4 *kp = (const uint4 *)(a.key + (size_t)l * a.K * 4 * FN + tg * 8);
-  u32 xn[4];  // raw words, prefetched one transform ahead; the masks are applied when they are consumed (an
-              // AND right behind the load would wait for it)
-  xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256), xn[3] = __ldg(dp + 384);
+  // The next digit's four words per thread are fetched one transform ahead by an asynchronous copy
+  // (cp.async, LDGSTS) into the unused tail of the exchange buffer the current transform does NOT use: no
+  // registers are held across the transform and the fetch cannot be scheduled late (with plain loads ptxas
+  // sank them to the end of the loop body to save registers, exposing their whole latency).  A thread reads
+  // back only what it wrote itself, so cp.async.wait_group is all the synchronisation needed.
+  u32 *stage0 = bufA0 + FPADN + tg, *stage1 = stage0 + KSS_BUFA;  // 4 words each at +0, +128, +256, +384
+  auto fetch = [&](u32 *st, const u32 *src) {
+#ifdef FHESI_EMU
+    st[0] = src[0], st[128] = src[128], st[256] = src[256], st[384] = src[384];
+#else
+    const u32 sa = (u32)__cvta_generic_to_shared(st);
+    asm volatile(
+        "cp.async.ca.shared.global [%0], [%1], 4;\n\t"
+        "cp.async.ca.shared.global [%0 + 512], [%1 + 512], 4;\n\t"
+        "cp.async.ca.shared.global [%0 + 1024], [%1 + 1024], 4;\n\t"
+        "cp.async.ca.shared.global [%0 + 1536], [%1 + 1536], 4;\n\t"
+        "cp.async.commit_group;" ::"r"(sa), "l"(src) : "memory");
+#endif
+  };
+  fetch(stage0, dp);
   u32 tgl = 0;
   for (u32 k = 0; k < a.K; ++k) {
     u32 x[8];
-    x[0] = xn[0], x[1] = xn[1], x[2] = xn[2] & m2, x[3] = xn[3] & m3;
+#ifndef FHESI_EMU
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+    const u32 *st = (k & 1) ? stage1 : stage0;
+    x[0] = st[0], x[1] = st[128], x[2] = st[256] & m2, x[3] = st[384] & m3;
     if (k + 1 < a.K) {
       dp += c.n;
-      xn[0] = __ldg(dp), xn[1] = __ldg(dp + 128), xn[2] = __ldg(dp + 256), xn[3] = __ldg(dp + 384);
+      fetch((k & 1) ? stage0 : stage1, dp);
     }
     fwd1024<true, KSS_DFMA>(x, twf, A, bufA0 + tgl, bufB, g, tg, p, twd, negp, hic, zop);
     tgl ^= KSS_BUFA;
