@@ -1075,6 +1075,23 @@ int fhesi_embed_slots_dev(fhesi_ctx *c, const uint32_t *basis, uint32_t nslots, 
   }
   return 0;
 }
+int fhesi_decode_slots_dev(fhesi_ctx *c, const uint32_t *vander, uint32_t nslots, const uint32_t *msg,
+                           uint32_t *vals, size_t count) {
+  if (!c || !vander || !msg || !vals) return fail(FHESI_ERR_INVALID, "null argument");
+  const fhesi_info &I = c->info;
+  if (!nslots || I.n > 4096 || I.p >= (1ull << 26))
+    return fail(FHESI_ERR_INVALID, "fhesi_decode_slots_dev: needs nslots >= 1, n <= 4096 and p < 2^26");
+  CK(cudaSetDevice(c->device));
+  if (!count) return 0;
+  for (size_t off = 0; off < count; off += 65535) {  // gridDim.y limit
+    const size_t cnt = count - off < 65535 ? count - off : 65535;
+    dim3 grid((nslots + 127) / 128, (unsigned)cnt);
+    // the embedding kernel with the roles swapped: n "slots" in (the coefficients), nslots values out
+    KL(c, k_embed_slots, grid, 128, I.n * 4, vander, msg + off * I.n, vals + off * nslots, I.n, nslots, (u32)I.p);
+    CKL();
+  }
+  return 0;
+}
 int fhesi_ct_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uint32_t k,
                            uint32_t *out, size_t count) {
   if (!c || !in || !out) return fail(FHESI_ERR_INVALID, "null argument");

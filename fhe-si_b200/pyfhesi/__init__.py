@@ -72,6 +72,7 @@ SYMBOLS = {
     "fhesi_tprod_mul_poly_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
     "fhesi_tprod_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
     "fhesi_embed_slots_dev": (C.c_int, [_P, _P, _U32, _P, _P, _SZ]),
+    "fhesi_decode_slots_dev": (C.c_int, [_P, _P, _U32, _P, _P, _SZ]),
     "fhesi_ct_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
     "fhesi_reduce_wide_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
     "fhesi_ref_rows_host": (C.c_int, [_P, _P, _U32, _P, _P, _U32, _P]),
@@ -322,6 +323,10 @@ class Context:
 
     def embed_slots_dev(self, basis, nslots, vals, msg, count):
         self._ck(self.lib.fhesi_embed_slots_dev(self.h, _ptr(basis), nslots, _ptr(vals), _ptr(msg), count))
+
+    def decode_slots_dev(self, vander, nslots: int, msg, vals, count: int):
+        """PlaintextSpace::DecodeSlots for a batch: vals[c][k] = msg[c](root_k) mod p (vander[j][k] = root_k^j)."""
+        self._ck(self.lib.fhesi_decode_slots_dev(self.h, _ptr(vander), nslots, _ptr(msg), _ptr(vals), count))
 
     def ct_automorph_dev(self, inp, parts, k, out_wide, count):
         self._ck(self.lib.fhesi_ct_automorph_dev(self.h, _ptr(inp), parts, k, _ptr(out_wide), count))

@@ -218,6 +218,12 @@ int fhesi_tprod_automorph_dev(fhesi_ctx *ctx, const uint32_t *d_in, uint32_t par
  * fhesi_encrypt_dev takes.  Needs p < 2^26 and nslots <= 4096. */
 int fhesi_embed_slots_dev(fhesi_ctx *ctx, const uint32_t *d_basis, uint32_t nslots, const uint32_t *d_vals,
                           uint32_t *d_msg, size_t count);
+/* PlaintextSpace::DecodeSlots (PlaintextSpace.cpp:136-146) for a batch: vals[c][k] = msg[c](root_k) mod p, the
+ * value of the message polynomial at the root of slot k -- the same integer matrix product with the roles
+ * swapped.  vander: DEVICE uint32 [n][nslots], vander[j][k] = root_k^j mod p; msg: DEVICE uint32 [count][n]
+ * (what fhesi_decrypt_dev writes); vals: [count][nslots].  Needs p < 2^26 and n <= 4096. */
+int fhesi_decode_slots_dev(fhesi_ctx *ctx, const uint32_t *d_vander, uint32_t nslots, const uint32_t *d_msg,
+                           uint32_t *d_vals, size_t count);
 
 /* CiphertextPart::operator>>=(long k) (Ciphertext.cpp:54-59; DoubleCRT::automorph,
  * DoubleCRT.cpp:439-465): a(X) -> a(X^k) mod Phi_m.  The reference does NOT reduce the

@@ -496,6 +496,13 @@ def check_embed_slots(sc: Scenario, g, count=5):
             for coef in reversed(want):
                 acc = (acc * sl.roots[k] + coef) % p
             assert acc == int(vals[c, k]), f"slot {k} of row {c} does not decode"
+    # DecodeSlots on the device (fhesi_decode_slots_dev) undoes the embedding: exact against Horner evaluation
+    V = np.array([[pow(r, j, p) for r in sl.roots] for j in range(n)], dtype=np.uint32)
+    dV = d.to_device(V)
+    dback = d.alloc(count * nslots * 4)
+    d.decode_slots_dev(dV.ptr, nslots, dmsg.ptr, dback.ptr, count)
+    d.sync()
+    assert np.array_equal(dback.download((count, nslots)), vals), "decode_slots(embed_slots(v)) != v"
     # Against the REFERENCE's own PlaintextSpace::EmbedInSlots (oracle/_ref via tests/golden/ref_golden.json:
     # slot k holds (7k + 3) mod p).  Which root is slot 0 follows from the factoring order of Phi_m mod p, which
     # the reference does not pin, so the two agree up to a cyclic shift of the slot vector: the reference's
