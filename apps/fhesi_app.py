@@ -144,6 +144,84 @@ def keyswitch_and_sum_slots_batch(env, tprods, count, ksw, rot_k, rot_ksw):
     return [Ct(env, cur[i].clone(), 2) for i in range(count)]
 
 
+def _tensor_sum_keyswitch(env, ksw, terms):
+    """groups[g] = KeySwitch(ScaleDown(sum_t A_t[g] * B_t[g])): `terms` is a list of (A, B) pairs of
+    [G][ct_words(2)] tensors; every product of a term is one batched tensor call, the sum is taken in tensor
+    form (Matrix.cpp:80-97: products are summed before anything is reduced), then ONE ScaleDown and ONE key
+    switch over the G groups.  Sums mod p_i are exact, so the result equals the reference's one-at-a-time order."""
+    dev = env.dev
+    G = terms[0][0].shape[0]
+    tw = dev.tprod_words(3)
+    acc = env.empty(G * tw)
+    tmp = env.empty(G * tw) if len(terms) > 1 else None
+    for t, (A, B) in enumerate(terms):
+        dev.ct_tensor_dev(A.contiguous(), 2, B.contiguous(), 2, acc if t == 0 else tmp, G)
+        if t:
+            dev.tprod_add_dev(acc, tmp, 3, G)
+    c3 = env.empty(G * dev.ct_words(3))
+    dev.scaledown_dev(acc, 3, c3, G)
+    out = env.empty(G * dev.ct_words(2)).view(G, -1)
+    dev.keyswitch_dev(ksw, c3, out, G)
+    return out
+
+
+def _negated(env, cts):
+    """-c for a batch in coefficient form (Ciphertext *= -1, Ciphertext.cpp:233-244)."""
+    out = cts.clone()
+    if out.shape[0]:
+        env.dev.ct_mul_scalar_dev(out, -1, 2, out.shape[0])
+    return out
+
+
+def adjugate_and_det_batched(env, E, d, ksw):
+    """Matrix<Ciphertext>::Invert (Matrix.cpp:181-213) with Determinant's Laplace expansion along the first free
+    row (:223-262) and a key switch after every level -- the same circuit as the one-ciphertext-at-a-time
+    recursion, evaluated level by level: all minors of one size in a handful of batched calls, each distinct
+    minor once.  E: [d*d][ct_words(2)] entries, row-major.  -> (adj [d*d][cw] row-major, det [1][cw])."""
+    idx = tuple(range(d))
+    # minors needed, top-down: size s -> set of (rows, cols)
+    need = {d - 1: {(tuple(r for r in idx if r != i), tuple(c for c in idx if c != j)) for i in idx for j in idx}}
+    for s in range(d - 1, 1, -1):
+        need[s - 1] = {(rows[1:], tuple(c for c in cols if c != col)) for rows, cols in need[s] for col in cols}
+    val = {}  # (rows, cols) -> (tensor, row index in it)
+    ent = lambda r, c: r * d + c
+    for s in range(1, d):
+        keys = sorted(need[s])
+        if s == 1:
+            buf = E[torch.tensor([ent(r[0], c[0]) for r, c in keys], device=E.device)]
+        else:
+            terms = []
+            for t in range(s):
+                left = E[torch.tensor([ent(rows[0], cols[t]) for rows, cols in keys], device=E.device)]
+                if t % 2 == 1:
+                    left = _negated(env, left)
+                sub = [val[(rows[1:], tuple(c for c in cols if c != cols[t]))] for rows, cols in keys]
+                src = sub[0][0]
+                assert all(x[0] is src for x in sub)
+                right = src[torch.tensor([x[1] for x in sub], device=E.device)]
+                terms.append((left, right))
+            buf = _tensor_sum_keyswitch(env, ksw, terms)
+        for k, key in enumerate(keys):
+            val[key] = (buf, k)
+    # adj[j][i] = (-1)^(i+j) minor(without row i, col j)
+    top, order = None, []
+    for i in idx:
+        for j in idx:
+            b, k = val[(tuple(r for r in idx if r != i), tuple(c for c in idx if c != j))]
+            top = b
+            order.append((j * d + i, k, (i + j) % 2))
+    order.sort()
+    cof = top[torch.tensor([k for _, k, _ in order], device=E.device)]
+    odd = torch.tensor([pos for pos, (_, _, sgn) in enumerate(order) if sgn], device=E.device)
+    adj = cof.clone()
+    if len(odd):
+        adj[odd] = _negated(env, cof[odd])
+    # det = sum_i M[0][i] * adj[i][0]   (Matrix.cpp:205-211)
+    terms = [(E[ent(0, i):ent(0, i) + 1], adj[i * d:i * d + 1]) for i in idx]
+    det = _tensor_sum_keyswitch(env, ksw, terms)
+    return adj, det
+
+
 def rotation_exponents(g, m, usable):
     """k = g, g^2, g^4, ... (Regression.h:70-81)."""
     out, k, ns = [], g % m, usable
@@ -156,17 +234,18 @@ def rotation_exponents(g, m, usable):
 
 def embed_batch(env, slots, values):
     """values: int array [count][<= usable] -> uint32 message coefficients [count][n] on the device:
-    PlaintextSpace::EmbedInSlots for a whole batch (fhesi_embed_slots_dev, exact integer arithmetic)."""
+    PlaintextSpace::EmbedInSlots for a whole batch (fhesi_embed_slots_dev, exact integer arithmetic).
+    The host only hands over the raw values; reduction mod p and the padding to the slot count happen
+    on the device."""
     dev = env.dev
     cnt, width = values.shape
-    v = np.zeros((max(cnt, 1), slots.total), dtype=np.int32)
-    if cnt:
-        v[:cnt, :width] = values % slots.p
     if not hasattr(slots, "d_basis") or slots.d_basis.device != torch.device(env.device):
         slots.d_basis = torch.from_numpy(slots.basis.astype(np.int32)).to(env.device)
-    d_vals = torch.from_numpy(v).to(env.device)
     d_msgs = torch.empty((max(cnt, 1), dev.n), dtype=torch.int32, device=env.device)
     if cnt:
+        raw = torch.from_numpy(np.ascontiguousarray(values, dtype=np.int64)).to(env.device)
+        d_vals = torch.zeros((cnt, slots.total), dtype=torch.int32, device=env.device)
+        d_vals[:, :width] = torch.remainder(raw, slots.p).to(torch.int32)
         dev.embed_slots_dev(slots.d_basis, slots.total, d_vals, d_msgs, cnt)
     return d_msgs
 

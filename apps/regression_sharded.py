@@ -41,8 +41,8 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-from fhesi_app import (Ct, Env, Slots, embed_batch, encrypt_batch,  # noqa: E402
-                       keyswitch_and_sum_slots_batch)
+from fhesi_app import (Ct, Env, Slots, _tensor_sum_keyswitch, adjugate_and_det_batched, embed_batch,  # noqa: E402
+                       encrypt_batch, keyswitch_and_sum_slots_batch)
 
 
 def determinant(M, rows, cols, reduce):
@@ -239,13 +239,13 @@ def run(args, rank, world, local, quiet=False):
             parts.append(padded)
         data = np.concatenate(parts) if parts else np.zeros((0, d + 1), np.int64)
         nb = len(data) // block
-        mine = (data % p).reshape(nb, block, d + 1).transpose(0, 2, 1)
+        mine = data.reshape(nb, block, d + 1).transpose(0, 2, 1)
     else:                                               # fewer files than ranks: split the global block list
         lo, hi = shard_bounds(nblocks, rank, world)
         nb = hi - lo
         data = np.zeros((nblocks * block, d + 1), dtype=np.int64)
         data[:N] = raw
-        mine = (data[lo * block:hi * block] % p).reshape(max(nb, 0), block, d + 1).transpose(0, 2, 1)
+        mine = data[lo * block:hi * block].reshape(max(nb, 0), block, d + 1).transpose(0, 2, 1)
     d_msgs = embed_batch(env, slots, np.ascontiguousarray(mine).reshape(nb * (d + 1), block))
     dev.sync()
     t_batch = time.perf_counter()
@@ -274,57 +274,36 @@ def run(args, rank, world, local, quiet=False):
         ct.keyswitch_(ksw)
 
     sums = keyswitch_and_sum_slots_batch(env, total, len(pairs), ksw, rot_k, rot_ksw)
-    xty = sums[:d]
-    xtx = [[None] * d for _ in range(d)]
-    it = iter(sums[d:])
+    S = torch.stack([c.buf for c in sums])                # [14][cw]: X^T y (d of them), then the upper triangle of X^T X
+    xty = S[:d]
+    tri = {}
+    it = iter(range(d, len(sums)))
     for i in range(d):
         for j in range(i, d):
-            xtx[i][j] = next(it)
-            xtx[j][i] = xtx[i][j]
+            tri[(i, j)] = tri[(j, i)] = next(it)
+    E = S[torch.tensor([tri[(i, j)] for i in range(d) for j in range(d)], device=device)]  # X^T X, row-major
     if d == 1:
-        det, theta = xtx[0][0], [xty[0]]
+        det_b, theta_b = E[0:1].clone(), xty[0:1].clone()
     else:
-        idx = list(range(d))
-        adj = [[None] * d for _ in range(d)]
-        for i in range(d):                                # Matrix::Invert, Matrix.cpp:181-213
-            for j in range(d):
-                c = determinant(xtx, [r for r in idx if r != i], [c_ for c_ in idx if c_ != j], reduce)
-                adj[j][i] = c.neg_() if (i + j) % 2 == 1 else c
-        det = None
-        for i in range(d):
-            tmp = xtx[0][i].copy().mul(adj[i][0])
-            det = tmp if det is None else det.add_(tmp)
-        reduce(det)
-        theta = []
-        for i in range(d):                                # dataCopy *= last; MapAll(KS)
-            acc = None
-            for kx in range(d):
-                tmp = adj[i][kx].copy().mul(xty[kx])
-                acc = tmp if acc is None else acc.add_(tmp)
-            reduce(acc)
-            theta.append(acc)
-    # masking noise in every slot but the first (Regression.h:180-189)
-    to_dev = lambda a: torch.from_numpy(a).to(device)
-    for ct in theta + [det]:
-        vals = [0] + [int(v) for v in nrng.integers(0, p, size=slots.total - 1)]
-        v = np.zeros(slots.total, dtype=np.int64)
-        v[:] = vals
-        noise_msg = ((v @ slots.basis) % p).astype(np.uint32)[None]
-        nz = env.empty(dev.ct_words(2))
-        dev.encrypt_dev(dpk, to_dev(noise_msg.view(np.int32)),
-                        to_dev(nrng.integers(0, 2, size=(1, n), dtype=np.uint8)),
-                        to_dev(np.rint(nrng.normal(0.0, 3.2, size=(1, 2, n))).astype(np.int32)), nz, 1)
-        ct.add_(Ct(env, nz, 2))
+        # Matrix::Invert (adjugate, Matrix.cpp:181-213) level by level, then dataCopy *= last; MapAll(KS)
+        adj, det_b = adjugate_and_det_batched(env, E, d, ksw)
+        A = adj.view(d, d, -1)
+        theta_b = _tensor_sum_keyswitch(env, ksw, [(A[:, kx], xty[kx:kx + 1].expand(d, -1)) for kx in range(d)])
+    res_b = torch.cat([theta_b, det_b])                   # theta_0 .. theta_{d-1}, det
+    # masking noise in every slot but the first (Regression.h:180-189), all d + 1 ciphertexts at once
+    nv = np.zeros((d + 1, slots.total), dtype=np.int64)
+    nv[:, 1:] = nrng.integers(0, p, size=(d + 1, slots.total - 1))
+    noise = encrypt_batch(env, dpk, embed_batch(env, slots, nv), d + 1, nrng)
+    dev.ct_add_dev(res_b, noise, 2, d + 1)
     dev.sync()
     t_reg = time.perf_counter()
 
-    # ---- Decryption
-    out = []
-    for ct in theta + [det]:
-        mbuf = torch.empty(n, dtype=torch.int32, device=device)
-        dev.decrypt_dev(dsk, ct.buf, 2, mbuf, 1)
-        dev.sync()
-        out.append(slots.decode0(mbuf.cpu().numpy().view(np.uint32)))
+    # ---- Decryption: one batched call, one read-back
+    mbuf = torch.empty((d + 1, n), dtype=torch.int32, device=device)
+    dev.decrypt_dev(dsk, res_b, 2, mbuf, d + 1)
+    dev.sync()
+    hm = mbuf.cpu().numpy().view(np.uint32)
+    out = [slots.decode0(hm[i]) for i in range(d + 1)]
     t_dec = time.perf_counter()
     gc.enable()
 
@@ -354,7 +333,7 @@ def run(args, rank, world, local, quiet=False):
         dev.lib.fhesi_ksw_destroy(k)
     dev.lib.fhesi_key_destroy(dpk)
     dev.lib.fhesi_key_destroy(dsk)
-    del env, cts, partial, total, sums, theta, det
+    del env, cts, partial, total, sums, res_b
     dev.close()
     if rank == 0 and not quiet:
         print(f"Setup time: {t_setup - t_start:.3f}\nBatch time: {t_batch - t_setup:.3f}\n"

@@ -35,6 +35,13 @@ def test_sharded_regression_world2_emu(emu_lib):
     assert out["theta_det"] == out["expected"]
 
 
+def test_regression_dim4_level_batched_adjugate_emu(emu_lib):
+    """d = 4: the adjugate goes through 1x1, 2x2 and 3x3 minors, each level batched (apps/fhesi_app.py
+    adjugate_and_det_batched); theta * det and det must equal RegressPT mod p."""
+    out = run_app(["--dim", "4", "--points", "30", "--prime", "23", "--gen", "7", "--lib", emu_lib, "--cpu-tensors"], 1)
+    assert out["correct"] and out["theta_det"] == out["expected"], out
+
+
 def test_sharded_regression_from_shard_files_world2_emu(emu_lib, tmp_path):
     """README:82-84: the data split into files by the generator; each rank takes whole files and cuts
     each into its own blocks (3 files of 17, 17, 16 points, blocks of 8 -> 3 + 3 + 2 blocks, the last of each file ragged or full;
