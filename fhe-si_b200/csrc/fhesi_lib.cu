@@ -55,12 +55,80 @@ struct DevTmp {
   }
 };
 
+// ---------------------------------------------------------------------------------------
+// Per-device cache of device memory released by destroyed contexts.  A client that builds a context per
+// request (one regression, one statistics job) would otherwise pay cudaMalloc for every table, scratch arena
+// and pooled buffer again -- and cudaFree, a device-wide synchronisation, for every block of the context it
+// just dropped; on a busy box those calls stall for tens of milliseconds.  Blocks enter the cache only from
+// fhesi_ctx_destroy (after its cudaDeviceSynchronize: nothing in flight can still touch them) and leave it
+// for a new owner of at least the same size; fhesi_trim_cache gives everything back to the driver.
+// ---------------------------------------------------------------------------------------
+#include <mutex>
+struct DeviceCache {
+  std::mutex mu;
+  std::multimap<size_t, void *> blocks;
+  size_t bytes = 0;
+};
+static DeviceCache &device_cache(int dev) {
+  static std::mutex mu;
+  static std::map<int, DeviceCache> caches;
+  std::lock_guard<std::mutex> lk(mu);
+  return caches[dev];
+}
+static const size_t kCacheCapBytes = (size_t)24 << 30;
+// a cached block of at least `bytes` and at most 2x + 1 MiB of it, or nullptr; *got = its real size
+static void *cache_take(int dev, size_t bytes, size_t *got) {
+  DeviceCache &dc = device_cache(dev);
+  std::lock_guard<std::mutex> lk(dc.mu);
+  auto it = dc.blocks.lower_bound(bytes);
+  if (it == dc.blocks.end() || it->first > 2 * bytes + ((size_t)1 << 20)) return nullptr;
+  void *p = it->second;
+  *got = it->first;
+  dc.bytes -= it->first;
+  dc.blocks.erase(it);
+  return p;
+}
+static void cache_put(int dev, void *p, size_t bytes) {
+  if (!p) return;
+  DeviceCache &dc = device_cache(dev);
+  std::lock_guard<std::mutex> lk(dc.mu);
+  if (dc.bytes + bytes > kCacheCapBytes) {
+    cudaFree(p);
+    return;
+  }
+  dc.blocks.emplace(bytes, p);
+  dc.bytes += bytes;
+}
+// cudaMalloc through the cache: *cap receives the real size of the block
+static cudaError_t cached_malloc(int dev, void **p, size_t bytes, size_t *cap) {
+  size_t got = 0;
+  if ((*p = cache_take(dev, bytes, &got))) {
+    *cap = got;
+    return cudaSuccess;
+  }
+  *cap = bytes;
+  return cudaMalloc(p, bytes);
+}
+int fhesi_trim_cache(int device) {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cudaSetDevice(device) != cudaSuccess) return FHESI_ERR_CUDA;
+  DeviceCache &dc = device_cache(device);
+  std::lock_guard<std::mutex> lk(dc.mu);
+  cudaDeviceSynchronize();
+  for (auto &kv : dc.blocks) cudaFree(kv.second);
+  dc.blocks.clear();
+  dc.bytes = 0;
+  cudaSetDevice(cur);
+  return 0;
+}
+
 struct fhesi_ctx {
   fhesi_info info{};
   DevCtx dc{};
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
-  std::vector<void *> tables;  // device allocations owned by the context
+  std::vector<std::pair<void *, size_t>> tables;  // device allocations owned by the context (pointer, bytes)
   Arena scratch;
   std::vector<PrimeConst> h_pc;
   std::vector<u32> h_garner, h_Pfull, h_Phalf;  // host copies for the by-value CRT tables
@@ -170,9 +238,10 @@ static u32 ilog2_ceil(u64 x) {
 template <class T>
 static int upload(fhesi_ctx *c, const std::vector<T> &h, const T **d) {
   void *p = nullptr;
-  CK(cudaMalloc(&p, h.size() * sizeof(T) + 16));
+  size_t cap = 0;
+  CK(cached_malloc(c->device, &p, h.size() * sizeof(T) + 16, &cap));
   CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-  c->tables.push_back(p);
+  c->tables.push_back(std::make_pair(p, cap));
   *d = (const T *)p;
   return 0;
 }
@@ -427,16 +496,17 @@ void fhesi_ctx_destroy(fhesi_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (void *p : c->tables) cudaFree(p);
+  // everything goes to the device's cache (see DeviceCache), not back to the driver: the device is idle now
+  for (auto &t : c->tables) cache_put(c->device, t.first, t.second);
   for (auto &kv : c->pool_free)
-    for (void *p : kv.second) cudaFree(p);
+    for (void *p : kv.second) cache_put(c->device, p, kv.first);
   // blocks still handed out (a caller's buffers, key images whose handle was never destroyed) die with
   // the context they were allocated from
-  for (auto &kv : c->pool_size) cudaFree(kv.first);
-  if (c->scratch.ptr) cudaFree(c->scratch.ptr);
-  if (c->lane_scratch.ptr) cudaFree(c->lane_scratch.ptr);
-  if (c->stage.ptr) cudaFree(c->stage.ptr);
-  if (c->work.ptr) cudaFree(c->work.ptr);
+  for (auto &kv : c->pool_size) cache_put(c->device, kv.first, kv.second);
+  cache_put(c->device, c->scratch.ptr, c->scratch.cap);
+  cache_put(c->device, c->lane_scratch.ptr, c->lane_scratch.cap);
+  cache_put(c->device, c->stage.ptr, c->stage.cap);
+  cache_put(c->device, c->work.ptr, c->work.cap);
   prof_clear(c);
   for (auto e : c->pipe_events) cudaEventDestroy(e);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
@@ -468,14 +538,14 @@ int fhesi_sync(fhesi_ctx *c) {
 int fhesi_malloc(fhesi_ctx *c, size_t bytes, void **d) {
   if (!c || !d) return fail(FHESI_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
-  const size_t sz = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+  size_t sz = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
   auto it = c->pool_free.find(sz);
   if (it != c->pool_free.end() && !it->second.empty()) {
     *d = it->second.back();
     it->second.pop_back();
     c->pool_idle_bytes -= sz;
   } else {
-    CK(cudaMalloc(d, sz));
+    CK(cached_malloc(c->device, d, sz, &sz));  // sz becomes the block's real size: it returns to that bucket
   }
   c->pool_size[*d] = sz;
   return 0;
@@ -536,12 +606,11 @@ size_t fhesi_tprod_bytes(const fhesi_ctx *c, uint32_t parts) {
 
 static int scratch(fhesi_ctx *c, size_t bytes, u32 **p) {
   if (c->scratch.cap < bytes) {
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->scratch.ptr) CK(cudaFree(c->scratch.ptr));
+    CK(cudaStreamSynchronize(c->stream));  // the arena is only ever used by work on this stream
+    cache_put(c->device, c->scratch.ptr, c->scratch.cap);
     c->scratch.ptr = nullptr;
     c->scratch.cap = 0;
-    CK(cudaMalloc(&c->scratch.ptr, bytes));
-    c->scratch.cap = bytes;
+    CK(cached_malloc(c->device, &c->scratch.ptr, bytes, &c->scratch.cap));
   }
   *p = (u32 *)c->scratch.ptr;
   return 0;
@@ -992,8 +1061,9 @@ static int automorph_table(fhesi_ctx *c, uint32_t k, u32 **out) {
       tab[e] = (i << 1) | neg;
     }
     void *pt = nullptr;
-    CK(cudaMalloc(&pt, h * 4));
-    c->tables.push_back(pt);
+    size_t cap = 0;
+    CK(cached_malloc(c->device, &pt, h * 4, &cap));
+    c->tables.push_back(std::make_pair(pt, cap));
     d_tab = (u32 *)pt;
     CK(cudaMemcpyAsync(d_tab, tab.data(), h * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));  // tab is a stack-lifetime host buffer
@@ -1405,8 +1475,7 @@ int fhesi_mult_relin_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *a, 
     if (c->work.ptr) CK(cudaFree(c->work.ptr));
     c->work.ptr = nullptr;
     c->work.cap = 0;
-    CK(cudaMalloc(&c->work.ptr, (nt + nc) * 4));
-    c->work.cap = (nt + nc) * 4;
+    CK(cached_malloc(c->device, &c->work.ptr, (nt + nc) * 4, &c->work.cap));
   }
   u32 *d_t = (u32 *)c->work.ptr, *d_c = d_t + nt;
   int rc = 0;
@@ -1432,8 +1501,7 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
     if (c->stage.ptr) CK(cudaFree(c->stage.ptr));
     c->stage.ptr = nullptr;
     c->stage.cap = 0;
-    CK(cudaMalloc(&c->stage.ptr, 3 * bytes + 64));
-    c->stage.cap = 3 * bytes + 64;
+    CK(cached_malloc(c->device, &c->stage.ptr, 3 * bytes + 64, &c->stage.cap));
   }
   if (!c->h2d_stream) {
     CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));

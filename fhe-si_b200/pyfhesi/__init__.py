@@ -71,6 +71,7 @@ SYMBOLS = {
     "fhesi_tprod_add_poly_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
     "fhesi_tprod_mul_poly_dev": (C.c_int, [_P, _P, _U32, _P, _U32, _SZ]),
     "fhesi_tprod_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),
+    "fhesi_trim_cache": (C.c_int, [C.c_int]),
     "fhesi_embed_slots_dev": (C.c_int, [_P, _P, _U32, _P, _P, _SZ]),
     "fhesi_decode_slots_dev": (C.c_int, [_P, _P, _U32, _P, _P, _SZ]),
     "fhesi_ct_automorph_dev": (C.c_int, [_P, _P, _U32, _U32, _P, _SZ]),

@@ -71,6 +71,10 @@ const char *fhesi_version(void);
 int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p, uint32_t decompSize, uint64_t xi,
                      int device, fhesi_ctx **out);
 void fhesi_ctx_destroy(fhesi_ctx *ctx);
+/* Device memory of a destroyed context (tables, scratch, pooled buffers) is kept in a per-device cache for
+ * the next context instead of going back to the driver (cudaFree synchronises the whole device; a client that
+ * builds one context per request would pay for it on every request).  This returns the cache to the driver. */
+int fhesi_trim_cache(int device);
 int fhesi_ctx_info(const fhesi_ctx *ctx, fhesi_info *out);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL = own stream. */
 int fhesi_ctx_set_stream(fhesi_ctx *ctx, void *cuda_stream);
