@@ -107,8 +107,27 @@ class Ct:
 
 
 class Env:
-    def __init__(self, dev, device):
+    def __init__(self, dev, device, staging_bytes=0):
         self.dev, self.device = dev, device
+        # pinned staging for the application's host -> device copies, made at start-up like the context itself
+        # (a pageable cudaMemcpy goes through the driver's own bounce buffer and stalls for tens of
+        # milliseconds every few calls on a busy host)
+        self.pinned = None
+        if staging_bytes and str(device).startswith("cuda"):
+            self.pinned = torch.empty(int(staging_bytes), dtype=torch.uint8).pin_memory()
+
+    def to_device(self, arr):
+        """numpy array -> device tensor, through the pinned staging buffer when it fits."""
+        arr = np.ascontiguousarray(arr)
+        t = torch.from_numpy(arr)
+        if self.pinned is None or arr.nbytes > self.pinned.numel():
+            return t.to(self.device)
+        stage = self.pinned[:arr.nbytes].view(t.dtype).view(t.shape)
+        stage.copy_(t)
+        out = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        out.copy_(stage, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the staging buffer is reused by the next call
+        return out
 
     def empty(self, words):
         return torch.empty(int(words), dtype=torch.int32, device=self.device)
@@ -243,7 +262,7 @@ def embed_batch(env, slots, values):
         slots.d_basis = torch.from_numpy(slots.basis.astype(np.int32)).to(env.device)
     d_msgs = torch.empty((max(cnt, 1), dev.n), dtype=torch.int32, device=env.device)
     if cnt:
-        raw = torch.from_numpy(np.ascontiguousarray(values, dtype=np.int64)).to(env.device)
+        raw = env.to_device(np.ascontiguousarray(values, dtype=np.int32))
         d_vals = torch.zeros((cnt, slots.total), dtype=torch.int32, device=env.device)
         d_vals[:, :width] = torch.remainder(raw, slots.p).to(torch.int32)
         dev.embed_slots_dev(slots.d_basis, slots.total, d_vals, d_msgs, cnt)

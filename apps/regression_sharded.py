@@ -191,7 +191,7 @@ def run(args, rank, world, local, quiet=False):
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         dev.set_stream(stream.cuda_stream)
-    env = Env(dev, device)
+    env = Env(dev, device, staging_bytes=(nblocks + 8) * (d + 1) * block * 4)
     from pyfhesi.hostkeys import prepare as prepare_host_layer
     prepare_host_layer(args.lib)  # build-if-stale + dlopen of the C++ host layer: start-up, not key generation
     if not args.cpu_tensors:  # load torch's generator kernels now: process start-up, like the CUDA context
@@ -253,9 +253,16 @@ def run(args, rank, world, local, quiet=False):
         data = np.zeros((nblocks * block, d + 1), dtype=np.int64)
         data[:N] = raw
         mine = data[lo * block:hi * block].reshape(max(nb, 0), block, d + 1).transpose(0, 2, 1)
-    d_msgs = embed_batch(env, slots, np.ascontiguousarray(mine).reshape(nb * (d + 1), block))
+    t_b0 = time.perf_counter()
+    vals = np.ascontiguousarray(mine).reshape(nb * (d + 1), block)
+    t_b1 = time.perf_counter()
+    d_msgs = embed_batch(env, slots, vals)
+    t_b2 = time.perf_counter()
     dev.sync()
     t_batch = time.perf_counter()
+    if os.environ.get("FHESI_APP_TIMING"):
+        print(f"batch: blocks {t_b0 - t_setup:.4f}  transpose {t_b1 - t_b0:.4f}  embed enqueue {t_b2 - t_b1:.4f}  "
+              f"sync {t_batch - t_b2:.4f}", file=sys.stderr)
     if t_keygen is None:  # the keys: join the draws, then the device half (1 ms)
         draw_thread.join()
         draws = box["draws"]

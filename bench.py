@@ -279,11 +279,12 @@ def _regression_files(tmpdir):
     return prefix
 
 
-def run_regression_ours(args, rank, local_rank, world, lib_path, runs=5):
+def run_regression_ours(args, rank, local_rank, world, lib_path, runs=7):
     """apps/regression_sharded.py on the N GPUs of this job, reading the 8 shard files; the clock is the
     reference driver's (key generation .. decryption, Test_Regression.cpp:24-63), max over ranks.  The first run
-    pays one-off costs (buffer pool growth, first use of every kernel at these sizes); all runs are reported,
-    `value` is the best."""
+    pays one-off costs (first allocation of every buffer, first use of every kernel at these sizes); all runs are
+    reported, `value` is the MEDIAN of the runs after the first (a shared box shows occasional stalls of tens of
+    milliseconds in host-side calls; the median is robust to them without hiding them)."""
     import tempfile
     import types
     import torch
@@ -307,11 +308,13 @@ def run_regression_ours(args, rank, local_rank, world, lib_path, runs=5):
     if rank == 0:
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
-    best = min(res, key=lambda r: r["value"])
+    warm = sorted(res[1:] or res, key=lambda r: r["value"])
+    best = warm[(len(warm) - 1) // 2]  # the median run (its phases are the ones reported)
     if not all(r["correct"] for r in res):
         raise SystemExit("bench: the encrypted regression does not decrypt to RegressPT mod p: %r" % (res[0],))
     return {"metric": REG_METRIC, "value": best["value"], "unit": "s", "higher_is_better": False, "n_gpus": world,
-            "runs_s": [r["value"] for r in res], "clock": best["clock"], "phases_s": best["phases_s"],
+            "runs_s": [r["value"] for r in res], "best_s": warm[0]["value"], "first_run_s": res[0]["value"],
+            "value_is": "median of the runs after the first", "clock": best["clock"], "phases_s": best["phases_s"],
             "setup_split_s": best["setup_split_s"], "config": dict(best["config"], d=REG["d"], N=REG["n"]),
             "theta_det": best["theta_det"], "expected": best["expected"], "correct": True,
             "scaling": "strong (the 392 data blocks are dealt to the ranks; keys and the 4x4 tail are replicated)"}
