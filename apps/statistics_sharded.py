@@ -80,7 +80,7 @@ def main():
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         dev.set_stream(stream.cuda_stream)
-    env = Env(dev, device)
+    env = Env(dev, device, staging_bytes=(nblocks + 8) * (d + 1) * block * 4)
     from pyfhesi.hostkeys import prepare as prepare_host_layer
     prepare_host_layer(args.lib)  # build-if-stale + dlopen of the C++ host layer: start-up, not key generation
     if not args.cpu_tensors:  # load torch's generator kernels now: process start-up, like the CUDA context
