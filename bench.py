@@ -191,7 +191,7 @@ def bench_config(batch, world):
 
 def workload_name():
     return (f"{'cfg2' if CFG['logQ'] == 256 else 'cfg5'}: TestAddMul logQ={CFG['logQ']} p={CFG['p']} g={CFG['g']} "
-            f"(m=1018, phi(m)=508, D={(CFG['logQ'] + 23) // 24}), "
+            f"(m={CFG['p'] - 1}, phi(m)={(CFG['p'] - 1) // 2 - 1}, D={(CFG['logQ'] + 23) // 24}), "
             "batched c=a; c*=b; ApplyKeySwitch(c) on fresh encryptions")
 
 
@@ -706,10 +706,14 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="ciphertext pairs per GPU per step (SURVEY.md §8d: B in {1, 64, 1024, 8192})")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-regression", action="store_true", help="skip the Test_Regression leg (BASELINE metric 2)")
+    ap.add_argument("--prime", type=int, default=1019, choices=[1019, 2027],
+                    help="plaintext modulus p (m = p - 1); 2027 is the reference README's second family (N = 2048), "
+                         "not a BASELINE configuration")
     ap.add_argument("--logq", type=int, default=256, choices=[128, 256, 512],
                     help="BASELINE config 5 sweep; the headline metric is quoted at 256")
     args = ap.parse_args()
     CFG["logQ"] = args.logq
+    CFG["p"] = args.prime
     global METRIC
     METRIC = f"ciphertext mult+relin/sec at logQ={args.logq}"
     rank = int(os.environ.get("RANK", 0))

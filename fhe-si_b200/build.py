@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfhesi_b200.so")
 SOURCES = ["fhesi_lib.cu"]
-HEADERS = ["modarith.cuh", "kernels_generic.cuh", "kernels_fused.cuh", "../../include/fhesi.h"]
+HEADERS = ["modarith.cuh", "kernels_generic.cuh", "kernels_fused.cuh", "kernels_fused2k.cuh", "../../include/fhesi.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--expt-extended-lambda", "-diag-suppress", "550",

@@ -12,6 +12,7 @@
 #include "../../include/fhesi.h"
 #include "kernels_generic.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_fused2k.cuh"
 
 // ---------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -315,7 +316,7 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   // split-key key switch: halves of 32*ws bits (kernels_fused.cuh).  Needs W >= 2 and the
   // single-accumulator bound; inner products are non-negative and must stay below P_s / 2.
   u32 Ls = 0, ws = 0;
-  if (c->tfree && W >= 2 && N == 1024) {
+  if (c->tfree && W >= 2 && (N == 1024 || N == 2048)) {
     ws = (W + 1) / 2;
     const double need_s = dbits + 32.0 * ws + lg2n + std::log2(3.0 * D) + 1 + 0.1;
     double b2 = 0;
@@ -434,6 +435,7 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   DevCtx &dc = c->dc;
   dc.n = n; dc.N = N; dc.logN = ilog2_ceil(N); dc.W = W; dc.logQ = logQ; dc.D = D; dc.dbits = dbits;
   dc.h = h; dc.Lmax = L; dc.CW = CW; dc.ptxt = (u32)p_pt;
+  dc.sshift = N == 2048 ? 2 : 1;
   c->h_pc = pc;
   c->h_garner = gar;
   c->h_Pfull = Pf;
@@ -447,12 +449,14 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
     fhesi_ctx_destroy(c);
     return rc;
   }
-  if (N == FN) {  // the fused kernels' per-thread twiddle layout, laid out once
-    std::vector<uint2> lf((size_t)L * FTW_ENTRIES), li((size_t)L * FTW_ENTRIES);
+  if (N == FN || N == FT<T2K>::N) {  // the fused kernels' per-thread twiddle layout, laid out once
+    const u32 entries = N == FN ? FTW_ENTRIES : FT<T2K>::ENTRIES;
+    std::vector<uint2> lf((size_t)L * entries), li((size_t)L * entries);
     for (u32 l = 0; l < L; ++l)
-      for (u32 e = 0; e < FTW_ENTRIES; ++e) {
-        lf[(size_t)l * FTW_ENTRIES + e] = twsf[(size_t)l * N + ftw_source_index(e)];
-        li[(size_t)l * FTW_ENTRIES + e] = twsi[(size_t)l * N + ftw_source_index(e)];
+      for (u32 e = 0; e < entries; ++e) {
+        const u32 src = N == FN ? ftw_source_index(e) : ftw_source_index_t<T2K>(e);
+        lf[(size_t)l * entries + e] = twsf[(size_t)l * N + src];
+        li[(size_t)l * entries + e] = twsi[(size_t)l * N + src];
       }
     if ((rc = upload(c, lf, &dc.ftw_fwd)) || (rc = upload(c, li, &dc.ftw_inv))) {
       fhesi_ctx_destroy(c);
@@ -481,8 +485,9 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   ev = getenv("FHESI_NO_FUSED");
   if (ev && atoi(ev) > 0) c->use_fused = false;
   if (!fused_supported(dc)) c->use_fused = false;
+  if (dc.N != FN && !c->info.Ls) c->use_fused = false;  // N = 2048 has the split-key kernel only
   if (c->use_fused) {
-    rc = fused_configure();
+    rc = dc.N == FN ? fused_configure() : fused2k_configure();
     if (rc) {
       fhesi_ctx_destroy(c);
       return fail(FHESI_ERR_CUDA, "cudaFuncSetAttribute failed for the fused kernels");
@@ -729,15 +734,21 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
   {
     double best = 0;
     for (u32 o = 1; o <= 4; ++o) {
-      const double ctas = (double)I.Lt * (double)((cnt + KG * o - 1) / (KG * o));
+      const u32 kg = I.N == FN ? KG : KG2;
+      const double ctas = (double)I.Lt * (double)((cnt + kg * o - 1) / (kg * o));
       const double waves = ctas / c->sm_count;
       const double eff = waves / std::ceil(waves) / (1.0 + 0.04 / o);
       if (eff > best * 1.0001) best = eff, opg = o;
     }
   }
   FusedTensorArgs t{resid, out, I.Lt, (u32)cnt, opg, (u32)to_tprod};
-  dim3 grid(I.Lt, (unsigned)((cnt + KG * opg - 1) / (KG * opg)));
-  KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
+  if (I.N == FN) {
+    dim3 grid(I.Lt, (unsigned)((cnt + KG * opg - 1) / (KG * opg)));
+    KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
+  } else {
+    dim3 grid(I.Lt, (unsigned)((cnt + KG2 * opg - 1) / (KG2 * opg)));
+    KL(c, k_fused_tensor_2k, grid, KG2 * T2K, FUSED2K_SMEM_WORDS * 4, c->dc, t);
+  }
   CKL();
   return 0;
 }
@@ -1349,8 +1360,13 @@ static int fused_ks_from_digits(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *d
   const fhesi_info &I = c->info;
   if (I.Ls && ksw->d_key_split) {  // split-key path: res holds [cnt][4][Ls][n]
     FusedKsArgs k{digits, ksw->d_key_split, res, ksw->parts * I.D, I.Ls, (u32)cnt};
-    dim3 grid(I.Ls, (unsigned)((cnt + KSS - 1) / KSS));
-    KL(c, k_fused_keyswitch_split, grid, KSS * 128, KSS_SMEM_WORDS * 4, c->dc, k);
+    if (I.N == FN) {
+      dim3 grid(I.Ls, (unsigned)((cnt + KSS - 1) / KSS));
+      KL(c, k_fused_keyswitch_split, grid, KSS * 128, KSS_SMEM_WORDS * 4, c->dc, k);
+    } else {
+      dim3 grid(I.Ls, (unsigned)((cnt + KSS2 - 1) / KSS2));
+      KL(c, k_fused_keyswitch_split_2k, grid, KSS2 * T2K, KSS2K_SMEM_WORDS * 4, c->dc, k);
+    }
     CKL();
     return launch_crt_split(c, res, I.Ls, out, cnt * 2);
   }

@@ -283,7 +283,7 @@ __device__ __forceinline__ void phim_store_1024(const u32 *nat, u32 *__restrict_
   }
 }
 
-static bool fused_supported(const DevCtx &dc) { return dc.N == FN && dc.n <= 512; }
+static bool fused_supported(const DevCtx &dc) { return (dc.N == FN && dc.n <= 512) || (dc.N == 2048 && dc.n <= 1024); }
 
 // multiword two's complement (W words) -> residue in [0,2p), scaled by s_v (DevCtx::cwr).
 // Lazy: 4 word products are summed in 64 bits (< 2^64) and Montgomery-reduced once.

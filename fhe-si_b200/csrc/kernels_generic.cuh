@@ -50,7 +50,7 @@ struct DevCtx {
   // cwr[l][v][W] = p - (2^(32W) * s_v mod p); s_0 = 1 (plain result after Montgomery
   // reduction), s_1 = p_pt / N * R (Montgomery form of the tensor's left operand)
   const u32 *cwr;                         // [Lmax][2][CW]
-  u32 pad_;
+  u32 sshift;                             // store_index() block: 1 (16 positions) or 2 (32, N = 2048)
 };
 
 // Storage order of transform-domain vectors.  Position i of the in-place DIF output lives at
@@ -58,7 +58,12 @@ struct DevCtx {
 // odd ones.  This is the natural register order of the fused N=1024 kernels
 // (kernels_fused.cuh: thread t, register r <-> storage index 8t + r), which lets them read
 // key tiles with 128-bit loads; pointwise kernels do not care.  Needs N >= 16.
-__device__ __forceinline__ u32 store_index(u32 i) { return (i & ~15u) | ((i & 1u) << 3) | ((i >> 1) & 7u); }
+// With sshift = 2 (N = 2048: 256 threads per transform, kernels_fused2k.cuh) the block is 32 positions: the low
+// five bits (j:3, b:2) of a position are stored as (b:2, j:3).
+__device__ __forceinline__ u32 store_index(u32 i, u32 sshift = 1) {
+  const u32 blk = (8u << sshift) - 1u;
+  return (i & ~blk) | ((i & ((1u << sshift) - 1u)) << 3) | ((i >> sshift) & 7u);
+}
 
 // ---------------------------------------------------------------------------------------
 // shared-memory radix-2 NTT, one butterfly per thread per stage
@@ -180,7 +185,7 @@ __global__ void k_fwd(DevCtx c, FwdArgs a) {
   __syncthreads();
   ntt_fwd_smem(x, c.tw_fwd + (size_t)l * c.N, c.N, p, pinv);
   u32 *dst = a.dst + ((size_t)q * a.L + l) * c.N;
-  for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) dst[store_index(i)] = full_reduce(x[i], p);
+  for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) dst[store_index(i, c.sshift)] = full_reduce(x[i], p);
 }
 
 // Phi_m reduction for m = 2h, h odd prime: X^h = -1 and Phi_m = sum_{i<h} (-1)^i X^i.
@@ -226,7 +231,7 @@ __global__ void k_inv(DevCtx c, InvArgs a) {
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv;
   const u32 *src = a.src + ((size_t)q * a.L + l) * c.N;
-  for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) x[i] = src[store_index(i)];
+  for (u32 i = threadIdx.x; i < c.N; i += blockDim.x) x[i] = src[store_index(i, c.sshift)];
   __syncthreads();
   ntt_inv_smem(x, c.tw_inv + (size_t)l * c.N, c.N, p, pinv);
   u32 *dst = a.dst + ((size_t)q * a.L + l) * c.n;

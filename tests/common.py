@@ -14,6 +14,9 @@ CONFIGS = {
     "cfg4": (176, 1019, 3),
     "cfg5_128": (128, 1019, 3),
     "cfg5_512": (512, 1019, 3),
+    # the reference README's second parameter family (README:35-37): p = 2027, m = 2026, phi(m) = 1012, N = 2048
+    "p2027": (256, 2027, 3),
+    "p2027_176": (176, 2027, 3),
 }
 
 

@@ -41,6 +41,7 @@ struct BlockState {
   std::unique_ptr<std::barrier<>> bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<std::unique_ptr<std::barrier<>>> group_bar;  // 128-thread named barriers
+  std::vector<std::unique_ptr<std::barrier<>>> group_bar256;  // 256-thread named barriers
   std::vector<uint64_t> shfl;  // one slot per thread
   std::vector<uint32_t> smem;
   unsigned nthreads = 0;
@@ -63,6 +64,10 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
   for (unsigned g = 0; g < (T + 127) / 128; ++g) {
     unsigned cnt = std::min(128u, T - g * 128);
     st.group_bar.emplace_back(new std::barrier<>(cnt));
+  }
+  for (unsigned g = 0; g < (T + 255) / 256; ++g) {
+    unsigned cnt = std::min(256u, T - g * 256);
+    st.group_bar256.emplace_back(new std::barrier<>(cnt));
   }
   st.shfl.assign(T, 0);
   st.smem.assign(smem_bytes / 4 + 64, 0);
@@ -144,6 +149,11 @@ template <class T>
 inline T __ldg(const T *p) { return *p; }
 // named barrier over the 128-thread group `g` of the block (bar.sync g+1, 128 on the GPU)
 inline void fhesi_group_sync(unsigned g) { emu::t_block->group_bar[g]->arrive_and_wait(); }
+template <int T>
+inline void fhesi_group_sync_t(unsigned g) {
+  static_assert(T == 128 || T == 256, "named barrier sizes the emulator knows");
+  (T == 128 ? emu::t_block->group_bar[g] : emu::t_block->group_bar256[g])->arrive_and_wait();
+}
 inline uint64_t __umul64hi(uint64_t a, uint64_t b) {
   return (uint64_t)(((unsigned __int128)a * b) >> 64);
 }

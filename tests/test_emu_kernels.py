@@ -76,3 +76,11 @@ def test_emu_mult_relin_cfg2(emu_lib):
     sc = Scenario(*CONFIGS["cfg2"], seed=2, lib_path=emu_lib)
     P.check_mult_relin(sc, count=1)
     P.check_rotate_keyswitch(sc, CONFIGS["cfg2"][2], count=1, compare_steps=False)  # fused N=1024 digit kernel
+
+
+def test_emu_fused_2048_p2027(emu_lib):
+    """phi(m) = 1012 (p = 2027): the fused N = 2048 kernels (256 threads per transform, kernels_fused2k.cuh)."""
+    sc = Scenario(*CONFIGS["p2027_176"], seed=5, lib_path=emu_lib)
+    assert sc.dev.N == 2048 and sc.dev.Ls and sc.dev.Ls < sc.dev.Lk
+    P.check_mult_relin(sc, count=1)
+    P.check_pieces(sc, count=1)

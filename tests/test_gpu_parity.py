@@ -36,6 +36,33 @@ def test_mult_relin_wide(name, cuda_lib):
     P.check_mult_relin_wide(*CONFIGS[name], cuda_lib, pairs=24 if name == "cfg5_512" else 64)
 
 
+def test_fused_2048_p2027(cuda_lib):
+    """The README's second family, p = 2027 (phi(m) = 1012, N = 2048): fused 256-thread kernels against the
+    oracle and the C restatement, and against the generic kernels (FHESI_NO_FUSED) byte for byte."""
+    import os
+    sc = scenario("p2027", cuda_lib)
+    assert sc.dev.N == 2048 and sc.dev.Ls
+    P.check_mult_relin(sc, count=3)
+    P.check_mult_relin(sc, count=2, host=True)
+    P.check_pieces(sc, count=2)
+    P.check_tensor_accumulate(sc, count=5)
+    P.check_encrypt_decrypt(sc, count=2)
+    P.check_edge_cases(sc, counts=(0, 1, 5))
+    P.check_rotate_keyswitch(sc, CONFIGS["p2027"][2], count=2)
+    P.check_mult_relin_wide(*CONFIGS["p2027_176"], cuda_lib, pairs=16, seeds=(7,))
+    _, cts = sc.fresh(8)
+    fused = sc.dev_mult_relin(cts[:4], cts[4:])
+    os.environ["FHESI_NO_FUSED"] = "1"
+    try:
+        gen = Scenario(*CONFIGS["p2027"], seed=20240611, lib_path=cuda_lib)
+        # same keys (same seed), generic kernels
+        _, cts2 = gen.fresh(8)
+        assert np.array_equal(gen.pack_cts(cts2), sc.pack_cts(cts))
+        assert np.array_equal(gen.dev_mult_relin(cts2[:4], cts2[4:]), fused)
+    finally:
+        del os.environ["FHESI_NO_FUSED"]
+
+
 def test_mult_relin_host_and_random_cfg2(cuda_lib):
     sc = scenario("cfg2", cuda_lib)
     P.check_mult_relin(sc, count=2, host=True)
