@@ -557,13 +557,14 @@ def run_ours(args, rank, local_rank, world):
         # therefore counted per class and expressed in Shoup-modmul equivalents (one Shoup product =
         # 2 IMAD + 1 IMAD.HI; one 64-bit multiply-accumulate = 1 IMAD.WIDE, about 0.66 of a Shoup product):
         # achieved / peak is then the fraction of the pipe's time spent on algorithmic instructions, the
-        # quantity ncu reports as sm__inst_executed_pipe_fmaheavy (profiles/r02_summary.md).
+        # quantity ncu reports as sm__inst_executed_pipe_fmaheavy (profiles/r02_ncu_full_summary.txt).
         cost = {"lo": 1.0 / pipes["imad_lo32"], "hi": 1.0 / pipes["imad_hi32"], "wide": 1.0 / pipes["imad_wide64"]}
         shoup_cost = 2 * cost["lo"] + cost["hi"]
         peak32 = 1.0 / shoup_cost  # Shoup products per second when nothing else shares the pipe
         work_all = kernel_pipe_work_per_op(dev)
         pipe_s = lambda w: w["lo"] * cost["lo"] + w["hi"] * cost["hi"] + w["wide"] * cost["wide"]
-        base = lambda k: {"k_residues_t": "k_residues"}.get(k.split("<")[0], k.split("<")[0])  # template instances
+        base = lambda k: {"k_residues_t": "k_residues", "k_fused_tensor_2k": "k_fused_tensor",  # template instances, N = 2048
+                          "k_fused_keyswitch_split_2k": "k_fused_keyswitch_split"}.get(k.split("<")[0], k.split("<")[0])
         work = {k: work_all[base(k)] for k in prof if base(k) in work_all}
         top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
         tname, (tcnt, tms) = top
@@ -591,7 +592,7 @@ def run_ours(args, rank, local_rank, world):
             "traffic": traffic * ops_timed / max(tcnt, 1) if traffic else None,
             "traffic_unit": "bytes per launch: the kernel's compulsory HBM traffic (every input word read once, every "
                             "output word written once; key tiles and tables stay in L2), confirmed against ncu "
-                            "dram__bytes_read.sum + dram__bytes_write.sum of the same launch in profiles/r02_summary.md",
+                            "dram__bytes_read.sum + dram__bytes_write.sum of the same launch in profiles/r02_ncu_full_summary.txt",
             "peak_source": "measured in this run (fhesi_pipe_peak: register-resident ILP-8 chains of one instruction "
                            "class on all SMs)",
             "peak_montgomery32_Gmodmul_s": peak_mont32 / 1e9,
@@ -662,7 +663,7 @@ def kernel_pipe_work_per_op(dev):
     K = 3 * D
     garner = lambda L: L * (L - 1) // 2
     horner = lambda L: L * (L + 1) // 2
-    tr = 4608 if N == 1024 else (N // 2) * int(math.log2(N))
+    tr = 4608 if N == 1024 else (10240 if N == 2048 else (N // 2) * int(math.log2(N)))  # fused: the last stage's twiddle is 1
 
     def w(modmul=0, montmul=0, mac=0, red=0, red_hi=0):
         return {"lo": 2 * modmul + montmul + red + red_hi, "hi": modmul + red_hi, "wide": 2 * montmul + mac + red,

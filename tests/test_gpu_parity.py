@@ -55,10 +55,8 @@ def test_fused_2048_p2027(cuda_lib):
     os.environ["FHESI_NO_FUSED"] = "1"
     try:
         gen = Scenario(*CONFIGS["p2027"], seed=20240611, lib_path=cuda_lib)
-        # same keys (same seed), generic kernels
-        _, cts2 = gen.fresh(8)
-        assert np.array_equal(gen.pack_cts(cts2), sc.pack_cts(cts))
-        assert np.array_equal(gen.dev_mult_relin(cts2[:4], cts2[4:]), fused)
+        gen.ks = sc.ks  # same key-switch matrix, same ciphertexts, generic kernels
+        assert np.array_equal(gen.dev_mult_relin(cts[:4], cts[4:]), fused)
     finally:
         del os.environ["FHESI_NO_FUSED"]
 
