@@ -375,8 +375,9 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         # NCCL's own log (NCCL_DEBUG=INFO: communicator, rank count, transports) is left at the level the
         # launcher asked for; it only moves off stdout -- which carries the one JSON line -- to stderr
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # (unconditionally: a level set in /etc/nccl.conf instead of the environment still prints its
+        # "NCCL version" banner, which landed on stdout ahead of the JSON line in profiles/r02_bench_8gpu_logq*.json)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import build as fhesi_build

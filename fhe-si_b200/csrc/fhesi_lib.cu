@@ -1,5 +1,6 @@
 // fhesi_lib.cu -- context set-up and the C ABI of libfhesi_b200.so (include/fhesi.h).
 // Built for sm_100a only; there is no CPU fallback anywhere in this library.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -135,6 +136,9 @@ struct fhesi_ctx {
   std::vector<u32> h_garner, h_Pfull, h_Phalf;  // host copies for the by-value CRT tables
   std::map<std::pair<int, u32>, std::vector<unsigned char>> crt_tables;
   std::map<u32, u32 *> automorph_tabs;  // Galois element -> device permutation table
+  // general m (not 2 * odd prime): column j lists the non-zero (i, coefficient) of X^(n+j) mod Phi_m,
+  // j < max(n - 1, m - n); empty for m = 2h
+  std::vector<std::vector<std::pair<u32, int>>> red_cols;
   // fhesi_malloc / fhesi_free pool
   std::map<size_t, std::vector<void *>> pool_free;
   std::map<void *, size_t> pool_size;
@@ -198,12 +202,13 @@ static void prof_begin(fhesi_ctx *c, const char *name) {
 static void prof_end(fhesi_ctx *c) {
   if (c->prof_on) cudaEventRecord(c->prof_recs.back().e1, c->stream);
 }
-#define KL(c, kern, grid, block, smem, ...)                                \
+#define KLN(c, name, kern, grid, block, smem, ...)                         \
   do {                                                                     \
-    prof_begin((c), #kern);                                                \
+    prof_begin((c), name);                                                 \
     FHESI_LAUNCH(kern, grid, block, smem, (c)->stream, __VA_ARGS__);       \
     prof_end((c));                                                         \
   } while (0)
+#define KL(c, kern, ...) KLN(c, #kern, kern, __VA_ARGS__)
 // One device allocation shared by the key images made in one call (a whole set-up's matrices come out of
 // fhesi_keygen_batch together): cudaMalloc costs ~0.1 ms a piece, three per matrix used to dominate key set-up
 struct KeyBlock {
@@ -236,6 +241,52 @@ static u32 ilog2_ceil(u64 x) {
   while ((1ull << k) < x) ++k;
   return k;
 }
+// Phi_m(X) = prod_{d | m} (X^d - 1)^mu(m/d), dense, degree phi(m)  (NumbTh.cpp:142-159 computes the same polynomial)
+static std::vector<long long> h_cyclotomic(u32 m) {
+  auto mobius = [](u32 x) {
+    int mu = 1;
+    for (u32 q = 2; q * q <= x; ++q)
+      if (x % q == 0) {
+        x /= q;
+        if (x % q == 0) return 0;
+        mu = -mu;
+      }
+    return x > 1 ? -mu : mu;
+  };
+  std::vector<long long> a(1, 1);
+  for (u32 d = 1; d <= m; ++d)  // numerator
+    if (m % d == 0 && mobius(m / d) == 1) {
+      std::vector<long long> b(a.size() + d, 0);
+      for (size_t i = 0; i < a.size(); ++i) b[i + d] += a[i], b[i] -= a[i];
+      a.swap(b);
+    }
+  for (u32 d = 1; d <= m; ++d)  // exact division by X^d - 1: a[i] = q[i - d] - q[i]
+    if (m % d == 0 && mobius(m / d) == -1) {
+      std::vector<long long> q(a.size() - d, 0);
+      for (size_t i = 0; i < q.size(); ++i) q[i] = (i >= d ? q[i - d] : 0) - a[i];
+      a.swap(q);
+    }
+  return a;
+}
+// columns X^(n+j) mod Phi_m for j < J as sparse (row, coefficient) lists; false if a coefficient leaves [-64, 64]
+static bool h_reduction_columns(const std::vector<long long> &phi, u32 J, std::vector<std::vector<std::pair<u32, int>>> &cols) {
+  const u32 n = (u32)phi.size() - 1;
+  std::vector<long long> r(n);
+  for (u32 i = 0; i < n; ++i) r[i] = -phi[i];  // X^n
+  cols.assign(J, {});
+  for (u32 j = 0; j < J; ++j) {
+    for (u32 i = 0; i < n; ++i)
+      if (r[i]) {
+        if (r[i] > 64 || r[i] < -64) return false;
+        cols[j].push_back(std::make_pair(i, (int)r[i]));
+      }
+    const long long top = r[n - 1];  // times X, minus top * Phi_m
+    for (u32 i = n - 1; i > 0; --i) r[i] = r[i - 1] - top * phi[i];
+    r[0] = -top * phi[0];
+  }
+  return true;
+}
+
 template <class T>
 static int upload(fhesi_ctx *c, const std::vector<T> &h, const T **d) {
   void *p = nullptr;
@@ -251,10 +302,13 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
                      int device, fhesi_ctx **out) {
   if (!out) return fail(FHESI_ERR_INVALID, "out is NULL");
   *out = nullptr;
-  if (m < 6 || (m & 1)) return fail(FHESI_ERR_UNSUPPORTED, "m must be 2*p' with p' an odd prime");
-  const u32 h = m / 2;
-  if (!(h & 1) || !h_is_prime(h))
-    return fail(FHESI_ERR_UNSUPPORTED, "m must be 2*p' with p' an odd prime");
+  if (m < 3 || m > 8192) return fail(FHESI_ERR_UNSUPPORTED, "m must be in [3, 8192]");
+  // m = 2h with h an odd prime (every parameter set of the reference's clients): Phi_m = sum (-X)^i and the
+  // remainder is a fold written into the kernels.  Any other m takes Phi_m as a sparse remainder table.
+  const bool twoh = m >= 6 && !(m & 1) && ((m / 2) & 1) && h_is_prime(m / 2);
+  const u32 h = twoh ? m / 2 : 0;
+  std::vector<long long> phi;
+  if (!twoh) phi = h_cyclotomic(m);
   if (logQ < 8 || logQ > 512) return fail(FHESI_ERR_UNSUPPORTED, "logQ must be in [8, 512]");
   if (decompSize < 1 || decompSize > 3)
     return fail(FHESI_ERR_UNSUPPORTED, "decompSize must be 1..3 (digits must stay below 2^29)");
@@ -268,19 +322,57 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
 
   fhesi_ctx *c = new fhesi_ctx();
   c->device = device;
-  const u32 n = h - 1;
+  const u32 n = twoh ? h - 1 : (u32)phi.size() - 1;
   u32 N = 16;  // store_index() needs N >= 16
   while (N < 2 * n - 1) N <<= 1;
-  if (N > 2048) {
+  if (N > 2048 || n < 2) {
     delete c;
-    return fail(FHESI_ERR_UNSUPPORTED, "phi(m) > 1024 not supported");
+    return fail(FHESI_ERR_UNSUPPORTED, "phi(m) must be in [2, 1024]");
+  }
+  // growth of one ring product: |a b mod Phi_m|_inf <= G |a|_inf |b|_inf.  2h: the fold adds three runs of the
+  // linear convolution, G = 2n - 2 (kept at 2n).  General m: from the remainder table, row by row.
+  double G = 2.0 * n;
+  std::vector<u32> red, red_wide;
+  if (!twoh) {
+    const u32 J = std::max(N - n, m - n);
+    if (!h_reduction_columns(phi, J, c->red_cols)) {
+      delete c;
+      return fail(FHESI_ERR_UNSUPPORTED, "X^j mod Phi_m has coefficients beyond +-64 for this m");
+    }
+    std::vector<double> g(n);
+    for (u32 i = 0; i < n; ++i) g[i] = i + 1;  // terms of the linear convolution at degree i
+    for (u32 j = 0; j + 1 < n; ++j)
+      for (auto &e : c->red_cols[j]) g[e.first] += std::abs(e.second) * (double)(2 * n - 1 - (n + j));
+    G = *std::max_element(g.begin(), g.end());
+    // rows of the gather, columns j < jmax: [n + 1 row starts][(j, coefficient) pairs]
+    auto csr = [&](u32 jmax) {
+      std::vector<u32> cnt(n + 1, 0);
+      for (u32 j = 0; j < jmax; ++j)
+        for (auto &e : c->red_cols[j]) cnt[e.first + 1]++;
+      for (u32 i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+      std::vector<u32> t(n + 1 + 2 * (size_t)cnt[n], 0), fill(cnt.begin(), cnt.end() - 1);
+      for (u32 i = 0; i <= n; ++i) t[i] = cnt[i];
+      for (u32 j = 0; j < jmax; ++j)
+        for (auto &e : c->red_cols[j]) {
+          const u32 at = fill[e.first]++;
+          t[n + 1 + 2 * at] = j;
+          t[n + 1 + 2 * at + 1] = (u32)e.second;
+        }
+      return t;
+    };
+    red = csr(n - 1);        // a product of two ring elements: degree <= 2n - 2
+    red_wide = csr(N - n);   // anything a transform-domain vector can hold (tensor form times a plaintext)
   }
   const u32 W = (logQ + 31) / 32, dbits = 8 * decompSize;
   const u32 D = (logQ + dbits - 1) / dbits;
 
   // number of 30-bit primes needed by each stage (DESIGN.md "chain sizing")
-  const double lg2n = std::log2(2.0 * n), lgp = std::log2((double)p_pt);
-  const double need_t = 2.0 * logQ - 2 + lgp + lg2n + std::log2(3.0) + std::log2((double)xi) + 1 + 0.1;
+  const double lg2n = std::log2(G), lgp = std::log2((double)p_pt);
+  double need_t = 2.0 * logQ - 2 + lgp + lg2n + std::log2(3.0) + std::log2((double)xi) + 1 + 0.1;
+  // General m is no throughput configuration: give the tensor chain at least the reference's own sizing rule
+  // (FHEContext.cpp:83-85: 2 log q + log p + 2 log phi(m) + log 2 + log xi), so that the tensor-form plaintext
+  // operators (Ciphertext.cpp:157-159,252-256) have the head-room they have there.
+  if (!twoh) need_t = std::max(need_t, 2.0 * logQ + lgp + 2 * std::log2((double)n) + 1 + std::log2((double)xi) + 0.1);
   const double need_k = dbits + (logQ - 1) + lg2n + std::log2(3.0 * D) + 1 + 0.1;
   const double need_e = logQ + lg2n + 10 + 1 + 0.1;
   std::vector<u32> primes;
@@ -446,6 +538,11 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
       (rc = upload(c, gar, &dc.garner)) || (rc = upload(c, Pf, &dc.Pfull)) ||
       (rc = upload(c, Ph, &dc.Phalf)) || (rc = upload(c, twsf, &dc.tws_fwd)) ||
       (rc = upload(c, twsi, &dc.tws_inv)) || (rc = upload(c, cwr, &dc.cwr)) || (rc = upload(c, twdf, &dc.twd_fwd))) {
+    fhesi_ctx_destroy(c);
+    return rc;
+  }
+  dc.red = dc.red_wide = nullptr;
+  if (!twoh && ((rc = upload(c, red, &dc.red)) || (rc = upload(c, red_wide, &dc.red_wide)))) {
     fhesi_ctx_destroy(c);
     return rc;
   }
@@ -744,10 +841,12 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
   FusedTensorArgs t{resid, out, I.Lt, (u32)cnt, opg, (u32)to_tprod};
   if (I.N == FN) {
     dim3 grid(I.Lt, (unsigned)((cnt + KG * opg - 1) / (KG * opg)));
-    KL(c, k_fused_tensor, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
+    const auto kern = c->dc.h ? k_fused_tensor<false> : k_fused_tensor<true>;
+    KLN(c, "k_fused_tensor", kern, grid, KG * 128, FUSED_SMEM_WORDS * 4, c->dc, t);
   } else {
     dim3 grid(I.Lt, (unsigned)((cnt + KG2 * opg - 1) / (KG2 * opg)));
-    KL(c, k_fused_tensor_2k, grid, KG2 * T2K, FUSED2K_SMEM_WORDS * 4, c->dc, t);
+    const auto kern = c->dc.h ? k_fused_tensor_2k<false> : k_fused_tensor_2k<true>;
+    KLN(c, "k_fused_tensor_2k", kern, grid, KG2 * T2K, FUSED2K_SMEM_WORDS * 4, c->dc, t);
   }
   CKL();
   return 0;
@@ -1062,21 +1161,40 @@ int fhesi_reduce_wide_dev(fhesi_ctx *c, const uint32_t *in, uint32_t Win, uint32
 // device table of the signed index permutation of X -> X^k (one per Galois element, kept for reuse)
 static int automorph_table(fhesi_ctx *c, uint32_t k, u32 **out) {
   const fhesi_info &I = c->info;
-  const u32 h = I.m / 2;
   u32 *&d_tab = c->automorph_tabs[k % I.m];
   if (!d_tab) {
-    std::vector<u32> tab(h, 0xFFFFFFFFu);
-    for (u32 i = 0; i < I.n; ++i) {
-      u32 e = (u32)(((u64)i * k) % I.m), neg = 0;
-      if (e >= h) { e -= h; neg = 1; }
-      tab[e] = (i << 1) | neg;
+    std::vector<u32> tab;
+    if (c->dc.h) {
+      const u32 h = c->dc.h;
+      tab.assign(h, 0xFFFFFFFFu);
+      for (u32 i = 0; i < I.n; ++i) {
+        u32 e = (u32)(((u64)i * k) % I.m), neg = 0;
+        if (e >= h) { e -= h; neg = 1; }
+        tab[e] = (i << 1) | neg;
+      }
+    } else {
+      // general m: X^i -> X^(i k mod m), positions >= n expanded through X^(n+j) mod Phi_m; rows by output index
+      std::vector<std::vector<std::pair<u32, int>>> rows(I.n);
+      for (u32 i = 0; i < I.n; ++i) {
+        const u32 e = (u32)(((u64)i * k) % I.m);
+        if (e < I.n) rows[e].push_back(std::make_pair(i, 1));
+        else
+          for (auto &t : c->red_cols[e - I.n]) rows[t.first].push_back(std::make_pair(i, t.second));
+      }
+      tab.assign(I.n + 1, 0);
+      for (u32 i = 0; i < I.n; ++i) tab[i + 1] = tab[i] + (u32)rows[i].size();
+      for (u32 i = 0; i < I.n; ++i)
+        for (auto &t : rows[i]) {
+          tab.push_back(t.first);
+          tab.push_back((u32)t.second);
+        }
     }
     void *pt = nullptr;
     size_t cap = 0;
-    CK(cached_malloc(c->device, &pt, h * 4, &cap));
+    CK(cached_malloc(c->device, &pt, tab.size() * 4, &cap));
     c->tables.push_back(std::make_pair(pt, cap));
     d_tab = (u32 *)pt;
-    CK(cudaMemcpyAsync(d_tab, tab.data(), h * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));  // tab is a stack-lifetime host buffer
   }
   *out = d_tab;
@@ -1136,7 +1254,8 @@ int fhesi_tprod_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, 
   if ((rc = r0.alloc(words * 4)) || (rc = r1.alloc(words * 4))) return rc;
   // transform domain -> coefficient residues (Phi_m fold included) -> signed permutation -> back
   if ((rc = launch_inv(c, in, I.Lt, r0.u(), npolys))) return rc;
-  KL(c, k_automorph_res, nblk(words), 256, 0, c->dc, r0.u(), d_tab, r1.u(), I.Lt, npolys);
+  if (c->dc.h) KL(c, k_automorph_res, nblk(words), 256, 0, c->dc, r0.u(), d_tab, r1.u(), I.Lt, npolys);
+  else KL(c, k_automorph_res_csr, nblk(words), 256, 0, c->dc, r0.u(), d_tab, r1.u(), I.Lt, npolys);
   CKL();
   return launch_fwd(c, r1.u(), SRC_RES, 0, SC_NINV, I.Lt, out, npolys);
 }
@@ -1185,7 +1304,8 @@ int fhesi_ct_automorph_dev(fhesi_ctx *c, const uint32_t *in, uint32_t parts, uin
   u32 *d_tab = nullptr;
   int rc = automorph_table(c, k, &d_tab);
   if (rc) return rc;
-  if (npolys) KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, out, npolys);
+  if (npolys && c->dc.h) KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, out, npolys);
+  else if (npolys) KL(c, k_automorph_csr, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, out, npolys);
   CKL();
   return 0;
 }
@@ -1362,10 +1482,12 @@ static int fused_ks_from_digits(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *d
     FusedKsArgs k{digits, ksw->d_key_split, res, ksw->parts * I.D, I.Ls, (u32)cnt};
     if (I.N == FN) {
       dim3 grid(I.Ls, (unsigned)((cnt + KSS - 1) / KSS));
-      KL(c, k_fused_keyswitch_split, grid, KSS * 128, KSS_SMEM_WORDS * 4, c->dc, k);
+      const auto kern = c->dc.h ? k_fused_keyswitch_split<false> : k_fused_keyswitch_split<true>;
+      KLN(c, "k_fused_keyswitch_split", kern, grid, KSS * 128, KSS_SMEM_WORDS * 4, c->dc, k);
     } else {
       dim3 grid(I.Ls, (unsigned)((cnt + KSS2 - 1) / KSS2));
-      KL(c, k_fused_keyswitch_split_2k, grid, KSS2 * T2K, KSS2K_SMEM_WORDS * 4, c->dc, k);
+      const auto kern = c->dc.h ? k_fused_keyswitch_split_2k<false> : k_fused_keyswitch_split_2k<true>;
+      KLN(c, "k_fused_keyswitch_split_2k", kern, grid, KSS2 * T2K, KSS2K_SMEM_WORDS * 4, c->dc, k);
     }
     CKL();
     return launch_crt_split(c, res, I.Ls, out, cnt * 2);
@@ -1373,8 +1495,9 @@ static int fused_ks_from_digits(fhesi_ctx *c, const fhesi_ksw *ksw, const u32 *d
   const bool tfree = c->tfree && ksw->d_key_bal;
   FusedKsArgs k{digits, tfree ? ksw->d_key_bal : ksw->d_key, res, ksw->parts * I.D, I.Lk, (u32)cnt};
   dim3 grid(I.Lk, (unsigned)((cnt + KSG - 1) / KSG));
-  if (tfree) KL(c, k_fused_keyswitch<true>, grid, KSG * 128, KS_SMEM_WORDS * 4, c->dc, k);
-  else KL(c, k_fused_keyswitch<false>, grid, KSG * 128, KS_SMEM_WORDS * 4, c->dc, k);
+  const auto kern = tfree ? (c->dc.h ? k_fused_keyswitch<true, false> : k_fused_keyswitch<true, true>)
+                          : (c->dc.h ? k_fused_keyswitch<false, false> : k_fused_keyswitch<false, true>);
+  KLN(c, tfree ? "k_fused_keyswitch<true>" : "k_fused_keyswitch<false>", kern, grid, KSG * 128, KS_SMEM_WORDS * 4, c->dc, k);
   CKL();
   return launch_crt(c, res, I.Lk, CRT_REDUCE_Q, out, I.W, cnt * 2);
 }
@@ -1463,15 +1586,16 @@ int fhesi_rotate_keyswitch_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_
   u32 *d_tab = nullptr;
   int rc = automorph_table(c, k, &d_tab);
   if (rc) return rc;
-  if (c->use_fused) return fused_rotate_keyswitch(c, ksw, in, d_tab, out, count);
-  // generic kernels: the three steps separately
+  if (c->use_fused && c->dc.h) return fused_rotate_keyswitch(c, ksw, in, d_tab, out, count);
+  // generic kernels, or general m (the rotation is a sparse matrix, not a signed permutation): three steps
   PoolTmp wide(c), red(c);
   const size_t npolys = count * 2;
   if ((rc = wide.alloc(npolys * I.n * (I.W + 1) * 4)) || (rc = red.alloc(npolys * I.n * I.W * 4))) return rc;
-  KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, wide.u(), npolys);
+  if (c->dc.h) KL(c, k_automorph, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, wide.u(), npolys);
+  else KL(c, k_automorph_csr, nblk(npolys * I.n, 128), 128, 0, c->dc, in, d_tab, wide.u(), npolys);
   CKL();
   if ((rc = fhesi_reduce_wide_dev(c, wide.u(), I.W + 1, red.u(), 2, count))) return rc;
-  return keyswitch_generic(c, ksw, red.u(), out, count);
+  return fhesi_keyswitch_dev(c, ksw, red.u(), out, count);
 }
 
 int fhesi_mult_relin_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *a, const uint32_t *b,

@@ -283,6 +283,24 @@ __device__ __forceinline__ void phim_store_1024(const u32 *nat, u32 *__restrict_
   }
 }
 
+// General m (DevCtx::red, h == 0): the sparse remainder rows instead of the fold; T threads per transform.  The fused
+// kernels take the choice as a template parameter GEN, so that the m = 2h instances compile exactly as without it
+// (k_fused_keyswitch_split sits at 128 registers: a run-time branch costs it spills).
+template <int T>
+__device__ __forceinline__ void phim_store_csr(const u32 *nat, u32 *__restrict__ dst, const u32 *__restrict__ red, u32 n,
+                                               u32 tg, u32 p) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u32 i = j * T + tg;
+    if (i < n) dst[i] = phim_row_csr(nat, red, n, i, p);
+  }
+}
+#define PHIM_STORE_1024(NAT, DST)                                   \
+  do {                                                              \
+    if (!GEN) phim_store_1024((NAT), (DST), c.h, tg, p);            \
+    else phim_store_csr<128>((NAT), (DST), c.red, c.n, tg, p);      \
+  } while (0)
+
 static bool fused_supported(const DevCtx &dc) { return (dc.N == FN && dc.n <= 512) || (dc.N == 2048 && dc.n <= 1024); }
 
 // multiword two's complement (W words) -> residue in [0,2p), scaled by s_v (DevCtx::cwr).
@@ -473,6 +491,7 @@ struct FusedTensorArgs {
 };
 #define KG 6
 #define FUSED_SMEM_WORDS (2 * FTW_WORDS + KG * 3 * FPADN)
+template <bool GEN>
 __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTensorArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
@@ -526,7 +545,7 @@ __global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTen
       } else {
         u32 *bufA = (flip++ & 1) ? bufA1 : bufA0;
         inv1024(y, twi, A, bufA, bufB, bufA, g, tg, p);
-        phim_store_1024(bufA, a.res + ((op * 3 + k) * a.Lt + l) * (size_t)c.n, c.h, tg, p);
+        PHIM_STORE_1024(bufA, a.res + ((op * 3 + k) * a.Lt + l) * (size_t)c.n);
       }
     }
   }
@@ -547,7 +566,7 @@ struct FusedKsArgs {
 // intermediate reduction (nor its 16 partial-sum registers) is needed.
 #define KSG 6
 #define KS_SMEM_WORDS (2 * FTW_WORDS + KSG * 3 * FPADN)
-template <bool TFREE>
+template <bool TFREE, bool GEN>
 __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
@@ -621,9 +640,9 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
   }
   fhesi_group_sync(g);  // every warp is done with the forward transforms' buffers
   inv1024(t0, twi, A, bufA0, bufB, bufA0, g, tg, p);
-  phim_store_1024(bufA0, a.res + ((op * 2 + 0) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+  PHIM_STORE_1024(bufA0, a.res + ((op * 2 + 0) * a.Lk + l) * (size_t)c.n);
   inv1024(t1, twi, A, bufA1, bufB, bufA1, g, tg, p);
-  phim_store_1024(bufA1, a.res + ((op * 2 + 1) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+  PHIM_STORE_1024(bufA1, a.res + ((op * 2 + 1) * a.Lk + l) * (size_t)c.n);
 }
 // ---------------------------------------------------------------------------------------
 // split-key key switch.  Every key polynomial K (mod q) is stored as two non-negative halves,
@@ -641,6 +660,7 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
 #define KSS_BUFA 2048u  // word distance of the two alternating exchange buffers (a power of two: XOR toggle)
 #define KSS_SMEM_WORDS (2 * FTW_WORDS + FTD_WORDS + KSS * (2 * KSS_BUFA + FPADN))
 // key: [Ls][K][4][N] balanced, followed by the offset-correction table [Ls][4][N] (k_split_corr)
+template <bool GEN>
 __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
@@ -727,7 +747,7 @@ __global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c
     }
     u32 *bufA = bufA0 + ((h & 1) ? KSS_BUFA : 0u);
     inv1024(t, twi, A, bufA, bufB, bufA, g, tg, p);
-    phim_store_1024(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+    PHIM_STORE_1024(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n);
   }
 }
 // Offset correction of the split key switch: the kernel accumulates (x - ch) * K with ch = p >> 1,
@@ -800,17 +820,13 @@ __global__ void k_digits_automorph(DevCtx c, const u32 *in, const u32 *tab, u32 
   for (u32 d = 0; d < c.D; ++d) out[(poly * c.D + d) * c.n + j] = digit_from_words(w, W, c.logQ, c.dbits, d);
 }
 
+template <class K>
+static int fused_set_smem(K kern, size_t words) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)) == cudaSuccess ? 0 : -1;
+}
 static int fused_configure() {
-  cudaError_t e = cudaFuncSetAttribute(k_fused_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(FUSED_SMEM_WORDS * 4));
-  if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(k_fused_keyswitch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(KS_SMEM_WORDS * 4));
-  if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(k_fused_keyswitch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(KS_SMEM_WORDS * 4));
-  if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(k_fused_keyswitch_split, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(KSS_SMEM_WORDS * 4));
-  return e == cudaSuccess ? 0 : -1;
+  return fused_set_smem(k_fused_tensor<false>, FUSED_SMEM_WORDS) || fused_set_smem(k_fused_tensor<true>, FUSED_SMEM_WORDS) ||
+         fused_set_smem(k_fused_keyswitch<true, false>, KS_SMEM_WORDS) || fused_set_smem(k_fused_keyswitch<false, false>, KS_SMEM_WORDS) ||
+         fused_set_smem(k_fused_keyswitch<true, true>, KS_SMEM_WORDS) || fused_set_smem(k_fused_keyswitch<false, true>, KS_SMEM_WORDS) ||
+         fused_set_smem(k_fused_keyswitch_split<false>, KSS_SMEM_WORDS) || fused_set_smem(k_fused_keyswitch_split<true>, KSS_SMEM_WORDS);
 }

@@ -189,6 +189,7 @@ __device__ __forceinline__ void phim_store_t(const u32 *nat, u32 *__restrict__ d
 #define KG2 3
 #define T2K 256
 #define FUSED2K_SMEM_WORDS (2 * FT<T2K>::WORDS + KG2 * (2 * FT<T2K>::BUFA + FT<T2K>::BUFB))
+template <bool GEN>
 __global__ void __launch_bounds__(KG2 *T2K, 1) k_fused_tensor_2k(DevCtx c, FusedTensorArgs a) {
   typedef FT<T2K> F;
   FHESI_SMEM(sm);
@@ -231,7 +232,8 @@ __global__ void __launch_bounds__(KG2 *T2K, 1) k_fused_tensor_2k(DevCtx c, Fused
       } else {
         u32 *bufA = (flip++ & 1) ? bufA1 : bufA0;
         inv_t<T2K>(y, twi, A, bufA, bufB, bufA, g, tg, p);
-        phim_store_t<T2K>(bufA, a.res + ((op * 3 + k) * a.Lt + l) * (size_t)c.n, c.h, tg, p);
+        if (!GEN) phim_store_t<T2K>(bufA, a.res + ((op * 3 + k) * a.Lt + l) * (size_t)c.n, c.h, tg, p);
+        else phim_store_csr<T2K>(bufA, a.res + ((op * 3 + k) * a.Lt + l) * (size_t)c.n, c.red, c.n, tg, p);
       }
     }
   }
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(KG2 *T2K, 1) k_fused_tensor_2k(DevCtx c, Fused
 // ---------------------------------------------------------------------------------------
 #define KSS2 2
 #define KSS2K_SMEM_WORDS (2 * FT<T2K>::WORDS + KSS2 * (2 * FT<T2K>::BUFA + FT<T2K>::BUFB))
+template <bool GEN>
 __global__ void __launch_bounds__(KSS2 *T2K, 1) k_fused_keyswitch_split_2k(DevCtx c, FusedKsArgs a) {
   typedef FT<T2K> F;
   FHESI_SMEM(sm);
@@ -302,15 +305,13 @@ __global__ void __launch_bounds__(KSS2 *T2K, 1) k_fused_keyswitch_split_2k(DevCt
     }
     u32 *bufA = (h & 1) ? bufA1 : bufA0;
     inv_t<T2K>(t, twi, A, bufA, bufB, bufA, g, tg, p);
-    phim_store_t<T2K>(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+    if (!GEN) phim_store_t<T2K>(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n, c.h, tg, p);
+        else phim_store_csr<T2K>(bufA, a.res + ((op * 4 + h) * a.Lk + l) * (size_t)c.n, c.red, c.n, tg, p);
   }
 }
 
 static int fused2k_configure() {
-  cudaError_t e = cudaFuncSetAttribute(k_fused_tensor_2k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(FUSED2K_SMEM_WORDS * 4));
-  if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(k_fused_keyswitch_split_2k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(KSS2K_SMEM_WORDS * 4));
-  return e == cudaSuccess ? 0 : -1;
+  return fused_set_smem(k_fused_tensor_2k<false>, FUSED2K_SMEM_WORDS) || fused_set_smem(k_fused_tensor_2k<true>, FUSED2K_SMEM_WORDS) ||
+         fused_set_smem(k_fused_keyswitch_split_2k<false>, KSS2K_SMEM_WORDS) ||
+         fused_set_smem(k_fused_keyswitch_split_2k<true>, KSS2K_SMEM_WORDS);
 }

@@ -51,7 +51,29 @@ struct DevCtx {
   // reduction), s_1 = p_pt / N * R (Montgomery form of the tensor's left operand)
   const u32 *cwr;                         // [Lmax][2][CW]
   u32 sshift;                             // store_index() block: 1 (16 positions) or 2 (32, N = 2048)
+  // General m (h == 0): the remainder by Phi_m (CModulus.cpp:128-129, NTL rem) as a sparse gather.  Row i lists the
+  // non-zero coefficients of X^i in X^(n+j) mod Phi_m, j < n - 1: [n + 1 row starts][(j, coefficient) pairs].
+  // NULL for m = 2h (h an odd prime), whose fold is written out in phim_reduce_store / phim_store_*.
+  const u32 *red;
+  const u32 *red_wide;                    // the same with j < N - n: every position a transform-domain vector can hold
 };
+
+// one row of the general-m remainder: x[0..2n-1) holds a product (values < 2p), returns coefficient i in [0,p)
+__device__ __forceinline__ u32 phim_row_csr(const u32 *x, const u32 *__restrict__ red, u32 n, u32 i, u32 p) {
+  const u32 p2 = 2 * p;
+  u32 s = x[i];
+  const u32 *ent = red + n + 1;
+  for (u32 t = red[i], e = red[i + 1]; t < e; ++t) {
+    const u32 v = x[n + ent[2 * t]];
+    int cf = (int)ent[2 * t + 1];  // small: +-1 for every m with at most two odd prime factors
+    if (cf > 0) {
+      do s = csub(s + v, p2); while (--cf);
+    } else {
+      do s = csub(s + p2 - v, p2); while (++cf);
+    }
+  }
+  return full_reduce(s, p);
+}
 
 // Storage order of transform-domain vectors.  Position i of the in-place DIF output lives at
 // store_index(i): inside every block of 16 positions the 8 even ones come first, then the 8
@@ -237,7 +259,7 @@ __global__ void k_inv(DevCtx c, InvArgs a) {
   u32 *dst = a.dst + ((size_t)q * a.L + l) * c.n;
   const int *e = a.e ? a.e + (size_t)q * c.n : nullptr;
   const u32 *msg = (a.msg && !(q & 1)) ? a.msg + (size_t)(q >> 1) * c.n : nullptr;
-  phim_reduce_store(x, y, c.N, c.h, p, [&](u32 i, u32 v) {
+  auto store = [&](u32 i, u32 v) {
     if (e) {
       int ev = e[i];
       u32 er = ev < 0 ? p - ((u32)(-ev)) % p : ((u32)ev) % p;
@@ -256,7 +278,12 @@ __global__ void k_inv(DevCtx c, InvArgs a) {
       }
     }
     dst[i] = v;
-  });
+  };
+  if (c.h) {
+    phim_reduce_store(x, y, c.N, c.h, p, store);
+  } else {  // general m
+    for (u32 i = threadIdx.x; i < c.n; i += blockDim.x) store(i, phim_row_csr(x, c.red_wide, c.n, i, p));
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -421,6 +448,27 @@ __global__ void k_tprod_reduce_world(DevCtx c, const u32 *in, u32 world, u32 L, 
   out[idx] = s;
 }
 
+// General m: a(X^k) mod Phi_m is a sparse integer matrix (the index map i -> i k mod m followed by the
+// remainder by Phi_m); tab = [n + 1 row starts][(source index, coefficient) pairs], one row per output coefficient
+__global__ void k_automorph_res_csr(DevCtx c, const u32 *in, const u32 *tab, u32 *out, u32 L, size_t npolys) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npolys * L * c.n) return;
+  const u32 j = (u32)(idx % c.n);
+  const size_t row = idx / c.n;  // poly * L + l
+  const u32 p = c.pc[row % L].p;
+  const u32 *base = in + row * c.n, *ent = tab + c.n + 1;
+  u32 s = 0;
+  for (u32 t = tab[j], e = tab[j + 1]; t < e; ++t) {
+    const u32 v = base[ent[2 * t]];
+    int cf = (int)ent[2 * t + 1];
+    if (cf > 0) {
+      do s = csub(s + v, p); while (--cf);
+    } else {
+      do s = csub(s + p - v, p); while (++cf);
+    }
+  }
+  out[idx] = s;
+}
 // ---------------------------------------------------------------------------------------
 // CRT: Garner mixed radix -> multiword -> centre -> mode-specific rounding
 // ---------------------------------------------------------------------------------------
@@ -865,6 +913,38 @@ __global__ void k_automorph(DevCtx c, const u32 *in, const u32 *tab, u32 *out, s
     o[k] = (u32)t;
     c2 = (u32)(t >> 32);
   }
+}
+// General m: the same through the sparse matrix of k_automorph_res_csr, on two's-complement words.
+// out is [..][n][W+1]: a row's coefficients sum to far less than 2^32 in magnitude.
+__global__ void k_automorph_csr(DevCtx c, const u32 *in, const u32 *tab, u32 *out, size_t npolys) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npolys * c.n) return;
+  const size_t poly = idx / c.n;
+  const u32 j = (u32)(idx % c.n), W = c.W, Wo = W + 1;
+  const u32 *base = in + poly * c.n * W, *ent = tab + c.n + 1;
+  u32 acc[17];  // W <= 16
+#pragma unroll
+  for (int k = 0; k < 17; ++k) acc[k] = 0;
+  for (u32 t = tab[j], e = tab[j + 1]; t < e; ++t) {
+    const u32 *src = base + (size_t)ent[2 * t] * W;
+    const int cf = (int)ent[2 * t + 1];
+    const u32 neg = cf < 0 ? 0xFFFFFFFFu : 0u, ext = (src[W - 1] >> 31) ? 0xFFFFFFFFu : 0u;
+    for (int rep = cf < 0 ? -cf : cf; rep > 0; --rep) {
+      u32 carry = neg & 1u;  // -v = ~v + 1
+#pragma unroll
+      for (int k = 0; k < 17; ++k) {
+        if ((u32)k < Wo) {
+          const u64 sum = (u64)acc[k] + (((u32)k < W ? src[k] : ext) ^ neg) + carry;
+          acc[k] = (u32)sum;
+          carry = (u32)(sum >> 32);
+        }
+      }
+    }
+  }
+  u32 *o = out + idx * Wo;
+#pragma unroll
+  for (int k = 0; k < 17; ++k)
+    if ((u32)k < Wo) o[k] = acc[k];
 }
 
 // ---------------------------------------------------------------------------------------

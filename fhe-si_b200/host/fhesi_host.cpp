@@ -1603,6 +1603,30 @@ static void AutomorphSmallPhim(const int32_t *a, int32_t *out, unsigned n, unsig
   }
   FoldTopSmall(v, out, n);
 }
+// Any other m: the linear product / the index map, then the remainder by Phi_m (RemPhim's general branch)
+static void RemSmallGeneral(const std::vector<int64_t> &v, int32_t *out, const PAlgebra &zms) {
+  ZZX a;
+  a.rep.v.resize(v.size());
+  for (size_t i = 0; i < v.size(); ++i) a.rep.v[i] = ZZ((long)v[i]);
+  a.normalize();
+  RemPhim(a, zms);
+  const unsigned n = zms.phiM();
+  for (unsigned j = 0; j < n; ++j) out[j] = (long)j <= deg(a) ? (int32_t)to_long(a.rep.v[j]) : 0;
+}
+static void MulSmallGeneral(const int32_t *a, const int32_t *b, int32_t *out, const PAlgebra &zms) {
+  const unsigned n = zms.phiM();
+  std::vector<int64_t> v(2 * (size_t)n - 1, 0);
+  for (unsigned i = 0; i < n; ++i)
+    if (a[i])
+      for (unsigned j = 0; j < n; ++j) v[i + j] += (int64_t)a[i] * b[j];
+  RemSmallGeneral(v, out, zms);
+}
+static void AutomorphSmallGeneral(const int32_t *a, int32_t *out, const PAlgebra &zms, unsigned k) {
+  const unsigned n = zms.phiM(), m = zms.M();
+  std::vector<int64_t> v(m, 0);
+  for (unsigned i = 0; i < n; ++i) v[(unsigned)(((uint64_t)i * k) % m)] += a[i];
+  RemSmallGeneral(v, out, zms);
+}
 // The whole set-up's draws in the layout fhesi_keygen_batch consumes: secret key; public key (its Gaussian,
 // then its uniform polynomial: FHE-SI.cpp:44-47) stored as the LAST entry; the s^2 -> s matrix (3 source rows
 // 1, s, s^2) preceded by the throw-away key FHE-SI.cpp:222 samples; one rotation matrix per rot_k (2 source
@@ -1631,7 +1655,6 @@ extern "C" int fhesih_keydraws_flat(uint32_t m, uint32_t logQ, uint64_t p, uint3
     const size_t pw = (size_t)n * W, Km = (size_t)(3 + 2 * n_rot) * D;
     std::vector<uint32_t> raw((Km + 1) * ((size_t)n + 1));
     const bool twoh = m % 2 == 0 && (m / 2) % 2 == 1 && n + 1 == m / 2;  // m = 2h, h an odd prime (every device context)
-    if (!twoh) Error("fhesih_keydraws_flat: m must be 2 * (odd prime)");
     std::vector<int32_t> tmp(n);
     SampleHWtSmall(sk_out, 64, n);                            // FHESISecKey::Init
     SampleGaussianRaw(raw.data() + Km * ((size_t)n + 1), n);  // FHESIPubKey::Init: c0's Gaussian ...
@@ -1641,7 +1664,8 @@ extern "C" int fhesih_keydraws_flat(uint32_t m, uint32_t logQ, uint64_t p, uint3
       std::fill(src, src + n, 0);
       src[0] = 1;
       memcpy(src + n, sk_out, n * 4);
-      MulSmallPhim(sk_out, sk_out, src + 2 * (size_t)n, n);
+      if (twoh) MulSmallPhim(sk_out, sk_out, src + 2 * (size_t)n, n);
+      else MulSmallGeneral(sk_out, sk_out, src + 2 * (size_t)n, context.zMstar);
       DrawMatrixFlat(A, raw.data(), 3 * (size_t)D, n, W, logQ);
     }
     for (uint32_t r = 0; r < n_rot; ++r) {                    // KeySwitchSI(sk, k): InitAutomorph
@@ -1649,7 +1673,8 @@ extern "C" int fhesih_keydraws_flat(uint32_t m, uint32_t logQ, uint64_t p, uint3
       int32_t *rs = src + (3 + 2 * (size_t)r) * n;
       std::fill(rs, rs + n, 0);
       rs[0] = 1;                                              // 1(X^k) = 1
-      AutomorphSmallPhim(sk_out, rs + n, n, m, rot_k[r]);
+      if (twoh) AutomorphSmallPhim(sk_out, rs + n, n, m, rot_k[r]);
+      else AutomorphSmallGeneral(sk_out, rs + n, context.zMstar, rot_k[r]);
       const size_t off = (3 + 2 * (size_t)r) * D;
       DrawMatrixFlat(A + off * pw, raw.data() + off * ((size_t)n + 1), 2 * (size_t)D, n, W, logQ);
     }

@@ -65,8 +65,11 @@ const char *fhesi_last_error(void);
 const char *fhesi_version(void);
 
 /* ---- context: FHEcontext::Init + SetUpSIContext (FHEContext.h:105-118, FHEContext.cpp:83-85).
- * m must be 2*p' with p' an odd prime (every parameter set the reference intends,
- * README:35-37).  xi is the number of tensor products that may be summed in
+ * Any m in [3, 8192] with 2 <= phi(m) <= 1024, as the reference's Bluestein transform serves any m
+ * (bluestein.cpp:93-144, CModulus.cpp:110-132).  m = 2*p' with p' an odd prime (every parameter set the
+ * reference's clients use, README:35-37) has the remainder by Phi_m written into the kernels
+ * as a fold; every other m takes it from a sparse table built here (X^j mod Phi_m must have coefficients
+ * within +-64, true of every m in range).  xi is the number of tensor products that may be summed in
  * tprod form before ScaleDown (SetUpSIContext's argument). */
 int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p, uint32_t decompSize, uint64_t xi,
                      int device, fhesi_ctx **out);

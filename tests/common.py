@@ -19,15 +19,30 @@ CONFIGS = {
     "p2027_176": (176, 2027, 3),
 }
 
+# General m (not 2 * odd prime): Phi_m is taken as a sparse remainder table (DevCtx::red).  (logQ, p, g, m):
+# a power of two, an odd prime, prime powers, three odd prime factors (Phi_105 has a coefficient -2; X^j mod Phi_105
+# reaches +-2), phi(m) > m / 2 and < m / 2, and two sizes that take the fused kernels (N = 1024: 256 < phi(m) <= 512).
+GENERAL_M = {
+    "m16": (80, 17, 3, 16),
+    "m17": (80, 2, 3, 17),
+    "m36": (100, 37, 5, 36),
+    "m45": (80, 181, 2, 45),
+    "m105": (80, 211, 2, 105),
+    "m128": (128, 257, 3, 128),
+    "m1320": (100, 1321, 13, 1320),
+    "m771": (128, 2, 5, 771),
+}
+
 
 class Scenario:
-    def __init__(self, logq, p, g, seed=1, xi=1, lib_path=None, device=0):
-        self.octx = O.Context(p - 1, logq, p, g).setup_si(xi)
+    def __init__(self, logq, p, g, seed=1, xi=1, lib_path=None, device=0, m=None):
+        m = p - 1 if m is None else m  # the reference's clients take m = p - 1; the library takes any m
+        self.octx = O.Context(m, logq, p, g).setup_si(xi)
         self.rng = O.Rng(seed)
         self.sk = O.SecKey.generate(self.octx, self.rng)
         self.pk = O.PubKey.generate(self.sk, self.rng)
         self.ks = O.KeySwitch.init_s2(self.sk, self.rng)
-        self.dev = pyfhesi.Context(p - 1, logq, p, 3, xi, device, lib_path=lib_path)
+        self.dev = pyfhesi.Context(m, logq, p, 3, xi, device, lib_path=lib_path)
         self.logq, self.p = logq, p
         self._ksw = None
         self._pk = None

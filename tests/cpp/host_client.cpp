@@ -79,7 +79,7 @@ int main(int argc, char **argv) {
   Save(dir + "/mul_scalar_m7.bin", sc);
 
   Ciphertext au = a;
-  au >>= 3;
+  au >>= ((p - 1) % 3 ? 3 : 5);  // 3 is a unit of every m = 2 * prime of the BASELINE configs; 3 | m takes 5
   Save(dir + "/automorph_3.bin", au);
 
   // keys as DoubleCRT rows over the reference chain (Serialization.cpp:56-65)

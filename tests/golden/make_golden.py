@@ -56,7 +56,7 @@ def outputs(ctx, sk, ks, cts):
     sq = O.mult_relin(ks, mr, mr)
     out["square_relin"] = O.export_ciphertext(sq)
     out["mul_scalar_m7"] = O.export_ciphertext(a.copy().mul_scalar(-7))
-    out["automorph_3"] = O.export_ciphertext(a.copy().automorph(3))
+    out["automorph_3"] = O.export_ciphertext(a.copy().automorph(3 if ctx.m % 3 else 5))  # as host_client.cpp
     # second group
     acc = a.copy().mul(b).add(b.copy().mul(b))
     out["tensor_accumulate"] = O.export_ciphertext(acc)

@@ -24,6 +24,10 @@ SEED = 20240611
 CONFIGS = {  # name: (logQ, p, g) -- BASELINE.json configs 1-5 (g = 3 for p = 1019)
     "cfg1": (80, 23, 7), "cfg2": (256, 1019, 3), "cfg3": (100, 1019, 3), "cfg4": (176, 1019, 3),
     "cfg5_128": (128, 1019, 3), "cfg5_512": (512, 1019, 3),
+    # m = p - 1 = 2 q^k, k >= 2: not 2 * prime (the remainder by Phi_m is no longer the alternating fold), yet Z_m^* is
+    # still cyclic, which the reference's PlaintextSpace::FindSlots needs (PlaintextSpace.cpp:80-96).  m = 18, 162,
+    # 250, 1458 (phi = 6, 54, 100, 486: transform lengths 16, 128, 256 and the fused 1024).
+    "gm18": (80, 19, 5), "gm162": (100, 163, 5), "gm250": (100, 251, 3), "gm1458": (128, 1459, 5),
 }
 FILES = ["context", "ct0", "ct1", "add", "tensor_scaledown", "mult_relin", "decrypt_mult_relin", "square_relin",
          "mul_scalar_m7", "automorph_3", "pk", "mult_relin_roundtrip", "pk_roundtrip", "tensor_accumulate",
@@ -46,7 +50,12 @@ def main():
         raise SystemExit("oracle/_ref is not built and /root/reference is not mounted")
     gold = {"seed": SEED, "generator": "oracle/_ref/golden_client_ref: reference sources + oracle/ntl_compat",
             "configs": {}}
+    only = sys.argv[1:]  # names: regenerate these and keep the other entries of the committed file
+    if only:
+        gold = json.load(open(os.path.join(HERE, "ref_golden.json")))
     for name, (logq, p, g) in CONFIGS.items():
+        if only and name not in only:
+            continue
         out = run(exes["golden_client_ref"], logq, p, g)
         entry = {"params": {"logQ": logq, "p": p, "g": g},
                  "sha256": {f: hashlib.sha256(b).hexdigest() for f, b in out.items()}}

@@ -43,6 +43,7 @@ def test_no_cpu_fallback_without_gpu(cuda_lib):
 
 def test_bad_parameters_rejected(emu_lib):
     import pyfhesi
-    for args in ((21, 80, 23), (24, 80, 23), (22, 4, 23), (22, 80, 1)):
+    # m out of range, phi(m) < 2, phi(m) > 1024, logQ too small, p < 2 (any other m is served: test_emu_general_m)
+    for args in ((2, 80, 23), (9000, 80, 23), (6151, 80, 23), (22, 4, 23), (22, 80, 1)):
         with pytest.raises(pyfhesi.FhesiError):
             pyfhesi.Context(*args, lib_path=emu_lib)

@@ -84,3 +84,37 @@ def test_emu_fused_2048_p2027(emu_lib):
     assert sc.dev.N == 2048 and sc.dev.Ls and sc.dev.Ls < sc.dev.Lk
     P.check_mult_relin(sc, count=1)
     P.check_pieces(sc, count=1)
+
+
+@pytest.mark.parametrize("name", ["m16", "m17", "m36", "m45", "m105", "m128"])
+def test_emu_general_m(name, emu_lib):
+    """Any m, not only 2 * (odd prime): the remainder by Phi_m and the automorphisms as sparse integer matrices
+    (DevCtx::red, k_automorph_csr) against the oracle's NTL-style rem (bluestein.cpp:93-144 / CModulus.cpp:128-129
+    serve every m in the reference)."""
+    from common import GENERAL_M
+    logq, p, g, m = GENERAL_M[name]
+    sc = Scenario(logq, p, g, seed=17, xi=3, lib_path=emu_lib, m=m)
+    assert sc.dev.n == sc.octx.phim and sc.dev.info.m == m
+    P.check_mult_relin(sc, count=2)
+    P.check_mult_relin(sc, count=1, random_inputs=True)
+    P.check_pieces(sc, count=1)
+    P.check_tensor_accumulate(sc, count=3)
+    P.check_encrypt_decrypt(sc, count=2)
+    P.check_coeff_ops(sc, count=2)
+    P.check_mul_plain(sc, count=1)
+    P.check_rotate_keyswitch(sc, g, count=1)
+    P.check_edge_cases(sc, counts=(0, 1, 3))
+    P.check_ref_rows(sc)
+
+
+def test_emu_general_m_fused(emu_lib):
+    """256 < phi(m) <= 512 takes the fused N = 1024 kernels' general-m instances (GEN = true)."""
+    from common import GENERAL_M
+    logq, p, g, m = GENERAL_M["m1320"]
+    sc = Scenario(logq, p, g, seed=23, lib_path=emu_lib, m=m)
+    assert sc.dev.N == 1024 and sc.dev.n == 320
+    sc.dev.profile_enable(True)
+    P.check_mult_relin(sc, count=1)
+    assert "k_fused_keyswitch_split" in sc.dev.profile_report() or "k_fused_keyswitch<true>" in sc.dev.profile_report()
+    sc.dev.profile_enable(False)
+    P.check_rotate_keyswitch(sc, g, count=1)

@@ -79,7 +79,7 @@ def check_against_golden(out, name):
     sys.path.insert(0, os.path.join(ROOT, "apps"))
     from fhesi_app import Slots
     m, p = P["p"] - 1, P["p"]
-    slots = Slots(m, p, P["g"], [(-1) ** i for i in range(m // 2)])
+    slots = Slots(m, p, P["g"], ctx.ring.PhimX)
     vals = [(i * 7 + 3) % p for i in range(slots.total)]
     pad = lambda c: list(c) + [0] * (ctx.phim - len(c))
     ours = pad(O.import_zzx(rd("embed_slots"), 0, ctx.phim)[0])
@@ -91,6 +91,12 @@ def check_against_golden(out, name):
 
 def test_host_client_matches_oracle_cfg1_emu(emu_lib, tmp_path):
     check_against_golden(run_client(emu_lib, tmp_path, "cfg1"), "cfg1")
+
+
+@pytest.mark.parametrize("name", ["gm18", "gm162"])
+def test_host_client_general_m_emu(emu_lib, tmp_path, name):
+    """m = 2 q^k (not 2 * prime): the C++ classes over the general-m kernels write the reference's bytes."""
+    check_against_golden(run_client(emu_lib, tmp_path, name), name)
 
 
 def _write_data(path, d, n, seed=12345):
