@@ -45,7 +45,17 @@ __device__ __forceinline__ u32 fpad1(u32 i) { return i + ((i >> 7) << 4); }
 __device__ __forceinline__ u32 fpad2(u32 i) { return i + ((i >> 4) << 1); }
 
 // Shoup multiplication by a fixed w: (w, floor(w 2^32 / p)); any x < 2^32 -> [0, 2p)
+#ifdef MULW_NEGP
+// x w - q p as (x w) + q (-p): the low product no longer waits for the quotient (dependent depth 2 instead of 3)
+__device__ __forceinline__ u32 mulw(u32 x, uint2 w, u32 p) {
+  const u32 t = x * w.x, q = __umulhi(x, w.y);
+  u32 r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(0u - p), "r"(t));
+  return r;
+}
+#else
 __device__ __forceinline__ u32 mulw(u32 x, uint2 w, u32 p) { return x * w.x - __umulhi(x, w.y) * p; }
+#endif
 
 // The 21 twiddles a thread needs live in shared memory as tws[s * 128 + tg], s = 0..20
 // (0-6 pass 1, 7-13 pass 2, 14-20 pass 3); one table per direction, shared by the CTA.
@@ -489,10 +499,15 @@ struct FusedTensorArgs {
                      // to_tprod == 1: [count][3][Lt][N]   transform-domain tprod
   u32 Lt, count, ops_per_group, to_tprod;
 };
-#define KG 6
+#ifndef KG
+#define KG 2         // transform groups per CTA: 2 x 3 CTAs per SM measured 3 % faster than 6 x 1
+#endif
+#ifndef KG_MINB
+#define KG_MINB 3    // resident CTAs per SM asked of ptxas
+#endif
 #define FUSED_SMEM_WORDS (2 * FTW_WORDS + KG * 3 * FPADN)
 template <bool GEN>
-__global__ void __launch_bounds__(KG * 128, 1) k_fused_tensor(DevCtx c, FusedTensorArgs a) {
+__global__ void __launch_bounds__(KG * 128, KG_MINB) k_fused_tensor(DevCtx c, FusedTensorArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
@@ -653,7 +668,12 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
 // multiply-accumulates.  Requires the single-accumulator (TFREE) bound.
 // key: [Ls][K][4][N] balanced;  res: [count][4][Ls][n] in the order b_lo, b_hi, A_lo, A_hi.
 // ---------------------------------------------------------------------------------------
-#define KSS 4
+#ifndef KSS
+#define KSS 1        // transform groups (ciphertexts) per CTA: 1 x 4 CTAs per SM measured 2 % faster than 4 x 1
+#endif
+#ifndef KSS_MINB
+#define KSS_MINB 4   // resident CTAs per SM asked of ptxas (KSS * KSS_MINB * 128 threads at <= 128 registers)
+#endif
 #ifndef KSS_DFMA
 #define KSS_DFMA false
 #endif
@@ -661,23 +681,23 @@ __global__ void __launch_bounds__(KSG * 128, 1) k_fused_keyswitch(DevCtx c, Fuse
 #define KSS_SMEM_WORDS (2 * FTW_WORDS + FTD_WORDS + KSS * (2 * KSS_BUFA + FPADN))
 // key: [Ls][K][4][N] balanced, followed by the offset-correction table [Ls][4][N] (k_split_corr)
 template <bool GEN>
-__global__ void __launch_bounds__(KSS * 128, 1) k_fused_keyswitch_split(DevCtx c, FusedKsArgs a) {
+__global__ void __launch_bounds__(KSS * 128, KSS_MINB) k_fused_keyswitch_split(DevCtx c, FusedKsArgs a) {
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + FTW_WORDS);
   const u32 g = threadIdx.x >> 7, tg = threadIdx.x & 127;
-  const u32 l = blockIdx.x;
+    const u32 l = blockIdx.x;
   double2 *twd = (double2 *)(sm + 2 * FTW_WORDS);
   fill_tw_table(twf, c.ftw_fwd + (size_t)l * FTW_ENTRIES);
   fill_tw_table(twi, c.ftw_inv + (size_t)l * FTW_ENTRIES);
-  fill_twd_table(twd, c.twd_fwd + (size_t)l * FN);
+  if (KSS_DFMA) fill_twd_table(twd, c.twd_fwd + (size_t)l * FN);
   __syncthreads();
-  const size_t op = (size_t)blockIdx.y * KSS + g;
-  if (op >= a.count) return;
   const PrimeConst pc = c.pc[l];
   const u32 p = pc.p, pinv = pc.pinv, p2 = 2 * p;
   const u32 negp = pc.negp, hic = pc.hic, zop = pc.zop;  // loaded, hence opaque: see mulw_dfma
   u32 *bufA0 = sm + 2 * FTW_WORDS + FTD_WORDS + g * (2 * KSS_BUFA + FPADN), *bufB = bufA0 + 2 * KSS_BUFA;
   const XAddr A = make_xaddr(tg);
+  const size_t op = (size_t)blockIdx.y * KSS + g;
+  if (op >= a.count) return;  // only group barriers from here on
   u64 acc[4][8];
 #pragma unroll
   for (int h = 0; h < 4; ++h)
