@@ -833,7 +833,7 @@ static int launch_fused_tensor(fhesi_ctx *c, const u32 *a, const u32 *b, u32 *re
     for (u32 o = 1; o <= 4; ++o) {
       const u32 kg = I.N == FN ? KG : KG2;
       const double ctas = (double)I.Lt * (double)((cnt + kg * o - 1) / (kg * o));
-      const double waves = ctas / (c->sm_count * (I.N == FN ? KG_MINB : 1));
+      const double waves = ctas / (c->sm_count * (I.N == FN ? KG_MINB : KG2_MINB));
       const double eff = waves / std::ceil(waves) / (1.0 + 0.04 / o);
       if (eff > best * 1.0001) best = eff, opg = o;
     }

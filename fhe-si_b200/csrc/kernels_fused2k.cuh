@@ -186,11 +186,16 @@ __device__ __forceinline__ void phim_store_t(const u32 *nat, u32 *__restrict__ d
 // ---------------------------------------------------------------------------------------
 // tensor product: one T-thread group per (prime, ciphertext pair)
 // ---------------------------------------------------------------------------------------
-#define KG2 3
+#ifndef KG2
+#define KG2 1        // transform groups per CTA (1 x 3 CTAs per SM measured 6 % faster than 3 x 1)
+#endif
+#ifndef KG2_MINB
+#define KG2_MINB 3   // resident CTAs per SM asked of ptxas
+#endif
 #define T2K 256
 #define FUSED2K_SMEM_WORDS (2 * FT<T2K>::WORDS + KG2 * (2 * FT<T2K>::BUFA + FT<T2K>::BUFB))
 template <bool GEN>
-__global__ void __launch_bounds__(KG2 *T2K, 1) k_fused_tensor_2k(DevCtx c, FusedTensorArgs a) {
+__global__ void __launch_bounds__(KG2 *T2K, KG2_MINB) k_fused_tensor_2k(DevCtx c, FusedTensorArgs a) {
   typedef FT<T2K> F;
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + F::WORDS);
@@ -243,10 +248,15 @@ __global__ void __launch_bounds__(KG2 *T2K, 1) k_fused_tensor_2k(DevCtx c, Fused
 // split-key key switch (see k_fused_keyswitch_split): key [Ls][K][4][N] balanced + correction table [Ls][4][N];
 // res [count][4][Ls][n] in the order b_lo, b_hi, A_lo, A_hi
 // ---------------------------------------------------------------------------------------
-#define KSS2 2
+#ifndef KSS2
+#define KSS2 1       // transform groups (ciphertexts) per CTA (1 x 2 CTAs per SM measured 10 % faster than 2 x 1)
+#endif
+#ifndef KSS2_MINB
+#define KSS2_MINB 2
+#endif
 #define KSS2K_SMEM_WORDS (2 * FT<T2K>::WORDS + KSS2 * (2 * FT<T2K>::BUFA + FT<T2K>::BUFB))
 template <bool GEN>
-__global__ void __launch_bounds__(KSS2 *T2K, 1) k_fused_keyswitch_split_2k(DevCtx c, FusedKsArgs a) {
+__global__ void __launch_bounds__(KSS2 *T2K, KSS2_MINB) k_fused_keyswitch_split_2k(DevCtx c, FusedKsArgs a) {
   typedef FT<T2K> F;
   FHESI_SMEM(sm);
   uint2 *twf = (uint2 *)sm, *twi = (uint2 *)(sm + F::WORDS);

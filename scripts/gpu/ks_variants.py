@@ -51,6 +51,10 @@ def run(lib, B=8192, steps=6, logq=256, p=1019, ref=None):
 
 def main():
     default = os.path.join(ROOT, "fhe-si_b200", "libfhesi_b200.so")
+    prime = 2027 if "--p2027" in sys.argv else 1019
+    global run
+    run0 = run
+    run = lambda lib, **kw: run0(lib, p=prime, **kw)
     if "--single" in sys.argv:  # the default build only (what ncu is pointed at: scripts/gpu/r02_profile.sh)
         print(json.dumps(run(default, steps=2)[0]), flush=True)
         return
