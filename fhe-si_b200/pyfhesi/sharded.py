@@ -34,6 +34,8 @@ def sharded_tensor_sum(ctx, a: torch.Tensor, b: torch.Tensor, parts_a: int = 2, 
     po = parts_a + parts_b - 1
     count_local = a.shape[0]
     local = torch.zeros((po, ctx.Lt, ctx.N), dtype=torch.int32, device=a.device)
+    if local.is_cuda:  # the fill ran on torch's current stream, the accumulation runs on the context's
+        torch.cuda.current_stream(local.device).synchronize()
     if count_local:
         ctx.ct_tensor_dev(a, parts_a, b, parts_b, local, count_local, accumulate=True)
     ctx.sync()
