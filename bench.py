@@ -375,8 +375,11 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         # NCCL's own log (NCCL_DEBUG=INFO: communicator, rank count, transports) is left at the level the
         # launcher asked for; it only moves off stdout -- which carries the one JSON line -- to stderr
-        # (unconditionally: a level set in /etc/nccl.conf instead of the environment still prints its
-        # "NCCL version" banner, which landed on stdout ahead of the JSON line in profiles/r02_bench_8gpu_logq*.json)
+        # NCCL honours NCCL_DEBUG_FILE only above the VERSION level, and at VERSION (the level this pool's boxes
+        # run at when nothing is set) its "NCCL version" banner goes to stdout ahead of the JSON line
+        # (profiles/r02_bench_8gpu_logq*.json).  An unset / VERSION level is therefore RAISED to WARN -- never lowered.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -460,8 +463,14 @@ def run_ours(args, rank, local_rank, world):
     sampler.join()
 
     # ---- e2e: pinned host buffers -> H2D -> hot path -> D2H, all inside the timed region
-    h_a = torch.from_numpy(h_ct[:B].view(np.int32).reshape(B, ct_words).copy()).pin_memory()
-    h_b = torch.from_numpy(h_ct[B:].view(np.int32).reshape(B, ct_words).copy()).pin_memory()
+    # (operands in write-combined page-locked memory, fhesi_host_alloc: the CPU only writes them; the result in
+    # ordinary page-locked memory, the CPU reads it -- profiles/r02c_pcie_probe_8gpu.txt)
+    wc = not os.environ.get("FHESI_BENCH_NO_WC")
+    np_a = dev.host_alloc((B, ct_words), np.int32, write_combined=wc)
+    np_b = dev.host_alloc((B, ct_words), np.int32, write_combined=wc)
+    np_a[...] = h_ct[:B].view(np.int32).reshape(B, ct_words)
+    np_b[...] = h_ct[B:].view(np.int32).reshape(B, ct_words)
+    h_a, h_b = torch.from_numpy(np_a), torch.from_numpy(np_b)
     h_o = torch.empty((B, ct_words), dtype=torch.int32).pin_memory()
 
     def e2e_step():
@@ -558,7 +567,7 @@ def run_ours(args, rank, local_rank, world):
         # therefore counted per class and expressed in Shoup-modmul equivalents (one Shoup product =
         # 2 IMAD + 1 IMAD.HI; one 64-bit multiply-accumulate = 1 IMAD.WIDE, about 0.66 of a Shoup product):
         # achieved / peak is then the fraction of the pipe's time spent on algorithmic instructions, the
-        # quantity ncu reports as sm__inst_executed_pipe_fmaheavy (profiles/r02_ncu_full_summary.txt).
+        # quantity ncu reports as sm__inst_executed_pipe_fmaheavy (profiles/r02c_ncu_full_summary.txt).
         cost = {"lo": 1.0 / pipes["imad_lo32"], "hi": 1.0 / pipes["imad_hi32"], "wide": 1.0 / pipes["imad_wide64"]}
         shoup_cost = 2 * cost["lo"] + cost["hi"]
         peak32 = 1.0 / shoup_cost  # Shoup products per second when nothing else shares the pipe
@@ -593,7 +602,7 @@ def run_ours(args, rank, local_rank, world):
             "traffic": traffic * ops_timed / max(tcnt, 1) if traffic else None,
             "traffic_unit": "bytes per launch: the kernel's compulsory HBM traffic (every input word read once, every "
                             "output word written once; key tiles and tables stay in L2), confirmed against ncu "
-                            "dram__bytes_read.sum + dram__bytes_write.sum of the same launch in profiles/r02_ncu_full_summary.txt",
+                            "dram__bytes_read.sum + dram__bytes_write.sum of the same launch in profiles/r02c_ncu_full_summary.txt",
             "peak_source": "measured in this run (fhesi_pipe_peak: register-resident ILP-8 chains of one instruction "
                            "class on all SMs)",
             "peak_montgomery32_Gmodmul_s": peak_mont32 / 1e9,
@@ -633,7 +642,7 @@ def run_ours(args, rank, local_rank, world):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_words * 4,
                     "d2h_bytes_per_step": B * ct_words * 4, "ms_per_step": e2e_ms,
-                    "api": "fhesi_mult_relin_host (pinned host buffers)",
+                    "api": "fhesi_mult_relin_host (page-locked host buffers; operands write-combined)" if wc else "fhesi_mult_relin_host (pinned host buffers)",
                     "host_copy_bound": {"ms_per_step": pcie_ms, "ops_s": world * B / (pcie_ms * 1e-3),
                                         "GBs_all_ranks": world * 3 * B * ct_words * 4 / (pcie_ms * 1e-3) / 1e9,
                                         "e2e_over_bound": e2e_value / (world * B / (pcie_ms * 1e-3)),

@@ -686,6 +686,16 @@ int fhesi_h2d_async(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
+int fhesi_host_alloc(size_t bytes, int write_combined, void **out) {
+  if (!out) return fail(FHESI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  CK(cudaHostAlloc(out, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return 0;
+}
+int fhesi_host_free(void *p) {
+  if (p) CK(cudaFreeHost(p));
+  return 0;
+}
 int fhesi_d2h(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
   if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
   CK(cudaSetDevice(c->device));

@@ -45,6 +45,8 @@ SYMBOLS = {
     "fhesi_h2d": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_h2d_async": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_d2h": (C.c_int, [_P, _P, _P, _SZ]),
+    "fhesi_host_alloc": (C.c_int, [_SZ, C.c_int, C.POINTER(_P)]),
+    "fhesi_host_free": (C.c_int, [_P]),
     "fhesi_d2d": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_ct_mul_plain_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),
     "fhesi_ct_bytes": (_SZ, [_P, _U32]),
@@ -194,6 +196,23 @@ class Context:
     def to_device(self, arr: np.ndarray) -> DeviceBuffer:
         arr = np.ascontiguousarray(arr)
         return DeviceBuffer(self, max(arr.nbytes, 16)).upload(arr)
+
+    def host_alloc(self, shape, dtype=np.uint32, write_combined: bool = False) -> np.ndarray:
+        """Page-locked host array for the *_host entry points (fhesi_host_alloc); write_combined=True for operands the
+        CPU only writes.  The memory lives until host_free(array)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _P()
+        self._ck(self.lib.fhesi_host_alloc(nbytes, 1 if write_combined else 0, C.byref(p)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._host_blocks = getattr(self, "_host_blocks", {})
+        self._host_blocks[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        p = getattr(self, "_host_blocks", {}).pop(arr.ctypes.data, None)
+        if p is not None:
+            self._ck(self.lib.fhesi_host_free(p))
 
     def ct_words(self, parts: int) -> int:
         return parts * self.n * self.W

@@ -93,6 +93,13 @@ int fhesi_h2d(fhesi_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
  * work of the previous one. */
 int fhesi_h2d_async(fhesi_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int fhesi_d2h(fhesi_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+/* Page-locked host memory for the buffers handed to the *_host entry points (new: the reference has no device).
+ * write_combined != 0 is for buffers the CPU only WRITES (operands on their way up): the device reads them
+ * without snooping the CPU caches.  Measured with all eight GPUs of a box copying at once: the slowest ranks move
+ * a step's bytes in 47.7 ms instead of 52.0 ms (profiles/r02c_pcie_probe_8gpu.txt); CPU reads of such memory are
+ * slow, so results belong in ordinary page-locked memory (write_combined = 0). */
+int fhesi_host_alloc(size_t bytes, int write_combined, void **out);
+int fhesi_host_free(void *p);
 int fhesi_d2d(fhesi_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
 size_t fhesi_ct_bytes(const fhesi_ctx *ctx, uint32_t parts);    /* parts*n*W*4      */
 size_t fhesi_tprod_bytes(const fhesi_ctx *ctx, uint32_t parts); /* parts*Lt*N*4     */

@@ -187,6 +187,9 @@ inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); r
 template <class T>
 inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+enum { cudaHostAllocDefault = 0, cudaHostAllocWriteCombined = 4 };
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
