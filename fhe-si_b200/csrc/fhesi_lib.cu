@@ -146,6 +146,8 @@ struct fhesi_ctx {
   u32 chunk = 128;        // ciphertexts per pass through the scratch arena (generic path)
   u32 fused_chunk = 8192; // same for the fused path: large, so the grid is many waves deep
   bool use_fused = true;
+  bool crt_direct = true;        // ScaleDown through k_crt_direct (FHESI_NO_CRT_DIRECT=1: k_crt)
+  bool crt_force_exact = false;  // FHESI_CRT_FORCE_EXACT=1: every thread of k_crt_direct takes the exact routine
   bool tfree = false;  // every prime satisfies 3D (p/2)^2 < 2^63 (single-accumulator key switch)
   // launch accounting / per-kernel CUDA-event profiler (bench.py "roofline", "gpu_launches")
   uint64_t launches = 0;
@@ -577,6 +579,10 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   if (ev) c->pipe_taper = atoi(ev) > 0;
   ev = getenv("FHESI_PIPE_LANES");
   if (ev && atoi(ev) > 0) c->pipe_lanes = atoi(ev) > 1 ? 2 : 1;
+  ev = getenv("FHESI_NO_CRT_DIRECT");
+  if (ev && atoi(ev) > 0) c->crt_direct = false;
+  ev = getenv("FHESI_CRT_FORCE_EXACT");
+  if (ev && atoi(ev) > 0) c->crt_force_exact = true;
   ev = getenv("FHESI_NO_SPLIT");
   if (ev && atoi(ev) > 0) c->info.Ls = 0, c->info.split_words = 0;
   ev = getenv("FHESI_NO_FUSED");
@@ -776,6 +782,81 @@ static const CrtTables<ML> &crt_tables(fhesi_ctx *c, u32 L) {
   }
   return *reinterpret_cast<const CrtTables<ML> *>(raw.data());
 }
+// tables of k_crt_direct for the first L primes and the limb window of this context's logQ; cached like crt_tables
+template <int ML, int NL>
+static const CrtDirectTables<ML, NL> &crt_direct_tables(fhesi_ctx *c, u32 L, u32 j0, u32 nl) {
+  std::vector<unsigned char> &raw = c->crt_tables[std::make_pair(1000 + ML, L)];
+  if (raw.empty()) {
+    raw.assign(sizeof(CrtDirectTables<ML, NL>), 0);
+    CrtDirectTables<ML, NL> &T = *reinterpret_cast<CrtDirectTables<ML, NL> *>(raw.data());
+    const u32 LM = c->dc.Lmax;
+    const u32 *P = &c->h_Pfull[(size_t)L * LM];  // LM words of prod_{i<L} p_i
+    T.j0 = j0, T.nl = nl, T.force_exact = c->crt_force_exact;
+    // 28-bit limb `j` of a little-endian word array
+    auto limb = [&](const u32 *w, u32 j) -> u32 {
+      const u32 o = CRT_LB * j, k = o >> 5, sh = o & 31;
+      const u64 lo = k < LM ? w[k] : 0u, hi = k + 1 < LM ? w[k + 1] : 0u;
+      return (u32)((lo | (hi << 32)) >> sh) & CRT_LMASK;
+    };
+    {  // limbs of 2^(28 (j0 + nl)) - P: complement every limb of P up to the window's top, plus one
+      u32 carry = 1;
+      for (u32 j = 0; j < j0 + nl; ++j) {
+        const u32 t = (CRT_LMASK ^ limb(P, j)) + carry;
+        carry = t >> CRT_LB;
+        if (j >= j0) T.NP[j - j0] = t & CRT_LMASK;
+      }
+    }
+    std::vector<u32> q(LM);
+    for (u32 i = 0; i < L; ++i) {
+      const u64 p = c->h_pc[i].p;
+      u64 rem = 0;
+      for (int k = (int)LM - 1; k >= 0; --k) {  // C_i = P / p_i, exact
+        const u64 cur = (rem << 32) | P[k];
+        q[k] = (u32)(cur / p);
+        rem = cur % p;
+      }
+      u64 cm = 0;  // C_i mod p_i
+      for (int k = (int)LM - 1; k >= 0; --k) cm = (u64)((((unsigned __int128)cm << 32) | q[k]) % p);
+      const u64 yi = h_invmod(cm, p);
+      T.p[i] = (u32)p;
+      T.yinv[i] = (u32)yi;
+      T.yinvq[i] = (u32)((yi << 32) / p);
+      T.rfix[i] = (u32)((1ull << 58) / p);
+      for (u32 j = 0; j < nl; ++j) T.C[i][j] = limb(q.data(), j0 + j);
+    }
+  }
+  return *reinterpret_cast<const CrtDirectTables<ML, NL> *>(raw.data());
+}
+template <int ML, int NL>
+static bool launch_crt_direct_t(fhesi_ctx *c, const CrtArgs &a, u32 j0, u32 nl) {
+  if (nl > (u32)NL) return false;
+  const int B = 128;
+  const unsigned g = (unsigned)((a.total + B - 1) / B);
+  const CrtDirectTables<ML, NL> &T = crt_direct_tables<ML, NL>(c, a.L, j0, nl);
+  if (nl == (u32)NL) {
+    const auto kern = k_crt_direct<ML, NL, true>;
+    KLN(c, "k_crt_direct<ML>", kern, g, B, NL * B * 4, c->dc, a, T);
+  } else {
+    const auto kern = k_crt_direct<ML, NL, false>;
+    KLN(c, "k_crt_direct<ML>", kern, g, B, NL * B * 4, c->dc, a, T);
+  }
+  return true;
+}
+// ScaleDown modes through k_crt_direct when the window fits an instantiation; false = use k_crt
+static bool launch_crt_direct(fhesi_ctx *c, const CrtArgs &a) {
+  if (!c->crt_direct || (a.mode != CRT_SCALEDOWN && a.mode != CRT_SCALEDOWN_DIGITS)) return false;
+  const u32 logQ = c->dc.logQ, hl = (logQ - 1) / CRT_LB, j0 = hl >= 2 ? hl - 2 : 0, j1 = (2 * logQ - 1) / CRT_LB;
+  const u32 nl = j1 - j0 + 1, L = a.L;
+  if (29.0 * L < 2.0 * logQ + 2) return false;  // the chain must reach past bit 2 logQ (always true of a tensor chain)
+  if (L <= 8) return launch_crt_direct_t<8, 7>(c, a, j0, nl);
+  if (L <= 10) return launch_crt_direct_t<10, 8>(c, a, j0, nl);
+  if (L <= 13) return launch_crt_direct_t<13, 9>(c, a, j0, nl);
+  if (L <= 18) return launch_crt_direct_t<18, 12>(c, a, j0, nl);
+  if (L <= 20) return launch_crt_direct_t<20, 13>(c, a, j0, nl);
+  if (L <= 28) return launch_crt_direct_t<28, 17>(c, a, j0, nl);
+  if (L <= 36) return launch_crt_direct_t<36, 21>(c, a, j0, nl);
+  return launch_crt_direct_t<40, 25>(c, a, j0, nl);
+}
 template <int ML>
 static void launch_crt_t(fhesi_ctx *c, const CrtArgs &a) {
   const int B = 128;
@@ -805,6 +886,10 @@ static int launch_crt(fhesi_ctx *c, const u32 *res, u32 L, u32 mode, u32 *out, u
                       size_t npolys) {
   if (!npolys) return 0;
   CrtArgs a{res, L, mode, out, Wout, npolys * c->dc.n};
+  if (launch_crt_direct(c, a)) {
+    CKL();
+    return 0;
+  }
   // DECRYPT multiplies by p_pt before the shift: two words of head-room
   u32 need = L + (mode == CRT_DECRYPT ? 2 : 0);
   if (need <= 8) launch_crt_t<8>(c, a);

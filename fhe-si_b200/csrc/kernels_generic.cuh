@@ -675,6 +675,177 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a, const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// ScaleDown without the mixed-radix triangle.  Only the bits [logQ - 1, 2 logQ) of the centred integer x are
+// needed (the rounding bit and the logQ bits that survive the shift), so x is taken from the explicit CRT sum
+//     x = sum_i y_i (P / p_i)  -  (k + c) P,      y_i = r_i (P / p_i)^-1 mod p_i,
+//     k = floor(sum_i y_i / p_i),   c = [x mod P > P / 2],
+// evaluated on a WINDOW of 28-bit limbs j0 .. j1 only (j0 = two limbs below the rounding bit's limb, j1 = the limb of
+// bit 2 logQ - 1).  In radix 2^28 a column sum_i y_i C_ij of up to 40 products (30 x 28 bits) fits 64 bits, so the inner
+// loop is ONE multiply-accumulate per term with no carry handling: L Shoup products + (L + 1) NL multiply-accumulates
+// instead of L (L - 1) / 2 Shoup products + L (L + 1) / 2 multiply-accumulates with carry chains.  What the window
+// cannot see is bounded, and a thread that cannot PROVE its result exact recomputes it with the full mixed-radix
+// routine (crt_exact_limbs):
+//   * k and c come from F = sum_i y_i floor(2^58 / p_i): sum y_i / p_i lies in [F, F + L 2^30) 2^-58, so they are
+//     certain unless the fraction of F is within 2^36 of 1 (k) or of 1/2 from below (c);
+//   * the limbs below j0 contribute a carry of less than L 2^30 + 1 into limb j0, i.e. at most +161 / -1 into limb
+//     j0 + 1; if that limb is not within 256 of wrapping, limbs j0 + 2 and up are exact.  (j0 = 0: nothing is cut.)
+// The first event has probability about 5e-7 per coefficient, the second 2e-6.  FHESI_CRT_FORCE_EXACT=1 sends every
+// thread down the exact routine, FHESI_NO_CRT_DIRECT=1 uses k_crt; the parity tests run all three and require
+// equal bytes.
+// ---------------------------------------------------------------------------------------
+#define CRT_LB 28u
+#define CRT_LMASK ((1u << CRT_LB) - 1u)
+template <int ML, int NL>
+struct CrtDirectTables {
+  u32 p[ML], yinv[ML], yinvq[ML];  // (P / p_i)^-1 mod p_i and its Shoup quotient
+  u32 rfix[ML];                    // floor(2^58 / p_i)
+  u32 C[ML][NL];                   // limbs j0 .. j0 + NL - 1 of P / p_i
+  u32 NP[NL];                      // the same limbs of 2^(28 (j0 + nl)) - P: adding (k + c) NP subtracts (k + c) P
+  u32 j0, nl, force_exact, pad_;
+};
+// the exact centred x over the context's first L primes, limbs j0 .. j0 + nl - 1 (two's complement): the rare path
+static __device__ __noinline__ void crt_exact_limbs(const DevCtx &c, const u32 *res, size_t stride, int L, u32 j0, u32 nl,
+                                                    u32 *out) {
+  u32 v[FHESI_MAX_PRIMES], acc[FHESI_MAX_PRIMES + 1];
+  for (int j = 0; j < L; ++j) v[j] = res[(size_t)j * stride];
+  for (int j = 1; j < L; ++j) {  // mixed-radix digits (NumbTh.cpp:307-335 computes the same integer incrementally)
+    const u32 p = c.pc[j].p, pinv = c.pc[j].pinv;
+    u32 t = v[j];
+    for (int i = 0; i < j; ++i) {
+      const u32 vi = csub(v[i], p);  // v_i < p_i < 2 p_j
+      // garner[j][i] = p_i^-1 R mod p_j: the Montgomery product is (t - v_i) / p_i mod p_j
+      t = csub(mont_mul(t + p - vi, c.garner[(size_t)j * c.Lmax + i], p, pinv), p);
+    }
+    v[j] = t;
+  }
+  for (int k = 0; k <= L; ++k) acc[k] = 0;
+  for (int i = L - 1; i >= 0; --i) {
+    u64 carry = v[i];
+    const u32 p = c.pc[i].p;
+    for (int k = 0; k < L; ++k) {
+      carry += (u64)acc[k] * p;
+      acc[k] = (u32)carry;
+      carry >>= 32;
+    }
+  }
+  const u32 *Ph = c.Phalf + (size_t)L * c.Lmax, *Pf = c.Pfull + (size_t)L * c.Lmax;
+  bool gt = false;
+  for (int k = L - 1; k >= 0; --k)
+    if (acc[k] != Ph[k]) {
+      gt = acc[k] > Ph[k];
+      break;
+    }
+  if (gt) {
+    u32 borrow = 0;
+    for (int k = 0; k < L; ++k) {
+      const u64 t = (u64)acc[k] - Pf[k] - borrow;
+      acc[k] = (u32)t;
+      borrow = (u32)(t >> 63);
+    }
+  }
+  const u32 sign = (acc[L - 1] >> 31) ? 0xFFFFFFFFu : 0u;
+  auto word = [&](u32 k) -> u64 { return k < (u32)L ? acc[k] : sign; };
+  for (u32 j = 0; j < nl; ++j) {
+    const u32 o = CRT_LB * (j0 + j), w = o >> 5, sh = o & 31;
+    out[j] = (u32)(((word(w) | (word(w + 1) << 32)) >> sh)) & CRT_LMASK;
+  }
+}
+// dynamic smem: NL * blockDim.x words.  Modes CRT_SCALEDOWN and CRT_SCALEDOWN_DIGITS only.
+// FULLW: the window is exactly NL limbs (the bound becomes a compile-time constant: no predicates in the rows)
+template <int ML, int NL, bool FULLW>
+__global__ void __launch_bounds__(128) k_crt_direct(DevCtx c, CrtArgs a, const __grid_constant__ CrtDirectTables<ML, NL> T) {
+  FHESI_SMEM(sm);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < a.total;
+  const size_t poly = active ? idx / c.n : 0;
+  const u32 coef = active ? (u32)(idx % c.n) : 0;
+  const int L = (int)a.L;
+  const u32 j0 = T.j0, nl = FULLW ? (u32)NL : T.nl;
+  const u32 *res = a.res + (size_t)poly * L * c.n + coef;
+  u32 rr[ML];  // every residue is requested before the first is used: one round trip to HBM, not L
+#pragma unroll
+  for (int i = 0; i < ML; ++i) rr[i] = (active && i < L) ? __ldg(res + (size_t)i * c.n) : 0u;
+  u64 col[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) col[j] = 0;
+  u64 F = 0;
+#pragma unroll
+  for (int i = 0; i < ML; ++i) {
+    if (i < L) {
+      const u32 r = rr[i];
+      const u32 p = T.p[i];
+      const u32 y = csub(r * T.yinv[i] - __umulhi(r, T.yinvq[i]) * p, p);
+      F += (u64)y * T.rfix[i];  // < 2^58 each
+#pragma unroll
+      for (int j = 0; j < NL; ++j)
+        if ((u32)j < nl) col[j] += (u64)y * T.C[i][j];  // < 2^58 each, at most 40 of them
+    }
+  }
+  const u64 frac = F & ((1ull << 58) - 1), D = 1ull << 36, HALF = 1ull << 57;
+  const u32 kc = (u32)(F >> 58) + (frac > HALF ? 1u : 0u);
+  bool unsure = T.force_exact || frac >= (1ull << 58) - D || (frac <= HALF && frac + D > HALF);
+  u32 limb[NL];
+  {
+    u64 carry = 0;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      limb[j] = 0;
+      if ((u32)j < nl) {
+        carry += col[j] + (u64)kc * T.NP[j];
+        limb[j] = (u32)carry & CRT_LMASK;
+        carry >>= CRT_LB;
+      }
+    }
+  }
+  if (j0 && (limb[1] < 256u || limb[1] >= (1u << CRT_LB) - 256u)) unsure = true;
+  if (unsure && active) {  // (through a buffer of its own: handing out limb[] would move it from registers to local memory)
+    u32 ex[NL];
+    crt_exact_limbs(c, res, c.n, L, j0, nl, ex);
+#pragma unroll
+    for (int j = 0; j < NL; ++j)
+      if ((u32)j < nl) limb[j] = ex[j];
+  }
+  const u32 W = c.W, logQ = c.logQ, base = CRT_LB * j0;
+  {  // += 2^(logQ-1)
+    const u32 hb = logQ - 1 - base, hl = hb / CRT_LB, hs = hb - hl * CRT_LB;
+    u32 carry = 0;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const u32 t = limb[j] + ((j == (int)hl) ? (1u << hs) : 0u) + carry;
+      limb[j] = t & CRT_LMASK;
+      carry = t >> CRT_LB;
+    }
+  }
+  // runtime-offset bit fields through shared memory (column per thread); limbs outside the window are never part of
+  // a kept bit, so they read as zero
+  u32 *colm = sm + threadIdx.x;
+  const u32 stride = blockDim.x;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) colm[j * stride] = limb[j];
+  if (!active) return;
+  auto limb_at = [&](u32 q) -> u64 { return q < nl ? colm[q * stride] : 0u; };
+  auto bits_at = [&](u32 o, u32 nb) -> u32 {  // nb <= 32 bits from absolute bit position o >= base
+    const u32 q = (o - base) / CRT_LB, r = (o - base) - q * CRT_LB;
+    const u64 v = limb_at(q) | (limb_at(q + 1) << CRT_LB) | (limb_at(q + 2) << (2 * CRT_LB));
+    const u32 w = (u32)(v >> r);
+    return nb >= 32 ? w : (w & ((1u << nb) - 1u));
+  };
+  if (a.mode == CRT_SCALEDOWN_DIGITS) {
+    // digit d of the non-negative residue mod q of y = (x + q/2) >> logQ  (Ciphertext.cpp:92-103)
+    for (u32 d = 0; d < c.D; ++d)
+      a.out[((size_t)poly * c.D + d) * c.n + coef] = bits_at(logQ + c.dbits * d, min(c.dbits, logQ - c.dbits * d));
+    return;
+  }
+  u32 *o = a.out + idx * W;  // CRT_SCALEDOWN: logQ bits, the top word sign-extended
+  const u32 tb = (logQ - 1) & 31;
+  for (u32 k = 0; k < W; ++k) {
+    u32 w = bits_at(logQ + 32 * k, (k == W - 1) ? tb + 1 : 32);
+    if (k == W - 1 && tb != 31) w = (u32)((int)(w << (31 - tb)) >> (31 - tb));
+    o[k] = w;
+  }
+}
+
 // CRT for the split-key key switch: two non-negative values lo, hi < P/2 (Ls primes each) ->
 // Reduce(lo + 2^(32 ws) hi).  res: [npolys][2][L][n];  out: [npolys][n][W].
 struct CrtSplitArgs {
@@ -692,12 +863,17 @@ __global__ void __launch_bounds__(128) k_crt_split(DevCtx c, CrtSplitArgs a, con
   const u32 coef = active ? (u32)(idx % c.n) : 0;
   const int L = (int)a.L;
   const u32 stride = blockDim.x;
+  u32 vv[2][ML];  // both halves' residues are requested before the first is used (one round trip to HBM)
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+    for (int j = 0; j < ML; ++j)
+      vv[hf][j] = (active && j < L) ? __ldg(a.res + (((size_t)poly * 2 + hf) * L + j) * c.n + coef) : 0u;
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
     u32 v[ML];
 #pragma unroll
-    for (int j = 0; j < ML; ++j)
-      v[j] = (active && j < L) ? a.res[(((size_t)poly * 2 + hf) * L + j) * c.n + coef] : 0u;
+    for (int j = 0; j < ML; ++j) v[j] = vv[hf][j];
 #pragma unroll
     for (int j = 1; j < ML; ++j) {
       if (j < L) {

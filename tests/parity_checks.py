@@ -607,3 +607,27 @@ def check_keygen_batch(lib, cfg, xi, rot, seed=5):
     assert pk2 and np.array_equal(pkw2, k["pk"])
 
 
+
+
+def check_crt_direct_paths(cfg, lib_path, count=3, m=None, seed=5):
+    """ScaleDown three ways -- k_crt_direct (windowed explicit CRT), the same kernel with every thread forced down its
+    exact mixed-radix routine (FHESI_CRT_FORCE_EXACT=1), and k_crt (FHESI_NO_CRT_DIRECT=1) -- must each give the
+    oracle's bytes: mult+relin (ScaleDown fused with the digits) on fresh and on full-range operands, tensor +
+    ScaleDown, and the extreme operands of check_edge_cases (zero and unit polynomials make x tiny, the case in which
+    the quotient k cannot be read off the fixed-point sum and the kernel must fall back on its own)."""
+    import os
+    for env in ({}, {"FHESI_CRT_FORCE_EXACT": "1"}, {"FHESI_NO_CRT_DIRECT": "1"}):
+        os.environ.update(env)
+        try:
+            sc = Scenario(*cfg, seed=seed, lib_path=lib_path, m=m)
+        finally:
+            for k in env:
+                del os.environ[k]
+        sc.dev.profile_enable(True)
+        check_mult_relin(sc, count=count)
+        check_mult_relin(sc, count=count, random_inputs=True)
+        check_pieces(sc, count=2)
+        check_edge_cases(sc, counts=(1, 5))
+        prof = sc.dev.profile_report()
+        assert ("k_crt_direct<ML>" in prof) == ("FHESI_NO_CRT_DIRECT" not in env), prof
+        sc.dev.close()

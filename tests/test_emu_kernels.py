@@ -118,3 +118,9 @@ def test_emu_general_m_fused(emu_lib):
     assert "k_fused_keyswitch_split" in sc.dev.profile_report() or "k_fused_keyswitch<true>" in sc.dev.profile_report()
     sc.dev.profile_enable(False)
     P.check_rotate_keyswitch(sc, g, count=1)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3"])
+def test_emu_crt_direct_paths(name, emu_lib):
+    """cfg1 (logQ = 80: the window starts at word 0, nothing is cut) and cfg3 (logQ = 100: two guard words)."""
+    P.check_crt_direct_paths(CONFIGS[name], emu_lib, count=2 if name == "cfg1" else 1)

@@ -89,6 +89,13 @@ def test_general_m(name, cuda_lib):
         P.check_ref_rows(sc)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5_128", "cfg5_512", "p2027_176"])
+def test_crt_direct_paths(name, cuda_lib):
+    """ScaleDown through the windowed explicit CRT, through its exact fallback on every thread, and through the
+    mixed-radix kernel: three implementations, one set of bytes (the oracle's)."""
+    P.check_crt_direct_paths(CONFIGS[name], cuda_lib, count=2 if name == "cfg5_512" else 3)
+
+
 def test_mult_relin_host_and_random_cfg2(cuda_lib):
     sc = scenario("cfg2", cuda_lib)
     P.check_mult_relin(sc, count=2, host=True)
