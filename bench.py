@@ -456,6 +456,7 @@ def run_ours(args, rank, local_rank, world):
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    crt_fallbacks = dev.crt_fallbacks()  # since the context was created: warm-up + timed steps
     launches = dev.launches()
     prof = dev.profile_report()
     dev.profile_enable(False)
@@ -651,6 +652,7 @@ def run_ours(args, rank, local_rank, world):
             "exchange": exchange,
             "regression": regression,
             "gpu_launches": launches,
+            "crt_fallback_rate": crt_fallbacks / max(1.0, 3.0 * n * B * (args.steps + args.warmup)),
             "clocks": sampler.result(),
         }
         print(json.dumps(line), flush=True)

@@ -148,6 +148,7 @@ struct fhesi_ctx {
   bool use_fused = true;
   bool crt_direct = true;        // ScaleDown through k_crt_direct (FHESI_NO_CRT_DIRECT=1: k_crt)
   bool crt_force_exact = false;  // FHESI_CRT_FORCE_EXACT=1: every thread of k_crt_direct takes the exact routine
+  unsigned long long *d_crt_fallbacks = nullptr;  // device counter of k_crt_direct threads that were not certain
   bool tfree = false;  // every prime satisfies 3D (p/2)^2 < 2^63 (single-accumulator key switch)
   // launch accounting / per-kernel CUDA-event profiler (bench.py "roofline", "gpu_launches")
   uint64_t launches = 0;
@@ -565,6 +566,14 @@ int fhesi_ctx_create(uint32_t m, uint32_t logQ, uint64_t p_pt, uint32_t decompSi
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   {
+    void *pc = nullptr;
+    size_t cap = 0;
+    CK(cached_malloc(c->device, &pc, 16, &cap));
+    CK(cudaMemset(pc, 0, 16));
+    c->tables.push_back(std::make_pair(pc, cap));
+    c->d_crt_fallbacks = (unsigned long long *)pc;
+  }
+  {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c->device));
     if (prop.multiProcessorCount > 0) c->sm_count = prop.multiProcessorCount;
@@ -692,6 +701,15 @@ int fhesi_h2d_async(fhesi_ctx *c, void *dst, const void *src, size_t bytes) {
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
+int fhesi_crt_fallbacks(fhesi_ctx *c, uint64_t *count) {
+  if (!c || !count) return fail(FHESI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, c->d_crt_fallbacks, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *count = v;
+  return 0;
+}
 int fhesi_host_alloc(size_t bytes, int write_combined, void **out) {
   if (!out) return fail(FHESI_ERR_INVALID, "out is NULL");
   *out = nullptr;
@@ -792,6 +810,7 @@ static const CrtDirectTables<ML, NL> &crt_direct_tables(fhesi_ctx *c, u32 L, u32
     const u32 LM = c->dc.Lmax;
     const u32 *P = &c->h_Pfull[(size_t)L * LM];  // LM words of prod_{i<L} p_i
     T.j0 = j0, T.nl = nl, T.force_exact = c->crt_force_exact;
+    T.fallbacks = c->d_crt_fallbacks;
     // 28-bit limb `j` of a little-endian word array
     auto limb = [&](const u32 *w, u32 j) -> u32 {
       const u32 o = CRT_LB * j, k = o >> 5, sh = o & 31;
@@ -821,7 +840,11 @@ static const CrtDirectTables<ML, NL> &crt_direct_tables(fhesi_ctx *c, u32 L, u32
       T.p[i] = (u32)p;
       T.yinv[i] = (u32)yi;
       T.yinvq[i] = (u32)((yi << 32) / p);
-      T.rfix[i] = (u32)((1ull << 58) / p);
+      {
+        const unsigned __int128 rf = ((unsigned __int128)1 << 84) / p;  // < 2^55
+        T.rfix_hi[i] = (u32)(rf >> 28);
+        T.rfix_lo[i] = (u32)rf & ((1u << 28) - 1u);
+      }
       for (u32 j = 0; j < nl; ++j) T.C[i][j] = limb(q.data(), j0 + j);
     }
   }

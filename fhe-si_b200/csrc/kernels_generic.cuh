@@ -686,11 +686,13 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a, const __grid_c
 // instead of L (L - 1) / 2 Shoup products + L (L + 1) / 2 multiply-accumulates with carry chains.  What the window
 // cannot see is bounded, and a thread that cannot PROVE its result exact recomputes it with the full mixed-radix
 // routine (crt_exact_limbs):
-//   * k and c come from F = sum_i y_i floor(2^58 / p_i): sum y_i / p_i lies in [F, F + L 2^30) 2^-58, so they are
-//     certain unless the fraction of F is within 2^36 of 1 (k) or of 1/2 from below (c);
+//   * k and c come from the fixed-point sum F = sum_i y_i floor(2^84 / p_i), kept to 56 fraction bits:
+//     sum y_i / p_i lies in [T, T + 256) 2^-56 with T = floor(F / 2^28), so they are certain unless the fraction of T
+//     is within 256 of 1 (k) or of 1/2 from below (c).  (x of a tensor product is roughly normal around 0 with
+//     |x| ~ 2^-17 P: with 22 fraction bits, the first version, one coefficient in fifty was "unsure".)
 //   * the limbs below j0 contribute a carry of less than L 2^30 + 1 into limb j0, i.e. at most +161 / -1 into limb
 //     j0 + 1; if that limb is not within 256 of wrapping, limbs j0 + 2 and up are exact.  (j0 = 0: nothing is cut.)
-// The first event has probability about 5e-7 per coefficient, the second 2e-6.  FHESI_CRT_FORCE_EXACT=1 sends every
+// The first event needs |x| < 2^-48 P, the second has probability 2e-6 per coefficient.  FHESI_CRT_FORCE_EXACT=1 sends every
 // thread down the exact routine, FHESI_NO_CRT_DIRECT=1 uses k_crt; the parity tests run all three and require
 // equal bytes.
 // ---------------------------------------------------------------------------------------
@@ -699,10 +701,11 @@ __global__ void __launch_bounds__(128) k_crt(DevCtx c, CrtArgs a, const __grid_c
 template <int ML, int NL>
 struct CrtDirectTables {
   u32 p[ML], yinv[ML], yinvq[ML];  // (P / p_i)^-1 mod p_i and its Shoup quotient
-  u32 rfix[ML];                    // floor(2^58 / p_i)
+  u32 rfix_hi[ML], rfix_lo[ML];    // floor(2^84 / p_i) = rfix_hi 2^28 + rfix_lo
   u32 C[ML][NL];                   // limbs j0 .. j0 + NL - 1 of P / p_i
   u32 NP[NL];                      // the same limbs of 2^(28 (j0 + nl)) - P: adding (k + c) NP subtracts (k + c) P
   u32 j0, nl, force_exact, pad_;
+  unsigned long long *fallbacks;   // threads that took the exact routine (fhesi_crt_fallbacks), device counter
 };
 // the exact centred x over the context's first L primes, limbs j0 .. j0 + nl - 1 (two's complement): the rare path
 static __device__ __noinline__ void crt_exact_limbs(const DevCtx &c, const u32 *res, size_t stride, int L, u32 j0, u32 nl,
@@ -769,22 +772,24 @@ __global__ void __launch_bounds__(128) k_crt_direct(DevCtx c, CrtArgs a, const _
   u64 col[NL];
 #pragma unroll
   for (int j = 0; j < NL; ++j) col[j] = 0;
-  u64 F = 0;
+  u64 Fh = 0, Fl = 0;
 #pragma unroll
   for (int i = 0; i < ML; ++i) {
     if (i < L) {
       const u32 r = rr[i];
       const u32 p = T.p[i];
       const u32 y = csub(r * T.yinv[i] - __umulhi(r, T.yinvq[i]) * p, p);
-      F += (u64)y * T.rfix[i];  // < 2^58 each
+      Fh += (u64)y * T.rfix_hi[i];  // < 2^57 each
+      Fl += (u64)y * T.rfix_lo[i];  // < 2^58 each
 #pragma unroll
       for (int j = 0; j < NL; ++j)
         if ((u32)j < nl) col[j] += (u64)y * T.C[i][j];  // < 2^58 each, at most 40 of them
     }
   }
-  const u64 frac = F & ((1ull << 58) - 1), D = 1ull << 36, HALF = 1ull << 57;
-  const u32 kc = (u32)(F >> 58) + (frac > HALF ? 1u : 0u);
-  bool unsure = T.force_exact || frac >= (1ull << 58) - D || (frac <= HALF && frac + D > HALF);
+  const u64 Tq = Fh + (Fl >> 28);  // floor(F / 2^28): sum y_i / p_i in units of 2^-56, low by less than 256
+  const u64 frac = Tq & ((1ull << 56) - 1), D = 256, HALF = 1ull << 55;
+  const u32 kc = (u32)(Tq >> 56) + (frac > HALF ? 1u : 0u);
+  bool unsure = T.force_exact || frac >= (1ull << 56) - D || (frac <= HALF && frac + D > HALF);
   u32 limb[NL];
   {
     u64 carry = 0;
@@ -801,6 +806,7 @@ __global__ void __launch_bounds__(128) k_crt_direct(DevCtx c, CrtArgs a, const _
   if (j0 && (limb[1] < 256u || limb[1] >= (1u << CRT_LB) - 256u)) unsure = true;
   if (unsure && active) {  // (through a buffer of its own: handing out limb[] would move it from registers to local memory)
     u32 ex[NL];
+    if (!T.force_exact) atomicAdd(T.fallbacks, 1ull);
     crt_exact_limbs(c, res, c.n, L, j0, nl, ex);
 #pragma unroll
     for (int j = 0; j < NL; ++j)

@@ -45,6 +45,7 @@ SYMBOLS = {
     "fhesi_h2d": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_h2d_async": (C.c_int, [_P, _P, _P, _SZ]),
     "fhesi_d2h": (C.c_int, [_P, _P, _P, _SZ]),
+    "fhesi_crt_fallbacks": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "fhesi_host_alloc": (C.c_int, [_SZ, C.c_int, C.POINTER(_P)]),
     "fhesi_host_free": (C.c_int, [_P]),
     "fhesi_d2d": (C.c_int, [_P, _P, _P, _SZ]),
@@ -196,6 +197,12 @@ class Context:
     def to_device(self, arr: np.ndarray) -> DeviceBuffer:
         arr = np.ascontiguousarray(arr)
         return DeviceBuffer(self, max(arr.nbytes, 16)).upload(arr)
+
+    def crt_fallbacks(self) -> int:
+        """Coefficients whose ScaleDown took k_crt_direct's exact fallback since the context was created."""
+        v = C.c_uint64()
+        self._ck(self.lib.fhesi_crt_fallbacks(self.h, C.byref(v)))
+        return v.value
 
     def host_alloc(self, shape, dtype=np.uint32, write_combined: bool = False) -> np.ndarray:
         """Page-locked host array for the *_host entry points (fhesi_host_alloc); write_combined=True for operands the

@@ -98,6 +98,11 @@ int fhesi_d2h(fhesi_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
  * without snooping the CPU caches.  Measured with all eight GPUs of a box copying at once: the slowest ranks move
  * a step's bytes in 47.7 ms instead of 52.0 ms (profiles/r02c_pcie_probe_8gpu.txt); CPU reads of such memory are
  * slow, so results belong in ordinary page-locked memory (write_combined = 0). */
+/* ScaleDown (Ciphertext.cpp:194-218) reads the centred integer off a windowed explicit CRT sum and falls back, per
+ * coefficient, on the full mixed-radix reconstruction when it cannot prove the window exact (kernels_generic.cuh,
+ * k_crt_direct).  This is the number of coefficients that took the fallback since the context was created
+ * (expected: about two per million). */
+int fhesi_crt_fallbacks(fhesi_ctx *ctx, uint64_t *count);
 int fhesi_host_alloc(size_t bytes, int write_combined, void **out);
 int fhesi_host_free(void *p);
 int fhesi_d2d(fhesi_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);

@@ -22,8 +22,8 @@ def run(lib, B=8192, steps=6, logq=256, p=1019, ref=None):
     kA = rng.integers(0, 2**32, size=(3 * D, n, W), dtype=np.uint32)
     ksw = dev.ksw_create(kb, kA, 3)
     g = torch.Generator(device="cuda").manual_seed(11)
-    a = torch.randint(0, 2**31 - 1, (B, 2, n, W), device="cuda", dtype=torch.int32, generator=g)
-    b = torch.randint(0, 2**31 - 1, (B, 2, n, W), device="cuda", dtype=torch.int32, generator=g)
+    a = torch.randint(-2**31, 2**31 - 1, (B, 2, n, W), device="cuda", dtype=torch.int32, generator=g)  # full-range coefficients
+    b = torch.randint(-2**31, 2**31 - 1, (B, 2, n, W), device="cuda", dtype=torch.int32, generator=g)
     out = torch.empty_like(a)
     torch.cuda.synchronize()
     for _ in range(3):

@@ -630,4 +630,12 @@ def check_crt_direct_paths(cfg, lib_path, count=3, m=None, seed=5):
         check_edge_cases(sc, counts=(1, 5))
         prof = sc.dev.profile_report()
         assert ("k_crt_direct<ML>" in prof) == ("FHESI_NO_CRT_DIRECT" not in env), prof
+        if not env:
+            # the fallback is for the rare coefficient: tiny x (the zero and unit operands above: counted) aside, fresh
+            # encryptions must stay on the windowed path -- a wide "unsure" band is a 2 x slowdown, not a wrong bit
+            before = sc.dev.crt_fallbacks()
+            assert before > 0, "the extreme operands must have taken the exact routine"
+            _, cts = sc.fresh(8)
+            sc.dev_mult_relin(cts[:4], cts[4:])
+            assert sc.dev.crt_fallbacks() - before <= max(2, 4 * 3 * sc.dev.n // 1000), "k_crt_direct falls back too often"
         sc.dev.close()

@@ -120,7 +120,13 @@ def test_emu_general_m_fused(emu_lib):
     P.check_rotate_keyswitch(sc, g, count=1)
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg3"])
+@pytest.mark.parametrize("name", ["cfg1", "m36"])
 def test_emu_crt_direct_paths(name, emu_lib):
-    """cfg1 (logQ = 80: the window starts at word 0, nothing is cut) and cfg3 (logQ = 100: two guard words)."""
-    P.check_crt_direct_paths(CONFIGS[name], emu_lib, count=2 if name == "cfg1" else 1)
+    """cfg1 (logQ = 80: the limb window starts at limb 0, nothing is cut) and m = 36 at logQ = 100 (the window starts
+    at limb 1: guard limb and cut-off carry in play).  The BASELINE sizes run on the B200 (test_crt_direct_paths)."""
+    from common import GENERAL_M
+    if name in CONFIGS:
+        P.check_crt_direct_paths(CONFIGS[name], emu_lib, count=2)
+    else:
+        logq, p, g, m = GENERAL_M[name]
+        P.check_crt_direct_paths((logq, p, g), emu_lib, count=2, m=m)
