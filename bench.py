@@ -568,7 +568,7 @@ def run_ours(args, rank, local_rank, world):
         # therefore counted per class and expressed in Shoup-modmul equivalents (one Shoup product =
         # 2 IMAD + 1 IMAD.HI; one 64-bit multiply-accumulate = 1 IMAD.WIDE, about 0.66 of a Shoup product):
         # achieved / peak is then the fraction of the pipe's time spent on algorithmic instructions, the
-        # quantity ncu reports as sm__inst_executed_pipe_fmaheavy (profiles/r02c_ncu_full_summary.txt).
+        # quantity ncu reports as sm__inst_executed_pipe_fmaheavy (profiles/r02f_ncu_full_summary.txt).
         cost = {"lo": 1.0 / pipes["imad_lo32"], "hi": 1.0 / pipes["imad_hi32"], "wide": 1.0 / pipes["imad_wide64"]}
         shoup_cost = 2 * cost["lo"] + cost["hi"]
         peak32 = 1.0 / shoup_cost  # Shoup products per second when nothing else shares the pipe
@@ -603,7 +603,7 @@ def run_ours(args, rank, local_rank, world):
             "traffic": traffic * ops_timed / max(tcnt, 1) if traffic else None,
             "traffic_unit": "bytes per launch: the kernel's compulsory HBM traffic (every input word read once, every "
                             "output word written once; key tiles and tables stay in L2), confirmed against ncu "
-                            "dram__bytes_read.sum + dram__bytes_write.sum of the same launch in profiles/r02c_ncu_full_summary.txt",
+                            "dram__bytes_read.sum + dram__bytes_write.sum of the same launch in profiles/r02f_ncu_full_summary.txt",
             "peak_source": "measured in this run (fhesi_pipe_peak: register-resident ILP-8 chains of one instruction "
                            "class on all SMs)",
             "peak_montgomery32_Gmodmul_s": peak_mont32 / 1e9,
