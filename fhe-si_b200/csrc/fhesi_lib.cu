@@ -1766,20 +1766,21 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->lane_stream, cudaStreamNonBlocking));
   }
-  // pipeline chunk: ~14 chunks per call, a multiple of 12 (whole CTAs in both fused kernels), between
-  // 252 (below that the grids are too few waves deep) and 576 (above, the compute stream's lag
-  // behind the upload -- one chunk -- costs more than the better kernel efficiency returns);
-  // measured on a B200 behind PCIe gen5 with two compute lanes, batch 8192: 384 -> 705 k ops/s,
-  // 576 -> 708 k, 768 -> 702 k, 1024 -> 669 k, 1536 -> 658 k
+  // pipeline chunk: ~21 chunks per call, a multiple of 12, between 252 (below that the grids are too few waves
+  // deep) and 384 (above, the compute stream's lag behind the upload -- one chunk -- costs more than the better
+  // kernel efficiency returns).  Measured on a B200 behind PCIe gen5 with two compute lanes, batch 8192, with the
+  // round-2 kernels (8.6 ms of compute against 10.5 ms of copies; scripts/gpu/e2e_sweep.py): half chunk + 384s + half
+  // chunk 730 k ops/s, 384s alone 721 k, 288s 719 k, 576s with quarter and half chunks at the ends (the round-1
+  // optimum, when compute took 10 ms) 704 k, 768s 707 k, 192s 697 k
   size_t PC = c->pipe_chunk;
   if (!PC) {
-    PC = ((count / 14 + 11) / 12) * 12;
+    PC = ((count / 21 + 11) / 12) * 12;
     if (PC < 252) PC = 252;
-    if (PC > 576) PC = 576;
+    if (PC > 384) PC = 384;
   }
-  // chunk schedule: full chunks in the middle, a quarter and a half chunk at either end when the
-  // batch is long enough -- the first upload and the last compute + download are the only parts
-  // of the call that do not overlap anything (FHESI_PIPE_TAPER=0 turns the taper off)
+  // chunk schedule: full chunks in the middle, a half chunk at either end when the batch is long enough -- the
+  // first upload and the last compute + download are the only parts of the call that do not overlap anything
+  // (FHESI_PIPE_TAPER=0 turns the taper off)
   std::vector<size_t> sizes;
   if (const char *sched = getenv("FHESI_PIPE_SCHED")) {
     // explicit schedule for tuning runs: "192,384,*1536,384,192" -- head sizes, one repeated
@@ -1810,13 +1811,13 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
     sizes.insert(sizes.end(), tail.begin(), tail.end());
   } else {
     size_t rest = count;
-    const size_t q = ((PC / 4 + 11) / 12) * 12, h = ((PC / 2 + 11) / 12) * 12;
+    const size_t h = ((PC / 2 + 11) / 12) * 12;
     const bool taper = c->pipe_taper && count >= 6 * PC;
     std::vector<size_t> tail;
     if (taper) {
-      sizes.push_back(q), sizes.push_back(h);
-      tail.push_back(h), tail.push_back(q);
-      rest -= 2 * (q + h);
+      sizes.push_back(h);
+      tail.push_back(h);
+      rest -= 2 * h;
     }
     while (rest) {
       const size_t t = rest < PC ? rest : PC;
