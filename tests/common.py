@@ -21,7 +21,7 @@ CONFIGS = {
 
 # General m (not 2 * odd prime): Phi_m is taken as a sparse remainder table (DevCtx::red).  (logQ, p, g, m):
 # a power of two, an odd prime, prime powers, three odd prime factors (Phi_105 has a coefficient -2; X^j mod Phi_105
-# reaches +-2), phi(m) > m / 2 and < m / 2, and two sizes that take the fused kernels (N = 1024: 256 < phi(m) <= 512).
+# reaches +-2), phi(m) > m / 2 and < m / 2, and sizes that take the fused kernels (256 < phi(m) <= 1024).
 GENERAL_M = {
     "m16": (80, 17, 3, 16),
     "m17": (80, 2, 3, 17),
@@ -31,6 +31,7 @@ GENERAL_M = {
     "m128": (128, 257, 3, 128),
     "m1320": (100, 1321, 13, 1320),
     "m771": (128, 2, 5, 771),
+    "m1285": (100, 257, 2, 1285),  # phi = 1024: the fused N = 2048 kernels' general-m instances, n = N / 2 exactly
 }
 
 

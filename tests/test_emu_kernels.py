@@ -120,6 +120,17 @@ def test_emu_general_m_fused(emu_lib):
     P.check_rotate_keyswitch(sc, g, count=1)
 
 
+def test_emu_general_m_fused_2048(emu_lib):
+    """phi(m) = 1024 (m = 5 * 257): the N = 2048 fused kernels' general-m instances."""
+    from common import GENERAL_M
+    logq, p, g, m = GENERAL_M["m1285"]
+    sc = Scenario(logq, p, g, seed=29, lib_path=emu_lib, m=m)
+    assert sc.dev.N == 2048 and sc.dev.n == 1024
+    sc.dev.profile_enable(True)
+    P.check_mult_relin(sc, count=1)
+    assert "k_fused_keyswitch_split_2k" in sc.dev.profile_report()
+
+
 @pytest.mark.parametrize("name", ["cfg1", "m36"])
 def test_emu_crt_direct_paths(name, emu_lib):
     """cfg1 (logQ = 80: the limb window starts at limb 0, nothing is cut) and m = 36 at logQ = 100 (the window starts

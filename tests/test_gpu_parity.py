@@ -61,7 +61,7 @@ def test_fused_2048_p2027(cuda_lib):
         del os.environ["FHESI_NO_FUSED"]
 
 
-@pytest.mark.parametrize("name", ["m16", "m17", "m36", "m45", "m105", "m128", "m1320", "m771"])
+@pytest.mark.parametrize("name", ["m16", "m17", "m36", "m45", "m105", "m128", "m1320", "m771", "m1285"])
 def test_general_m(name, cuda_lib):
     """Any m (bluestein.cpp:93-144 and CModulus.cpp:110-132 serve every m in the reference): the remainder by
     Phi_m and the automorphisms as sparse integer matrices.  m1320 and m771 (phi = 320, 512) run the fused
@@ -70,11 +70,11 @@ def test_general_m(name, cuda_lib):
     logq, p, g, m = GENERAL_M[name]
     sc = Scenario(logq, p, g, seed=20240611, xi=3, lib_path=cuda_lib, m=m)
     assert sc.dev.n == sc.octx.phim and sc.dev.info.m == m
-    big = sc.dev.N == 1024
+    big = sc.dev.N >= 1024
     sc.dev.profile_enable(True)
     P.check_mult_relin(sc, count=2 if big else 4)
     prof = sc.dev.profile_report()
-    assert ("k_fused_keyswitch_split" in prof or "k_fused_keyswitch<true>" in prof) == big, prof
+    assert any(k.startswith("k_fused_keyswitch") for k in prof) == big, prof
     sc.dev.profile_enable(False)
     P.check_mult_relin(sc, count=2, random_inputs=True)
     P.check_mult_relin(sc, count=2, host=True)
