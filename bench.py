@@ -684,10 +684,10 @@ def kernel_pipe_work_per_op(dev):
         "k_residues": w(mac=4 * n * Lt * W, red_hi=4 * n * Lt * ((W + 3) // 4)),
         "k_fused_tensor": w(modmul=7 * Lt * tr, montmul=4 * Lt * N),
         "k_crt": w(modmul=3 * n * garner(Lt), mac=3 * n * horner(Lt)),
-        # windowed explicit CRT: L Shoup products (y_i), L multiply-accumulates for the quotient, (L + 1) NL for the
+        # windowed explicit CRT: L Shoup products (y_i), 2 L multiply-accumulates for the quotient, (L + 1) NL for the
         # 28-bit limb columns, NL = limbs from two below the rounding bit's up to bit 2 logQ - 1
         "k_crt_direct": w(modmul=3 * n * Lt,
-                          mac=3 * n * (Lt + (Lt + 1) * ((2 * dev.info.logQ - 1) // 28 - max((dev.info.logQ - 1) // 28 - 2, 0) + 1))),
+                          mac=3 * n * (2 * Lt + (Lt + 1) * ((2 * dev.info.logQ - 1) // 28 - max((dev.info.logQ - 1) // 28 - 2, 0) + 1))),
         "k_fused_keyswitch_split": w(modmul=(K + 4) * Ls * tr, mac=4 * K * Ls * N, red=4 * Ls * N),
         "k_fused_keyswitch": w(modmul=(K + 2) * Lk * tr, mac=2 * K * Lk * N, red=2 * Lk * N),
         "k_crt_split": w(modmul=4 * n * garner(Ls), mac=4 * n * horner(Ls)),
