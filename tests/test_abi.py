@@ -47,3 +47,18 @@ def test_bad_parameters_rejected(emu_lib):
     for args in ((2, 80, 23), (9000, 80, 23), (6151, 80, 23), (22, 4, 23), (22, 80, 1)):
         with pytest.raises(pyfhesi.FhesiError):
             pyfhesi.Context(*args, lib_path=emu_lib)
+
+
+def test_host_alloc_roundtrip(emu_lib):
+    """fhesi_host_alloc / fhesi_host_free (page-locked staging; write-combined for operands): the array is writable,
+    readable and released; the fallback counter of the windowed CRT starts at zero."""
+    import numpy as np
+    import pyfhesi
+    ctx = pyfhesi.Context(22, 80, 23, lib_path=emu_lib)
+    for wc in (False, True):
+        a = ctx.host_alloc((3, ctx.n, ctx.W), np.uint32, write_combined=wc)
+        a[...] = np.arange(a.size, dtype=np.uint32).reshape(a.shape)
+        assert int(a.sum()) == a.size * (a.size - 1) // 2
+        ctx.host_free(a)
+    assert ctx.crt_fallbacks() == 0
+    ctx.close()
