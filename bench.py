@@ -279,7 +279,7 @@ def _regression_files(tmpdir):
     return prefix
 
 
-def run_regression_ours(args, rank, local_rank, world, lib_path, runs=11):
+def run_regression_ours(args, rank, local_rank, world, lib_path, runs=15):
     """apps/regression_sharded.py on the N GPUs of this job, reading the 8 shard files; the clock is the
     reference driver's (key generation .. decryption, Test_Regression.cpp:24-63), max over ranks.  The first run
     pays one-off costs (first allocation of every buffer, first use of every kernel at these sizes); all runs are
