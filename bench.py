@@ -390,12 +390,14 @@ def run_ours(args, rank, local_rank, world):
     lib_path = fhesi_build.build()
     logq, p, g = CFG["logQ"], CFG["p"], CFG["g"]
 
-    # ---- BASELINE.json's second metric: Test_Regression d=4 N=100000 (config 4).  It runs FIRST, in a process that
-    # holds nothing else yet: measured after the throughput legs (gigabytes of device and page-locked buffers alive,
-    # the big context's arenas) the same runs scatter between 17 and 70 ms, alone they repeat to within a millisecond
-    # (profiles/r02h_bench_1gpu_fresh_box.json against scripts/gpu/reg_runs.py)
+    # ---- BASELINE.json's second metric: Test_Regression d=4 N=100000 (config 4).  Its clock is 17 ms of mostly
+    # host-side work and is sensitive to what else the box is doing.  Measured on fresh boxes: at one GPU the runs
+    # repeat to within a millisecond when the leg comes FIRST and scatter between 17 and 70 ms after the throughput
+    # legs (profiles/r02h_bench_1gpu_fresh_box.json); under torchrun it is the other way round -- while the ranks'
+    # start-up is still paging the image in, the first leg scatters up to 0.4 s, after the throughput legs it repeats
+    # (profiles/r02g_bench_2gpu.json, r02f_bench_8gpu.json).  Every run and its phases are in the JSON either way.
     regression = None
-    if not args.no_regression:
+    if not args.no_regression and world == 1:
         regression = run_regression_ours(args, rank, local_rank, world, lib_path)
 
     dev = pyfhesi.Context(p - 1, logq, p, 3, 1, local_rank, lib_path=lib_path)
@@ -542,6 +544,9 @@ def run_ours(args, rank, local_rank, world):
         exchange = {"what": "ncclAllGather of 14 x 3 x Lt x N words per rank + k_tprod_reduce_world",
                     "bytes_per_rank": part.numel() * 4, "bytes_received_per_rank": part.numel() * 4 * (world - 1),
                     "us": ex_ms * 1e3}
+
+    if not args.no_regression and world > 1:
+        regression = run_regression_ours(args, rank, local_rank, world, lib_path)
 
     ms_step = ms_total / args.steps
     if world > 1:
