@@ -158,6 +158,11 @@ struct fhesi_ctx {
   Arena stage;  // device staging for the *_host entry points
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the host pipeline
   std::vector<cudaEvent_t> pipe_events;
+  // fhesi_mult_relin_host_async: two staging halves used alternately; half_done[h] = everything of the last call that
+  // used half h has finished (recorded on the download stream after its last copy)
+  cudaEvent_t half_done[2] = {nullptr, nullptr};
+  bool half_used[2] = {false, false};
+  unsigned host_calls = 0;
   u32 pipe_chunk = 0;  // 0 = choose from the batch size; FHESI_PIPE_CHUNK overrides
   u32 pipe_taper = 1;  // FHESI_PIPE_TAPER=0: equal chunks
   int sm_count = 148;  // from the device at context creation
@@ -626,6 +631,8 @@ void fhesi_ctx_destroy(fhesi_ctx *c) {
   cache_put(c->device, c->work.ptr, c->work.cap);
   prof_clear(c);
   for (auto e : c->pipe_events) cudaEventDestroy(e);
+  for (auto e : c->half_done)
+    if (e) cudaEventDestroy(e);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->lane_stream) cudaStreamDestroy(c->lane_stream);
@@ -645,6 +652,15 @@ int fhesi_ctx_set_stream(fhesi_ctx *c, void *s) {
 int fhesi_sync(fhesi_ctx *c) {
   if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
   CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int fhesi_sync_all(fhesi_ctx *c) {
+  if (!c) return fail(FHESI_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  if (c->d2h_stream) CK(cudaStreamSynchronize(c->d2h_stream));
+  if (c->lane_stream) CK(cudaStreamSynchronize(c->lane_stream));
+  if (c->h2d_stream) CK(cudaStreamSynchronize(c->h2d_stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1748,19 +1764,28 @@ int fhesi_mult_relin_dev(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *a, 
 // Host-buffer entry point.  The batch is cut into pipeline chunks: chunk i+1 is uploaded on a
 // copy stream while chunk i computes on the context's stream and chunk i-1 is downloaded on a
 // second copy stream, so PCIe in both directions overlaps the kernels.
-int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_a, const uint32_t *h_b,
-                          uint32_t *h_out, size_t count) {
+// The same without the final wait: the call returns when everything is enqueued, and the NEXT call's uploads and
+// kernels overlap this call's last kernels and downloads (two staging halves, used alternately).  h_a and h_b must
+// stay untouched and h_out unread until fhesi_sync_all (or a later blocking fhesi_mult_relin_host) returns; a caller
+// that keeps several calls in flight gives each its own h_out.
+int fhesi_mult_relin_host_async(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_a, const uint32_t *h_b,
+                                uint32_t *h_out, size_t count) {
   if (!c || !ksw || !h_a || !h_b || !h_out) return fail(FHESI_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   if (!count) return 0;
   const size_t ctb = fhesi_ct_bytes(c, 2), bytes = count * ctb;
-  if (c->stage.cap < 3 * bytes + 64) {  // grow-only staging area, reused across calls
-    CK(cudaStreamSynchronize(c->stream));
+  if (c->stage.cap < 2 * (3 * bytes + 64)) {  // grow-only staging area (two halves), reused across calls
+    int rc = fhesi_sync_all(c);
+    if (rc) return rc;
     if (c->stage.ptr) CK(cudaFree(c->stage.ptr));
     c->stage.ptr = nullptr;
     c->stage.cap = 0;
-    CK(cached_malloc(c->device, &c->stage.ptr, 3 * bytes + 64, &c->stage.cap));
+    c->half_used[0] = c->half_used[1] = false;
+    CK(cached_malloc(c->device, &c->stage.ptr, 2 * (3 * bytes + 64), &c->stage.cap));
   }
+  const unsigned half = c->host_calls++ & 1;
+  for (int h = 0; h < 2; ++h)
+    if (!c->half_done[h]) CK(cudaEventCreateWithFlags(&c->half_done[h], cudaEventDisableTiming));
   if (!c->h2d_stream) {
     CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
@@ -1832,12 +1857,14 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->pipe_events.push_back(e);
   }
-  char *d = (char *)c->stage.ptr;
+  char *d = (char *)c->stage.ptr + (size_t)half * (c->stage.cap / 2 / 64 * 64);
   char *da = d, *db = d + bytes, *dout = d + 2 * bytes;
-  // the copy stream must not overtake work already queued on the compute stream
+  // the copy stream must not overtake work already queued on the compute stream, nor the last call that used
+  // this staging half
   CK(cudaEventRecord(c->pipe_events[0], c->stream));
   CK(cudaStreamWaitEvent(c->h2d_stream, c->pipe_events[0], 0));
   CK(cudaStreamWaitEvent(c->lane_stream, c->pipe_events[0], 0));
+  if (c->half_used[half]) CK(cudaStreamWaitEvent(c->h2d_stream, c->half_done[half], 0));
   // FHESI_PIPE_TRACE=1: per-chunk timeline (upload done / compute done / download done, ms from the
   // start of the call) on stderr -- a debugging aid, off by default
   static const bool trace = getenv("FHESI_PIPE_TRACE") && atoi(getenv("FHESI_PIPE_TRACE")) > 0;
@@ -1880,10 +1907,15 @@ int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_
     }
     for (auto &e : tev) cudaEventDestroy(e);
   }
-  CK(cudaStreamSynchronize(c->d2h_stream));
-  CK(cudaStreamSynchronize(c->lane_stream));
-  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaEventRecord(c->half_done[half], c->d2h_stream));  // every kernel of the call precedes its last download
+  c->half_used[half] = true;
   return 0;
+}
+int fhesi_mult_relin_host(fhesi_ctx *c, const fhesi_ksw *ksw, const uint32_t *h_a, const uint32_t *h_b,
+                          uint32_t *h_out, size_t count) {
+  int rc = fhesi_mult_relin_host_async(c, ksw, h_a, h_b, h_out, count);
+  if (rc || !count) return rc;
+  return fhesi_sync_all(c);
 }
 
 // ---------------------------------------------------------------------------------------

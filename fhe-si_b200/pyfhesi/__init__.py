@@ -60,6 +60,8 @@ SYMBOLS = {
     "fhesi_key_destroy": (None, [_P]),
     "fhesi_mult_relin_dev": (C.c_int, [_P, _P, _P, _P, _P, _SZ]),
     "fhesi_mult_relin_host": (C.c_int, [_P, _P, _P, _P, _P, _SZ]),
+    "fhesi_mult_relin_host_async": (C.c_int, [_P, _P, _P, _P, _P, _SZ]),
+    "fhesi_sync_all": (C.c_int, [_P]),
     "fhesi_ct_add_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),
     "fhesi_ct_sum_dev": (C.c_int, [_P, _P, _P, _U32, _SZ]),
     "fhesi_ct_mul_scalar_dev": (C.c_int, [_P, _P, C.c_int64, _U32, _SZ]),
@@ -301,6 +303,13 @@ class Context:
         self._ck(self.lib.fhesi_mult_relin_host(self.h, ksw, a.ctypes.data, b.ctypes.data,
                                                 out.ctypes.data, count))
         return out
+
+    def mult_relin_host_async(self, ksw, a, b, out, count):
+        """fhesi_mult_relin_host_async: host pointers / page-locked arrays; returns when enqueued (sync_all waits)."""
+        self._ck(self.lib.fhesi_mult_relin_host_async(self.h, ksw, _ptr(a), _ptr(b), _ptr(out), count))
+
+    def sync_all(self):
+        self._ck(self.lib.fhesi_sync_all(self.h))
 
     def ct_add_dev(self, io, other, parts, count):
         self._ck(self.lib.fhesi_ct_add_dev(self.h, _ptr(io), _ptr(other), parts, count))

@@ -151,6 +151,14 @@ int fhesi_mult_relin_dev(fhesi_ctx *ctx, const fhesi_ksw *ksw, const uint32_t *d
                          const uint32_t *d_b, uint32_t *d_out, size_t count);
 int fhesi_mult_relin_host(fhesi_ctx *ctx, const fhesi_ksw *ksw, const uint32_t *h_a,
                           const uint32_t *h_b, uint32_t *h_out, size_t count);
+/* The same, returning as soon as the batch is enqueued: a server that feeds batch after batch (Matrix.cpp's
+ * products over a stream of blocks) overlaps the next batch's uploads and kernels with this batch's last kernels
+ * and downloads.  h_a / h_b must stay untouched and h_out unread until fhesi_sync_all returns; calls in flight at
+ * the same time need an h_out each.  fhesi_sync_all waits for the context's stream AND the pipeline's copy streams
+ * (fhesi_sync waits for the context's stream only). */
+int fhesi_mult_relin_host_async(fhesi_ctx *ctx, const fhesi_ksw *ksw, const uint32_t *h_a,
+                                const uint32_t *h_b, uint32_t *h_out, size_t count);
+int fhesi_sync_all(fhesi_ctx *ctx);
 
 /* ---- the pieces, each batched over `count` independent ciphertexts -------------------- */
 

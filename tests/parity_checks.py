@@ -639,3 +639,21 @@ def check_crt_direct_paths(cfg, lib_path, count=3, m=None, seed=5):
             sc.dev_mult_relin(cts[:4], cts[4:])
             assert sc.dev.crt_fallbacks() - before <= max(2, 4 * 3 * sc.dev.n // 1000), "k_crt_direct falls back too often"
         sc.dev.close()
+
+
+def check_mult_relin_host_async(sc: Scenario, count=3):
+    """fhesi_mult_relin_host_async: three batches in flight (the staging halves are reused by the third), one
+    fhesi_sync_all; every batch must equal the oracle and the blocking call."""
+    batches = []
+    for _ in range(3):
+        A, B = sc.random_cts(count), sc.random_cts(count)
+        a = np.ascontiguousarray(sc.pack_cts(A), dtype=np.uint32)
+        b = np.ascontiguousarray(sc.pack_cts(B), dtype=np.uint32)
+        batches.append((A, B, a, b, np.zeros_like(a)))
+    for A, B, a, b, out in batches:
+        sc.dev.mult_relin_host_async(sc.ksw, a, b, out, count)
+    sc.dev.sync_all()
+    for A, B, a, b, out in batches:
+        for i in range(count):
+            assert_ct_equal(sc, out[i], O.mult_relin(sc.ks, A[i], B[i]), f"async batch [{i}]")
+        assert np.array_equal(out, sc.dev.mult_relin_host(sc.ksw, a, b))

@@ -18,6 +18,10 @@ def test_emu_mult_relin_cfg1(sc1):
     P.check_mult_relin(sc1, count=2, random_inputs=True)
 
 
+def test_emu_mult_relin_host_async_cfg1(sc1):
+    P.check_mult_relin_host_async(sc1, count=3)
+
+
 def test_emu_mult_relin_wide_cfg1(emu_lib):
     P.check_mult_relin_wide(*CONFIGS["cfg1"], emu_lib, pairs=16, seeds=(101, 202))
 

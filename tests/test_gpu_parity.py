@@ -96,6 +96,28 @@ def test_crt_direct_paths(name, cuda_lib):
     P.check_crt_direct_paths(CONFIGS[name], cuda_lib, count=2 if name == "cfg5_512" else 3)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_mult_relin_host_async(name, cuda_lib):
+    """Batches in flight across calls (the next call's uploads overlap this call's last kernels and downloads)."""
+    P.check_mult_relin_host_async(scenario(name, cuda_lib), count=5 if name == "cfg1" else 3)
+    import pyfhesi  # a long batch too: many pipeline chunks per call, both staging halves, against the device path
+    sc = scenario("cfg2", cuda_lib)
+    if name == "cfg2":
+        rng = np.random.default_rng(3)
+        shape = (700, 2, sc.dev.n, sc.dev.W)
+        ins = [(rng.integers(0, 2**32, size=shape, dtype=np.uint32), rng.integers(0, 2**32, size=shape, dtype=np.uint32))
+               for _ in range(3)]
+        outs = [np.zeros(shape, np.uint32) for _ in ins]
+        for (a, b), o in zip(ins, outs):
+            sc.dev.mult_relin_host_async(sc.ksw, a, b, o, shape[0])
+        sc.dev.sync_all()
+        for (a, b), o in zip(ins, outs):
+            da, db, do = sc.dev.to_device(a), sc.dev.to_device(b), sc.dev.alloc(a.nbytes)
+            sc.dev.mult_relin_dev(sc.ksw, da.ptr, db.ptr, do.ptr, shape[0])
+            sc.dev.sync()
+            assert np.array_equal(o, do.download(shape))
+
+
 def test_mult_relin_host_and_random_cfg2(cuda_lib):
     sc = scenario("cfg2", cuda_lib)
     P.check_mult_relin(sc, count=2, host=True)
