@@ -10,8 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, os.path.join(ROOT, "fhe-si_b200"))
 import pyfhesi  # noqa: E402
 
-SCHEDS = ["", "*384", "*288", "*336", "*240", "*192", "192,*384,192", "96,192,*384,192,96", "*384,192,96", "*336,168",
-          "*432", "*480", "144,*288,144"]
+SCHEDS = ["", "*384", "*768", "*1024", "*1536", "*2048", "*4096", "192,*768,192", "384,*1024", "*576", "*8192"]
 
 
 def main():
@@ -27,20 +26,29 @@ def main():
     ha[...] = rng.integers(0, 2**32, size=ha.shape, dtype=np.uint32)
     hb[...] = rng.integers(0, 2**32, size=hb.shape, dtype=np.uint32)
 
-    def call():
-        dev._ck(dev.lib.fhesi_mult_relin_host(dev.h, ksw, ha.ctypes.data, hb.ctypes.data, ho.ctypes.data, B))
+    ho2 = dev.host_alloc((B, 2, n, W), np.uint32, write_combined=False)
+    ASYNC = "--blocking" not in sys.argv
+
+    def call(i=0):
+        if ASYNC:
+            dev._ck(dev.lib.fhesi_mult_relin_host_async(dev.h, ksw, ha.ctypes.data, hb.ctypes.data,
+                                                        (ho, ho2)[i & 1].ctypes.data, B))
+        else:
+            dev._ck(dev.lib.fhesi_mult_relin_host(dev.h, ksw, ha.ctypes.data, hb.ctypes.data, ho.ctypes.data, B))
 
     for s in SCHEDS + [""]:
         if s:
             os.environ["FHESI_PIPE_SCHED"] = s
         else:
             os.environ.pop("FHESI_PIPE_SCHED", None)
-        for _ in range(2):
-            call()
+        for i in range(2):
+            call(i)
+        dev.sync_all()
         t0 = time.perf_counter()
         reps = 8
-        for _ in range(reps):
-            call()
+        for i in range(reps):
+            call(i)
+        dev.sync_all()
         ms = (time.perf_counter() - t0) * 1e3 / reps
         print(f"sched {s or 'default':40s} {ms:7.3f} ms/step  {B / ms * 1e3:9.0f} ops/s", flush=True)
 
