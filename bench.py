@@ -30,6 +30,10 @@ for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fhe-si_b200"), ROOT)
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# every kernel of the library is loaded when the CUDA context is created, not on its first launch inside a timed
+# region (the regression leg touches some forty kernels the throughput legs never launch)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import numpy as np  # noqa: E402
 
 SEED = 20240611
