@@ -129,6 +129,26 @@ class Env:
         torch.cuda.current_stream().synchronize()  # the staging buffer is reused by the next call
         return out
 
+    def staging_array(self, shape, dtype=np.int32):
+        """A zeroed numpy array that IS the pinned staging buffer (or an ordinary one when there is none / it is too
+        small): what is packed into it goes up with upload_staged() without another host copy."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if self.pinned is None or nbytes > self.pinned.numel():
+            return np.zeros(shape, dtype=dtype)
+        a = self.pinned[:nbytes].numpy().view(dtype).reshape(shape)
+        a.fill(0)
+        return a
+
+    def upload_staged(self, arr):
+        """staging_array() -> device tensor."""
+        if self.pinned is None or arr.nbytes > self.pinned.numel() or arr.ctypes.data != self.pinned.data_ptr():
+            return self.to_device(arr)
+        t = self.pinned[:arr.nbytes].view(torch.from_numpy(arr[:0]).dtype).view(arr.shape)
+        out = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the staging buffer is reused by the next call
+        return out
+
     def empty(self, words):
         return torch.empty(int(words), dtype=torch.int32, device=self.device)
 
@@ -262,7 +282,7 @@ def embed_batch(env, slots, values):
         slots.d_basis = torch.from_numpy(slots.basis.astype(np.int32)).to(env.device)
     d_msgs = torch.empty((max(cnt, 1), dev.n), dtype=torch.int32, device=env.device)
     if cnt:
-        raw = env.to_device(np.ascontiguousarray(values, dtype=np.int32))
+        raw = env.upload_staged(np.ascontiguousarray(values, dtype=np.int32))
         d_vals = torch.zeros((cnt, slots.total), dtype=torch.int32, device=env.device)
         d_vals[:, :width] = torch.remainder(raw, slots.p).to(torch.int32)
         dev.embed_slots_dev(slots.d_basis, slots.total, d_vals, d_msgs, cnt)

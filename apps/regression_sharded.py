@@ -172,6 +172,10 @@ def run(args, rank, world, local, quiet=False):
         files, file_blocks = [raw], [(N + block - 1) // block]
         nblocks = file_blocks[0]
     rows, labels = raw[:, :d].tolist(), raw[:, d].tolist()
+    # LoadData's result in the width the device takes (values are small: |x| <= 100, |label| < 2^31 checked here)
+    assert np.abs(raw).max(initial=0) < 2**31
+    raw32 = np.ascontiguousarray(raw, dtype=np.int32)
+    files32 = [np.ascontiguousarray(f, dtype=np.int32) for f in files]
     xi = max(nblocks, d)
     lgq = 4.5 * math.log(nslots) + max(1, d - 1) * (math.log(1280) + 2 * math.log(nslots) + math.log(xi))
     logq = int(math.ceil(lgq / math.log(2) + 24.7))     # Test_Regression.cpp:107-108
@@ -238,23 +242,30 @@ def run(args, rank, world, local, quiet=False):
     n = dev.n
     # all of this rank's plaintexts at once: [nb][d+1][block] slot values -> PlaintextSpace::EmbedInSlots
     # on the device (fhesi_embed_slots_dev, exact integer arithmetic)
+    # (one strided copy per file, straight into the final [block][column][slot] layout in 32-bit words: the values
+    # are small integers -- the first version padded, concatenated and transposed 64-bit copies, 6 ms of a 17 ms clock)
+    def pack(dst, rows):                                # rows [L][d+1] -> dst [ceil(L / block)][d+1][block], zero padded
+        full = len(rows) // block
+        if full:
+            dst[:full] = rows[:full * block].reshape(full, block, d + 1).transpose(0, 2, 1)
+        if len(rows) > full * block:
+            dst[full, :, :len(rows) - full * block] = rows[full * block:].T
     if len(files) >= world and len(files) > 1:          # whole files per rank, round-robin
-        parts = []
-        for k in range(rank, len(files), world):
-            padded = np.zeros((file_blocks[k] * block, d + 1), dtype=np.int64)
-            padded[:len(files[k])] = files[k]
-            parts.append(padded)
-        data = np.concatenate(parts) if parts else np.zeros((0, d + 1), np.int64)
-        nb = len(data) // block
-        mine = data.reshape(nb, block, d + 1).transpose(0, 2, 1)
+        own = list(range(rank, len(files), world))
+        nb = sum(file_blocks[k] for k in own)
+        vals3 = env.staging_array((nb, d + 1, block))
+        b0 = 0
+        for k in own:
+            pack(vals3[b0:b0 + file_blocks[k]], files32[k])
+            b0 += file_blocks[k]
     else:                                               # fewer files than ranks: split the global block list
         lo, hi = shard_bounds(nblocks, rank, world)
-        nb = hi - lo
-        data = np.zeros((nblocks * block, d + 1), dtype=np.int64)
-        data[:N] = raw
-        mine = data[lo * block:hi * block].reshape(max(nb, 0), block, d + 1).transpose(0, 2, 1)
+        nb = max(hi - lo, 0)
+        vals3 = env.staging_array((nb, d + 1, block))
+        if nb:
+            pack(vals3, raw32[lo * block:min(hi * block, N)])
     t_b0 = time.perf_counter()
-    vals = np.ascontiguousarray(mine).reshape(nb * (d + 1), block)
+    vals = vals3.reshape(nb * (d + 1), block)
     t_b1 = time.perf_counter()
     d_msgs = embed_batch(env, slots, vals)
     t_b2 = time.perf_counter()

@@ -306,6 +306,18 @@ static void SampleGaussianRaw(uint32_t *raw, long n) {
     raw[i + 1] = (uint32_t)RandomBnd(bignum);
   }
 }
+// The same draws from an explicit stream, one 64-bit word each and NO retry: returns false if a word would have been
+// rejected by RandomBnd (probability 2^-28 per draw) -- the caller then repeats the whole set-up sequentially
+static bool SampleGaussianRawNoRetry(RandomStream &rs, uint32_t *raw, long n) {
+  static const uint64_t bignum = 0xfffffff;  // RandomBnd(2^28 - 1): 28 bits, accepted when < bignum
+  bool ok = true;
+  for (long i = 0; i < n; i += 2) {
+    const uint64_t a = rs.next64() & bignum, b = rs.next64() & bignum;
+    ok &= a < bignum && b < bignum;
+    raw[i] = (uint32_t)a, raw[i + 1] = (uint32_t)b;
+  }
+  return ok;
+}
 static void GaussianFromRaw(int32_t *out, const uint32_t *raw, long n, double stdev) {
   static double const Pi = 4.0 * atan(1.0);
   static long const bignum = 0xfffffff;
@@ -1134,7 +1146,10 @@ struct KeyDrawSink {
   vector<Matrix> matrices;
 };
 static KeyDrawSink *g_drawSink = nullptr;
-static void SampleRandomWords(uint32_t *dst, unsigned n, unsigned W, unsigned k);
+static void SampleRandomWords(uint32_t *dst, unsigned n, unsigned W, unsigned k, RandomStream &rs);
+static void SampleRandomWords(uint32_t *dst, unsigned n, unsigned W, unsigned k) {
+  SampleRandomWords(dst, n, W, k, GlobalRandomStream());
+}
 // every coefficient fits an int32 (s, s^2, s(X^k): yes; an arbitrary imported key: maybe not)
 static bool SmallPoly(std::vector<int32_t> &dst, const ZZX &a, unsigned n) {
   dst.assign(n, 0);
@@ -1536,14 +1551,14 @@ extern "C" int fhesih_keygen(uint32_t m, uint32_t logQ, uint64_t p, uint32_t g, 
 // into the arrays the device consumes (no ZZ / ZZX temporaries).
 // SampleRandom(poly, 2^k, n) (Util.cpp:49-56): per coefficient RandomBits(k) - 2^(k-1), as W-word two's
 // complement: subtracting 2^(k-1) mod 2^k flips bit k-1, and the flipped bit is the sign.
-static void SampleRandomWords(uint32_t *dst, unsigned n, unsigned W, unsigned k) {
+static void SampleRandomWords(uint32_t *dst, unsigned n, unsigned W, unsigned k, RandomStream &rs) {
   const size_t words64 = (k + 63) / 64, limbs = (k + 31) / 32, top = (k - 1) / 32;
   const uint32_t topbit = 1u << ((k - 1) % 32);
   if (limbs != W) Error("SampleRandomWords: word count does not match logQ");
   std::vector<uint32_t> w(2 * words64);
   for (unsigned i = 0; i < n; ++i) {
     for (size_t t = 0; t < words64; ++t) {
-      const uint64_t x = GlobalRandomStream().next64();
+      const uint64_t x = rs.next64();
       w[2 * t] = (uint32_t)x, w[2 * t + 1] = (uint32_t)(x >> 32);
     }
     if (k % 32) w[limbs - 1] &= (1u << (k % 32)) - 1;
@@ -1656,27 +1671,78 @@ extern "C" int fhesih_keydraws_flat(uint32_t m, uint32_t logQ, uint64_t p, uint3
     std::vector<uint32_t> raw((Km + 1) * ((size_t)n + 1));
     const bool twoh = m % 2 == 0 && (m / 2) % 2 == 1 && n + 1 == m / 2;  // m = 2h, h an odd prime (every device context)
     std::vector<int32_t> tmp(n);
-    SampleHWtSmall(sk_out, 64, n);                            // FHESISecKey::Init
-    SampleGaussianRaw(raw.data() + Km * ((size_t)n + 1), n);  // FHESIPubKey::Init: c0's Gaussian ...
-    SampleRandomWords(A + Km * pw, n, W, logQ);               // ... then c1
-    {                                                         // KeySwitchSI(sk): InitS2
-      SampleHWtSmall(tmp.data(), 64, n);                      // the throw-away key of FHE-SI.cpp:222
-      std::fill(src, src + n, 0);
-      src[0] = 1;
-      memcpy(src + n, sk_out, n * 4);
-      if (twoh) MulSmallPhim(sk_out, sk_out, src + 2 * (size_t)n, n);
-      else MulSmallGeneral(sk_out, sk_out, src + 2 * (size_t)n, context.zMstar);
-      DrawMatrixFlat(A, raw.data(), 3 * (size_t)D, n, W, logQ);
-    }
-    for (uint32_t r = 0; r < n_rot; ++r) {                    // KeySwitchSI(sk, k): InitAutomorph
-      SampleHWtSmall(tmp.data(), 64, n);                      // :233
-      int32_t *rs = src + (3 + 2 * (size_t)r) * n;
-      std::fill(rs, rs + n, 0);
-      rs[0] = 1;                                              // 1(X^k) = 1
-      if (twoh) AutomorphSmallPhim(sk_out, rs + n, n, m, rot_k[r]);
-      else AutomorphSmallGeneral(sk_out, rs + n, context.zMstar, rot_k[r]);
-      const size_t off = (3 + 2 * (size_t)r) * D;
-      DrawMatrixFlat(A + off * pw, raw.data() + off * ((size_t)n + 1), 2 * (size_t)D, n, W, logQ);
+    // The long draws -- a uniform polynomial and a Gaussian's uniforms per matrix entry -- have a fixed length in
+    // stream words, and the ChaCha20 stream is seekable: the walk below only runs the short, data-dependent draws
+    // (the Hamming-weight keys) and notes where every long one starts; they are then filled on all cores, each from
+    // its own position of the same stream.  Same words as the sequential walk (tests/test_host_cpp.py); the
+    // SplitMix test stream, FHESIH_SEQ_DRAWS=1 and the one-in-2^28 rejected Gaussian word take the sequential walk.
+    RandomStream &gs = GlobalRandomStream();
+    const uint64_t pos_start = gs.test ? 0 : gs.position();
+    struct Seg { uint32_t *A, *raw; uint64_t pos; bool gauss_first; };
+    std::vector<Seg> segs;
+    const uint64_t lenA = (uint64_t)n * ((logQ + 63) / 64), lenG = 2 * (((uint64_t)n + 1) / 2);
+    const char *seq_env = getenv("FHESIH_SEQ_DRAWS");
+    bool parallel = !gs.test && !(seq_env && *seq_env);
+    for (int pass = 0; pass < 2; ++pass) {
+      uint64_t pos = 0;
+      auto long_draws = [&](uint32_t *Ad, uint32_t *rawd, size_t K) {  // K entries: uniform polynomial, then Gaussian
+        if (!parallel) return DrawMatrixFlat(Ad, rawd, K, n, W, logQ);
+        for (size_t k = 0; k < K; ++k, pos += lenA + lenG) segs.push_back(Seg{Ad + k * pw, rawd + k * ((size_t)n + 1), pos, false});
+      };
+      auto short_draw = [&](int32_t *out) {
+        if (parallel) gs.seek(pos);
+        SampleHWtSmall(out, 64, n);
+        if (parallel) pos = gs.position();
+      };
+      segs.clear();
+      if (parallel) pos = gs.position();
+      short_draw(sk_out);                                       // FHESISecKey::Init
+      if (parallel) {                                           // FHESIPubKey::Init: c0's Gaussian, then c1
+        segs.push_back(Seg{A + Km * pw, raw.data() + Km * ((size_t)n + 1), pos, true});
+        pos += lenA + lenG;
+      } else {
+        SampleGaussianRaw(raw.data() + Km * ((size_t)n + 1), n);
+        SampleRandomWords(A + Km * pw, n, W, logQ);
+      }
+      {                                                         // KeySwitchSI(sk): InitS2
+        short_draw(tmp.data());                                 // the throw-away key of FHE-SI.cpp:222
+        std::fill(src, src + n, 0);
+        src[0] = 1;
+        memcpy(src + n, sk_out, n * 4);
+        if (twoh) MulSmallPhim(sk_out, sk_out, src + 2 * (size_t)n, n);
+        else MulSmallGeneral(sk_out, sk_out, src + 2 * (size_t)n, context.zMstar);
+        long_draws(A, raw.data(), 3 * (size_t)D);
+      }
+      for (uint32_t r = 0; r < n_rot; ++r) {                    // KeySwitchSI(sk, k): InitAutomorph
+        short_draw(tmp.data());                                 // :233
+        int32_t *rs = src + (3 + 2 * (size_t)r) * n;
+        std::fill(rs, rs + n, 0);
+        rs[0] = 1;                                              // 1(X^k) = 1
+        if (twoh) AutomorphSmallPhim(sk_out, rs + n, n, m, rot_k[r]);
+        else AutomorphSmallGeneral(sk_out, rs + n, context.zMstar, rot_k[r]);
+        const size_t off = (3 + 2 * (size_t)r) * D;
+        long_draws(A + off * pw, raw.data() + off * ((size_t)n + 1), 2 * (size_t)D);
+      }
+      if (!parallel) break;
+      gs.seek(pos);  // the stream continues after the last long draw
+      std::atomic<bool> ok{true};
+      const RandomStream keyed = gs;  // same key; every worker seeks its own copy
+      ParallelFor(segs.size(), [&](size_t i) {
+        RandomStream t = keyed;
+        t.seek(segs[i].pos);
+        bool good = true;
+        if (segs[i].gauss_first) {
+          good = SampleGaussianRawNoRetry(t, segs[i].raw, n);
+          SampleRandomWords(segs[i].A, n, W, logQ, t);
+        } else {
+          SampleRandomWords(segs[i].A, n, W, logQ, t);
+          good = SampleGaussianRawNoRetry(t, segs[i].raw, n);
+        }
+        if (!good) ok = false;
+      });
+      if (ok && !getenv("FHESIH_TEST_REJECT")) break;  // (the variable: a test's way to take the next two lines)
+      parallel = false;  // a rejected word shifts everything after it: walk the stream in order instead
+      gs.seek(pos_start);
     }
     const double T2 = now();
     // the floating-point half of every Gaussian polynomial, on all cores

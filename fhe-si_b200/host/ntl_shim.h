@@ -630,6 +630,15 @@ struct RandomStream {
     if (e && std::string(e) == "splitmix64") test = true;
     else seed_from_os();
   }
+  // The ChaCha20 stream is block-counter mode: the number of 64-bit words drawn so far, and random access to any
+  // word of the stream (fhesih_keydraws_flat fills the long, fixed-length draws of a key set-up on several cores)
+  uint64_t position() const { return counter * 8 - have; }
+  void seek(uint64_t pos) {
+    const uint64_t c0 = pos / (8 * LANES) * LANES;
+    chacha_blocks(c0);
+    counter = c0 + LANES;
+    have = (unsigned)(8 * LANES - (pos - c0 * 8));
+  }
   uint64_t next64() {
     if (test) {
       state += 0x9E3779B97F4A7C15ull;

@@ -341,3 +341,13 @@ def test_reference_clients_run_unchanged_gpu(cuda_lib, tmp_path):
 @pytest.mark.parametrize("name", sorted(REF_GOLD["configs"]))
 def test_host_client_matches_oracle_gpu(cuda_lib, tmp_path, name):
     check_against_golden(run_client(cuda_lib, tmp_path, name), name)
+
+
+def test_keydraws_parallel_fill_matches_sequential_walk_emu(emu_lib):
+    """The long draws of a key set-up filled on several cores from their positions in the ChaCha20 stream
+    (fhesih_keydraws_flat) against the in-order walk of the same stream, in a process that runs the real stream."""
+    build_host(emu_lib)
+    env = {k: v for k, v in os.environ.items() if k not in ("FHESI_TEST_RNG", "FHESIH_SEQ_DRAWS")}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpp", "keydraws_parallel_check.py"), emu_lib],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "parallel == sequential" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
